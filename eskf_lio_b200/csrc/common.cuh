@@ -1,0 +1,191 @@
+// common.cuh — device helpers shared by the hot-path kernels (sm_100a).
+//
+// Exact-arithmetic contract: everything that decides a voxel key or feeds the
+// fp64 master statistics of the map uses round-to-nearest intrinsics
+// (__dmul_rn/__dadd_rn/__ddiv_rn), which nvcc never contracts into FMAs, in
+// the same evaluation order as the reference's Eigen/Open3D expressions built
+// without FMA (CMakeLists.txt:6-9):  ((a0*b0 + a1*b1) + a2*b2) [+ t].
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace eskf {
+
+constexpr int kKeyBits = 21;
+constexpr int64_t kKeyBias = 1 << 20;
+constexpr uint64_t kEmptyKey = ~0ull;
+
+// ------------------------------------------------------------- exact fp64
+__device__ __forceinline__ double dot3_rn(double a0, double b0, double a1, double b1, double a2,
+                                          double b2) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1)), __dmul_rn(a2, b2));
+}
+
+// Open3D PointCloud::Transform / Eigen Isometry3d * Vector3d:  (R p) + t.
+// T points at 12 doubles: R row-major (9) then t (3).
+__device__ __forceinline__ void transform_point_rn(const double* __restrict__ T, double& x,
+                                                   double& y, double& z) {
+  const double px = x, py = y, pz = z;
+  x = __dadd_rn(dot3_rn(T[0], px, T[1], py, T[2], pz), T[9]);
+  y = __dadd_rn(dot3_rn(T[3], px, T[4], py, T[5], pz), T[10]);
+  z = __dadd_rn(dot3_rn(T[6], px, T[7], py, T[8], pz), T[11]);
+}
+
+// C <- (R C) R^T, row-major 3x3, same association as Eigen's R * C * R^T.
+__device__ __forceinline__ void rotate_cov_rn(const double* __restrict__ R, double* C) {
+  double A[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      A[3 * i + j] = dot3_rn(R[3 * i], C[j], R[3 * i + 1], C[3 + j], R[3 * i + 2], C[6 + j]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      C[3 * i + j] = dot3_rn(A[3 * i], R[3 * j], A[3 * i + 1], R[3 * j + 1], A[3 * i + 2], R[3 * j + 2]);
+}
+
+// getVoxelIndex (src/LocalMap.cpp:114-118, src/CloudPreprocessor.cpp:129-133):
+// floor(p / voxel) with a true IEEE division, then a truncating cast.
+__device__ __forceinline__ int voxel_coord(double p, double voxel) {
+  return static_cast<int>(floor(__ddiv_rn(p, voxel)));
+}
+
+__device__ __forceinline__ bool coord_in_range(int k) { return k > -kKeyBias && k < kKeyBias; }
+
+// ------------------------------------------------------------------- keys
+// table key: three biased 21-bit fields, (kx, ky, kz) lexicographic
+__host__ __device__ __forceinline__ uint64_t pack_key(int x, int y, int z) {
+  return (static_cast<uint64_t>(x + kKeyBias) << 42) | (static_cast<uint64_t>(y + kKeyBias) << 21) |
+         static_cast<uint64_t>(z + kKeyBias);
+}
+
+__host__ __device__ __forceinline__ void unpack_key(uint64_t k, int& x, int& y, int& z) {
+  x = static_cast<int>((k >> 42) & 0x1FFFFF) - static_cast<int>(kKeyBias);
+  y = static_cast<int>((k >> 21) & 0x1FFFFF) - static_cast<int>(kKeyBias);
+  z = static_cast<int>(k & 0x1FFFFF) - static_cast<int>(kKeyBias);
+}
+
+// murmur3 fmix64
+__host__ __device__ __forceinline__ uint64_t hash_key(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ULL;
+  k ^= k >> 33;
+  return k;
+}
+
+// 21-bit -> 63-bit Morton spreading (x bit i -> bit 3i)
+__host__ __device__ __forceinline__ uint64_t spread3(uint32_t v) {
+  uint64_t x = v & 0x1FFFFF;
+  x = (x | (x << 32)) & 0x1F00000000FFFFull;
+  x = (x | (x << 16)) & 0x1F0000FF0000FFull;
+  x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+  x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+  x = (x | (x << 2)) & 0x1249249249249249ull;
+  return x;
+}
+
+__host__ __device__ __forceinline__ uint32_t compact3(uint64_t x) {
+  x &= 0x1249249249249249ull;
+  x = (x | (x >> 2)) & 0x10C30C30C30C30C3ull;
+  x = (x | (x >> 4)) & 0x100F00F00F00F00Full;
+  x = (x | (x >> 8)) & 0x1F0000FF0000FFull;
+  x = (x | (x >> 16)) & 0x1F00000000FFFFull;
+  x = (x | (x >> 32)) & 0x1FFFFF;
+  return static_cast<uint32_t>(x);
+}
+
+// Morton code of coordinates rebased to the batch minimum (all >= 0):
+// x -> bits 3i+2, y -> 3i+1, z -> 3i
+__host__ __device__ __forceinline__ uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) {
+  return (spread3(x) << 2) | (spread3(y) << 1) | spread3(z);
+}
+
+// --------------------------------------------------------- cache-global IO
+template <typename T>
+__device__ __forceinline__ T ld_cg(const T* p) {
+  return __ldcg(p);
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ------------------------------------------------------------ grid barrier
+// Software grid-wide barrier for persistent kernels launched cooperatively
+// (all CTAs co-resident).  Every spin is bounded: on timeout the error word
+// is set and the caller must bail out, so a logic error can never hang the GPU.
+struct GridBarrier {
+  unsigned count;
+  unsigned gen;
+  unsigned error;
+  unsigned pad;
+};
+
+constexpr unsigned kSpinLimit = 1u << 24;  // x >= 64 ns sleeps: > 1 s
+
+__device__ __forceinline__ bool grid_sync(GridBarrier* gb, unsigned nblocks) {
+  __shared__ unsigned s_ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned ok = 1;
+    if (nblocks > 1) {
+      const unsigned gen = ld_acquire_u32(&gb->gen);
+      __threadfence();
+      const unsigned arrived = atomicAdd(&gb->count, 1u);
+      if (arrived == nblocks - 1) {
+        atomicExch(&gb->count, 0u);
+        __threadfence();
+        st_release_u32(&gb->gen, gen + 1);
+      } else {
+        unsigned spins = 0;
+        while (ld_acquire_u32(&gb->gen) == gen) {
+          __nanosleep(64);
+          if (++spins > kSpinLimit || ld_acquire_u32(&gb->error) != 0) {
+            atomicExch(&gb->error, 1u);
+            ok = 0;
+            break;
+          }
+        }
+      }
+      __threadfence();
+    }
+    s_ok = ok;
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
+
+// ------------------------------------------------------------ block helpers
+__device__ __forceinline__ int warp_reduce_min(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_reduce_max(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ unsigned warp_reduce_add(unsigned v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_reduce_add(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace eskf

@@ -1,0 +1,226 @@
+// internal.h — handle layouts and host helpers behind include/eskf_gpu.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/eskf_gpu.h"
+#include "common.cuh"
+
+namespace eskf {
+
+// ------------------------------------------------------------------ errors
+void set_error(const char* fmt, ...);
+
+#define ESKF_CUDA(call)                                                                  \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      eskf::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return ESKF_ERR_CUDA;                                                              \
+    }                                                                                    \
+  } while (0)
+
+#define ESKF_TRY(call)            \
+  do {                            \
+    int s__ = (call);             \
+    if (s__ != ESKF_OK) return s__; \
+  } while (0)
+
+#define ESKF_REQUIRE(cond, msg)                   \
+  do {                                            \
+    if (!(cond)) {                                \
+      eskf::set_error("invalid argument: %s", msg); \
+      return ESKF_ERR_INVALID;                    \
+    }                                             \
+  } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return ESKF_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    size_t want = need + need / 4 + 256;
+    ESKF_CUDA(cudaMalloc(&p, want));
+    bytes = want;
+    return ESKF_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+// ---------------------------------------------------------------- layouts
+// One voxel of the open-addressing table, 64 B = two 32 B sectors.  Sector 0
+// is all a probe needs (key) plus the mean; sector 1 is the covariance.  The
+// mean is stored relative to the voxel centre so fp32 keeps ~3e-8 m.
+struct __align__(16) VoxelSlot {
+  uint64_t key;    // pack_key(), kEmptyKey when free
+  uint32_t count;  // numPoints (capped)
+  uint32_t pad0;
+  float mx, my, mz;  // mean - (k + 0.5) * voxel
+  float pad1;
+  float c00, c01, c02, c11;
+  float c12, c22, pad2, pad3;
+};
+static_assert(sizeof(VoxelSlot) == 64, "VoxelSlot must be 64 bytes");
+
+constexpr int kMasterStride = 12;  // fp64 master: mean[3] + cov[9] per slot
+
+struct DeskewSeg {
+  uint32_t begin, end;
+  double T[12];
+};
+
+// written by the voxelize kernel, read by its consumers
+struct VoxelHeader {
+  int mn[3];      // min voxel coordinate per axis   (memset 0x7F before launch)
+  int nmx[3];     // min of the NEGATED coordinate   (same)
+  int pad[2];
+  // --- zeroed before launch
+  unsigned error;    // bit0: coordinate out of range, bit1: barrier timeout
+  unsigned sel;      // which ping-pong buffer holds the sorted (key, idx)
+  unsigned n_out;    // runs (mode 0) or kept points (mode 1)
+  unsigned bits;     // bits per axis of the rebased coordinates
+  GridBarrier gb;
+};
+
+}  // namespace eskf
+
+struct eskf_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 0;
+  uint64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // scratch
+  eskf::DevBuf stage;      // AoS upload / download staging
+  eskf::DevBuf sortbuf;    // keyA keyB idxA idxB
+  eskf::DevBuf hist;       // 2 x [G][256] + blk counts
+  eskf::DevBuf hdr;        // VoxelHeader
+  eskf::DevBuf runs;       // run_start / keep_flag / kept_src / kept_pos
+  eskf::DevBuf sorted_xyz; // positions gathered in sorted order (kNN)
+  eskf::DevBuf segs;       // deskew segments
+  eskf::DevBuf work;       // align working positions (SoA)
+  eskf::DevBuf partials;   // align per-block partial sums
+  eskf::DevBuf astate;     // align state + traces
+  eskf::DevBuf misc;       // small outputs (query / export counters)
+  void* pinned = nullptr;  // pinned host scratch for small read-backs
+  size_t pinned_bytes = 0;
+  eskf_cloud* tmp_cloud[3] = {nullptr, nullptr, nullptr};  // host-buffer entry points
+  int max_blocks_voxelize = 0;
+  int max_blocks_align = 0;
+};
+
+struct eskf_cloud {
+  eskf_ctx* ctx = nullptr;
+  size_t n = 0, cap = 0;
+  double* xyz = nullptr;  // SoA: x[cap] y[cap] z[cap]
+  double* cov = nullptr;  // SoA: 9 x [cap], row-major entry index outermost
+  float4* c4 = nullptr;   // fp32 mirror of the covariance: (c00 c01 c02 c11)
+  float2* c2 = nullptr;   //                                (c12 c22)
+  uint32_t* src = nullptr;
+  bool has_cov = false, has_c32 = false, has_src = false;
+  double* x() const { return xyz; }
+  double* y() const { return xyz + cap; }
+  double* z() const { return xyz + 2 * cap; }
+};
+
+struct eskf_map {
+  eskf_ctx* ctx = nullptr;
+  double voxel = 0.0;
+  uint32_t cap_pts = 0;
+  uint64_t n_slots = 0;  // power of two
+  eskf::VoxelSlot* slots = nullptr;
+  double* master = nullptr;            // [n_slots][12]
+  unsigned long long* d_count = nullptr;  // occupied voxels (+1 word: table-full error)
+  uint64_t count_upper = 0;            // host-side upper bound of *d_count
+};
+
+namespace eskf {
+
+// pinned scratch of at least `bytes`
+int ctx_pinned(eskf_ctx* ctx, size_t bytes, void** out);
+int cloud_reserve(eskf_cloud* c, size_t cap, bool with_cov);
+int cloud_build_c32(eskf_cloud* c);
+
+// voxelize.cu ------------------------------------------------------------
+struct VoxelizeArgs {
+  const double* in_x;
+  const double* in_y;
+  const double* in_z;
+  int in_stride;
+  double* out_x;
+  double* out_y;
+  double* out_z;
+  double* cov;       // SoA 9 x pitch, rotated in place by T1 (nullable)
+  size_t cov_pitch;
+  unsigned n;
+  double voxel;
+  int has_T1;
+  double T1[12];
+  const DeskewSeg* segs;
+  int n_segs;
+  int mode;  // 0: runs in sorted order (map insert), 1: kept points in source order (preprocess)
+};
+// After it returns (asynchronously): ctx->hdr holds the VoxelHeader; the
+// sorted (key, idx) are in sort buffer hdr.sel; mode 0: runs[0..n_out] =
+// run starts (+ sentinel n); mode 1: kept_src / kept_pos lists and the
+// sorted-order position arrays.
+int voxelize(eskf_ctx* ctx, const VoxelizeArgs& a);
+
+struct SortView {
+  uint64_t* key[2];
+  uint32_t* idx[2];
+  uint32_t* run_start;  // mode 0
+  uint32_t* keep_flag;  // mode 1
+  uint32_t* kept_src;
+  uint32_t* kept_pos;
+  double* sx;
+  double* sy;
+  double* sz;
+  VoxelHeader* hdr;
+};
+SortView sort_view(eskf_ctx* ctx, unsigned n);
+
+// local_map.cu ------------------------------------------------------------
+int map_reserve(eskf_map* m, uint64_t incoming_points);
+
+// preprocess.cu -----------------------------------------------------------
+int compute_deskew_segments(const double* point_time, size_t n, const eskf_state* states,
+                            size_t n_states, std::vector<DeskewSeg>* out);
+
+// registration.cu ---------------------------------------------------------
+struct AlignArgs {
+  const eskf_map* map;
+  const eskf_cloud* cloud;
+  double guess[16];
+  int max_iteration;
+  int neighbor_mode;
+  double trans_sq_thr;
+  double cos_thr;
+  int fixed_iterations;  // > 0: run exactly this many, ignore convergence
+  int fp64_math;
+  uint8_t* d_hit;        // device, optional: hit mask of iteration 0
+};
+int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align_info* info);
+
+inline void count_launch(eskf_ctx* ctx, int n = 1) { ctx->launches += n; }
+
+}  // namespace eskf

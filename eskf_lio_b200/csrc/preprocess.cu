@@ -1,0 +1,528 @@
+// preprocess.cu — CloudPreprocessor (src/CloudPreprocessor.cpp) on the device.
+//
+//   process (:10-23)      T_il transform + deskew + downsample/covariances
+//   deskew  (:25-74)      the per-IMU-interval rigid transforms are tiny host
+//                         work (<= ~45 poses per sweep); the 64k-point apply
+//                         is fused into the voxelize kernel's first phase
+//   voxelDownsampleAndEstimateCovariances (:76-127)
+//                         first-point-per-voxel == run heads of the stable
+//                         radix sort; 30-NN covariance = K4 below
+//
+// K4: one warp per kept point.  The points are sorted by the Morton code of
+// their voxel, so an aligned 2^L-voxel block is ONE contiguous range of the
+// sorted array.  The warp searches the 3x3x3 blocks around the query at level
+// L (27 lanes binary-search the 27 ranges at once), keeps an exact top-30 in
+// registers (one entry per lane, shuffle insertion), and stops when the 30th
+// distance is inside the searched neighbourhood; otherwise L += 1.  That is an
+// exact k-NN (same set as the reference's KD-tree, Open3D KDTreeFlann with
+// KDTreeSearchParamKNN() => k = 30) with bounded work in sparse regions.
+#include <cmath>
+#include <limits>
+
+#include "internal.h"
+
+namespace eskf {
+
+namespace {
+
+constexpr int kKnn = 30;  // open3d::geometry::KDTreeSearchParamKNN() default
+
+struct KnnParams {
+  const uint64_t* key[2];
+  const VoxelHeader* hdr;
+  const double* sx;  // positions in sorted order
+  const double* sy;
+  const double* sz;
+  const uint32_t* sidx[2];  // sorted position -> source index
+  const uint32_t* kept_src;
+  const uint32_t* kept_pos;
+  const double* px;  // positions in source order
+  const double* py;
+  const double* pz;
+  unsigned n;
+  double voxel;
+  double* ox;
+  double* oy;
+  double* oz;
+  double* ocov;
+  size_t opitch;
+  uint32_t* osrc;
+  float4* oc4;
+  float2* oc2;
+};
+
+__device__ __forceinline__ unsigned lower_bound_u64(const uint64_t* a, unsigned lo, unsigned hi,
+                                                    uint64_t v) {
+  while (lo < hi) {
+    const unsigned mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// symmetric 3x3 Jacobi eigen-decomposition (cyclic sweeps), fully unrolled so
+// everything stays in registers.  w descending, V columns = eigenvectors.
+__device__ __forceinline__ void eig_sym3(const double* C, double* w, double* V) {
+  double a00 = C[0], a01 = 0.5 * (C[1] + C[3]), a02 = 0.5 * (C[2] + C[6]);
+  double a11 = C[4], a12 = 0.5 * (C[5] + C[7]), a22 = C[8];
+  double u[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    const double off = a01 * a01 + a02 * a02 + a12 * a12;
+    const double diag = a00 * a00 + a11 * a11 + a22 * a22;
+    if (off <= 1e-34 * diag || off == 0.0) break;
+    // rotation in plane (p, q): A <- J^T A J
+#define ESKF_JACOBI(app, aqq, apq, akp, akq, up0, uq0, up1, uq1, up2, uq2)          \
+    if (apq != 0.0) {                                                                \
+      const double theta = (aqq - app) / (2.0 * apq);                                \
+      const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0)); \
+      const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;                        \
+      app = app - tt * apq;                                                          \
+      aqq = aqq + tt * apq;                                                          \
+      apq = 0.0;                                                                     \
+      const double kp = akp, kq = akq;                                               \
+      akp = c * kp - s * kq;                                                         \
+      akq = s * kp + c * kq;                                                         \
+      double x0 = up0, y0 = uq0; up0 = c * x0 - s * y0; uq0 = s * x0 + c * y0;       \
+      double x1 = up1, y1 = uq1; up1 = c * x1 - s * y1; uq1 = s * x1 + c * y1;       \
+      double x2 = up2, y2 = uq2; up2 = c * x2 - s * y2; uq2 = s * x2 + c * y2;       \
+    }
+    ESKF_JACOBI(a00, a11, a01, a02, a12, u[0], u[1], u[3], u[4], u[6], u[7])  // (0,1), k = 2
+    ESKF_JACOBI(a00, a22, a02, a01, a12, u[0], u[2], u[3], u[5], u[6], u[8])  // (0,2), k = 1
+    ESKF_JACOBI(a11, a22, a12, a01, a02, u[1], u[2], u[4], u[5], u[7], u[8])  // (1,2), k = 0
+#undef ESKF_JACOBI
+  }
+  // sort descending (3 elements)
+  double ev[3] = {a00, a11, a22};
+  int o0 = 0, o1 = 1, o2 = 2;
+  if (ev[o0] < ev[o1]) { int t = o0; o0 = o1; o1 = t; }
+  if (ev[o1] < ev[o2]) { int t = o1; o1 = o2; o2 = t; }
+  if (ev[o0] < ev[o1]) { int t = o0; o0 = o1; o1 = t; }
+  const int ord[3] = {o0, o1, o2};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    w[j] = ord[j] == 0 ? a00 : (ord[j] == 1 ? a11 : a22);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      V[3 * i + j] = ord[j] == 0 ? u[3 * i] : (ord[j] == 1 ? u[3 * i + 1] : u[3 * i + 2]);
+  }
+}
+
+__global__ void __launch_bounds__(128) knn_cov_kernel(KnnParams P) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned n_kept = P.hdr->n_out;
+  const unsigned sel = P.hdr->sel;
+  const uint64_t* keys = P.key[sel];
+  const uint32_t* sidx = P.sidx[sel];
+  const int m0 = P.hdr->mn[0], m1 = P.hdr->mn[1], m2 = P.hdr->mn[2];
+  const int M0 = -P.hdr->nmx[0] - m0, M1 = -P.hdr->nmx[1] - m1, M2 = -P.hdr->nmx[2] - m2;
+  const unsigned n = P.n;
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+  const int K = kKnn < static_cast<int>(n) ? kKnn : static_cast<int>(n);
+
+  for (unsigned r = warp; r < n_kept; r += nwarps) {
+    const unsigned j0 = P.kept_pos[r];
+    const double qx = P.sx[j0], qy = P.sy[j0], qz = P.sz[j0];
+    const uint64_t mk = __ldg(keys + j0);
+    const int cx = static_cast<int>(compact3(mk >> 2));
+    const int cy = static_cast<int>(compact3(mk >> 1));
+    const int cz = static_cast<int>(compact3(mk));
+    double ld2 = kInf;   // lane l: l-th nearest so far
+    int lid = -1;
+    int cnt = 0;
+    double kth = kInf;
+    for (int L = 0; L <= kKeyBits; ++L) {
+      ld2 = kInf;
+      lid = -1;
+      cnt = 0;
+      kth = kInf;
+      const int bx = cx >> L, by = cy >> L, bz = cz >> L;
+      unsigned start = 0, end = 0;
+      if (lane < 27) {
+        const int nx = bx + static_cast<int>(lane % 3) - 1;
+        const int ny = by + static_cast<int>((lane / 3) % 3) - 1;
+        const int nz = bz + static_cast<int>(lane / 9) - 1;
+        if (nx >= 0 && ny >= 0 && nz >= 0 && nx <= (M0 >> L) && ny <= (M1 >> L) && nz <= (M2 >> L)) {
+          const uint64_t lo = morton3(nx, ny, nz) << (3 * L);
+          const uint64_t hi = lo + (1ull << (3 * L));
+          start = lower_bound_u64(keys, 0, n, lo);
+          end = lower_bound_u64(keys, start, n, hi);
+        }
+      }
+      for (int t = 0; t < 27; ++t) {
+        const unsigned s = __shfl_sync(0xffffffffu, start, t);
+        const unsigned e = __shfl_sync(0xffffffffu, end, t);
+        for (unsigned jb = s; jb < e; jb += 32) {
+          const unsigned j = jb + lane;
+          double d = kInf;
+          int id = -1;
+          if (j < e) {
+            const double dx = P.sx[j] - qx, dy = P.sy[j] - qy, dz = P.sz[j] - qz;
+            d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            id = static_cast<int>(__ldg(sidx + j));
+          }
+          unsigned bal = __ballot_sync(0xffffffffu, id >= 0 && d <= kth);
+          while (bal) {
+            const int src = __ffs(bal) - 1;
+            bal &= bal - 1;
+            const double cd = __shfl_sync(0xffffffffu, d, src);
+            const int cid = __shfl_sync(0xffffffffu, id, src);
+            // (d2, index) lexicographic order, like the oracle's heap
+            const int pos = __popc(__ballot_sync(0xffffffffu, ld2 < cd || (ld2 == cd && lid < cid)));
+            if (pos < K) {
+              const double up_d = __shfl_up_sync(0xffffffffu, ld2, 1);
+              const int up_i = __shfl_up_sync(0xffffffffu, lid, 1);
+              if (static_cast<int>(lane) > pos) {
+                ld2 = up_d;
+                lid = up_i;
+              } else if (static_cast<int>(lane) == pos) {
+                ld2 = cd;
+                lid = cid;
+              }
+              if (static_cast<int>(lane) >= K) {
+                ld2 = kInf;
+                lid = -1;
+              }
+              if (cnt < K) ++cnt;
+              kth = __shfl_sync(0xffffffffu, ld2, K - 1);
+            }
+          }
+        }
+      }
+      // the 3x3x3 neighbourhood already holds every point?
+      if ((M0 >> L) == 0 && (M1 >> L) == 0 && (M2 >> L) == 0) break;
+      if (cnt == K) {
+        const double span = static_cast<double>(1 << L);
+        const double ax = (static_cast<double>(m0) + static_cast<double>(bx) * span);
+        const double ay = (static_cast<double>(m1) + static_cast<double>(by) * span);
+        const double az = (static_cast<double>(m2) + static_cast<double>(bz) * span);
+        double bound = fmin(qx - (ax - span) * P.voxel, (ax + 2.0 * span) * P.voxel - qx);
+        bound = fmin(bound, fmin(qy - (ay - span) * P.voxel, (ay + 2.0 * span) * P.voxel - qy));
+        bound = fmin(bound, fmin(qz - (az - span) * P.voxel, (az + 2.0 * span) * P.voxel - qz));
+        bound -= 1e-9;
+        if (bound > 0.0 && kth <= bound * bound) break;
+      }
+    }
+    // Open3D utility::ComputeCovariance over the neighbours in ascending
+    // distance order, exact ops (src/CloudPreprocessor.cpp:111-118)
+    double nxp = 0.0, nyp = 0.0, nzp = 0.0;
+    if (lid >= 0) {
+      nxp = P.px[lid];
+      nyp = P.py[lid];
+      nzp = P.pz[lid];
+    }
+    double C[9];
+    if (cnt >= 3) {
+      double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int l = 0; l < cnt; ++l) {
+        const double x = __shfl_sync(0xffffffffu, nxp, l);
+        const double y = __shfl_sync(0xffffffffu, nyp, l);
+        const double z = __shfl_sync(0xffffffffu, nzp, l);
+        c[0] = __dadd_rn(c[0], x);
+        c[1] = __dadd_rn(c[1], y);
+        c[2] = __dadd_rn(c[2], z);
+        c[3] = __dadd_rn(c[3], __dmul_rn(x, x));
+        c[4] = __dadd_rn(c[4], __dmul_rn(x, y));
+        c[5] = __dadd_rn(c[5], __dmul_rn(x, z));
+        c[6] = __dadd_rn(c[6], __dmul_rn(y, y));
+        c[7] = __dadd_rn(c[7], __dmul_rn(y, z));
+        c[8] = __dadd_rn(c[8], __dmul_rn(z, z));
+      }
+      const double nn = static_cast<double>(cnt);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) c[k] = __ddiv_rn(c[k], nn);
+      C[0] = __dadd_rn(c[3], -__dmul_rn(c[0], c[0]));
+      C[4] = __dadd_rn(c[6], -__dmul_rn(c[1], c[1]));
+      C[8] = __dadd_rn(c[8], -__dmul_rn(c[2], c[2]));
+      C[1] = C[3] = __dadd_rn(c[4], -__dmul_rn(c[0], c[1]));
+      C[2] = C[6] = __dadd_rn(c[5], -__dmul_rn(c[0], c[2]));
+      C[5] = C[7] = __dadd_rn(c[7], -__dmul_rn(c[1], c[2]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) C[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    }
+    // regularise: U diag(1,1,1e-2) V^T (src/CloudPreprocessor.cpp:120-123);
+    // U == V for a symmetric PSD matrix
+    double wv[3], V[9], R[9];
+    eig_sym3(C, wv, V);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        R[3 * i + j] = (V[3 * i] * V[3 * j] + V[3 * i + 1] * V[3 * j + 1]) + 1e-2 * (V[3 * i + 2] * V[3 * j + 2]);
+    if (lane == 0) {
+      P.ox[r] = qx;
+      P.oy[r] = qy;
+      P.oz[r] = qz;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) P.ocov[k * P.opitch + r] = R[k];
+      P.osrc[r] = P.kept_src[r];
+      P.oc4[r] = make_float4(static_cast<float>(R[0]), static_cast<float>(R[1]),
+                             static_cast<float>(R[2]), static_cast<float>(R[4]));
+      P.oc2[r] = make_float2(static_cast<float>(R[5]), static_cast<float>(R[8]));
+    }
+  }
+}
+
+// ------------------------------------------------------------ host helpers
+struct HIso {
+  double R[9];
+  double t[3];
+};
+
+inline double hdot3(double a0, double b0, double a1, double b1, double a2, double b2) {
+  return (a0 * b0 + a1 * b1) + a2 * b2;
+}
+
+void quat_to_matrix(const double* q, double* R) {  // Eigen Quaterniond::toRotationMatrix
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1.0 - (txx + tyy);
+}
+
+HIso iso_mul(const HIso& a, const HIso& b) {
+  HIso r;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j)
+      r.R[3 * i + j] = hdot3(a.R[3 * i], b.R[j], a.R[3 * i + 1], b.R[3 + j], a.R[3 * i + 2], b.R[6 + j]);
+    r.t[i] = hdot3(a.R[3 * i], b.t[0], a.R[3 * i + 1], b.t[1], a.R[3 * i + 2], b.t[2]) + a.t[i];
+  }
+  return r;
+}
+
+HIso iso_inv(const HIso& a) {
+  HIso r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r.R[3 * i + j] = a.R[3 * j + i];
+  for (int i = 0; i < 3; ++i)
+    r.t[i] = -hdot3(r.R[3 * i], a.t[0], r.R[3 * i + 1], a.t[1], r.R[3 * i + 2], a.t[2]);
+  return r;
+}
+
+// Utils::interpolateSE3 (src/Utils.cpp:65-75) with Eigen's slerp
+HIso interpolate(const eskf_state& s1, const eskf_state& s2, double t) {
+  const double f = (t - s1.timestamp) / (s2.timestamp - s1.timestamp + 1e-6);
+  const double* a = s1.attitude_xyzw;
+  const double* b = s2.attitude_xyzw;
+  const double d = (a[0] * b[0] + a[1] * b[1]) + (a[2] * b[2] + a[3] * b[3]);
+  const double ad = std::fabs(d);
+  double s0, s1c;
+  if (ad >= 1.0 - std::numeric_limits<double>::epsilon()) {
+    s0 = 1.0 - f;
+    s1c = f;
+  } else {
+    const double th = std::acos(ad), sn = std::sin(th);
+    s0 = std::sin((1.0 - f) * th) / sn;
+    s1c = std::sin(f * th) / sn;
+  }
+  if (d < 0.0) s1c = -s1c;
+  double q[4];
+  for (int i = 0; i < 4; ++i) q[i] = s0 * a[i] + s1c * b[i];
+  HIso r;
+  quat_to_matrix(q, r.R);
+  for (int i = 0; i < 3; ++i) r.t[i] = s1.position[i] + f * (s2.position[i] - s1.position[i]);
+  return r;
+}
+
+}  // namespace
+
+// CloudPreprocessor::deskew (src/CloudPreprocessor.cpp:25-74) reduced to its
+// segment table: [begin, end) point ranges and the rigid transform of each.
+// Points outside every segment stay untouched — including the reference's
+// last segment, whose inner scan runs off the end (:54-65).
+int compute_deskew_segments(const double* point_time, size_t n, const eskf_state* states,
+                            size_t n_states, std::vector<DeskewSeg>* out) {
+  out->clear();
+  if (n == 0 || n_states == 0) return ESKF_OK;
+  const double end_time = point_time[n - 1];
+  long before = static_cast<long>(n_states) - 1;
+  while (before >= 0 && states[before].timestamp > end_time) --before;
+  if (before < 0) {
+    set_error("deskew: no state at or before the scan end time");
+    return ESKF_ERR_INVALID;
+  }
+  const long after = before + 1 < static_cast<long>(n_states) ? before + 1 : before;
+  const HIso end_inv = iso_inv(interpolate(states[before], states[after], end_time));
+  size_t start = 0, end = 0;
+  for (long s = 0; s <= after; ++s) {
+    start = end;
+    // first point at or after `start` whose time is not < the state's stamp
+    const double ts = states[s].timestamp;
+    size_t lo = start, hi = n;
+    if (start < n && !(point_time[start] < ts)) {
+      hi = start;  // common case for old states: nothing to consume
+    } else {
+      while (lo < hi) {
+        const size_t mid = (lo + hi) / 2;
+        if (point_time[mid] < ts) lo = mid + 1; else hi = mid;
+      }
+      hi = lo;
+    }
+    if (hi >= n) break;  // ran off the end: `end` never advances again
+    end = hi;
+    if (start == end) continue;
+    HIso st;
+    quat_to_matrix(states[s].attitude_xyzw, st.R);
+    for (int i = 0; i < 3; ++i) st.t[i] = states[s].position[i];
+    const HIso tf = iso_mul(end_inv, st);
+    DeskewSeg seg;
+    seg.begin = static_cast<uint32_t>(start);
+    seg.end = static_cast<uint32_t>(end);
+    for (int i = 0; i < 9; ++i) seg.T[i] = tf.R[i];
+    for (int i = 0; i < 3; ++i) seg.T[9 + i] = tf.t[i];
+    out->push_back(seg);
+  }
+  return ESKF_OK;
+}
+
+namespace {
+
+int check_header(eskf_ctx* ctx, unsigned* n_out) {
+  VoxelHeader* h = nullptr;
+  ESKF_TRY(ctx_pinned(ctx, sizeof(VoxelHeader), reinterpret_cast<void**>(&h)));
+  ESKF_CUDA(cudaMemcpyAsync(h, ctx->hdr.p, sizeof(VoxelHeader), cudaMemcpyDeviceToHost, ctx->stream));
+  ESKF_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h->gb.error) {
+    set_error("grid barrier timeout in voxelize kernel");
+    return ESKF_ERR_INTERNAL;
+  }
+  if (h->error & 1u) {
+    set_error("voxel coordinate outside the 21-bit key range");
+    return ESKF_ERR_RANGE;
+  }
+  *n_out = h->n_out;
+  return ESKF_OK;
+}
+
+// raw (device, xyz only) -> out (device, xyz + cov + src index)
+int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
+                      const std::vector<DeskewSeg>& segs, double voxel, eskf_cloud* out) {
+  const unsigned n = static_cast<unsigned>(raw->n);
+  ESKF_TRY(cloud_reserve(out, raw->n, true));
+  VoxelizeArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.in_x = raw->x();
+  a.in_y = raw->y();
+  a.in_z = raw->z();
+  a.in_stride = 1;
+  a.out_x = raw->x();
+  a.out_y = raw->y();
+  a.out_z = raw->z();
+  a.cov = nullptr;
+  a.n = n;
+  a.voxel = voxel;
+  a.has_T1 = T_il != nullptr;
+  if (T_il)
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) a.T1[3 * i + j] = T_il[4 * i + j];
+      a.T1[9 + i] = T_il[4 * i + 3];
+    }
+  if (!segs.empty()) {
+    const size_t bytes = segs.size() * sizeof(DeskewSeg);
+    ESKF_TRY(ctx->segs.ensure(bytes));
+    void* hp = nullptr;
+    ESKF_TRY(ctx_pinned(ctx, bytes, &hp));
+    std::memcpy(hp, segs.data(), bytes);
+    ESKF_CUDA(cudaMemcpyAsync(ctx->segs.p, hp, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    a.segs = ctx->segs.as<DeskewSeg>();
+    a.n_segs = static_cast<int>(segs.size());
+  }
+  a.mode = 1;
+  ESKF_TRY(voxelize(ctx, a));
+  SortView v = sort_view(ctx, n);
+  KnnParams P;
+  P.key[0] = v.key[0];
+  P.key[1] = v.key[1];
+  P.hdr = v.hdr;
+  P.sx = v.sx;
+  P.sy = v.sy;
+  P.sz = v.sz;
+  P.sidx[0] = v.idx[0];
+  P.sidx[1] = v.idx[1];
+  P.kept_src = v.kept_src;
+  P.kept_pos = v.kept_pos;
+  P.px = raw->x();
+  P.py = raw->y();
+  P.pz = raw->z();
+  P.n = n;
+  P.voxel = voxel;
+  P.ox = out->x();
+  P.oy = out->y();
+  P.oz = out->z();
+  P.ocov = out->cov;
+  P.opitch = out->cap;
+  P.osrc = out->src;
+  P.oc4 = out->c4;
+  P.oc2 = out->c2;
+  const unsigned blocks = std::min<unsigned>((n + 3) / 4, static_cast<unsigned>(ctx->sm_count) * 16u);
+  knn_cov_kernel<<<blocks, 128, 0, ctx->stream>>>(P);
+  ESKF_CUDA(cudaGetLastError());
+  count_launch(ctx);
+  unsigned n_out = 0;
+  ESKF_TRY(check_header(ctx, &n_out));
+  out->n = n_out;
+  out->has_cov = true;
+  out->has_c32 = true;
+  out->has_src = true;
+  return ESKF_OK;
+}
+
+}  // namespace
+}  // namespace eskf
+
+using namespace eskf;
+
+extern "C" {
+
+int eskf_preprocess_cloud(eskf_ctx* ctx, eskf_cloud* raw, const double* point_time,
+                          const double T_il[16], const eskf_state* states, size_t n_states,
+                          double voxel_size, eskf_cloud* out) {
+  ESKF_REQUIRE(ctx && raw && out, "null argument");
+  ESKF_REQUIRE(raw->ctx == ctx && out->ctx == ctx, "clouds belong to another context");
+  ESKF_REQUIRE(raw != out, "raw and out must be different clouds");
+  ESKF_REQUIRE(voxel_size > 0.0, "voxel_size must be positive");
+  ESKF_REQUIRE(raw->n < (1ull << 31), "cloud too large");
+  ESKF_CUDA(cudaSetDevice(ctx->device));
+  if (raw->n == 0) {
+    out->n = 0;
+    return ESKF_OK;
+  }
+  std::vector<DeskewSeg> segs;
+  if (n_states > 0) {
+    ESKF_REQUIRE(states && point_time, "deskew needs states and point_time");
+    ESKF_TRY(compute_deskew_segments(point_time, raw->n, states, n_states, &segs));
+  }
+  raw->has_cov = false;
+  raw->has_c32 = false;
+  return preprocess_device(ctx, raw, T_il, segs, voxel_size, out);
+}
+
+int eskf_preprocess(eskf_ctx* ctx, const double* xyz, const double* point_time, size_t n,
+                    const double T_il[16], const eskf_state* states, size_t n_states,
+                    double voxel_size, size_t* n_out, double* xyz_out, double* cov_out,
+                    uint32_t* src_index_out) {
+  ESKF_REQUIRE(ctx && n_out, "null argument");
+  *n_out = 0;
+  if (n == 0) return ESKF_OK;
+  ESKF_REQUIRE(xyz, "null xyz");
+  if (!ctx->tmp_cloud[1]) ESKF_TRY(eskf_cloud_create(ctx, n, &ctx->tmp_cloud[1]));
+  if (!ctx->tmp_cloud[2]) ESKF_TRY(eskf_cloud_create(ctx, n, &ctx->tmp_cloud[2]));
+  ESKF_TRY(eskf_cloud_upload(ctx->tmp_cloud[1], xyz, nullptr, n));
+  ESKF_TRY(eskf_preprocess_cloud(ctx, ctx->tmp_cloud[1], point_time, T_il, states, n_states,
+                                 voxel_size, ctx->tmp_cloud[2]));
+  return eskf_cloud_download(ctx->tmp_cloud[2], xyz_out, cov_out, src_index_out, n, n_out);
+}
+
+int eskf_downsample_cov(eskf_ctx* ctx, const double* xyz, size_t n, double voxel_size,
+                        size_t* n_out, double* xyz_out, double* cov_out, uint32_t* src_index_out) {
+  return eskf_preprocess(ctx, xyz, nullptr, n, nullptr, nullptr, 0, voxel_size, n_out, xyz_out,
+                         cov_out, src_index_out);
+}
+
+}  // extern "C"

@@ -1,0 +1,655 @@
+// registration.cu — K7/K8: ICP::align (src/Registration.cpp:7-35) as ONE
+// persistent cooperative kernel: every Gauss-Newton iteration
+//   transform (Registration.cpp:13,27)  ->  voxel lookup (LocalMap.cpp:93-100)
+//   ->  per-point J^T W J / J^T W r (Registration.cpp:83-102)
+//   ->  reduction (Registration.cpp:60-76)  ->  6x6 LDLT + se3ToSE3 (:78-79)
+//   ->  compose + convergence test (:20-25)
+// runs on the device with no host round trip; CTAs meet once per iteration
+// through a "last CTA solves, everyone waits on an epoch word" hand-off.
+//
+// Numerics (BASELINE.json north_star): the position pipeline is fp64 with the
+// reference's exact evaluation order (so voxel keys are bit-exact); the
+// per-point 3x3 algebra is fp32 (fp64 on request); the 27 partial sums are
+// accumulated in fp64 in a fixed order (deterministic for a given grid).
+//
+// HBM traffic per source point per iteration (1-neighbour): 24 B position
+// read + 24 B position write + 24 B source covariance + 64 B voxel slot
+// = 136 B.
+#include <cfloat>
+
+#include "internal.h"
+
+namespace eskf {
+
+namespace {
+
+constexpr int kT = 256;
+constexpr int kW = kT / 32;
+constexpr int kAcc = 28;  // A(6) B(9) D(6) b(6) + correspondence count
+
+struct AlignState {
+  double T_total[12];  // R row-major (9) + t (3)
+  double T_step[12];   // to be applied to the working cloud by the next iteration
+  float Rf[12];        // fp32 copy of T_total's rotation
+  int iter;
+  int converged;
+  int done;
+  int pad0;
+  unsigned long long n_corr;
+  unsigned block_counter;
+  unsigned epoch;
+  unsigned error;
+  unsigned pad1;
+};
+
+struct AlignParams {
+  const VoxelSlot* slots;
+  uint64_t mask;
+  double voxel;
+  const double* x0;
+  const double* y0;
+  const double* z0;
+  const float4* c4;
+  const float2* c2;
+  double* wx;
+  double* wy;
+  double* wz;
+  unsigned n;
+  double guess[12];
+  int max_iteration;
+  int neighbor_mode;
+  double trans_sq_thr;
+  double cos_thr;
+  int fixed_iterations;
+  int pad;
+  AlignState* st;
+  double* partials;  // [G][kAcc]
+  double* sums;      // [kAcc] (single_pass output / solve input)
+  double* trace_H;
+  double* trace_b;
+  unsigned long long* trace_ncorr;
+  double* trace_step;
+  uint8_t* hit;
+};
+
+// ------------------------------------------------------------ per point math
+template <typename F>
+__device__ __forceinline__ void point_terms(F px, F py, F pz, F rx, F ry, F rz, F m00, F m01,
+                                            F m02, F m11, F m12, F m22, double* acc) {
+  // W = M^-1 by cofactors (Eigen Matrix3d::inverse(), Registration.cpp:95)
+  const F c00 = m11 * m22 - m12 * m12;
+  const F c01 = m02 * m12 - m01 * m22;
+  const F c02 = m01 * m12 - m02 * m11;
+  const F det = m00 * c00 + m01 * c01 + m02 * c02;
+  const F inv = F(1) / det;
+  const F w00 = c00 * inv, w01 = c01 * inv, w02 = c02 * inv;
+  const F w11 = (m00 * m22 - m02 * m02) * inv;
+  const F w12 = (m01 * m02 - m00 * m12) * inv;
+  const F w22 = (m00 * m11 - m01 * m01) * inv;
+  // J = [I | -skew(p)]  =>  H = [[W, B], [B^T, D]],  B_i = p x W_i,  D = skew(p) B
+  const F b00 = py * w02 - pz * w01, b01 = pz * w00 - px * w02, b02 = px * w01 - py * w00;
+  const F b10 = py * w12 - pz * w11, b11 = pz * w01 - px * w12, b12 = px * w11 - py * w01;
+  const F b20 = py * w22 - pz * w12, b21 = pz * w02 - px * w22, b22 = px * w12 - py * w02;
+  const F d00 = py * b20 - pz * b10, d01 = py * b21 - pz * b11, d02 = py * b22 - pz * b12;
+  const F d11 = pz * b01 - px * b21, d12 = pz * b02 - px * b22;
+  const F d22 = px * b12 - py * b02;
+  // J^T W r = [W r ; p x (W r)]
+  const F g0 = w00 * rx + w01 * ry + w02 * rz;
+  const F g1 = w01 * rx + w11 * ry + w12 * rz;
+  const F g2 = w02 * rx + w12 * ry + w22 * rz;
+  const F g3 = py * g2 - pz * g1, g4 = pz * g0 - px * g2, g5 = px * g1 - py * g0;
+  acc[0] += w00; acc[1] += w01; acc[2] += w02; acc[3] += w11; acc[4] += w12; acc[5] += w22;
+  acc[6] += b00; acc[7] += b01; acc[8] += b02;
+  acc[9] += b10; acc[10] += b11; acc[11] += b12;
+  acc[12] += b20; acc[13] += b21; acc[14] += b22;
+  acc[15] += d00; acc[16] += d01; acc[17] += d02; acc[18] += d11; acc[19] += d12; acc[20] += d22;
+  acc[21] += g0; acc[22] += g1; acc[23] += g2; acc[24] += g3; acc[25] += g4; acc[26] += g5;
+  acc[27] += 1.0;
+}
+
+// C' = R S R^T for symmetric S, 6 unique outputs
+template <typename F>
+__device__ __forceinline__ void rotate_sym(const F* R, F s00, F s01, F s02, F s11, F s12, F s22,
+                                           F* o) {
+  F t[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    t[3 * i + 0] = R[3 * i] * s00 + R[3 * i + 1] * s01 + R[3 * i + 2] * s02;
+    t[3 * i + 1] = R[3 * i] * s01 + R[3 * i + 1] * s11 + R[3 * i + 2] * s12;
+    t[3 * i + 2] = R[3 * i] * s02 + R[3 * i + 1] * s12 + R[3 * i + 2] * s22;
+  }
+  o[0] = t[0] * R[0] + t[1] * R[1] + t[2] * R[2];
+  o[1] = t[0] * R[3] + t[1] * R[4] + t[2] * R[5];
+  o[2] = t[0] * R[6] + t[1] * R[7] + t[2] * R[8];
+  o[3] = t[3] * R[3] + t[4] * R[4] + t[5] * R[5];
+  o[4] = t[3] * R[6] + t[4] * R[7] + t[5] * R[8];
+  o[5] = t[6] * R[6] + t[7] * R[7] + t[8] * R[8];
+}
+
+__constant__ int c_off7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0},
+                                 {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+
+// one pass over this CTA's points: transform, look up, accumulate
+template <typename F>
+__device__ __forceinline__ void accumulate_points(const AlignParams& P, const double* sT,
+                                                  const F* sR, bool first, bool write_hit,
+                                                  double* acc) {
+  const unsigned stride = gridDim.x * kT;
+  const int nn = P.neighbor_mode == 7 ? 7 : 1;
+  const double* sx = first ? P.x0 : P.wx;
+  const double* sy = first ? P.y0 : P.wy;
+  const double* sz = first ? P.z0 : P.wz;
+  for (unsigned i = blockIdx.x * kT + threadIdx.x; i < P.n; i += stride) {
+    double x = first ? __ldg(sx + i) : ld_cg(sx + i);
+    double y = first ? __ldg(sy + i) : ld_cg(sy + i);
+    double z = first ? __ldg(sz + i) : ld_cg(sz + i);
+    const float4 s4 = __ldg(P.c4 + i);
+    const float2 s2 = __ldg(P.c2 + i);
+    transform_point_rn(sT, x, y, z);
+    P.wx[i] = x;
+    P.wy[i] = y;
+    P.wz[i] = z;
+    const int kx = voxel_coord(x, P.voxel);
+    const int ky = voxel_coord(y, P.voxel);
+    const int kz = voxel_coord(z, P.voxel);
+    F cr[6];
+    bool rotated = false;
+    for (int o = 0; o < nn; ++o) {
+      const int vx = kx + c_off7[o][0], vy = ky + c_off7[o][1], vz = kz + c_off7[o][2];
+      const VoxelSlot* slot = nullptr;
+      if (coord_in_range(vx) && coord_in_range(vy) && coord_in_range(vz)) {
+        const uint64_t key = pack_key(vx, vy, vz);
+        uint64_t h = hash_key(key) & P.mask;
+        for (uint64_t probe = 0; probe <= P.mask; ++probe) {
+          const uint2 kw = __ldg(reinterpret_cast<const uint2*>(P.slots + h));
+          const uint64_t cur = (static_cast<uint64_t>(kw.y) << 32) | kw.x;
+          if (cur == key) {
+            slot = P.slots + h;
+            break;
+          }
+          if (cur == kEmptyKey) break;
+          h = (h + 1) & P.mask;
+        }
+      }
+      if (write_hit) P.hit[static_cast<size_t>(nn) * i + o] = slot != nullptr ? 1 : 0;
+      if (slot == nullptr) continue;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(slot) + 1);  // mx my mz -
+      const float4 c = __ldg(reinterpret_cast<const float4*>(slot) + 2);  // c00 c01 c02 c11
+      const float4 d = __ldg(reinterpret_cast<const float4*>(slot) + 3);  // c12 c22 - -
+      if (!rotated) {
+        rotate_sym<F>(sR, F(s4.x), F(s4.y), F(s4.z), F(s4.w), F(s2.x), F(s2.y), cr);
+        rotated = true;
+      }
+      // residual against the voxel mean, formed relative to the voxel centre
+      const double cx = __dmul_rn(static_cast<double>(vx) + 0.5, P.voxel);
+      const double cy = __dmul_rn(static_cast<double>(vy) + 0.5, P.voxel);
+      const double cz = __dmul_rn(static_cast<double>(vz) + 0.5, P.voxel);
+      const F rx = F(x - cx) - F(a.x), ry = F(y - cy) - F(a.y), rz = F(z - cz) - F(a.z);
+      point_terms<F>(F(x), F(y), F(z), rx, ry, rz, cr[0] + F(c.x), cr[1] + F(c.y), cr[2] + F(c.z),
+                     cr[3] + F(c.w), cr[4] + F(d.x), cr[5] + F(d.y), acc);
+    }
+  }
+}
+
+// deterministic CTA reduction of the 28 accumulators -> partials[blockIdx.x]
+__device__ __forceinline__ void block_reduce_store(double* acc, double (*s_part)[kAcc],
+                                                   double* out) {
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) {
+    const double v = warp_reduce_add(acc[k]);
+    if (lane == 0) s_part[w][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kAcc) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < kW; ++i) s += s_part[i][threadIdx.x];
+    out[threadIdx.x] = s;
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// sum partials[0..G) in a fixed order -> s_sum[kAcc]  (whole CTA cooperates)
+__device__ __forceinline__ void final_reduce(const double* partials, unsigned G,
+                                             double (*s_part)[kAcc], double* s_sum) {
+  const unsigned term = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  if (term < kAcc) {
+    double s = 0.0;
+    for (unsigned bb = grp; bb < G; bb += kW) s += ld_cg(partials + static_cast<size_t>(bb) * kAcc + term);
+    s_part[grp][term] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kAcc) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < kW; ++i) s += s_part[i][threadIdx.x];
+    s_sum[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+// Eigen LDLT<Matrix6d>::solve restated: diagonal pivoting, zero pivots -> 0
+__device__ void ldlt_solve6(const double* Hin, const double* bin, double* x) {
+  double A[6][6], L[6][6], D[6], y[6];
+  int perm[6];
+  for (int i = 0; i < 6; ++i) {
+    perm[i] = i;
+    D[i] = 0.0;
+    for (int j = 0; j < 6; ++j) {
+      A[i][j] = Hin[6 * i + j];
+      L[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+  }
+  for (int k = 0; k < 6; ++k) {
+    int piv = k;
+    double best = fabs(A[k][k]);
+    for (int i = k + 1; i < 6; ++i)
+      if (fabs(A[i][i]) > best) {
+        best = fabs(A[i][i]);
+        piv = i;
+      }
+    if (piv != k) {
+      for (int j = 0; j < 6; ++j) { double t = A[k][j]; A[k][j] = A[piv][j]; A[piv][j] = t; }
+      for (int i = 0; i < 6; ++i) { double t = A[i][k]; A[i][k] = A[i][piv]; A[i][piv] = t; }
+      for (int j = 0; j < k; ++j) { double t = L[k][j]; L[k][j] = L[piv][j]; L[piv][j] = t; }
+      int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+    }
+    const double d = A[k][k];
+    D[k] = d;
+    if (!(fabs(d) > 0.0)) {
+      if (k == 0) break;
+      continue;
+    }
+    for (int i = k + 1; i < 6; ++i) L[i][k] = A[i][k] / d;
+    for (int i = k + 1; i < 6; ++i)
+      for (int j = k + 1; j < 6; ++j) A[i][j] -= L[i][k] * d * L[j][k];
+  }
+  for (int i = 0; i < 6; ++i) y[i] = bin[perm[i]];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < i; ++j) y[i] -= L[i][j] * y[j];
+  for (int i = 0; i < 6; ++i) y[i] = (fabs(D[i]) > DBL_MIN) ? y[i] / D[i] : 0.0;
+  for (int i = 5; i >= 0; --i)
+    for (int j = i + 1; j < 6; ++j) y[i] -= L[j][i] * y[j];
+  for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
+}
+
+// Utils::se3ToSE3 (src/Utils.cpp:56-63) with computeJ (:40-54) and
+// rotationVectorToMatrix (:28-32, Eigen AngleAxisd::toRotationMatrix)
+__device__ void se3_to_SE3(const double* se3, double* T /* R(9) t(3) */) {
+  const double rx = se3[3], ry = se3[4], rz = se3[5];
+  const double n2 = rx * rx + ry * ry + rz * rz;
+  const double angle = sqrt(n2);
+  double ax = rx, ay = ry, az = rz;
+  if (n2 > 0.0) {
+    ax = rx / angle;
+    ay = ry / angle;
+    az = rz / angle;
+  }
+  double s, c;
+  sincos(angle, &s, &c);
+  double J[9];
+  if (angle < 1e-6) {
+    J[0] = 1; J[1] = 0; J[2] = 0; J[3] = 0; J[4] = 1; J[5] = 0; J[6] = 0; J[7] = 0; J[8] = 1;
+  } else {
+    const double f1 = s / angle, f2 = (1.0 - c) / angle, g = 1.0 - f1;
+    J[0] = f1 + g * ax * ax;      J[1] = g * ax * ay - f2 * az; J[2] = g * ax * az + f2 * ay;
+    J[3] = g * ay * ax + f2 * az; J[4] = f1 + g * ay * ay;      J[5] = g * ay * az - f2 * ax;
+    J[6] = g * az * ax - f2 * ay; J[7] = g * az * ay + f2 * ax; J[8] = f1 + g * az * az;
+  }
+  T[9] = J[0] * se3[0] + J[1] * se3[1] + J[2] * se3[2];
+  T[10] = J[3] * se3[0] + J[4] * se3[1] + J[5] * se3[2];
+  T[11] = J[6] * se3[0] + J[7] * se3[1] + J[8] * se3[2];
+  const double cx = (1.0 - c) * ax, cy = (1.0 - c) * ay, cz = (1.0 - c) * az;
+  const double sxv = s * ax, syv = s * ay, szv = s * az;
+  double tmp = cx * ay;
+  T[1] = tmp - szv; T[3] = tmp + szv;
+  tmp = cx * az;
+  T[2] = tmp + syv; T[6] = tmp - syv;
+  tmp = cy * az;
+  T[5] = tmp - sxv; T[7] = tmp + sxv;
+  T[0] = cx * ax + c; T[4] = cy * ay + c; T[8] = cz * az + c;
+}
+
+// thread 0 of the solving CTA: H/b -> step -> total, convergence, bookkeeping
+__device__ void solve_and_update(const AlignParams& P, const double* S, int it) {
+  AlignState* st = P.st;
+  double H[36], b[6], nb[6], se3[6], step[12], tot[12], old[12];
+  // unpack: A(6) B(9) D(6)
+  H[0] = S[0]; H[1] = S[1]; H[2] = S[2]; H[7] = S[3]; H[8] = S[4]; H[14] = S[5];
+  H[6] = S[1]; H[12] = S[2]; H[13] = S[4];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      H[6 * i + 3 + j] = S[6 + 3 * i + j];
+      H[6 * (3 + j) + i] = S[6 + 3 * i + j];
+    }
+  H[21] = S[15]; H[22] = S[16]; H[23] = S[17]; H[28] = S[18]; H[29] = S[19]; H[35] = S[20];
+  H[27] = S[16]; H[33] = S[17]; H[34] = S[19];
+  for (int i = 0; i < 6; ++i) {
+    b[i] = S[21 + i];
+    nb[i] = -b[i];
+  }
+  ldlt_solve6(H, nb, se3);  // JTJ.ldlt().solve(-JTr), Registration.cpp:78
+  se3_to_SE3(se3, step);
+  for (int i = 0; i < 12; ++i) old[i] = (it == 0) ? P.guess[i] : st->T_total[i];
+  // totalTransform = transformIter * totalTransform (Registration.cpp:20)
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j)
+      tot[3 * i + j] = step[3 * i] * old[j] + step[3 * i + 1] * old[3 + j] + step[3 * i + 2] * old[6 + j];
+    tot[9 + i] = (step[3 * i] * old[9] + step[3 * i + 1] * old[10] + step[3 * i + 2] * old[11]) + step[9 + i];
+  }
+  // convergenceCheck (Registration.cpp:37-50)
+  const double cosine = 0.5 * (((step[0] + step[4]) + step[8]) - 1.0);
+  const double tsq = step[9] * step[9] + step[10] * step[10] + step[11] * step[11];
+  const int conv = (cosine >= P.cos_thr && tsq <= P.trans_sq_thr) ? 1 : 0;
+  if (P.trace_H)
+    for (int i = 0; i < 36; ++i) P.trace_H[36 * it + i] = H[i];
+  if (P.trace_b)
+    for (int i = 0; i < 6; ++i) P.trace_b[6 * it + i] = b[i];
+  if (P.trace_ncorr) P.trace_ncorr[it] = static_cast<unsigned long long>(S[27]);
+  if (P.trace_step)
+    for (int i = 0; i < 12; ++i) P.trace_step[12 * it + i] = step[i];
+  for (int i = 0; i < 12; ++i) {
+    st->T_total[i] = tot[i];
+    st->T_step[i] = step[i];
+  }
+  for (int i = 0; i < 9; ++i) st->Rf[i] = static_cast<float>(tot[i]);
+  st->n_corr = static_cast<unsigned long long>(S[27]);
+  st->iter = it + 1;
+  st->converged = conv;
+  const int done = P.fixed_iterations > 0 ? (it + 1 >= P.fixed_iterations)
+                                          : (conv || it + 1 >= P.max_iteration);
+  st->done = done;
+}
+
+template <typename F>
+__global__ void __launch_bounds__(kT, 2) align_kernel(AlignParams P) {
+  __shared__ double s_T[12];
+  __shared__ F s_R[9];
+  __shared__ double s_part[kW][kAcc];
+  __shared__ double s_sum[kAcc];
+  __shared__ int s_last, s_done;
+  const unsigned G = gridDim.x, t = threadIdx.x;
+  AlignState* st = P.st;
+  const int max_it = P.fixed_iterations > 0 ? P.fixed_iterations : P.max_iteration;
+
+  for (int it = 0; it < max_it; ++it) {
+    // pose for this iteration: guess first, then the previous iteration's step
+    if (t < 12) s_T[t] = (it == 0) ? P.guess[t] : ld_cg(&st->T_step[t]);
+    if (t < 9) s_R[t] = (it == 0) ? F(P.guess[t])
+                                  : (sizeof(F) == 8 ? F(ld_cg(&st->T_total[t])) : F(ld_cg(&st->Rf[t])));
+    __syncthreads();
+
+    double acc[kAcc];
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+    accumulate_points<F>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0, acc);
+    block_reduce_store(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
+
+    // last CTA to arrive reduces the partials and solves
+    if (t == 0) {
+      const unsigned ticket = atomicAdd(&st->block_counter, 1u);
+      s_last = (ticket == G * static_cast<unsigned>(it + 1) - 1u) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      final_reduce(P.partials, G, s_part, s_sum);
+      if (t == 0) {
+        solve_and_update(P, s_sum, it);
+        __threadfence();
+        st_release_u32(&st->epoch, static_cast<unsigned>(it + 1));
+      }
+    }
+    // everyone waits for the solver (bounded spin)
+    if (t == 0) {
+      unsigned spins = 0;
+      int ok = 1;
+      while (ld_acquire_u32(&st->epoch) < static_cast<unsigned>(it + 1)) {
+        __nanosleep(32);
+        if (++spins > kSpinLimit || ld_acquire_u32(&st->error) != 0) {
+          atomicExch(&st->error, 1u);
+          ok = 0;
+          break;
+        }
+      }
+      __threadfence();
+      s_done = ok ? ld_cg(&st->done) : 1;
+    }
+    __syncthreads();
+    if (s_done) return;
+  }
+}
+
+// sharded mode, after the caller's all-reduce of `sums`: one thread solves
+__global__ void solve_kernel(AlignParams P, int it) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) solve_and_update(P, P.sums, it);
+}
+
+// sharded mode: pose-only transform of the working cloud is done by the next
+// single_pass launch, which needs `first`/guess semantics per iteration
+template <typename F>
+__global__ void __launch_bounds__(kT, 2) linearize_pass_kernel(AlignParams P, int it) {
+  __shared__ double s_T[12];
+  __shared__ F s_R[9];
+  __shared__ double s_part[kW][kAcc];
+  __shared__ double s_sum[kAcc];
+  __shared__ int s_flag;
+  const unsigned G = gridDim.x, t = threadIdx.x;
+  AlignState* st = P.st;
+  if (t < 12) s_T[t] = (it == 0) ? P.guess[t] : ld_cg(&st->T_step[t]);
+  if (t < 9) s_R[t] = (it == 0) ? F(P.guess[t]) : F(ld_cg(&st->Rf[t]));
+  __syncthreads();
+  double acc[kAcc];
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+  accumulate_points<F>(P, s_T, s_R, it == 0, false, acc);
+  block_reduce_store(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
+  if (t == 0) {
+    const unsigned ticket = atomicAdd(&st->block_counter, 1u);
+    s_flag = (ticket == G * static_cast<unsigned>(it + 1) - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_flag) {
+    __threadfence();
+    final_reduce(P.partials, G, s_part, s_sum);
+    if (t < kAcc) P.sums[t] = s_sum[t];
+  }
+}
+
+struct TraceLayout {
+  size_t o_state, o_sums, o_H, o_b, o_nc, o_step, total;
+};
+
+TraceLayout trace_layout(int max_it) {
+  TraceLayout L;
+  L.o_state = 0;
+  L.o_sums = 512;
+  L.o_H = L.o_sums + 32 * 8;
+  L.o_b = L.o_H + static_cast<size_t>(max_it) * 36 * 8;
+  L.o_nc = L.o_b + static_cast<size_t>(max_it) * 6 * 8;
+  L.o_step = L.o_nc + static_cast<size_t>(max_it) * 8;
+  L.total = L.o_step + static_cast<size_t>(max_it) * 12 * 8;
+  return L;
+}
+static_assert(sizeof(AlignState) <= 512, "AlignState grew past its slot");
+
+int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, TraceLayout* L, int* G) {
+  const eskf_map* m = a.map;
+  const eskf_cloud* c = a.cloud;
+  ESKF_REQUIRE(m && c, "null map/cloud");
+  ESKF_REQUIRE(m->ctx == ctx && c->ctx == ctx, "map/cloud belong to another context");
+  ESKF_REQUIRE(c->has_cov && c->has_c32, "registration needs a cloud with covariances");
+  ESKF_REQUIRE(a.neighbor_mode == 1 || a.neighbor_mode == 7, "neighbor_mode must be 1 or 7");
+  ESKF_REQUIRE(max_it > 0, "max_iteration must be positive");
+  ESKF_REQUIRE(c->n < (1ull << 31), "cloud too large");
+  const unsigned n = static_cast<unsigned>(c->n);
+  const size_t pitch = (static_cast<size_t>(n) + 63) / 64 * 64 + 64;
+  ESKF_TRY(ctx->work.ensure(pitch * 3 * sizeof(double)));
+  int g = static_cast<int>((n + kT - 1) / kT);
+  if (g > ctx->max_blocks_align) g = ctx->max_blocks_align;
+  if (g < 1) g = 1;
+  *G = g;
+  ESKF_TRY(ctx->partials.ensure(static_cast<size_t>(g) * kAcc * sizeof(double)));
+  *L = trace_layout(max_it);
+  ESKF_TRY(ctx->astate.ensure(L->total));
+  char* base = ctx->astate.as<char>();
+  std::memset(P, 0, sizeof *P);
+  P->slots = m->slots;
+  P->mask = m->n_slots - 1;
+  P->voxel = m->voxel;
+  P->x0 = c->x();
+  P->y0 = c->y();
+  P->z0 = c->z();
+  P->c4 = c->c4;
+  P->c2 = c->c2;
+  P->wx = ctx->work.as<double>();
+  P->wy = P->wx + pitch;
+  P->wz = P->wx + 2 * pitch;
+  P->n = n;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) P->guess[3 * i + j] = a.guess[4 * i + j];
+    P->guess[9 + i] = a.guess[4 * i + 3];
+  }
+  P->max_iteration = a.max_iteration;
+  P->neighbor_mode = a.neighbor_mode;
+  P->trans_sq_thr = a.trans_sq_thr;
+  P->cos_thr = a.cos_thr;
+  P->fixed_iterations = a.fixed_iterations;
+  P->st = reinterpret_cast<AlignState*>(base + L->o_state);
+  P->partials = ctx->partials.as<double>();
+  P->sums = reinterpret_cast<double*>(base + L->o_sums);
+  P->trace_H = reinterpret_cast<double*>(base + L->o_H);
+  P->trace_b = reinterpret_cast<double*>(base + L->o_b);
+  P->trace_ncorr = reinterpret_cast<unsigned long long*>(base + L->o_nc);
+  P->trace_step = reinterpret_cast<double*>(base + L->o_step);
+  P->hit = a.d_hit;
+  return ESKF_OK;
+}
+
+// copy state + traces back and fill the caller's outputs
+int read_back(eskf_ctx* ctx, const AlignArgs& a, const TraceLayout& L, int max_it, double T_out[16],
+              eskf_align_info* info) {
+  char* h = nullptr;
+  ESKF_TRY(ctx_pinned(ctx, L.total, reinterpret_cast<void**>(&h)));
+  const bool want_trace = info && (info->trace_H || info->trace_b || info->trace_ncorr || info->trace_step);
+  const size_t bytes = want_trace ? L.total : L.o_sums;
+  ESKF_CUDA(cudaMemcpyAsync(h, ctx->astate.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ESKF_CUDA(cudaStreamSynchronize(ctx->stream));
+  const AlignState* st = reinterpret_cast<const AlignState*>(h + L.o_state);
+  if (st->error) {
+    set_error("align kernel: iteration hand-off timed out");
+    return ESKF_ERR_INTERNAL;
+  }
+  const double* Tt = st->iter > 0 ? st->T_total : nullptr;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) T_out[4 * i + j] = Tt ? Tt[3 * i + j] : a.guess[4 * i + j];
+    T_out[4 * i + 3] = Tt ? Tt[9 + i] : a.guess[4 * i + 3];
+  }
+  T_out[12] = 0.0; T_out[13] = 0.0; T_out[14] = 0.0; T_out[15] = 1.0;
+  if (info) {
+    info->iterations = st->iter;
+    info->converged = st->converged;
+    info->n_corr_last = st->n_corr;
+    const int it = st->iter < max_it ? st->iter : max_it;
+    if (info->trace_H) std::memcpy(info->trace_H, h + L.o_H, static_cast<size_t>(it) * 36 * 8);
+    if (info->trace_b) std::memcpy(info->trace_b, h + L.o_b, static_cast<size_t>(it) * 6 * 8);
+    if (info->trace_ncorr) std::memcpy(info->trace_ncorr, h + L.o_nc, static_cast<size_t>(it) * 8);
+    if (info->trace_step) {
+      const double* s = reinterpret_cast<const double*>(h + L.o_step);
+      for (int k = 0; k < it; ++k) {
+        double* o = info->trace_step + 16 * k;
+        for (int i = 0; i < 3; ++i) {
+          for (int j = 0; j < 3; ++j) o[4 * i + j] = s[12 * k + 3 * i + j];
+          o[4 * i + 3] = s[12 * k + 9 + i];
+        }
+        o[12] = 0.0; o[13] = 0.0; o[14] = 0.0; o[15] = 1.0;
+      }
+    }
+  }
+  return ESKF_OK;
+}
+
+}  // namespace
+
+int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align_info* info) {
+  ESKF_CUDA(cudaSetDevice(ctx->device));
+  const int max_it = a.fixed_iterations > 0 ? a.fixed_iterations : a.max_iteration;
+  if (a.cloud && a.cloud->n == 0) {
+    // zero correspondences: zero step, "converged" after one iteration
+    // (Eigen LDLT of a zero matrix solves to zero)
+    for (int i = 0; i < 16; ++i) T_out[i] = a.guess[i];
+    if (info) {
+      info->iterations = 1;
+      info->converged = 1;
+      info->n_corr_last = 0;
+    }
+    return ESKF_OK;
+  }
+  AlignParams P;
+  TraceLayout L;
+  int G = 1;
+  ESKF_TRY(fill_params(ctx, a, max_it, &P, &L, &G));
+  ESKF_CUDA(cudaMemsetAsync(ctx->astate.p, 0, L.o_H, ctx->stream));
+  void* args[] = {&P};
+  void* fn = a.fp64_math ? reinterpret_cast<void*>(align_kernel<double>)
+                         : reinterpret_cast<void*>(align_kernel<float>);
+  ESKF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(kT), args, 0, ctx->stream));
+  count_launch(ctx);
+  return read_back(ctx, a, L, max_it, T_out, info);
+}
+
+int align_max_blocks(int sm_count, int* out) {
+  int a = 0, b = 0;
+  ESKF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, align_kernel<float>, kT, 0));
+  ESKF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, align_kernel<double>, kT, 0));
+  int per_sm = a < b ? a : b;
+  if (per_sm < 1) per_sm = 1;
+  *out = per_sm * sm_count;
+  return ESKF_OK;
+}
+
+// sharded registration: per iteration
+//   linearize_pass (local point range) -> caller's all-reduce of the 28 sums
+//   -> solve (identical on every rank) -> host reads `done`
+int align_sharded(eskf_ctx* ctx, const AlignArgs& a, eskf_allreduce_fn allreduce, void* user,
+                  double T_out[16], eskf_align_info* info) {
+  ESKF_CUDA(cudaSetDevice(ctx->device));
+  const int max_it = a.fixed_iterations > 0 ? a.fixed_iterations : a.max_iteration;
+  AlignParams P;
+  TraceLayout L;
+  int G = 1;
+  ESKF_TRY(fill_params(ctx, a, max_it, &P, &L, &G));
+  ESKF_CUDA(cudaMemsetAsync(ctx->astate.p, 0, L.o_H, ctx->stream));
+  int* h_done = nullptr;
+  ESKF_TRY(ctx_pinned(ctx, L.total + 64, reinterpret_cast<void**>(&h_done)));
+  h_done = reinterpret_cast<int*>(reinterpret_cast<char*>(h_done) + L.total);
+  for (int it = 0; it < max_it; ++it) {
+    if (P.n > 0) {
+      linearize_pass_kernel<float><<<G, kT, 0, ctx->stream>>>(P, it);
+      ESKF_CUDA(cudaGetLastError());
+      count_launch(ctx);
+    } else {
+      ESKF_CUDA(cudaMemsetAsync(P.sums, 0, kAcc * sizeof(double), ctx->stream));
+    }
+    if (allreduce) {
+      const int rc = allreduce(user, P.sums, kAcc, ctx->stream);
+      if (rc != 0) {
+        set_error("allreduce callback failed with %d", rc);
+        return ESKF_ERR_INTERNAL;
+      }
+    }
+    solve_kernel<<<1, 32, 0, ctx->stream>>>(P, it);
+    ESKF_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    if (a.fixed_iterations <= 0) {
+      ESKF_CUDA(cudaMemcpyAsync(h_done, &P.st->done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      ESKF_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (*h_done) break;
+    }
+  }
+  return read_back(ctx, a, L, max_it, T_out, info);
+}
+
+}  // namespace eskf

@@ -1,0 +1,379 @@
+// voxelize.cu — K1/K2/K3: transform + voxel key + radix sort by key + run heads,
+// as ONE persistent cooperative kernel (software grid barriers between phases,
+// so a 64k-point scan costs one launch instead of ~15).
+//
+// Replaces, on the device:
+//   - the getVoxelIndex + unordered_map passes of
+//     CloudPreprocessor::voxelDownsampleAndEstimateCovariances
+//     (src/CloudPreprocessor.cpp:85-99,129-133): first point (lowest input
+//     index) per voxel wins == head of each key run of a STABLE sort;
+//   - the per-point find-or-emplace ordering of LocalMap::updateLocalMap
+//     (src/LocalMap.cpp:47-58): points of one voxel are merged in input index
+//     order == order inside a key run of a stable sort;
+//   - PointCloud::Transform in front of both (src/CloudPreprocessor.cpp:16,
+//     src/LocalMap.cpp:15) and the per-segment deskew transform
+//     (src/CloudPreprocessor.cpp:67-72).
+//
+// Sort key: Morton code of the voxel coordinates rebased to the batch minimum
+// (so only ceil(3*bits/8) 8-bit LSD passes run, and an aligned 2^L block of
+// voxels is one contiguous key range — the k-NN search relies on that).
+#include <climits>
+
+#include "internal.h"
+
+namespace eskf {
+
+namespace {
+
+constexpr int kT = 256;  // threads per CTA
+constexpr int kW = kT / 32;
+
+struct VoxParams {
+  VoxelizeArgs a;
+  uint64_t* key[2];
+  uint32_t* idx[2];
+  unsigned* hist;       // [2][G][256]
+  unsigned* blk_count;  // [2][G]
+  VoxelHeader* hdr;
+  uint32_t* run_start;
+  uint32_t* keep_flag;
+  uint32_t* kept_src;
+  uint32_t* kept_pos;
+  double* sx;
+  double* sy;
+  double* sz;
+  unsigned chunk;  // elements per CTA, multiple of kT
+};
+
+__device__ __forceinline__ unsigned block_reduce_add(unsigned v, unsigned* s_tmp) {
+  v = warp_reduce_add(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
+  __syncthreads();
+  unsigned r = 0;
+#pragma unroll
+  for (int i = 0; i < kW; ++i) r += s_tmp[i];
+  return r;
+}
+
+// exclusive scan of one value per thread over the CTA (kT threads)
+__device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* s_tmp, unsigned* total) {
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= static_cast<unsigned>(o)) inc += u;
+  }
+  __syncthreads();
+  if (lane == 31) s_tmp[w] = inc;
+  __syncthreads();
+  unsigned woff = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < kW; ++i) {
+    unsigned c = s_tmp[i];
+    if (i < static_cast<int>(w)) woff += c;
+    tot += c;
+  }
+  if (total) *total = tot;
+  return woff + inc - v;
+}
+
+__global__ void __launch_bounds__(kT) voxelize_kernel(VoxParams P) {
+  const unsigned G = gridDim.x, b = blockIdx.x, t = threadIdx.x;
+  const unsigned w = t >> 5, lane = t & 31;
+  const unsigned n = P.a.n;
+  GridBarrier* gb = &P.hdr->gb;
+
+  const unsigned bbeg = min(n, b * P.chunk);
+  const unsigned bend = min(n, bbeg + P.chunk);
+  const unsigned wchunk = P.chunk / kW;
+  const unsigned wbeg = min(bend, bbeg + w * wchunk);
+  const unsigned wend = min(bend, wbeg + wchunk);
+
+  __shared__ unsigned s_whist[kW][256];
+  __shared__ unsigned s_off[kW][256];
+  __shared__ unsigned s_tmp[kW];
+
+  // ---------------------------------------------------------------- phase 0
+  // transform (+deskew) + voxel coordinate + batch min/max
+  {
+    int mn0 = INT_MAX, mn1 = INT_MAX, mn2 = INT_MAX;
+    int nm0 = INT_MAX, nm1 = INT_MAX, nm2 = INT_MAX;
+    bool bad = false;
+    const int stride = P.a.in_stride;
+    for (unsigned i = bbeg + t; i < bend; i += kT) {
+      double x = P.a.in_x[static_cast<size_t>(i) * stride];
+      double y = P.a.in_y[static_cast<size_t>(i) * stride];
+      double z = P.a.in_z[static_cast<size_t>(i) * stride];
+      if (P.a.has_T1) transform_point_rn(P.a.T1, x, y, z);
+      if (P.a.n_segs > 0) {
+        int lo = 0, hi = P.a.n_segs;  // first segment with end > i
+        while (lo < hi) {
+          int mid = (lo + hi) >> 1;
+          if (P.a.segs[mid].end > i) hi = mid; else lo = mid + 1;
+        }
+        if (lo < P.a.n_segs && i >= P.a.segs[lo].begin) transform_point_rn(P.a.segs[lo].T, x, y, z);
+      }
+      P.a.out_x[i] = x;
+      P.a.out_y[i] = y;
+      P.a.out_z[i] = z;
+      if (P.a.cov != nullptr && P.a.has_T1) {
+        double C[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) C[k] = P.a.cov[k * P.a.cov_pitch + i];
+        rotate_cov_rn(P.a.T1, C);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) P.a.cov[k * P.a.cov_pitch + i] = C[k];
+      }
+      const int kx = voxel_coord(x, P.a.voxel);
+      const int ky = voxel_coord(y, P.a.voxel);
+      const int kz = voxel_coord(z, P.a.voxel);
+      if (!(coord_in_range(kx) && coord_in_range(ky) && coord_in_range(kz))) bad = true;
+      P.key[1][i] = pack_key(kx, ky, kz);  // absolute key parked in buffer B
+      mn0 = min(mn0, kx); mn1 = min(mn1, ky); mn2 = min(mn2, kz);
+      nm0 = min(nm0, -kx); nm1 = min(nm1, -ky); nm2 = min(nm2, -kz);
+    }
+    mn0 = warp_reduce_min(mn0); mn1 = warp_reduce_min(mn1); mn2 = warp_reduce_min(mn2);
+    nm0 = warp_reduce_min(nm0); nm1 = warp_reduce_min(nm1); nm2 = warp_reduce_min(nm2);
+    if (lane == 0 && mn0 != INT_MAX) {
+      atomicMin(&P.hdr->mn[0], mn0); atomicMin(&P.hdr->mn[1], mn1); atomicMin(&P.hdr->mn[2], mn2);
+      atomicMin(&P.hdr->nmx[0], nm0); atomicMin(&P.hdr->nmx[1], nm1); atomicMin(&P.hdr->nmx[2], nm2);
+    }
+    if (bad) atomicOr(&P.hdr->error, 1u);
+  }
+  if (!grid_sync(gb, G)) return;
+
+  // ---------------------------------------------------------------- phase 1
+  // rebased Morton key + identity payload (own chunk only: no grid barrier)
+  const int m0 = ld_cg(&P.hdr->mn[0]), m1 = ld_cg(&P.hdr->mn[1]), m2 = ld_cg(&P.hdr->mn[2]);
+  unsigned bits;
+  {
+    const int e0 = -ld_cg(&P.hdr->nmx[0]) - m0;
+    const int e1 = -ld_cg(&P.hdr->nmx[1]) - m1;
+    const int e2 = -ld_cg(&P.hdr->nmx[2]) - m2;
+    const unsigned ex = static_cast<unsigned>(max(max(e0, e1), max(e2, 0)));
+    bits = ex == 0 ? 0u : (32u - static_cast<unsigned>(__clz(ex)));
+    if (bits > kKeyBits) bits = kKeyBits;
+  }
+  for (unsigned i = bbeg + t; i < bend; i += kT) {
+    int kx, ky, kz;
+    unpack_key(P.key[1][i], kx, ky, kz);
+    P.key[0][i] = morton3(static_cast<uint32_t>(kx - m0), static_cast<uint32_t>(ky - m1),
+                          static_cast<uint32_t>(kz - m2));
+    P.idx[0][i] = i;
+  }
+  if (b == 0 && t == 0) P.hdr->bits = bits;
+  __syncthreads();
+
+  // ------------------------------------------------------- LSD radix passes
+  const unsigned npass = (3u * bits + 7u) / 8u;
+  unsigned sel = 0;
+  for (unsigned p = 0; p < npass; ++p) {
+    const uint64_t* sk = P.key[sel];
+    const uint32_t* si = P.idx[sel];
+    const unsigned shift = 8u * p;
+    // A: per-warp digit histograms of the warp's contiguous sub-chunk
+    for (unsigned k = t; k < kW * 256; k += kT) (&s_whist[0][0])[k] = 0;
+    __syncthreads();
+    for (unsigned j = wbeg + lane; j < wend; j += 32) {
+      const unsigned d = static_cast<unsigned>(ld_cg(sk + j) >> shift) & 255u;
+      atomicAdd(&s_whist[w][d], 1u);
+    }
+    __syncthreads();
+    unsigned* histp = P.hist + static_cast<size_t>(p & 1u) * G * 256u;
+    {
+      unsigned s = 0;
+#pragma unroll
+      for (int i = 0; i < kW; ++i) s += s_whist[i][t];
+      histp[b * 256u + t] = s;
+    }
+    if (!grid_sync(gb, G)) return;
+    // B: global digit offsets for this CTA (every CTA redoes the tiny scan)
+    unsigned total = 0, pre = 0;
+#pragma unroll 4
+    for (unsigned bb = 0; bb < G; ++bb) {
+      const unsigned v = ld_cg(&histp[bb * 256u + t]);
+      if (bb < b) pre += v;
+      total += v;
+    }
+    // a digit shared by every key makes the pass the identity: skip it
+    // (decision is identical in every CTA; hist is double-buffered so the
+    // next pass may start writing without another barrier)
+    if (__syncthreads_or(total == n)) continue;
+    unsigned base = block_exclusive_scan(total, s_tmp, nullptr);
+    {
+      unsigned run = base + pre;
+#pragma unroll
+      for (int i = 0; i < kW; ++i) {
+        s_off[i][t] = run;
+        run += s_whist[i][t];
+      }
+    }
+    __syncthreads();
+    // C: stable scatter, one warp per contiguous sub-chunk, 32 keys a step
+    uint64_t* dk = P.key[sel ^ 1u];
+    uint32_t* di = P.idx[sel ^ 1u];
+    for (unsigned j0 = wbeg; j0 < wend; j0 += 32) {
+      const unsigned j = j0 + lane;
+      const bool valid = j < wend;
+      const unsigned am = __ballot_sync(0xffffffffu, valid);
+      if (valid) {
+        const uint64_t key = ld_cg(sk + j);
+        const uint32_t id = ld_cg(si + j);
+        const unsigned d = static_cast<unsigned>(key >> shift) & 255u;
+        const unsigned mask = __match_any_sync(am, d);
+        const unsigned leader = __ffs(mask) - 1;
+        const unsigned off = s_off[w][d];
+        __syncwarp(am);
+        if (lane == leader) s_off[w][d] = off + __popc(mask);
+        __syncwarp(am);
+        const unsigned dst = off + __popc(mask & ((1u << lane) - 1u));
+        dk[dst] = key;
+        di[dst] = id;
+      }
+    }
+    sel ^= 1u;
+    if (!grid_sync(gb, G)) return;
+  }
+  const uint64_t* sk = P.key[sel];
+  const uint32_t* si = P.idx[sel];
+  if (b == 0 && t == 0) P.hdr->sel = sel;
+
+  // ------------------------------------------------------------- run heads
+  if (P.a.mode == 0) {
+    // runs in sorted order: run_start[r] = first sorted position of run r
+    unsigned cnt = 0;
+    for (unsigned j = bbeg + t; j < bend; j += kT)
+      cnt += (j == 0 || ld_cg(sk + j - 1) != ld_cg(sk + j)) ? 1u : 0u;
+    cnt = block_reduce_add(cnt, s_tmp);
+    if (t == 0) P.blk_count[b] = cnt;
+    if (!grid_sync(gb, G)) return;
+    unsigned base = 0;
+    for (unsigned bb = t; bb < b; bb += kT) base += ld_cg(&P.blk_count[bb]);
+    base = block_reduce_add(base, s_tmp);
+    for (unsigned tile = bbeg; tile < bend; tile += kT) {
+      const unsigned j = tile + t;
+      const unsigned head = (j < bend && (j == 0 || ld_cg(sk + j - 1) != ld_cg(sk + j))) ? 1u : 0u;
+      unsigned tot;
+      const unsigned rank = block_exclusive_scan(head, s_tmp, &tot);
+      if (head) P.run_start[base + rank] = j;
+      base += tot;
+    }
+    if (b == G - 1 && t == 0) {
+      P.hdr->n_out = base;
+      P.run_start[base] = n;
+    }
+  } else {
+    // kept points (run heads) listed in ascending SOURCE index, plus the
+    // positions gathered into sorted order for the k-NN scan
+    for (unsigned j = bbeg + t; j < bend; j += kT) {
+      const bool head = (j == 0 || ld_cg(sk + j - 1) != ld_cg(sk + j));
+      const uint32_t id = ld_cg(si + j);
+      P.keep_flag[id] = head ? j + 1u : 0u;
+      P.sx[j] = ld_cg(P.a.out_x + id);
+      P.sy[j] = ld_cg(P.a.out_y + id);
+      P.sz[j] = ld_cg(P.a.out_z + id);
+    }
+    if (!grid_sync(gb, G)) return;
+    unsigned cnt = 0;
+    for (unsigned i = bbeg + t; i < bend; i += kT) cnt += ld_cg(&P.keep_flag[i]) != 0u ? 1u : 0u;
+    cnt = block_reduce_add(cnt, s_tmp);
+    if (t == 0) P.blk_count[G + b] = cnt;
+    if (!grid_sync(gb, G)) return;
+    unsigned base = 0;
+    for (unsigned bb = t; bb < b; bb += kT) base += ld_cg(&P.blk_count[G + bb]);
+    base = block_reduce_add(base, s_tmp);
+    for (unsigned tile = bbeg; tile < bend; tile += kT) {
+      const unsigned i = tile + t;
+      const unsigned f = i < bend ? ld_cg(&P.keep_flag[i]) : 0u;
+      unsigned tot;
+      const unsigned rank = block_exclusive_scan(f != 0u ? 1u : 0u, s_tmp, &tot);
+      if (f != 0u) {
+        P.kept_src[base + rank] = i;
+        P.kept_pos[base + rank] = f - 1u;
+      }
+      base += tot;
+    }
+    if (b == G - 1 && t == 0) P.hdr->n_out = base;
+  }
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+SortView sort_view(eskf_ctx* ctx, unsigned n) {
+  SortView v;
+  const size_t nn = align_up(static_cast<size_t>(n) + 1, 64);
+  char* p = ctx->sortbuf.as<char>();
+  v.key[0] = reinterpret_cast<uint64_t*>(p);
+  v.key[1] = v.key[0] + nn;
+  v.idx[0] = reinterpret_cast<uint32_t*>(v.key[1] + nn);
+  v.idx[1] = v.idx[0] + nn;
+  uint32_t* r = ctx->runs.as<uint32_t>();
+  v.run_start = r;
+  v.keep_flag = r + nn;
+  v.kept_src = r + 2 * nn;
+  v.kept_pos = r + 3 * nn;
+  v.sx = ctx->sorted_xyz.as<double>();
+  v.sy = v.sx + nn;
+  v.sz = v.sx + 2 * nn;
+  v.hdr = ctx->hdr.as<VoxelHeader>();
+  return v;
+}
+
+int voxelize(eskf_ctx* ctx, const VoxelizeArgs& a) {
+  ESKF_REQUIRE(a.n > 0, "voxelize: empty input");
+  ESKF_REQUIRE(a.voxel > 0.0, "voxel_size must be positive");
+  const unsigned n = a.n;
+  const size_t nn = align_up(static_cast<size_t>(n) + 1, 64);
+  ESKF_TRY(ctx->sortbuf.ensure(nn * (8 + 8 + 4 + 4)));
+  ESKF_TRY(ctx->runs.ensure(nn * 4 * 4));
+  if (a.mode == 1) ESKF_TRY(ctx->sorted_xyz.ensure(nn * 3 * 8));
+  ESKF_TRY(ctx->hdr.ensure(sizeof(VoxelHeader)));
+
+  int G = static_cast<int>((n + 4095u) / 4096u);
+  if (G > ctx->max_blocks_voxelize) G = ctx->max_blocks_voxelize;
+  if (G < 1) G = 1;
+  ESKF_TRY(ctx->hist.ensure(static_cast<size_t>(G) * (2 * 256 + 2) * sizeof(unsigned)));
+
+  VoxParams P;
+  P.a = a;
+  SortView v = sort_view(ctx, n);
+  P.key[0] = v.key[0];
+  P.key[1] = v.key[1];
+  P.idx[0] = v.idx[0];
+  P.idx[1] = v.idx[1];
+  P.hist = ctx->hist.as<unsigned>();
+  P.blk_count = P.hist + static_cast<size_t>(G) * 2 * 256;
+  P.hdr = v.hdr;
+  P.run_start = v.run_start;
+  P.keep_flag = v.keep_flag;
+  P.kept_src = v.kept_src;
+  P.kept_pos = v.kept_pos;
+  P.sx = v.sx;
+  P.sy = v.sy;
+  P.sz = v.sz;
+  P.chunk = static_cast<unsigned>(align_up((n + G - 1) / G, kT));
+
+  // header: min/max words to 0x7F7F7F7F (+inf for in-range ints), rest zero
+  ESKF_CUDA(cudaMemsetAsync(v.hdr, 0x7F, offsetof(VoxelHeader, error), ctx->stream));
+  ESKF_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(v.hdr) + offsetof(VoxelHeader, error), 0,
+                            sizeof(VoxelHeader) - offsetof(VoxelHeader, error), ctx->stream));
+  void* args[] = {&P};
+  ESKF_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(voxelize_kernel), dim3(G), dim3(kT),
+                                        args, 0, ctx->stream));
+  count_launch(ctx);
+  return ESKF_OK;
+}
+
+int voxelize_max_blocks(int sm_count, int* out) {
+  int per_sm = 0;
+  ESKF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, voxelize_kernel, kT, 0));
+  if (per_sm > 4) per_sm = 4;
+  *out = per_sm * sm_count;
+  return ESKF_OK;
+}
+
+}  // namespace eskf

@@ -1,0 +1,351 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through
+the C ABI, against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): voxel keys, occupancy and correspondence sets
+bit-exact; per-iteration H/b within 1e-4 relative (norm-wise); final pose
+within 1e-5 rad and 1e-5 m."""
+import numpy as np
+import pytest
+
+from eskf_lio_b200 import capi, synth as S
+from gpu_common import Frames, pose_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+H_TOL = 1e-4      # per-iteration H / b, norm-wise relative
+POSE_T_TOL = 1e-5  # metres
+POSE_R_TOL = 1e-5  # radians
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def frames(oracle):
+    return Frames(oracle, n_scans=5, seed=11, decim=2, voxel=0.5)
+
+
+def b_rel(bg, bo, Ho):
+    # b -> 0 at convergence: relative to max(|b|, |H| * 1e-3 m)
+    den = max(np.linalg.norm(bo), np.linalg.norm(Ho) * 1e-3 * 1e-3)
+    return float(np.linalg.norm(bg - bo) / den)
+
+
+# ------------------------------------------------------------------ clouds
+def test_cloud_roundtrip_and_transform_bit_exact(ctx, oracle, frames):
+    p, c = frames.ds[0]
+    cl = capi.Cloud(ctx).upload(p, c)
+    x, cv, _ = cl.download()
+    np.testing.assert_array_equal(x, p)
+    np.testing.assert_array_equal(cv, c)
+    T = frames.poses[3] @ S.perturbation()
+    cl.transform(T)
+    x, cv, _ = cl.download()
+    ox, oc = oracle.transform_cloud(p, c, T)
+    np.testing.assert_array_equal(x, ox)     # fp64, same evaluation order, no FMA
+    np.testing.assert_array_equal(cv, oc)
+
+
+def test_upload_f32_matches_widening(ctx, frames):
+    xyz = frames.raw[0][0][:1000]
+    cl = capi.Cloud(ctx).upload_f32(xyz.astype(np.float32))
+    x, _, _ = cl.download(want_cov=False)
+    np.testing.assert_array_equal(x, xyz)
+
+
+# --------------------------------------------------------------------- map
+@pytest.mark.parametrize("voxel", [0.1, 0.3, 0.5, 1.0])
+def test_voxel_keys_bit_exact(ctx, oracle, frames, voxel):
+    p, c = frames.ds[1]
+    T = frames.poses[1]
+    gm = capi.Map(ctx, voxel, 1000, 1 << 12)
+    gm.insert(p, c, T)
+    pw, _ = oracle.transform_cloud(p, c, T)
+    # add adversarial points on voxel faces
+    edge = np.array([[-0.1, -0.5, -0.0], [0.5, 0.4999999999999999, 0.0], [0.3, 0.6, 0.9],
+                     [voxel, -voxel, 2 * voxel], [np.nextafter(voxel, 0), voxel * 3, -voxel * 3]])
+    q = np.vstack([pw, edge])
+    keys, hit, count, mean, cov = gm.query(q)
+    np.testing.assert_array_equal(keys, oracle.voxel_index(q, voxel))
+    assert hit[:len(pw)].all()
+
+
+def test_map_insert_matches_oracle(ctx, oracle, frames):
+    om, gm = frames.build_maps(oracle, capi, ctx, 4)
+    ok, oc, omean, ocov = om.export()
+    gk, gc, gmean, gcov = gm.export()
+    assert gm.size() == om.size()
+    np.testing.assert_array_equal(gk, ok)                       # occupancy bit-exact
+    np.testing.assert_array_equal(gc.astype(np.uint64), oc)     # counts bit-exact
+    # running mean / covariance folded in input order with the reference's expression
+    np.testing.assert_array_equal(gmean, omean)
+    np.testing.assert_array_equal(gcov, ocov)
+
+
+def test_map_cap_and_long_runs(ctx, oracle):
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-1.0, 1.0, size=(6000, 3))
+    A = rng.normal(size=(6000, 3, 3))
+    cov = A @ A.transpose(0, 2, 1) + np.eye(3)
+    om = oracle.Map(1.0, 7)
+    gm = capi.Map(ctx, 1.0, 7, 1 << 10)
+    for k in range(3):
+        sl = slice(2000 * k, 2000 * (k + 1))
+        om.insert(pts[sl], cov[sl])
+        gm.insert(pts[sl], cov[sl], np.eye(4))
+    ok, oc, omean, ocov = om.export()
+    gk, gc, gmean, gcov = gm.export()
+    np.testing.assert_array_equal(gk, ok)
+    np.testing.assert_array_equal(gc.astype(np.uint64), oc)
+    assert gc.max() == 7
+    np.testing.assert_array_equal(gmean, omean)
+    np.testing.assert_array_equal(gcov, ocov)
+
+
+def test_map_growth_from_tiny_table(ctx, oracle, frames):
+    om = oracle.Map(0.1, 1000)
+    gm = capi.Map(ctx, 0.1, 1000, 16)
+    cap0 = gm.capacity()
+    for (p, c), T in zip(frames.ds[:3], frames.poses[:3]):
+        om.update(p, c, T, initialize=True)
+        gm.insert(p, c, T)
+    assert gm.capacity() > cap0
+    assert gm.size() == om.size()
+    gk, gc, gmean, _ = gm.export()
+    ok, oc, omean, _ = om.export()
+    np.testing.assert_array_equal(gk, ok)
+    np.testing.assert_array_equal(gc.astype(np.uint64), oc)
+    np.testing.assert_array_equal(gmean, omean)
+
+
+def test_map_evict_matches_oracle(ctx, oracle, frames):
+    om, gm = frames.build_maps(oracle, capi, ctx, 3)
+    pos = frames.poses[2][:3, 3]
+    for thr in (25.0, 12.0):
+        assert gm.evict(pos, thr) == om.evict(pos, thr)
+        gk, gc, gmean, gcov = gm.export()
+        ok, oc, omean, ocov = om.export()
+        np.testing.assert_array_equal(gk, ok)
+        np.testing.assert_array_equal(gc.astype(np.uint64), oc)
+        np.testing.assert_array_equal(gmean, omean)
+    # strict '>' at exactly the threshold
+    om2 = oracle.Map(1.0, 10)
+    gm2 = capi.Map(ctx, 1.0, 10, 64)
+    pts = np.array([[0.5, 0.5, 0.5], [3.5, 0.5, 0.5], [4.5, 0.5, 0.5]])
+    cv = np.repeat(np.eye(3)[None], 3, axis=0)
+    om2.insert(pts, cv)
+    gm2.insert(pts, cv, np.eye(4))
+    assert gm2.evict([0.5, 0.5, 0.5], 3.0) == om2.evict([0.5, 0.5, 0.5], 3.0) == 1
+    np.testing.assert_array_equal(gm2.export()[0], [[0, 0, 0], [3, 0, 0]])
+    # inserting after an eviction still works
+    gm2.insert(pts, cv, np.eye(4))
+    assert gm2.size() == 3
+
+
+def test_key_range_error(ctx):
+    gm = capi.Map(ctx, 0.01, 10, 64)
+    pts = np.array([[0.0, 0.0, 0.0], [2.0e4, 0.0, 0.0]])  # 2e6 voxels > 2^20
+    gm.insert(pts, np.repeat(np.eye(3)[None], 2, axis=0), np.eye(4))
+    with pytest.raises(capi.EskfError) as e:
+        gm.size()
+    assert e.value.status == 5
+
+
+# -------------------------------------------------------------- preprocess
+@pytest.mark.parametrize("voxel", [0.5, 0.3])
+def test_downsample_and_covariances(ctx, oracle, frames, voxel):
+    xyz, t = frames.raw[2]
+    op, oc, osrc = oracle.preprocess(xyz, t, frames.T_il, None, voxel)
+    gp, gc, gsrc = ctx.preprocess(xyz, t, frames.T_il, None, voxel)
+    np.testing.assert_array_equal(gsrc, osrc)     # kept set (first point per voxel) bit-exact
+    np.testing.assert_array_equal(gp, op)         # transformed positions bit-exact
+    err = np.abs(gc - oc).reshape(len(gc), -1).max(axis=1)
+    assert np.median(err) < 1e-12
+    assert err.max() < 1e-7, f"worst covariance mismatch {err.max()} at {err.argmax()}"
+
+
+def test_downsample_small_and_degenerate_inputs(ctx, oracle):
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 29, 31, 200):
+        pts = rng.normal(size=(n, 3)) * 2.0
+        op, oc, osrc = oracle.downsample_cov(pts, 0.5)
+        gp, gc, gsrc = ctx.downsample_cov(pts, 0.5)
+        np.testing.assert_array_equal(gsrc, osrc)
+        np.testing.assert_array_equal(gp, op)
+        np.testing.assert_allclose(gc, oc, atol=1e-7)
+    # all points in one voxel
+    pts = rng.uniform(0.01, 0.49, size=(500, 3))
+    gp, gc, gsrc = ctx.downsample_cov(pts, 0.5)
+    assert gsrc.tolist() == [0]
+    op, oc, _ = oracle.downsample_cov(pts, 0.5)
+    np.testing.assert_allclose(gc, oc, atol=1e-9)
+
+
+def test_preprocess_with_deskew(ctx, oracle, frames):
+    xyz, t = frames.raw[1]
+    t0, t1 = t[0], t[-1]
+    ts = t0 - 0.006 + 0.0025 * np.arange(48)
+    assert ts[-1] > t1
+    s = ts - t0
+    pos = np.stack([1.2 * s, 0.3 * s * s, 0.05 * np.sin(8 * s)], axis=1)
+    ang = 0.4 * s
+    quat = np.stack([0.02 * np.sin(ang), 0.01 * np.sin(ang), np.sin(ang / 2), np.cos(ang / 2)], axis=1)
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    # long history before the sweep, like the never-trimmed states_ deque
+    hist_ts = t0 - 0.006 - 0.0025 * np.arange(400, 0, -1)
+    ts = np.concatenate([hist_ts, ts])
+    pos = np.concatenate([np.zeros((400, 3)), pos])
+    quat = np.concatenate([np.tile([0, 0, 0, 1.0], (400, 1)), quat])
+    states = (ts, pos, quat)
+    op, oc, osrc = oracle.preprocess(xyz, t, frames.T_il, states, 0.5)
+    gp, gc, gsrc = ctx.preprocess(xyz, t, frames.T_il, states, 0.5)
+    np.testing.assert_array_equal(gsrc, osrc)
+    np.testing.assert_array_equal(gp, op)
+    assert np.abs(gc - oc).max() < 1e-7
+
+
+# ------------------------------------------------------------ registration
+def test_linearize_correspondences_and_Hb(ctx, oracle, frames):
+    om, gm = frames.build_maps(oracle, capi, ctx, 4)
+    p, c = frames.ds[4]
+    guess = frames.poses[4] @ S.perturbation()
+    pg, cg = oracle.transform_cloud(p, c, guess)
+    Ho, bo, hito, nco = om.linearize(pg, cg)
+    # identity pose on pre-transformed points: positions reach the kernel bit-exact
+    Hg, bg, hitg, ncg = ctx.linearize(gm, pg, cg)
+    np.testing.assert_array_equal(hitg, hito)      # correspondence set bit-exact
+    assert ncg == nco and nco > 1000
+    assert rel_err(Hg, Ho) < H_TOL and b_rel(bg, bo, Ho) < H_TOL
+    # fp64 per-point math variant: limited only by the fp32 table
+    Hd, bd, hitd, _ = ctx.linearize(gm, pg, cg, fp64_math=True)
+    np.testing.assert_array_equal(hitd, hito)
+    assert rel_err(Hd, Ho) < 1e-5 and b_rel(bd, bo, Ho) < 1e-5
+    # pose applied on the device: same keys as the oracle's Transform
+    Hg2, bg2, hitg2, _ = ctx.linearize(gm, p, c, T=guess)
+    np.testing.assert_array_equal(hitg2, hito)
+    assert rel_err(Hg2, Ho) < H_TOL and b_rel(bg2, bo, Ho) < H_TOL
+
+
+def test_align_pose_iterations_and_trace(ctx, oracle, frames):
+    om, gm = frames.build_maps(oracle, capi, ctx, 4)
+    p, c = frames.ds[4]
+    guess = frames.poses[4] @ S.perturbation()
+    ro = om.align(p, c, guess)
+    rg = ctx.align(gm, p, c, guess)
+    assert ro["converged"] and rg["converged"]
+    assert rg["iterations"] == ro["iterations"]
+    dt, dr = pose_err(ro["T"], rg["T"])
+    assert dt < POSE_T_TOL and dr < POSE_R_TOL, (dt, dr)
+    np.testing.assert_array_equal(rg["ncorr"], ro["ncorr"])
+    for k in range(ro["iterations"]):
+        assert rel_err(rg["H"][k], ro["H"][k]) < H_TOL, k
+        assert b_rel(rg["b"][k], ro["b"][k], ro["H"][k]) < H_TOL, k
+    gt_t, gt_r = pose_err(frames.poses[4], rg["T"])
+    assert gt_t < 0.02 and gt_r < 0.01
+
+
+def test_align_teacher_forced_correspondences_every_iteration(ctx, oracle, frames):
+    """Feed the oracle's own per-iteration clouds to the kernel: the
+    correspondence set of EVERY Gauss-Newton iteration must match bit for bit."""
+    om, gm = frames.build_maps(oracle, capi, ctx, 4)
+    p, c = frames.ds[4]
+    guess = frames.poses[4] @ S.perturbation(dt=(0.2, 0.1, -0.05), angle_deg=2.0)
+    ro = om.align(p, c, guess)
+    pk, ck = oracle.transform_cloud(p, c, guess)
+    for k in range(ro["iterations"]):
+        Ho, bo, hito, nco = om.linearize(pk, ck)
+        Hg, bg, hitg, ncg = ctx.linearize(gm, pk, ck)
+        np.testing.assert_array_equal(hitg, hito)
+        assert ncg == nco == ro["ncorr"][k]
+        assert rel_err(Hg, Ho) < H_TOL and b_rel(bg, bo, Ho) < H_TOL
+        pk, ck = oracle.transform_cloud(pk, ck, ro["step"][k])
+
+
+def test_align_direct7_extension(ctx, oracle, frames):
+    om, gm = frames.build_maps(oracle, capi, ctx, 4)
+    p, c = frames.ds[4]
+    guess = frames.poses[4] @ S.perturbation()
+    pg, cg = oracle.transform_cloud(p, c, guess)
+    Ho, bo, hito, nco = om.linearize(pg, cg, 7)
+    Hg, bg, hitg, ncg = ctx.linearize(gm, pg, cg, neighbor_mode=7)
+    np.testing.assert_array_equal(hitg, hito)
+    assert ncg == nco
+    assert rel_err(Hg, Ho) < H_TOL and b_rel(bg, bo, Ho) < H_TOL
+    ro = om.align(p, c, guess, neighbor_mode=7)
+    rg = ctx.align(gm, p, c, guess, neighbor_mode=7)
+    assert rg["iterations"] == ro["iterations"]
+    dt, dr = pose_err(ro["T"], rg["T"])
+    assert dt < POSE_T_TOL and dr < POSE_R_TOL
+
+
+def test_align_edge_cases(ctx, oracle, frames):
+    om, gm = frames.build_maps(oracle, capi, ctx, 2)
+    p, c = frames.ds[2]
+    # zero correspondences: returns the guess after one "converged" iteration
+    far = np.eye(4)
+    far[:3, 3] = [5000.0, 5000.0, 500.0]
+    rg = ctx.align(gm, p, c, far)
+    ro = om.align(p, c, far)
+    assert rg["iterations"] == ro["iterations"] == 1 and rg["converged"] and rg["ncorr"].tolist() == [0]
+    np.testing.assert_array_equal(rg["T"], far)
+    # empty cloud
+    rg = ctx.align(gm, np.zeros((0, 3)), np.zeros((0, 3, 3)), far)
+    assert rg["iterations"] == 1 and rg["converged"]
+    np.testing.assert_array_equal(rg["T"], far)
+    # max_iteration reached without convergence
+    guess = frames.poses[2] @ S.perturbation()
+    rg = ctx.align(gm, p, c, guess, max_iteration=2)
+    ro = om.align(p, c, guess, max_iteration=2)
+    assert rg["iterations"] == ro["iterations"] == 2 and not rg["converged"] and not ro["converged"]
+    dt, dr = pose_err(ro["T"], rg["T"])
+    assert dt < POSE_T_TOL and dr < POSE_R_TOL
+    # a single point
+    rg = ctx.align(gm, p[:1], c[:1], frames.poses[2])
+    ro = om.align(p[:1], c[:1], frames.poses[2])
+    assert rg["iterations"] == ro["iterations"]
+
+
+def test_device_resident_pipeline_matches_host_entry_points(ctx, oracle, frames):
+    """preprocess -> align -> insert on device-resident clouds (the bench path)
+    gives the same results as the host-buffer entry points."""
+    om, gm = frames.build_maps(oracle, capi, ctx, 3)
+    _, gm2 = frames.build_maps(oracle, capi, ctx, 3)
+    xyz, t = frames.raw[3]
+    raw = capi.Cloud(ctx).upload(xyz)
+    ds = capi.Cloud(ctx)
+    raw.preprocess_into(ds, None, frames.T_il, None, 0.5)
+    gp, gc, gsrc = ds.download(want_src=True)
+    hp, hc, hsrc = ctx.preprocess(xyz, t, frames.T_il, None, 0.5)
+    np.testing.assert_array_equal(gp, hp)
+    np.testing.assert_array_equal(gc, hc)
+    np.testing.assert_array_equal(gsrc, hsrc)
+    guess = frames.poses[3] @ S.perturbation()
+    r1 = gm.align_cloud(ds, guess, trace=True)
+    r2 = ctx.align(gm, hp, hc, guess)
+    np.testing.assert_array_equal(r1["T"], r2["T"])
+    assert r1["iterations"] == r2["iterations"]
+    gm.insert_cloud(ds, r1["T"])
+    gm2.insert(hp, hc, r2["T"])
+    a, b = gm.export(), gm2.export()
+    for u, v in zip(a, b):
+        np.testing.assert_array_equal(u, v)
+    # fixed-iteration variant runs exactly that many
+    ds2 = capi.Cloud(ctx).upload(hp, hc)
+    r3 = gm.align_cloud_fixed(ds2, guess, 7)
+    assert r3["iterations"] == 7
+
+
+def test_sharded_align_single_rank_equals_align(ctx, oracle, frames):
+    om, gm = frames.build_maps(oracle, capi, ctx, 4)
+    p, c = frames.ds[4]
+    guess = frames.poses[4] @ S.perturbation()
+    cl = capi.Cloud(ctx).upload(p, c)
+    r1 = gm.align_cloud(cl, guess, trace=True)
+    r2 = gm.align_cloud_sharded(cl, guess, None, trace=True)
+    assert r1["iterations"] == r2["iterations"]
+    dt, dr = pose_err(r1["T"], r2["T"])
+    assert dt < 1e-9 and dr < 1e-9
