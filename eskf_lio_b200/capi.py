@@ -242,7 +242,8 @@ class Cloud:
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().eskf_cloud_destroy(self._h)
+            if self.ctx._h.value:  # a closed context already released the device
+                lib().eskf_cloud_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -314,7 +315,8 @@ class Map:
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().eskf_map_destroy(self._h)
+            if self.ctx._h.value:  # a closed context already released the device
+                lib().eskf_map_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

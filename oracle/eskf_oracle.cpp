@@ -906,7 +906,12 @@ size_t orc_downsample_cov(const double* xyz, size_t n, double voxel_size, double
     first.emplace(pack_key(k[0], k[1], k[2]), static_cast<uint32_t>(i));
   }
   std::vector<std::pair<uint64_t, uint32_t>> kept(first.begin(), first.end());
-  std::sort(kept.begin(), kept.end());  // output order: ascending packed key
+  // the reference's output order is the unordered_map's iteration order
+  // (:97-99, unspecified); fixed here to ascending source index
+  std::sort(kept.begin(), kept.end(),
+            [](const std::pair<uint64_t, uint32_t>& a, const std::pair<uint64_t, uint32_t>& b) {
+              return a.second < b.second;
+            });
   const long long m = static_cast<long long>(kept.size());
   constexpr int K = 30;  // KDTreeSearchParamKNN() default
 #pragma omp parallel for schedule(dynamic, 64)

@@ -28,9 +28,9 @@
  * comments at each function.
  *
  * Output-order conventions where the reference's order is unspecified
- * (unordered_map iteration order, OpenMP critical order): ascending packed
- * voxel key for downsample output / map export; ascending source index for
- * correspondences.
+ * (unordered_map iteration order, OpenMP critical order): ascending source
+ * index for the downsample output and for correspondences; ascending packed
+ * voxel key (kx, ky, kz) for the map export.
  */
 #ifndef ESKF_ORACLE_H_
 #define ESKF_ORACLE_H_
@@ -148,7 +148,7 @@ void orc_knn_bruteforce(const double* xyz, size_t n, const double* queries, size
 void orc_cov_from_indices(const double* xyz, const int32_t* idx, int k, double out9[9]);
 void orc_regularize_cov(const double C9[9], double out9[9]);
 /* voxelDownsampleAndEstimateCovariances (:76-127).  Outputs sized >= n.
- * Returns the number of kept points (ascending packed key order). */
+ * Returns the number of kept points (ascending source index order). */
 size_t orc_downsample_cov(const double* xyz, size_t n, double voxel_size, double* out_xyz,
                           double* out_cov, uint32_t* out_src_index);
 /* deskew (:25-74), in place.  Returns 0, or -1 when the reference would

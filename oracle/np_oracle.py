@@ -130,14 +130,13 @@ class NpMap:
 
 def downsample_cov(xyz, voxel_size, k=30):
     """src/CloudPreprocessor.cpp:76-127 with cKDTree + a true SVD.
-    Output ascending packed voxel key (kx, ky, kz lexicographic)."""
+    Output in ascending source index order."""
     xyz = np.asarray(xyz, dtype=np.float64)
     keys = voxel_index(xyz, voxel_size).astype(np.int64)
     first = {}
     for i, kk in enumerate(map(tuple, keys)):
         first.setdefault(kk, i)
-    order = sorted(first.items())
-    src = np.array([i for _, i in order], dtype=np.int64)
+    src = np.array(sorted(first.values()), dtype=np.int64)
     tree = cKDTree(xyz)
     kk = min(k, len(xyz))
     _, nn = tree.query(xyz[src], k=kk)
