@@ -66,11 +66,12 @@ def lib():
     """Load libeskf_gpu.so (raises if it has not been built: no fallback)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(_build.LIB_PATH):
+        path = os.environ.get("ESKF_GPU_LIB") or _build.LIB_PATH  # env: kernel-variant experiments
+        if not os.path.exists(path):
             raise ImportError(
-                f"{_build.LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(the GPU path has no CPU fallback)")
-        L = C.CDLL(_build.LIB_PATH)
+        L = C.CDLL(path)
         L.eskf_last_error.restype = C.c_char_p
         for name in SYMBOLS:
             getattr(L, name)  # AttributeError if the ABI is incomplete

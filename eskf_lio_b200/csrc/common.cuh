@@ -78,6 +78,24 @@ __host__ __device__ __forceinline__ uint64_t hash_key(uint64_t k) {
   return k;
 }
 
+// Home slot of a voxel: murmur-mixed key.  (ESKF_BRICK_HASH=1 is an
+// experiment that keeps the 64 cells of a 4x4x4 brick in contiguous slots; on
+// B200 it measured SLOWER on the dense config — 1.69 ms vs 1.20 ms per
+// 10-iteration launch with a brick-sorted source — because linear probing
+// through interleaved bricks lengthens the miss chains; see DESIGN.md.)
+#ifndef ESKF_BRICK_HASH
+#define ESKF_BRICK_HASH 0
+#endif
+__host__ __device__ __forceinline__ uint64_t slot_hash(uint64_t key) {
+#if ESKF_BRICK_HASH
+  const uint64_t low = (3ull << 42) | (3ull << 21) | 3ull;
+  const uint64_t local = (((key >> 42) & 3ull) << 4) | (((key >> 21) & 3ull) << 2) | (key & 3ull);
+  return (hash_key(key & ~low) << 6) | local;
+#else
+  return hash_key(key);
+#endif
+}
+
 // 21-bit -> 63-bit Morton spreading (x bit i -> bit 3i)
 __host__ __device__ __forceinline__ uint64_t spread3(uint32_t v) {
   uint64_t x = v & 0x1FFFFF;

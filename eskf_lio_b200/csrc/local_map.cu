@@ -43,7 +43,7 @@ __device__ __forceinline__ void write_slot_payload(VoxelSlot* s, uint32_t count,
 // index, or ~0 when the table is full.  *is_new tells which.
 __device__ __forceinline__ uint64_t find_or_claim(VoxelSlot* slots, uint64_t mask, uint64_t key,
                                                   bool* is_new) {
-  uint64_t h = hash_key(key) & mask;
+  uint64_t h = slot_hash(key) & mask;
   for (uint64_t probe = 0; probe <= mask; ++probe) {
     unsigned long long* kp = reinterpret_cast<unsigned long long*>(&slots[h].key);
     unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
@@ -62,7 +62,7 @@ __device__ __forceinline__ uint64_t find_or_claim(VoxelSlot* slots, uint64_t mas
 }
 
 __device__ __forceinline__ uint64_t find_slot(const VoxelSlot* slots, uint64_t mask, uint64_t key) {
-  uint64_t h = hash_key(key) & mask;
+  uint64_t h = slot_hash(key) & mask;
   for (uint64_t probe = 0; probe <= mask; ++probe) {
     const uint64_t cur = slots[h].key;
     if (cur == key) return h;

@@ -132,13 +132,77 @@ __global__ void __launch_bounds__(128) knn_cov_kernel(KnnParams P) {
     int lid = -1;
     int cnt = 0;
     double kth = kInf;
+    // scan the points of the per-lane ranges [start, start + len) as ONE
+    // flattened candidate list (32 candidates per step, next batch prefetched)
+    auto scan_ranges = [&](unsigned start, unsigned len) {
+      unsigned off = len;  // inclusive scan of the lengths
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, off, o);
+        if (lane >= static_cast<unsigned>(o)) off += u;
+      }
+      const unsigned total = __shfl_sync(0xffffffffu, off, 31);
+      const unsigned excl = off - len;
+      auto fetch = [&](unsigned c, double& d, int& id) {
+        unsigned pos = 0;  // first range whose inclusive offset exceeds c
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+          const unsigned v = __shfl_sync(0xffffffffu, off, pos + step - 1);
+          if (v <= c) pos += step;
+        }
+        const unsigned s_t = __shfl_sync(0xffffffffu, start, pos);
+        const unsigned e_t = __shfl_sync(0xffffffffu, excl, pos);
+        d = kInf;
+        id = -1;
+        if (c < total) {
+          const unsigned j = s_t + (c - e_t);
+          const double dx = P.sx[j] - qx, dy = P.sy[j] - qy, dz = P.sz[j] - qz;
+          d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+          id = static_cast<int>(__ldg(sidx + j));
+        }
+      };
+      double d0, d1;
+      int id0, id1;
+      fetch(lane, d0, id0);
+      for (unsigned c = 0; c < total; c += 32) {
+        d1 = kInf;
+        id1 = -1;
+        if (c + 32 < total) fetch(c + 32 + lane, d1, id1);
+        unsigned bal = __ballot_sync(0xffffffffu, id0 >= 0 && d0 <= kth);
+        while (bal) {
+          const int src = __ffs(bal) - 1;
+          bal &= bal - 1;
+          const double cd = __shfl_sync(0xffffffffu, d0, src);
+          const int cid = __shfl_sync(0xffffffffu, id0, src);
+          // (d2, index) lexicographic order, like the oracle's heap
+          const int pos = __popc(__ballot_sync(0xffffffffu, ld2 < cd || (ld2 == cd && lid < cid)));
+          if (pos < K) {
+            const double up_d = __shfl_up_sync(0xffffffffu, ld2, 1);
+            const int up_i = __shfl_up_sync(0xffffffffu, lid, 1);
+            if (static_cast<int>(lane) > pos) {
+              ld2 = up_d;
+              lid = up_i;
+            } else if (static_cast<int>(lane) == pos) {
+              ld2 = cd;
+              lid = cid;
+            }
+            if (static_cast<int>(lane) >= K) {
+              ld2 = kInf;
+              lid = -1;
+            }
+            if (cnt < K) ++cnt;
+            kth = __shfl_sync(0xffffffffu, ld2, K - 1);
+          }
+        }
+        d0 = d1;
+        id0 = id1;
+      }
+    };
     for (int L = 0; L <= kKeyBits; ++L) {
-      ld2 = kInf;
-      lid = -1;
-      cnt = 0;
-      kth = kInf;
       const int bx = cx >> L, by = cy >> L, bz = cz >> L;
+      const double span = static_cast<double>(1 << L);
       unsigned start = 0, end = 0;
+      double box2 = kInf;  // squared distance from q to this lane's block (AABB)
       if (lane < 27) {
         const int nx = bx + static_cast<int>(lane % 3) - 1;
         const int ny = by + static_cast<int>((lane / 3) % 3) - 1;
@@ -148,52 +212,32 @@ __global__ void __launch_bounds__(128) knn_cov_kernel(KnnParams P) {
           const uint64_t hi = lo + (1ull << (3 * L));
           start = lower_bound_u64(keys, 0, n, lo);
           end = lower_bound_u64(keys, start, n, hi);
+          const double x0 = (static_cast<double>(m0) + static_cast<double>(nx) * span) * P.voxel;
+          const double y0 = (static_cast<double>(m1) + static_cast<double>(ny) * span) * P.voxel;
+          const double z0 = (static_cast<double>(m2) + static_cast<double>(nz) * span) * P.voxel;
+          const double w = span * P.voxel;
+          const double ex = fmax(fmax(x0 - qx, qx - (x0 + w)) - 1e-9, 0.0);
+          const double ey = fmax(fmax(y0 - qy, qy - (y0 + w)) - 1e-9, 0.0);
+          const double ez = fmax(fmax(z0 - qz, qz - (z0 + w)) - 1e-9, 0.0);
+          box2 = ex * ex + ey * ey + ez * ez;
         }
       }
-      for (int t = 0; t < 27; ++t) {
-        const unsigned s = __shfl_sync(0xffffffffu, start, t);
-        const unsigned e = __shfl_sync(0xffffffffu, end, t);
-        for (unsigned jb = s; jb < e; jb += 32) {
-          const unsigned j = jb + lane;
-          double d = kInf;
-          int id = -1;
-          if (j < e) {
-            const double dx = P.sx[j] - qx, dy = P.sy[j] - qy, dz = P.sz[j] - qz;
-            d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-            id = static_cast<int>(__ldg(sidx + j));
-          }
-          unsigned bal = __ballot_sync(0xffffffffu, id >= 0 && d <= kth);
-          while (bal) {
-            const int src = __ffs(bal) - 1;
-            bal &= bal - 1;
-            const double cd = __shfl_sync(0xffffffffu, d, src);
-            const int cid = __shfl_sync(0xffffffffu, id, src);
-            // (d2, index) lexicographic order, like the oracle's heap
-            const int pos = __popc(__ballot_sync(0xffffffffu, ld2 < cd || (ld2 == cd && lid < cid)));
-            if (pos < K) {
-              const double up_d = __shfl_up_sync(0xffffffffu, ld2, 1);
-              const int up_i = __shfl_up_sync(0xffffffffu, lid, 1);
-              if (static_cast<int>(lane) > pos) {
-                ld2 = up_d;
-                lid = up_i;
-              } else if (static_cast<int>(lane) == pos) {
-                ld2 = cd;
-                lid = cid;
-              }
-              if (static_cast<int>(lane) >= K) {
-                ld2 = kInf;
-                lid = -1;
-              }
-              if (cnt < K) ++cnt;
-              kth = __shfl_sync(0xffffffffu, ld2, K - 1);
-            }
-          }
-        }
-      }
+      const unsigned len = end - start;
+      const unsigned total = warp_reduce_add(len);
+      const bool all = (M0 >> L) == 0 && (M1 >> L) == 0 && (M2 >> L) == 0;
+      // fewer than K candidates cannot finish the search at this level
+      if (total < static_cast<unsigned>(K) && !all) continue;
+      ld2 = kInf;
+      lid = -1;
+      cnt = 0;
+      kth = kInf;
+      // the query's own block first (lane 13), then only the blocks that can
+      // still hold a point closer than the current K-th distance
+      scan_ranges(start, lane == 13 ? len : 0u);
+      scan_ranges(start, (lane != 13 && box2 <= kth) ? len : 0u);
       // the 3x3x3 neighbourhood already holds every point?
-      if ((M0 >> L) == 0 && (M1 >> L) == 0 && (M2 >> L) == 0) break;
+      if (all) break;
       if (cnt == K) {
-        const double span = static_cast<double>(1 << L);
         const double ax = (static_cast<double>(m0) + static_cast<double>(bx) * span);
         const double ay = (static_cast<double>(m1) + static_cast<double>(by) * span);
         const double az = (static_cast<double>(m2) + static_cast<double>(bz) * span);

@@ -73,9 +73,11 @@ struct AlignParams {
 };
 
 // ------------------------------------------------------------ per point math
+// adds the 27 unique terms of J^T W J / J^T W r (+ a correspondence count) of
+// one correspondence into v[0..27]
 template <typename F>
 __device__ __forceinline__ void point_terms(F px, F py, F pz, F rx, F ry, F rz, F m00, F m01,
-                                            F m02, F m11, F m12, F m22, double* acc) {
+                                            F m02, F m11, F m12, F m22, F* v) {
   // W = M^-1 by cofactors (Eigen Matrix3d::inverse(), Registration.cpp:95)
   const F c00 = m11 * m22 - m12 * m12;
   const F c01 = m02 * m12 - m01 * m22;
@@ -98,13 +100,13 @@ __device__ __forceinline__ void point_terms(F px, F py, F pz, F rx, F ry, F rz, 
   const F g1 = w01 * rx + w11 * ry + w12 * rz;
   const F g2 = w02 * rx + w12 * ry + w22 * rz;
   const F g3 = py * g2 - pz * g1, g4 = pz * g0 - px * g2, g5 = px * g1 - py * g0;
-  acc[0] += w00; acc[1] += w01; acc[2] += w02; acc[3] += w11; acc[4] += w12; acc[5] += w22;
-  acc[6] += b00; acc[7] += b01; acc[8] += b02;
-  acc[9] += b10; acc[10] += b11; acc[11] += b12;
-  acc[12] += b20; acc[13] += b21; acc[14] += b22;
-  acc[15] += d00; acc[16] += d01; acc[17] += d02; acc[18] += d11; acc[19] += d12; acc[20] += d22;
-  acc[21] += g0; acc[22] += g1; acc[23] += g2; acc[24] += g3; acc[25] += g4; acc[26] += g5;
-  acc[27] += 1.0;
+  v[0] += w00; v[1] += w01; v[2] += w02; v[3] += w11; v[4] += w12; v[5] += w22;
+  v[6] += b00; v[7] += b01; v[8] += b02;
+  v[9] += b10; v[10] += b11; v[11] += b12;
+  v[12] += b20; v[13] += b21; v[14] += b22;
+  v[15] += d00; v[16] += d01; v[17] += d02; v[18] += d11; v[19] += d12; v[20] += d22;
+  v[21] += g0; v[22] += g1; v[23] += g2; v[24] += g3; v[25] += g4; v[26] += g5;
+  v[27] += F(1);
 }
 
 // C' = R S R^T for symmetric S, 6 unique outputs
@@ -126,80 +128,179 @@ __device__ __forceinline__ void rotate_sym(const F* R, F s00, F s01, F s02, F s1
   o[5] = t[6] * R[6] + t[7] * R[7] + t[8] * R[8];
 }
 
+// Warp "reduce-scatter": every lane holds 32 partial terms; after 31 shuffles
+// lane l holds the warp total of term l.  Fixed order => deterministic.
+template <typename F>
+__device__ __forceinline__ F warp_reduce_scatter32(F* v, unsigned lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < o; ++j) {
+      const F a = v[j], b = v[j + o];
+      const F send = upper ? a : b;
+      const F keep = upper ? b : a;
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
 __constant__ int c_off7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0},
                                  {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
 
-// one pass over this CTA's points: transform, look up, accumulate
-template <typename F>
-__device__ __forceinline__ void accumulate_points(const AlignParams& P, const double* sT,
-                                                  const F* sR, bool first, bool write_hit,
-                                                  double* acc) {
-  const unsigned stride = gridDim.x * kT;
-  const int nn = P.neighbor_mode == 7 ? 7 : 1;
+__device__ __forceinline__ uint64_t load_key(const VoxelSlot* s) {
+  const uint2 kw = __ldg(reinterpret_cast<const uint2*>(s));
+  return (static_cast<uint64_t>(kw.y) << 32) | kw.x;
+}
+
+// finish a lookup whose first probe (slot h) returned `cur`
+__device__ __forceinline__ const VoxelSlot* resolve_probe(const VoxelSlot* slots, uint64_t mask,
+                                                          uint64_t key, uint64_t h, uint64_t cur) {
+  for (uint64_t probe = 0; probe <= mask; ++probe) {
+    if (cur == key) return slots + h;
+    if (cur == kEmptyKey) return nullptr;
+    h = (h + 1) & mask;
+    cur = load_key(slots + h);
+  }
+  return nullptr;
+}
+
+// One pass over this CTA's points: transform, look up, accumulate.
+// Work is dealt in warp tiles of 32*U consecutive points; the loads of the U
+// points of a lane are issued back to back (position -> first probe -> voxel
+// payload) so U independent dependent-load chains are in flight per thread.
+// Per tile the 28 per-lane partial terms (fp32) are folded with a warp
+// reduce-scatter and added to ONE fp64 accumulator per lane (lane l = term l).
+template <typename F, int U, int NN>
+__device__ __forceinline__ double accumulate_points(const AlignParams& P, const double* sT,
+                                                    const F* sR, bool first, bool write_hit) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned tile_pts = 32u * U;
+  const unsigned wglobal = blockIdx.x * kW + (threadIdx.x >> 5);
+  const unsigned wstride = gridDim.x * kW;
   const double* sx = first ? P.x0 : P.wx;
   const double* sy = first ? P.y0 : P.wy;
   const double* sz = first ? P.z0 : P.wz;
-  for (unsigned i = blockIdx.x * kT + threadIdx.x; i < P.n; i += stride) {
-    double x = first ? __ldg(sx + i) : ld_cg(sx + i);
-    double y = first ? __ldg(sy + i) : ld_cg(sy + i);
-    double z = first ? __ldg(sz + i) : ld_cg(sz + i);
-    const float4 s4 = __ldg(P.c4 + i);
-    const float2 s2 = __ldg(P.c2 + i);
-    transform_point_rn(sT, x, y, z);
-    P.wx[i] = x;
-    P.wy[i] = y;
-    P.wz[i] = z;
-    const int kx = voxel_coord(x, P.voxel);
-    const int ky = voxel_coord(y, P.voxel);
-    const int kz = voxel_coord(z, P.voxel);
-    F cr[6];
-    bool rotated = false;
-    for (int o = 0; o < nn; ++o) {
-      const int vx = kx + c_off7[o][0], vy = ky + c_off7[o][1], vz = kz + c_off7[o][2];
-      const VoxelSlot* slot = nullptr;
-      if (coord_in_range(vx) && coord_in_range(vy) && coord_in_range(vz)) {
-        const uint64_t key = pack_key(vx, vy, vz);
-        uint64_t h = hash_key(key) & P.mask;
-        for (uint64_t probe = 0; probe <= P.mask; ++probe) {
-          const uint2 kw = __ldg(reinterpret_cast<const uint2*>(P.slots + h));
-          const uint64_t cur = (static_cast<uint64_t>(kw.y) << 32) | kw.x;
-          if (cur == key) {
-            slot = P.slots + h;
-            break;
-          }
-          if (cur == kEmptyKey) break;
-          h = (h + 1) & P.mask;
+  const unsigned n_tiles = (P.n + tile_pts - 1) / tile_pts;
+  double acc = 0.0;
+  for (unsigned tile = wglobal; tile < n_tiles; tile += wstride) {
+    const unsigned start = tile * tile_pts + lane;
+    F v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = F(0);
+    double x[U], y[U], z[U];
+    bool valid[U];
+    // stage 1: positions
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned i = start + 32u * u;
+      valid[u] = i < P.n;
+      x[u] = y[u] = z[u] = 0.0;
+      if (valid[u]) {
+        x[u] = first ? __ldg(sx + i) : ld_cg(sx + i);
+        y[u] = first ? __ldg(sy + i) : ld_cg(sy + i);
+        z[u] = first ? __ldg(sz + i) : ld_cg(sz + i);
+      }
+    }
+    // stage 2: transform, write back, keys, first probes
+    int kx[U], ky[U], kz[U];
+    uint64_t key[U][NN], hh[U][NN], cur[U][NN];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned i = start + 32u * u;
+      if (valid[u]) {
+        transform_point_rn(sT, x[u], y[u], z[u]);
+        P.wx[i] = x[u];
+        P.wy[i] = y[u];
+        P.wz[i] = z[u];
+      }
+      kx[u] = voxel_coord(x[u], P.voxel);
+      ky[u] = voxel_coord(y[u], P.voxel);
+      kz[u] = voxel_coord(z[u], P.voxel);
+#pragma unroll
+      for (int o = 0; o < NN; ++o) {
+        const int vx = kx[u] + c_off7[o][0], vy = ky[u] + c_off7[o][1], vz = kz[u] + c_off7[o][2];
+        const bool ok = valid[u] && coord_in_range(vx) && coord_in_range(vy) && coord_in_range(vz);
+        key[u][o] = pack_key(vx, vy, vz);
+        hh[u][o] = slot_hash(key[u][o]) & P.mask;
+        cur[u][o] = ok ? load_key(P.slots + hh[u][o]) : kEmptyKey;
+      }
+    }
+    // stage 3: resolve the lookups
+    const VoxelSlot* slot[U][NN];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int o = 0; o < NN; ++o) {
+        slot[u][o] = resolve_probe(P.slots, P.mask, key[u][o], hh[u][o], cur[u][o]);
+        if (write_hit && valid[u])
+          P.hit[static_cast<size_t>(NN) * (start + 32u * u) + o] = slot[u][o] != nullptr ? 1 : 0;
+      }
+    // stage 4/5: payloads + per-point algebra
+    if (NN == 1) {
+      float4 pa[U], pc[U], pd[U], s4[U];
+      float2 s2[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (slot[u][0] != nullptr) {
+          pa[u] = __ldg(reinterpret_cast<const float4*>(slot[u][0]) + 1);  // mx my mz -
+          pc[u] = __ldg(reinterpret_cast<const float4*>(slot[u][0]) + 2);  // c00 c01 c02 c11
+          pd[u] = __ldg(reinterpret_cast<const float4*>(slot[u][0]) + 3);  // c12 c22 - -
+          s4[u] = __ldg(P.c4 + start + 32u * u);
+          s2[u] = __ldg(P.c2 + start + 32u * u);
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (slot[u][0] != nullptr) {
+          F cr[6];
+          rotate_sym<F>(sR, F(s4[u].x), F(s4[u].y), F(s4[u].z), F(s4[u].w), F(s2[u].x), F(s2[u].y), cr);
+          // residual against the voxel mean, formed relative to the voxel centre
+          const double cx = __dmul_rn(static_cast<double>(kx[u]) + 0.5, P.voxel);
+          const double cy = __dmul_rn(static_cast<double>(ky[u]) + 0.5, P.voxel);
+          const double cz = __dmul_rn(static_cast<double>(kz[u]) + 0.5, P.voxel);
+          const F rx = F(x[u] - cx) - F(pa[u].x), ry = F(y[u] - cy) - F(pa[u].y),
+                  rz = F(z[u] - cz) - F(pa[u].z);
+          point_terms<F>(F(x[u]), F(y[u]), F(z[u]), rx, ry, rz, cr[0] + F(pc[u].x),
+                         cr[1] + F(pc[u].y), cr[2] + F(pc[u].z), cr[3] + F(pc[u].w),
+                         cr[4] + F(pd[u].x), cr[5] + F(pd[u].y), v);
+        }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        bool any = false;
+#pragma unroll
+        for (int o = 0; o < NN; ++o) any = any || slot[u][o] != nullptr;
+        if (!any) continue;
+        const float4 s4 = __ldg(P.c4 + start + 32u * u);
+        const float2 s2 = __ldg(P.c2 + start + 32u * u);
+        F cr[6];
+        rotate_sym<F>(sR, F(s4.x), F(s4.y), F(s4.z), F(s4.w), F(s2.x), F(s2.y), cr);
+#pragma unroll
+        for (int o = 0; o < NN; ++o) {
+          if (slot[u][o] == nullptr) continue;
+          const float4 a = __ldg(reinterpret_cast<const float4*>(slot[u][o]) + 1);
+          const float4 c = __ldg(reinterpret_cast<const float4*>(slot[u][o]) + 2);
+          const float4 d = __ldg(reinterpret_cast<const float4*>(slot[u][o]) + 3);
+          const int vx = kx[u] + c_off7[o][0], vy = ky[u] + c_off7[o][1], vz = kz[u] + c_off7[o][2];
+          const double cx = __dmul_rn(static_cast<double>(vx) + 0.5, P.voxel);
+          const double cy = __dmul_rn(static_cast<double>(vy) + 0.5, P.voxel);
+          const double cz = __dmul_rn(static_cast<double>(vz) + 0.5, P.voxel);
+          const F rx = F(x[u] - cx) - F(a.x), ry = F(y[u] - cy) - F(a.y), rz = F(z[u] - cz) - F(a.z);
+          point_terms<F>(F(x[u]), F(y[u]), F(z[u]), rx, ry, rz, cr[0] + F(c.x), cr[1] + F(c.y),
+                         cr[2] + F(c.z), cr[3] + F(c.w), cr[4] + F(d.x), cr[5] + F(d.y), v);
         }
       }
-      if (write_hit) P.hit[static_cast<size_t>(nn) * i + o] = slot != nullptr ? 1 : 0;
-      if (slot == nullptr) continue;
-      const float4 a = __ldg(reinterpret_cast<const float4*>(slot) + 1);  // mx my mz -
-      const float4 c = __ldg(reinterpret_cast<const float4*>(slot) + 2);  // c00 c01 c02 c11
-      const float4 d = __ldg(reinterpret_cast<const float4*>(slot) + 3);  // c12 c22 - -
-      if (!rotated) {
-        rotate_sym<F>(sR, F(s4.x), F(s4.y), F(s4.z), F(s4.w), F(s2.x), F(s2.y), cr);
-        rotated = true;
-      }
-      // residual against the voxel mean, formed relative to the voxel centre
-      const double cx = __dmul_rn(static_cast<double>(vx) + 0.5, P.voxel);
-      const double cy = __dmul_rn(static_cast<double>(vy) + 0.5, P.voxel);
-      const double cz = __dmul_rn(static_cast<double>(vz) + 0.5, P.voxel);
-      const F rx = F(x - cx) - F(a.x), ry = F(y - cy) - F(a.y), rz = F(z - cz) - F(a.z);
-      point_terms<F>(F(x), F(y), F(z), rx, ry, rz, cr[0] + F(c.x), cr[1] + F(c.y), cr[2] + F(c.z),
-                     cr[3] + F(c.w), cr[4] + F(d.x), cr[5] + F(d.y), acc);
     }
+    acc += static_cast<double>(warp_reduce_scatter32<F>(v, lane));
   }
+  return acc;
 }
 
-// deterministic CTA reduction of the 28 accumulators -> partials[blockIdx.x]
-__device__ __forceinline__ void block_reduce_store(double* acc, double (*s_part)[kAcc],
-                                                   double* out) {
+// deterministic CTA reduction: lane l of every warp holds term l
+__device__ __forceinline__ void block_reduce_store(double acc, double (*s_part)[32], double* out) {
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < kAcc; ++k) {
-    const double v = warp_reduce_add(acc[k]);
-    if (lane == 0) s_part[w][k] = v;
-  }
+  s_part[w][lane] = acc;
   __syncthreads();
   if (threadIdx.x < kAcc) {
     double s = 0.0;
@@ -213,21 +314,70 @@ __device__ __forceinline__ void block_reduce_store(double* acc, double (*s_part)
 
 // sum partials[0..G) in a fixed order -> s_sum[kAcc]  (whole CTA cooperates)
 __device__ __forceinline__ void final_reduce(const double* partials, unsigned G,
-                                             double (*s_part)[kAcc], double* s_sum) {
+                                             double (*s_part)[32], double* s_sum) {
   const unsigned term = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  if (term < kAcc) {
-    double s = 0.0;
+  double s = 0.0;
+  if (term < kAcc)
     for (unsigned bb = grp; bb < G; bb += kW) s += ld_cg(partials + static_cast<size_t>(bb) * kAcc + term);
-    s_part[grp][term] = s;
-  }
+  s_part[grp][term] = s;
   __syncthreads();
   if (threadIdx.x < kAcc) {
-    double s = 0.0;
+    double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < kW; ++i) s += s_part[i][threadIdx.x];
-    s_sum[threadIdx.x] = s;
+    for (int i = 0; i < kW; ++i) t += s_part[i][threadIdx.x];
+    s_sum[threadIdx.x] = t;
   }
   __syncthreads();
+}
+
+// fast path of the 6x6 solve: LDL^T without pivoting, fully unrolled so the
+// matrix lives in registers.  Returns false (caller falls back to the pivoted
+// restatement of Eigen's LDLT below) unless every pivot is safely positive.
+__device__ __forceinline__ bool ldlt_solve6_nopivot(const double* H, const double* b, double* x) {
+  double A[6][6], D[6], y[6];
+  double maxd = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) A[i][j] = H[6 * i + j];
+    maxd = fmax(maxd, fabs(H[7 * i]));
+  }
+  const double tol = maxd * 1e-12;
+  bool ok = maxd > 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double d = A[k][k];
+#pragma unroll
+    for (int j = 0; j < k; ++j) d -= A[k][j] * A[k][j] * D[j];
+    ok = ok && (d > tol);
+    D[k] = d;
+    const double inv = 1.0 / d;
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) {
+      double s = A[i][k];
+#pragma unroll
+      for (int j = 0; j < k; ++j) s -= A[i][j] * A[k][j] * D[j];
+      A[i][k] = s * inv;
+    }
+  }
+  if (!ok) return false;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double s = b[i];
+#pragma unroll
+    for (int j = 0; j < i; ++j) s -= A[i][j] * y[j];
+    y[i] = s;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) y[i] /= D[i];
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double s = y[i];
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) s -= A[j][i] * x[j];
+    x[i] = s;
+  }
+  return true;
 }
 
 // Eigen LDLT<Matrix6d>::solve restated: diagonal pivoting, zero pivots -> 0
@@ -313,7 +463,7 @@ __device__ void se3_to_SE3(const double* se3, double* T /* R(9) t(3) */) {
 }
 
 // thread 0 of the solving CTA: H/b -> step -> total, convergence, bookkeeping
-__device__ void solve_and_update(const AlignParams& P, const double* S, int it) {
+__device__ __noinline__ void solve_and_update(const AlignParams& P, const double* S, int it) {
   AlignState* st = P.st;
   double H[36], b[6], nb[6], se3[6], step[12], tot[12], old[12];
   // unpack: A(6) B(9) D(6)
@@ -330,7 +480,8 @@ __device__ void solve_and_update(const AlignParams& P, const double* S, int it) 
     b[i] = S[21 + i];
     nb[i] = -b[i];
   }
-  ldlt_solve6(H, nb, se3);  // JTJ.ldlt().solve(-JTr), Registration.cpp:78
+  // JTJ.ldlt().solve(-JTr), Registration.cpp:78
+  if (!ldlt_solve6_nopivot(H, nb, se3)) ldlt_solve6(H, nb, se3);
   se3_to_SE3(se3, step);
   for (int i = 0; i < 12; ++i) old[i] = (it == 0) ? P.guess[i] : st->T_total[i];
   // totalTransform = transformIter * totalTransform (Registration.cpp:20)
@@ -363,11 +514,11 @@ __device__ void solve_and_update(const AlignParams& P, const double* S, int it) 
   st->done = done;
 }
 
-template <typename F>
-__global__ void __launch_bounds__(kT, 2) align_kernel(AlignParams P) {
+template <typename F, int U, int NN, int MINB>
+__global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
   __shared__ double s_T[12];
   __shared__ F s_R[9];
-  __shared__ double s_part[kW][kAcc];
+  __shared__ double s_part[kW][32];
   __shared__ double s_sum[kAcc];
   __shared__ int s_last, s_done;
   const unsigned G = gridDim.x, t = threadIdx.x;
@@ -381,10 +532,7 @@ __global__ void __launch_bounds__(kT, 2) align_kernel(AlignParams P) {
                                   : (sizeof(F) == 8 ? F(ld_cg(&st->T_total[t])) : F(ld_cg(&st->Rf[t])));
     __syncthreads();
 
-    double acc[kAcc];
-#pragma unroll
-    for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
-    accumulate_points<F>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0, acc);
+    const double acc = accumulate_points<F, U, NN>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0);
     block_reduce_store(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
 
     // last CTA to arrive reduces the partials and solves
@@ -407,7 +555,7 @@ __global__ void __launch_bounds__(kT, 2) align_kernel(AlignParams P) {
       unsigned spins = 0;
       int ok = 1;
       while (ld_acquire_u32(&st->epoch) < static_cast<unsigned>(it + 1)) {
-        __nanosleep(32);
+        __nanosleep(20);
         if (++spins > kSpinLimit || ld_acquire_u32(&st->error) != 0) {
           atomicExch(&st->error, 1u);
           ok = 0;
@@ -427,13 +575,13 @@ __global__ void solve_kernel(AlignParams P, int it) {
   if (threadIdx.x == 0 && blockIdx.x == 0) solve_and_update(P, P.sums, it);
 }
 
-// sharded mode: pose-only transform of the working cloud is done by the next
-// single_pass launch, which needs `first`/guess semantics per iteration
-template <typename F>
-__global__ void __launch_bounds__(kT, 2) linearize_pass_kernel(AlignParams P, int it) {
+// sharded mode: ONE linearisation of this rank's point range; the 28 sums go
+// to P.sums for the caller's all-reduce, solve_kernel follows
+template <typename F, int U, int NN, int MINB>
+__global__ void __launch_bounds__(kT, MINB) linearize_pass_kernel(AlignParams P, int it) {
   __shared__ double s_T[12];
   __shared__ F s_R[9];
-  __shared__ double s_part[kW][kAcc];
+  __shared__ double s_part[kW][32];
   __shared__ double s_sum[kAcc];
   __shared__ int s_flag;
   const unsigned G = gridDim.x, t = threadIdx.x;
@@ -441,10 +589,7 @@ __global__ void __launch_bounds__(kT, 2) linearize_pass_kernel(AlignParams P, in
   if (t < 12) s_T[t] = (it == 0) ? P.guess[t] : ld_cg(&st->T_step[t]);
   if (t < 9) s_R[t] = (it == 0) ? F(P.guess[t]) : F(ld_cg(&st->Rf[t]));
   __syncthreads();
-  double acc[kAcc];
-#pragma unroll
-  for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
-  accumulate_points<F>(P, s_T, s_R, it == 0, false, acc);
+  const double acc = accumulate_points<F, U, NN>(P, s_T, s_R, it == 0, false);
   block_reduce_store(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
   if (t == 0) {
     const unsigned ticket = atomicAdd(&st->block_counter, 1u);
@@ -456,6 +601,42 @@ __global__ void __launch_bounds__(kT, 2) linearize_pass_kernel(AlignParams P, in
     final_reduce(P.partials, G, s_part, s_sum);
     if (t < kAcc) P.sums[t] = s_sum[t];
   }
+}
+
+// kernel variants: (math type, points per lane U, neighbourhood, min CTAs/SM)
+struct Variant {
+  void* align;
+  void* pass;
+  int pts_per_block;
+  int per_sm;  // filled by align_max_blocks()
+};
+
+enum { V_F32_N1 = 0, V_F32_N7, V_F64_N1, V_F64_N7, V_COUNT };
+
+// measured on B200, dense config (2M pts, 10 iterations per launch):
+//   U=1/3 CTAs 1.267 ms, U=1/4 CTAs 1.246 ms, U=2/3 CTAs 1.303 ms,
+//   U=2/2 CTAs 1.396 ms, U=4/2 CTAs 1.417 ms  (profiles/r1_align_variants.md)
+#ifndef ESKF_ALIGN_U
+#define ESKF_ALIGN_U 1
+#endif
+#ifndef ESKF_ALIGN_MINB
+#define ESKF_ALIGN_MINB 3
+#endif
+
+Variant g_variants[V_COUNT] = {
+    {reinterpret_cast<void*>(align_kernel<float, ESKF_ALIGN_U, 1, ESKF_ALIGN_MINB>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, ESKF_ALIGN_U, 1, ESKF_ALIGN_MINB>),
+     kT * ESKF_ALIGN_U, 1},
+    {reinterpret_cast<void*>(align_kernel<float, 1, 7, 2>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 7, 2>), kT, 1},
+    {reinterpret_cast<void*>(align_kernel<double, 1, 1, 1>),
+     reinterpret_cast<void*>(linearize_pass_kernel<double, 1, 1, 1>), kT, 1},
+    {reinterpret_cast<void*>(align_kernel<double, 1, 7, 1>),
+     reinterpret_cast<void*>(linearize_pass_kernel<double, 1, 7, 1>), kT, 1},
+};
+
+int variant_index(const AlignArgs& a) {
+  return (a.fp64_math ? 2 : 0) + (a.neighbor_mode == 7 ? 1 : 0);
 }
 
 struct TraceLayout {
@@ -487,8 +668,10 @@ int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, T
   const unsigned n = static_cast<unsigned>(c->n);
   const size_t pitch = (static_cast<size_t>(n) + 63) / 64 * 64 + 64;
   ESKF_TRY(ctx->work.ensure(pitch * 3 * sizeof(double)));
-  int g = static_cast<int>((n + kT - 1) / kT);
-  if (g > ctx->max_blocks_align) g = ctx->max_blocks_align;
+  const Variant& var = g_variants[variant_index(a)];
+  int g = static_cast<int>((n + var.pts_per_block - 1) / var.pts_per_block);
+  const int g_max = var.per_sm * ctx->sm_count;
+  if (g > g_max) g = g_max;
   if (g < 1) g = 1;
   *G = g;
   ESKF_TRY(ctx->partials.ensure(static_cast<size_t>(g) * kAcc * sizeof(double)));
@@ -593,20 +776,22 @@ int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align
   ESKF_TRY(fill_params(ctx, a, max_it, &P, &L, &G));
   ESKF_CUDA(cudaMemsetAsync(ctx->astate.p, 0, L.o_H, ctx->stream));
   void* args[] = {&P};
-  void* fn = a.fp64_math ? reinterpret_cast<void*>(align_kernel<double>)
-                         : reinterpret_cast<void*>(align_kernel<float>);
+  void* fn = g_variants[variant_index(a)].align;
   ESKF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(kT), args, 0, ctx->stream));
   count_launch(ctx);
   return read_back(ctx, a, L, max_it, T_out, info);
 }
 
 int align_max_blocks(int sm_count, int* out) {
-  int a = 0, b = 0;
-  ESKF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, align_kernel<float>, kT, 0));
-  ESKF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, align_kernel<double>, kT, 0));
-  int per_sm = a < b ? a : b;
-  if (per_sm < 1) per_sm = 1;
-  *out = per_sm * sm_count;
+  int best = 1;
+  for (int v = 0; v < V_COUNT; ++v) {
+    int per_sm = 0;
+    ESKF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g_variants[v].align, kT, 0));
+    if (per_sm < 1) per_sm = 1;
+    g_variants[v].per_sm = per_sm;
+    if (per_sm > best) best = per_sm;
+  }
+  *out = best * sm_count;
   return ESKF_OK;
 }
 
@@ -627,8 +812,9 @@ int align_sharded(eskf_ctx* ctx, const AlignArgs& a, eskf_allreduce_fn allreduce
   h_done = reinterpret_cast<int*>(reinterpret_cast<char*>(h_done) + L.total);
   for (int it = 0; it < max_it; ++it) {
     if (P.n > 0) {
-      linearize_pass_kernel<float><<<G, kT, 0, ctx->stream>>>(P, it);
-      ESKF_CUDA(cudaGetLastError());
+      void* pargs[] = {&P, &it};
+      ESKF_CUDA(cudaLaunchKernel(g_variants[variant_index(a)].pass, dim3(G), dim3(kT), pargs, 0,
+                                 ctx->stream));
       count_launch(ctx);
     } else {
       ESKF_CUDA(cudaMemsetAsync(P.sums, 0, kAcc * sizeof(double), ctx->stream));

@@ -18,6 +18,7 @@
 // (so only ceil(3*bits/8) 8-bit LSD passes run, and an aligned 2^L block of
 // voxels is one contiguous key range — the k-NN search relies on that).
 #include <climits>
+#include <cstdlib>
 
 #include "internal.h"
 
@@ -333,7 +334,14 @@ int voxelize(eskf_ctx* ctx, const VoxelizeArgs& a) {
   if (a.mode == 1) ESKF_TRY(ctx->sorted_xyz.ensure(nn * 3 * 8));
   ESKF_TRY(ctx->hdr.ensure(sizeof(VoxelHeader)));
 
-  int G = static_cast<int>((n + 4095u) / 4096u);
+  // elements per CTA: small enough that a 64k-point scan spreads over ~64 SMs
+  // (the phases are latency-bound), large enough to keep the barriers cheap
+  static const unsigned epb = [] {
+    const char* e = getenv("ESKF_VOX_EPB");  // tuning knob
+    const int v = e ? atoi(e) : 0;
+    return v >= 256 ? static_cast<unsigned>(v) : 1024u;
+  }();
+  int G = static_cast<int>((n + epb - 1) / epb);
   if (G > ctx->max_blocks_voxelize) G = ctx->max_blocks_voxelize;
   if (G < 1) G = 1;
   ESKF_TRY(ctx->hist.ensure(static_cast<size_t>(G) * (2 * 256 + 2) * sizeof(unsigned)));

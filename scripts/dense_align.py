@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--mode", type=int, default=1)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--sort", type=int, default=0, help="1: sort the source by voxel brick on the host")
     a = ap.parse_args()
     ctx = capi.Context(0)
     rng = np.random.default_rng(44)
@@ -37,6 +38,10 @@ def main():
         gmap.insert(p, c, np.eye(4))
         left -= n
     p, c = S.dense_cloud(scene, a.src, rng)
+    if a.sort:
+        k = np.floor(p / a.voxel).astype(np.int64)
+        order = np.lexsort((k[:, 2], k[:, 1], k[:, 0], k[:, 2] >> 2, k[:, 1] >> 2, k[:, 0] >> 2))
+        p, c = np.ascontiguousarray(p[order]), np.ascontiguousarray(c[order])
     src = capi.Cloud(ctx, a.src).upload(p, c)
     guess = S.perturbation(dt=(0.03, -0.015, 0.01), angle_deg=0.3)
     for _ in range(a.warmup):
