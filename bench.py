@@ -284,7 +284,7 @@ def dense_roofline(ctx, capi, peak_gbs, peak_src):
     """BASELINE.json configs[2] on one GPU: align_kernel, fixed 10 GN iterations."""
     rng = np.random.default_rng(44)
     scene = S.block_scene()
-    gmap = capi.Map(ctx, DENSE_VOXEL, 1000, 1 << 24)
+    gmap = capi.Map(ctx, DENSE_VOXEL, 1000, 9_000_000)
     chunk = 2_500_000
     for _ in range(DENSE_MAP // chunk):
         p, c = S.dense_cloud(scene, chunk, rng)

@@ -226,6 +226,13 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
     }
     ctx->own_stream = true;
   }
+  // persisting-L2 carve-out for the map's tag array (registration.cu)
+  if (prop.persistingL2CacheMaxSize > 0 &&
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, prop.persistingL2CacheMaxSize) == cudaSuccess) {
+    ctx->l2_persist_bytes = static_cast<size_t>(prop.persistingL2CacheMaxSize);
+    ctx->l2_window_max = static_cast<size_t>(prop.accessPolicyMaxWindowSize);
+  }
+  cudaGetLastError();
   int st = voxelize_max_blocks(ctx->sm_count, &ctx->max_blocks_voxelize);
   if (st == ESKF_OK) st = align_max_blocks(ctx->sm_count, &ctx->max_blocks_align);
   if (st == ESKF_OK && cudaEventCreate(&ctx->ev0) != cudaSuccess) st = ESKF_ERR_CUDA;

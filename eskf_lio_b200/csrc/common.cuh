@@ -53,6 +53,19 @@ __device__ __forceinline__ int voxel_coord(double p, double voxel) {
   return static_cast<int>(floor(__ddiv_rn(p, voxel)));
 }
 
+// Same result as voxel_coord(p, voxel) without the fp64 division in the common
+// case: q = p * (1/voxel) is within 3*2^-53 |q| of the correctly rounded
+// quotient, so floor(q) can only differ when q sits that close to an integer;
+// then (about once per 1e9 coordinates) the exact division decides.
+__device__ __forceinline__ int voxel_coord(double p, double voxel, double inv_voxel) {
+  const double q = p * inv_voxel;
+  const double fl = floor(q);
+  const double fr = q - fl;
+  const double tol = fabs(q) * 4.5e-16 + 1e-300;
+  if (fr < tol || 1.0 - fr < tol) return static_cast<int>(floor(__ddiv_rn(p, voxel)));
+  return static_cast<int>(fl);
+}
+
 __device__ __forceinline__ bool coord_in_range(int k) { return k > -kKeyBias && k < kKeyBias; }
 
 // ------------------------------------------------------------------- keys
@@ -78,22 +91,29 @@ __host__ __device__ __forceinline__ uint64_t hash_key(uint64_t k) {
   return k;
 }
 
-// Home slot of a voxel: murmur-mixed key.  (ESKF_BRICK_HASH=1 is an
-// experiment that keeps the 64 cells of a 4x4x4 brick in contiguous slots; on
-// B200 it measured SLOWER on the dense config — 1.69 ms vs 1.20 ms per
-// 10-iteration launch with a brick-sorted source — because linear probing
-// through interleaved bricks lengthens the miss chains; see DESIGN.md.)
-#ifndef ESKF_BRICK_HASH
-#define ESKF_BRICK_HASH 0
-#endif
-__host__ __device__ __forceinline__ uint64_t slot_hash(uint64_t key) {
-#if ESKF_BRICK_HASH
-  const uint64_t low = (3ull << 42) | (3ull << 21) | 3ull;
-  const uint64_t local = (((key >> 42) & 3ull) << 4) | (((key >> 21) & 3ull) << 2) | (key & 3ull);
-  return (hash_key(key & ~low) << 6) | local;
-#else
-  return hash_key(key);
-#endif
+// Table addressing.  The table is probed through a compact array of 16-bit
+// TAGS (0 = empty slot); the 64 B voxel record at the same index is touched
+// only when the tag matches.  The tag array of a multi-million-voxel map
+// (2 B/slot) fits the 126 MB L2, so a lookup that misses never goes to HBM and
+// a hit costs exactly one 64 B record.  home = high-multiply of the low hash
+// word into [0, n_slots) (n_slots need not be a power of two).
+// (A 4x4x4 "brick" hash that keeps neighbouring voxels in adjacent slots was
+// tried and measured SLOWER on B200 — 1.69 vs 1.20 ms per 10-iteration dense
+// launch — linear probing through interleaved bricks lengthens miss chains.)
+using tag_t = uint16_t;  // 2 B/slot: the tag array of 16M slots is 32 MB
+struct SlotAddr {
+  uint32_t home;
+  tag_t tag;
+};
+__host__ __device__ __forceinline__ SlotAddr slot_addr(uint64_t key, uint32_t n_slots) {
+  const uint64_t h = hash_key(key);
+  SlotAddr a;
+  a.home = static_cast<uint32_t>(((h & 0xffffffffull) * static_cast<uint64_t>(n_slots)) >> 32);
+  a.tag = static_cast<tag_t>((h >> 48) | 1u);
+  return a;
+}
+__host__ __device__ __forceinline__ uint32_t next_slot(uint32_t h, uint32_t n_slots) {
+  return h + 1u == n_slots ? 0u : h + 1u;
 }
 
 // 21-bit -> 63-bit Morton spreading (x bit i -> bit 3i)

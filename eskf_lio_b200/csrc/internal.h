@@ -66,9 +66,9 @@ struct DevBuf {
 };
 
 // ---------------------------------------------------------------- layouts
-// One voxel of the open-addressing table, 64 B = two 32 B sectors.  Sector 0
-// is all a probe needs (key) plus the mean; sector 1 is the covariance.  The
-// mean is stored relative to the voxel centre so fp32 keeps ~3e-8 m.
+// One voxel record of the open-addressing table, 64 B = one HBM access.
+// Sector 0: key (verifies a tag match), count, mean; sector 1: covariance.
+// The mean is stored relative to the voxel centre so fp32 keeps ~3e-8 m.
 struct __align__(16) VoxelSlot {
   uint64_t key;    // pack_key(), kEmptyKey when free
   uint32_t count;  // numPoints (capped)
@@ -126,6 +126,8 @@ struct eskf_ctx {
   eskf_cloud* tmp_cloud[3] = {nullptr, nullptr, nullptr};  // host-buffer entry points
   int max_blocks_voxelize = 0;
   int max_blocks_align = 0;
+  size_t l2_persist_bytes = 0;  // persisting-L2 carve-out (0 = unavailable)
+  size_t l2_window_max = 0;     // max access-policy window
 };
 
 struct eskf_cloud {
@@ -146,8 +148,9 @@ struct eskf_map {
   eskf_ctx* ctx = nullptr;
   double voxel = 0.0;
   uint32_t cap_pts = 0;
-  uint64_t n_slots = 0;  // power of two
-  eskf::VoxelSlot* slots = nullptr;
+  uint64_t n_slots = 0;                // < 2^32, any size
+  eskf::tag_t* tags = nullptr;         // [n_slots] 0 = empty; probed instead of the records
+  eskf::VoxelSlot* slots = nullptr;    // [n_slots] 64 B records
   double* master = nullptr;            // [n_slots][12]
   unsigned long long* d_count = nullptr;  // occupied voxels (+1 word: table-full error)
   uint64_t count_upper = 0;            // host-side upper bound of *d_count

@@ -1,8 +1,10 @@
 // local_map.cu — the voxel hash map of LocalMap (src/LocalMap.cpp,
 // include/ESKF_LIO/LocalMap.hpp) as an open-addressing table in HBM.
 //
-// Layout: slots[n_slots] (64 B each: key, count, fp32 mean-relative-to-centre,
-// fp32 covariance) is what the registration kernel gathers; master[n_slots][12]
+// Layout: tags[n_slots] (2 B each, 0 = empty) is the array that is PROBED —
+// small enough to live in the 126 MB L2; slots[n_slots] (64 B records: key,
+// count, fp32 mean-relative-to-centre, fp32 covariance) is what the
+// registration kernel gathers on a tag match; master[n_slots][12]
 // keeps the fp64 running mean / covariance so that inserts reproduce
 // Voxel::addPoint (LocalMap.hpp:79-87) bit for bit.  The raw per-voxel point
 // list of the reference (LocalMap.hpp:67) is dropped: only save() and the GUI
@@ -39,42 +41,52 @@ __device__ __forceinline__ void write_slot_payload(VoxelSlot* s, uint32_t count,
   s->pad3 = 0.f;
 }
 
+constexpr uint32_t kNoSlot = 0xffffffffu;
+
 // find the slot of `key`, claiming an empty one if absent.  Returns the slot
-// index, or ~0 when the table is full.  *is_new tells which.
-__device__ __forceinline__ uint64_t find_or_claim(VoxelSlot* slots, uint64_t mask, uint64_t key,
-                                                  bool* is_new) {
-  uint64_t h = slot_hash(key) & mask;
-  for (uint64_t probe = 0; probe <= mask; ++probe) {
-    unsigned long long* kp = reinterpret_cast<unsigned long long*>(&slots[h].key);
-    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
-    if (cur == kEmptyKey) cur = atomicCAS(kp, kEmptyKey, key);
-    if (cur == kEmptyKey) {
-      *is_new = true;
-      return h;
+// index, or kNoSlot when the table is full.  *is_new tells which.
+// Within one kernel every key is handled by exactly one thread (one thread per
+// key run), so a tag match whose record key is not (yet) ours is another voxel.
+__device__ __forceinline__ uint32_t find_or_claim(tag_t* tags, VoxelSlot* slots, uint32_t n_slots,
+                                                  uint64_t key, bool* is_new) {
+  const SlotAddr a = slot_addr(key, n_slots);
+  uint32_t h = a.home;
+  for (uint32_t probe = 0; probe < n_slots; ++probe) {
+    tag_t t = *reinterpret_cast<volatile tag_t*>(tags + h);
+    if (t == 0u) {
+      t = atomicCAS(reinterpret_cast<unsigned short*>(tags + h), static_cast<unsigned short>(0), a.tag);
+      if (t == 0u) {
+        slots[h].key = key;
+        *is_new = true;
+        return h;
+      }
     }
-    if (cur == key) {
+    if (t == a.tag && *reinterpret_cast<volatile uint64_t*>(&slots[h].key) == key) {
       *is_new = false;
       return h;
     }
-    h = (h + 1) & mask;
+    h = next_slot(h, n_slots);
   }
-  return ~0ull;
+  return kNoSlot;
 }
 
-__device__ __forceinline__ uint64_t find_slot(const VoxelSlot* slots, uint64_t mask, uint64_t key) {
-  uint64_t h = slot_hash(key) & mask;
-  for (uint64_t probe = 0; probe <= mask; ++probe) {
-    const uint64_t cur = slots[h].key;
-    if (cur == key) return h;
-    if (cur == kEmptyKey) return ~0ull;
-    h = (h + 1) & mask;
+__device__ __forceinline__ uint32_t find_slot(const tag_t* tags, const VoxelSlot* slots,
+                                              uint32_t n_slots, uint64_t key) {
+  const SlotAddr a = slot_addr(key, n_slots);
+  uint32_t h = a.home;
+  for (uint32_t probe = 0; probe < n_slots; ++probe) {
+    const tag_t t = tags[h];
+    if (t == 0u) return kNoSlot;
+    if (t == a.tag && slots[h].key == key) return h;
+    h = next_slot(h, n_slots);
   }
-  return ~0ull;
+  return kNoSlot;
 }
 
-__global__ void clear_slots_kernel(VoxelSlot* slots, uint64_t n) {
+__global__ void clear_slots_kernel(VoxelSlot* slots, tag_t* tags, uint64_t n) {
   const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
+  tags[i] = 0u;
   uint4* p = reinterpret_cast<uint4*>(slots + i);
   p[0] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
   p[1] = make_uint4(0u, 0u, 0u, 0u);
@@ -86,9 +98,10 @@ __global__ void clear_slots_kernel(VoxelSlot* slots, uint64_t n) {
 // order with the exact expression of Voxel::addPoint (LocalMap.hpp:79-87):
 //   mean = (n * mean + p) / (n + 1) ; cov likewise ; hard cap on n.
 struct InsertParams {
+  tag_t* tags;
   VoxelSlot* slots;
   double* master;
-  uint64_t mask;
+  uint32_t n_slots;
   unsigned long long* d_count;
   const uint64_t* key[2];
   const uint32_t* idx[2];
@@ -116,12 +129,12 @@ __global__ void __launch_bounds__(128) insert_runs_kernel(InsertParams P) {
     const int ky = static_cast<int>(compact3(mk >> 1)) + m1;
     const int kz = static_cast<int>(compact3(mk)) + m2;
     bool is_new;
-    const uint64_t s = find_or_claim(P.slots, P.mask, pack_key(kx, ky, kz), &is_new);
-    if (s == ~0ull) {
+    const uint32_t s = find_or_claim(P.tags, P.slots, P.n_slots, pack_key(kx, ky, kz), &is_new);
+    if (s == kNoSlot) {
       atomicAdd(P.d_count + 1, 1ull);  // table full: reported by the host
       continue;
     }
-    double* M = P.master + s * kMasterStride;
+    double* M = P.master + static_cast<size_t>(s) * kMasterStride;
     double mean[3], C[9];
     uint32_t cnt = 0;
     if (is_new) {
@@ -166,12 +179,14 @@ __global__ void __launch_bounds__(128) insert_runs_kernel(InsertParams P) {
 // evict != 0 a voxel survives iff NOT needsPointRemoval (src/LocalMap.cpp:149-154):
 //   |(k + 0.5) * voxel - pos| > dist_thresh  ->  erased.
 struct RehashParams {
+  const tag_t* old_tags;
   const VoxelSlot* old_slots;
   const double* old_master;
   uint64_t old_n;
+  tag_t* tags;
   VoxelSlot* slots;
   double* master;
-  uint64_t mask;
+  uint32_t n_slots;
   unsigned long long* d_count;  // [0] survivors, [1] table-full errors, [2] removed
   int evict;
   double pos[3];
@@ -182,9 +197,9 @@ struct RehashParams {
 __global__ void __launch_bounds__(256) rehash_kernel(RehashParams P) {
   for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < P.old_n;
        i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    if (P.old_tags[i] == 0u) continue;
     const VoxelSlot* o = P.old_slots + i;
     const uint64_t key = o->key;
-    if (key == kEmptyKey) continue;
     if (P.evict) {
       int kx, ky, kz;
       unpack_key(key, kx, ky, kz);
@@ -198,8 +213,8 @@ __global__ void __launch_bounds__(256) rehash_kernel(RehashParams P) {
       }
     }
     bool is_new;
-    const uint64_t s = find_or_claim(P.slots, P.mask, key, &is_new);
-    if (s == ~0ull) {
+    const uint32_t s = find_or_claim(P.tags, P.slots, P.n_slots, key, &is_new);
+    if (s == kNoSlot) {
       atomicAdd(P.d_count + 1, 1ull);
       continue;
     }
@@ -213,14 +228,14 @@ __global__ void __launch_bounds__(256) rehash_kernel(RehashParams P) {
     // key words already claimed; write count + pad
     reinterpret_cast<uint2*>(dst)[1] = make_uint2(v0.z, v0.w);
     const double* om = P.old_master + i * kMasterStride;
-    double* nm = P.master + s * kMasterStride;
+    double* nm = P.master + static_cast<size_t>(s) * kMasterStride;
 #pragma unroll
     for (int k = 0; k < kMasterStride; ++k) nm[k] = om[k];
   }
 }
 
-__global__ void query_kernel(const VoxelSlot* slots, const double* master, uint64_t mask,
-                             double voxel, const double* xyz_aos, unsigned n, int32_t* key_xyz,
+__global__ void query_kernel(const tag_t* tags, const VoxelSlot* slots, const double* master,
+                             uint32_t n_slots, double voxel, const double* xyz_aos, unsigned n, int32_t* key_xyz,
                              uint8_t* hit, uint32_t* count, double* mean, double* cov) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -232,25 +247,28 @@ __global__ void query_kernel(const VoxelSlot* slots, const double* master, uint6
     key_xyz[3 * i + 1] = ky;
     key_xyz[3 * i + 2] = kz;
   }
-  uint64_t s = ~0ull;
+  uint32_t s = kNoSlot;
   if (coord_in_range(kx) && coord_in_range(ky) && coord_in_range(kz))
-    s = find_slot(slots, mask, pack_key(kx, ky, kz));
-  const bool found = s != ~0ull;
+    s = find_slot(tags, slots, n_slots, pack_key(kx, ky, kz));
+  const bool found = s != kNoSlot;
   if (hit) hit[i] = found ? 1 : 0;
   if (count) count[i] = found ? slots[s].count : 0u;
   if (mean)
-    for (int k = 0; k < 3; ++k) mean[3 * i + k] = found ? master[s * kMasterStride + k] : 0.0;
+    for (int k = 0; k < 3; ++k)
+      mean[3 * i + k] = found ? master[static_cast<size_t>(s) * kMasterStride + k] : 0.0;
   if (cov)
-    for (int k = 0; k < 9; ++k) cov[9 * i + k] = found ? master[s * kMasterStride + 3 + k] : 0.0;
+    for (int k = 0; k < 9; ++k)
+      cov[9 * i + k] = found ? master[static_cast<size_t>(s) * kMasterStride + 3 + k] : 0.0;
 }
 
-__global__ void export_kernel(const VoxelSlot* slots, const double* master, uint64_t n_slots,
+__global__ void export_kernel(const tag_t* tags, const VoxelSlot* slots, const double* master,
+                              uint64_t n_slots,
                               unsigned long long* cursor, uint64_t capacity, uint64_t* keys,
                               uint32_t* count, double* stats) {
   for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n_slots;
        i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    if (tags[i] == 0u) continue;
     const uint64_t key = slots[i].key;
-    if (key == kEmptyKey) continue;
     const unsigned long long o = atomicAdd(cursor, 1ull);
     if (o >= capacity) continue;
     keys[o] = key;
@@ -259,43 +277,60 @@ __global__ void export_kernel(const VoxelSlot* slots, const double* master, uint
   }
 }
 
-int alloc_table(eskf_ctx* ctx, uint64_t n_slots, VoxelSlot** slots, double** master) {
-  ESKF_CUDA(cudaMalloc(reinterpret_cast<void**>(slots), n_slots * sizeof(VoxelSlot)));
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(master), n_slots * kMasterStride * sizeof(double));
+int alloc_table(eskf_ctx* ctx, uint64_t n_slots, tag_t** tags, VoxelSlot** slots, double** master) {
+  if (n_slots >= (1ull << 32) - 2) {
+    set_error("voxel table of %llu slots exceeds the 32-bit slot index", static_cast<unsigned long long>(n_slots));
+    return ESKF_ERR_CAPACITY;
+  }
+  *tags = nullptr;
+  *slots = nullptr;
+  *master = nullptr;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(tags), n_slots * sizeof(tag_t));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(slots), n_slots * sizeof(VoxelSlot));
+  if (e == cudaSuccess)
+    e = cudaMalloc(reinterpret_cast<void**>(master), n_slots * kMasterStride * sizeof(double));
   if (e != cudaSuccess) {
-    cudaFree(*slots);
+    if (*tags) cudaFree(*tags);
+    if (*slots) cudaFree(*slots);
+    *tags = nullptr;
     *slots = nullptr;
-    set_error("cudaMalloc(master) failed: %s", cudaGetErrorString(e));
+    set_error("cudaMalloc(voxel table, %llu slots) failed: %s", static_cast<unsigned long long>(n_slots),
+              cudaGetErrorString(e));
     return ESKF_ERR_CUDA;
   }
   const unsigned blocks = static_cast<unsigned>((n_slots + 255) / 256);
-  clear_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(*slots, n_slots);
+  clear_slots_kernel<<<blocks, 256, 0, ctx->stream>>>(*slots, *tags, n_slots);
   ESKF_CUDA(cudaGetLastError());
   count_launch(ctx);
   return ESKF_OK;
 }
 
-uint64_t pow2_at_least(uint64_t v) {
-  uint64_t p = 1024;
-  while (p < v) p <<= 1;
-  return p;
+// table size for `voxels` occupied voxels: load factor <= 1/2 keeps linear
+// probing short; no power-of-two rounding so the tag array stays as small
+// (= as L2-resident) as possible
+uint64_t table_size_for(uint64_t voxels) {
+  const uint64_t v = voxels < 1024 ? 1024 : voxels;
+  return (2 * v + 63) / 64 * 64;
 }
 
 // move the map into a table of new_slots slots (optionally evicting)
 int rebuild(eskf_map* m, uint64_t new_slots, int evict, const double* pos, double thresh,
             uint64_t* removed) {
   eskf_ctx* ctx = m->ctx;
+  tag_t* nt = nullptr;
   VoxelSlot* ns = nullptr;
   double* nm = nullptr;
-  ESKF_TRY(alloc_table(ctx, new_slots, &ns, &nm));
+  ESKF_TRY(alloc_table(ctx, new_slots, &nt, &ns, &nm));
   ESKF_CUDA(cudaMemsetAsync(m->d_count, 0, 4 * sizeof(unsigned long long), ctx->stream));
   RehashParams P;
+  P.old_tags = m->tags;
   P.old_slots = m->slots;
   P.old_master = m->master;
   P.old_n = m->n_slots;
+  P.tags = nt;
   P.slots = ns;
   P.master = nm;
-  P.mask = new_slots - 1;
+  P.n_slots = static_cast<uint32_t>(new_slots);
   P.d_count = m->d_count;
   P.evict = evict;
   P.pos[0] = pos ? pos[0] : 0.0;
@@ -312,8 +347,10 @@ int rebuild(eskf_map* m, uint64_t new_slots, int evict, const double* pos, doubl
   ESKF_CUDA(cudaMemcpyAsync(h, m->d_count, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                             ctx->stream));
   ESKF_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(m->tags);
   cudaFree(m->slots);
   cudaFree(m->master);
+  m->tags = nt;
   m->slots = ns;
   m->master = nm;
   m->n_slots = new_slots;
@@ -339,7 +376,7 @@ int map_reserve(eskf_map* m, uint64_t incoming) {
   ESKF_CUDA(cudaStreamSynchronize(ctx->stream));
   m->count_upper = h[0];
   if ((m->count_upper + incoming) * 2 <= m->n_slots) return ESKF_OK;
-  return rebuild(m, pow2_at_least((m->count_upper + incoming) * 4), 0, nullptr, 0.0, nullptr);
+  return rebuild(m, table_size_for((m->count_upper + incoming) * 5 / 4), 0, nullptr, 0.0, nullptr);
 }
 
 }  // namespace eskf
@@ -358,8 +395,8 @@ int eskf_map_create(eskf_ctx* ctx, double voxel_size, uint32_t max_points_per_vo
   m->ctx = ctx;
   m->voxel = voxel_size;
   m->cap_pts = max_points_per_voxel;
-  m->n_slots = pow2_at_least(std::max<uint64_t>(capacity_hint, 1024) * 2);
-  int st = alloc_table(ctx, m->n_slots, &m->slots, &m->master);
+  m->n_slots = table_size_for(capacity_hint);
+  int st = alloc_table(ctx, m->n_slots, &m->tags, &m->slots, &m->master);
   if (st != ESKF_OK) {
     delete m;
     return st;
@@ -368,6 +405,7 @@ int eskf_map_create(eskf_ctx* ctx, double voxel_size, uint32_t max_points_per_vo
   if (e == cudaSuccess) e = cudaMemsetAsync(m->d_count, 0, 4 * sizeof(unsigned long long), ctx->stream);
   if (e != cudaSuccess) {
     set_error("map counters: %s", cudaGetErrorString(e));
+    cudaFree(m->tags);
     cudaFree(m->slots);
     cudaFree(m->master);
     delete m;
@@ -381,6 +419,7 @@ int eskf_map_destroy(eskf_map* m) {
   if (!m) return ESKF_OK;
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
+  cudaFree(m->tags);
   cudaFree(m->slots);
   cudaFree(m->master);
   cudaFree(m->d_count);
@@ -420,9 +459,10 @@ int eskf_map_insert_cloud(eskf_map* m, eskf_cloud* cloud, const double T[16]) {
   cloud->has_c32 = false;  // fp32 mirror is stale after the in-place transform
   SortView v = sort_view(ctx, a.n);
   InsertParams P;
+  P.tags = m->tags;
   P.slots = m->slots;
   P.master = m->master;
-  P.mask = m->n_slots - 1;
+  P.n_slots = static_cast<uint32_t>(m->n_slots);
   P.d_count = m->d_count;
   P.key[0] = v.key[0];
   P.key[1] = v.key[1];
@@ -515,7 +555,8 @@ int eskf_map_query(eskf_map* m, const double* xyz, size_t n, int32_t* key_xyz, u
   ESKF_CUDA(cudaMemcpyAsync(d, xyz, n * 24, cudaMemcpyHostToDevice, ctx->stream));
   const unsigned blocks = static_cast<unsigned>((n + 127) / 128);
   query_kernel<<<blocks, 128, 0, ctx->stream>>>(
-      m->slots, m->master, m->n_slots - 1, m->voxel, reinterpret_cast<const double*>(d),
+      m->tags, m->slots, m->master, static_cast<uint32_t>(m->n_slots), m->voxel,
+      reinterpret_cast<const double*>(d),
       static_cast<unsigned>(n), reinterpret_cast<int32_t*>(d + o_key),
       reinterpret_cast<uint8_t*>(d + o_hit), reinterpret_cast<uint32_t*>(d + o_cnt),
       reinterpret_cast<double*>(d + o_mean), reinterpret_cast<double*>(d + o_cov));
@@ -548,7 +589,7 @@ int eskf_map_export(eskf_map* m, size_t capacity, size_t* n, int32_t* key_xyz, u
   ESKF_CUDA(cudaMemsetAsync(d + o_cur, 0, 8, ctx->stream));
   const unsigned blocks = static_cast<unsigned>(std::min<uint64_t>((m->n_slots + 255) / 256, 148ull * 16));
   export_kernel<<<blocks, 256, 0, ctx->stream>>>(
-      m->slots, m->master, m->n_slots, reinterpret_cast<unsigned long long*>(d + o_cur), nv,
+      m->tags, m->slots, m->master, m->n_slots, reinterpret_cast<unsigned long long*>(d + o_cur), nv,
       reinterpret_cast<uint64_t*>(d), reinterpret_cast<uint32_t*>(d + o_cnt),
       reinterpret_cast<double*>(d + o_stats));
   ESKF_CUDA(cudaGetLastError());

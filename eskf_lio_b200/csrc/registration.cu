@@ -16,6 +16,7 @@
 // read + 24 B position write + 24 B source covariance + 64 B voxel slot
 // = 136 B.
 #include <cfloat>
+#include <cstdlib>
 
 #include "internal.h"
 
@@ -26,6 +27,10 @@ namespace {
 constexpr int kT = 256;
 constexpr int kW = kT / 32;
 constexpr int kAcc = 28;  // A(6) B(9) D(6) b(6) + correspondence count
+
+#ifndef ESKF_PIPELINED
+#define ESKF_PIPELINED 1
+#endif
 
 struct AlignState {
   double T_total[12];  // R row-major (9) + t (3)
@@ -43,8 +48,10 @@ struct AlignState {
 };
 
 struct AlignParams {
+  const tag_t* tags;  // probed (L2-resident); 0 = empty
   const VoxelSlot* slots;
-  uint64_t mask;
+  uint32_t n_slots;
+  uint32_t pad_slots;
   double voxel;
   const double* x0;
   const double* y0;
@@ -154,14 +161,17 @@ __device__ __forceinline__ uint64_t load_key(const VoxelSlot* s) {
   return (static_cast<uint64_t>(kw.y) << 32) | kw.x;
 }
 
-// finish a lookup whose first probe (slot h) returned `cur`
-__device__ __forceinline__ const VoxelSlot* resolve_probe(const VoxelSlot* slots, uint64_t mask,
-                                                          uint64_t key, uint64_t h, uint64_t cur) {
-  for (uint64_t probe = 0; probe <= mask; ++probe) {
-    if (cur == key) return slots + h;
-    if (cur == kEmptyKey) return nullptr;
-    h = (h + 1) & mask;
-    cur = load_key(slots + h);
+// finish a lookup whose first tag probe (slot h) returned `t`: walk the tag
+// array (L2) and touch a 64 B record (HBM) only on a tag match
+__device__ __forceinline__ const VoxelSlot* resolve_probe(const tag_t* tags,
+                                                          const VoxelSlot* slots, uint32_t n_slots,
+                                                          uint64_t key, SlotAddr a, tag_t t) {
+  uint32_t h = a.home;
+  for (uint32_t probe = 0; probe < n_slots; ++probe) {
+    if (t == 0u) return nullptr;
+    if (t == a.tag && load_key(slots + h) == key) return slots + h;
+    h = next_slot(h, n_slots);
+    t = __ldg(tags + h);
   }
   return nullptr;
 }
@@ -198,22 +208,26 @@ __device__ __forceinline__ double accumulate_points(const AlignParams& P, const 
       valid[u] = i < P.n;
       x[u] = y[u] = z[u] = 0.0;
       if (valid[u]) {
-        x[u] = first ? __ldg(sx + i) : ld_cg(sx + i);
-        y[u] = first ? __ldg(sy + i) : ld_cg(sy + i);
-        z[u] = first ? __ldg(sz + i) : ld_cg(sz + i);
+        // streamed once per iteration: evict-first, so the position stream does
+        // not push the map's tags / touched voxel records out of L2
+        x[u] = __ldcs(sx + i);
+        y[u] = __ldcs(sy + i);
+        z[u] = __ldcs(sz + i);
       }
     }
     // stage 2: transform, write back, keys, first probes
     int kx[U], ky[U], kz[U];
-    uint64_t key[U][NN], hh[U][NN], cur[U][NN];
+    uint64_t key[U][NN];
+    SlotAddr addr[U][NN];
+    tag_t tag0[U][NN];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const unsigned i = start + 32u * u;
       if (valid[u]) {
         transform_point_rn(sT, x[u], y[u], z[u]);
-        P.wx[i] = x[u];
-        P.wy[i] = y[u];
-        P.wz[i] = z[u];
+        __stcs(P.wx + i, x[u]);
+        __stcs(P.wy + i, y[u]);
+        __stcs(P.wz + i, z[u]);
       }
       kx[u] = voxel_coord(x[u], P.voxel);
       ky[u] = voxel_coord(y[u], P.voxel);
@@ -223,8 +237,12 @@ __device__ __forceinline__ double accumulate_points(const AlignParams& P, const 
         const int vx = kx[u] + c_off7[o][0], vy = ky[u] + c_off7[o][1], vz = kz[u] + c_off7[o][2];
         const bool ok = valid[u] && coord_in_range(vx) && coord_in_range(vy) && coord_in_range(vz);
         key[u][o] = pack_key(vx, vy, vz);
-        hh[u][o] = slot_hash(key[u][o]) & P.mask;
-        cur[u][o] = ok ? load_key(P.slots + hh[u][o]) : kEmptyKey;
+        addr[u][o] = slot_addr(key[u][o], P.n_slots);
+#if defined(ESKF_ABLATE) && ESKF_ABLATE == 1
+        tag0[u][o] = static_cast<tag_t>(ok ? (addr[u][o].home & 1u) : 0u);
+#else
+        tag0[u][o] = ok ? __ldg(P.tags + addr[u][o].home) : static_cast<tag_t>(0);
+#endif
       }
     }
     // stage 3: resolve the lookups
@@ -233,7 +251,26 @@ __device__ __forceinline__ double accumulate_points(const AlignParams& P, const 
     for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int o = 0; o < NN; ++o) {
-        slot[u][o] = resolve_probe(P.slots, P.mask, key[u][o], hh[u][o], cur[u][o]);
+#if defined(ESKF_ABLATE) && ESKF_ABLATE == 1   // experiment: no table access at all
+        slot[u][o] = nullptr;
+        if (tag0[u][o] == 12345u) v[27] += F(1);
+#elif defined(ESKF_ABLATE) && ESKF_ABLATE == 2  // experiment: tag probes only, no records
+        {
+          uint32_t h = addr[u][o].home;
+          tag_t t = tag0[u][o];
+          int found = 0;
+          for (uint32_t probe = 0; probe < P.n_slots; ++probe) {
+            if (t == 0u) break;
+            if (t == addr[u][o].tag) { found = 1; break; }
+            h = next_slot(h, P.n_slots);
+            t = __ldg(P.tags + h);
+          }
+          v[27] += F(found);
+          slot[u][o] = nullptr;
+        }
+#else
+        slot[u][o] = resolve_probe(P.tags, P.slots, P.n_slots, key[u][o], addr[u][o], tag0[u][o]);
+#endif
         if (write_hit && valid[u])
           P.hit[static_cast<size_t>(NN) * (start + 32u * u) + o] = slot[u][o] != nullptr ? 1 : 0;
       }
@@ -247,8 +284,8 @@ __device__ __forceinline__ double accumulate_points(const AlignParams& P, const 
           pa[u] = __ldg(reinterpret_cast<const float4*>(slot[u][0]) + 1);  // mx my mz -
           pc[u] = __ldg(reinterpret_cast<const float4*>(slot[u][0]) + 2);  // c00 c01 c02 c11
           pd[u] = __ldg(reinterpret_cast<const float4*>(slot[u][0]) + 3);  // c12 c22 - -
-          s4[u] = __ldg(P.c4 + start + 32u * u);
-          s2[u] = __ldg(P.c2 + start + 32u * u);
+          s4[u] = __ldcs(P.c4 + start + 32u * u);
+          s2[u] = __ldcs(P.c2 + start + 32u * u);
         }
 #pragma unroll
       for (int u = 0; u < U; ++u)
@@ -272,8 +309,8 @@ __device__ __forceinline__ double accumulate_points(const AlignParams& P, const 
 #pragma unroll
         for (int o = 0; o < NN; ++o) any = any || slot[u][o] != nullptr;
         if (!any) continue;
-        const float4 s4 = __ldg(P.c4 + start + 32u * u);
-        const float2 s2 = __ldg(P.c2 + start + 32u * u);
+        const float4 s4 = __ldcs(P.c4 + start + 32u * u);
+        const float2 s2 = __ldcs(P.c2 + start + 32u * u);
         F cr[6];
         rotate_sym<F>(sR, F(s4.x), F(s4.y), F(s4.z), F(s4.w), F(s2.x), F(s2.y), cr);
 #pragma unroll
@@ -293,6 +330,181 @@ __device__ __forceinline__ double accumulate_points(const AlignParams& P, const 
       }
     }
     acc += static_cast<double>(warp_reduce_scatter32<F>(v, lane));
+  }
+  return acc;
+}
+
+// ------------------------------------------------------------------------
+// Hot path (1-neighbour): the same work as accumulate_points as a 3-stage
+// software pipeline over warp tiles of 32 points.  Every loop trip issues, back
+// to back and mutually independent,
+//     the position loads of tile t+2          (HBM / L2 stream)
+//     the 16 B tag-group load of tile t+1     (L2-resident tag array)
+//     the 64 B voxel record + source covariance of tile t   (HBM / L2)
+// and only then consumes them: scan the tags of t+1 -> candidate slot (the
+// record is prefetched, evict_last, so the voxels a registration keeps touching
+// stay in L2 across Gauss-Newton iterations), fp32 algebra of tile t, fp64
+// transform + key + hash of tile t+2.  A trip therefore waits for ONE memory
+// round trip instead of three dependent ones.
+struct PtState {  // a transformed point waiting for its lookup
+  double x, y, z;
+  int kx, ky, kz;
+  uint32_t home;
+  uint32_t tag;   // 0 = no lookup (invalid lane / out of key range)
+  uint32_t cand;  // candidate slot after the tag scan, kNoCand if none
+};
+constexpr uint32_t kNoCand = 0xffffffffu;
+
+__device__ __forceinline__ void prefetch_record(const void* p) {
+  asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
+}
+
+// scan 8 tags (w) starting at slot h for `tag`; returns the matching slot,
+// kNoCand on an empty slot, or kMore if the group is exhausted
+constexpr uint32_t kMore = 0xfffffffeu;
+__device__ __forceinline__ uint32_t scan_tag_group(uint4 w, uint32_t h, uint32_t tag) {
+  const uint64_t lo = (static_cast<uint64_t>(w.y) << 32) | w.x;
+  const uint64_t hi = (static_cast<uint64_t>(w.w) << 32) | w.z;
+  for (uint32_t k = h & 7u; k < 8u; ++k) {
+    const uint32_t t = static_cast<uint32_t>((k < 4u ? lo >> (16u * k) : hi >> (16u * (k - 4u))) & 0xffffu);
+    if (t == 0u) return kNoCand;
+    if (t == tag) return (h & ~7u) + k;
+  }
+  return kMore;
+}
+
+template <typename F>
+__device__ __forceinline__ double accumulate_points_pipelined(const AlignParams& P,
+                                                              const double* sT, const F* sR,
+                                                              bool first, bool write_hit) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned wglobal = blockIdx.x * kW + (threadIdx.x >> 5);
+  const unsigned wstride = gridDim.x * kW;
+  const double* sx = first ? P.x0 : P.wx;
+  const double* sy = first ? P.y0 : P.wy;
+  const double* sz = first ? P.z0 : P.wz;
+  const unsigned n_tiles = (P.n + 31u) / 32u;
+  const double inv_voxel = 1.0 / P.voxel;
+
+  // fp64 transform, write-back, voxel key, table address of one raw point
+  auto xform = [&](unsigned tile, double rx, double ry, double rz, PtState& s) {
+    const unsigned i = tile * 32u + lane;
+    s.x = rx; s.y = ry; s.z = rz;
+    s.kx = s.ky = s.kz = 0;
+    s.home = 0;
+    s.tag = 0;
+    s.cand = kNoCand;
+    if (tile >= n_tiles || i >= P.n) return;
+    transform_point_rn(sT, s.x, s.y, s.z);
+    P.wx[i] = s.x;
+    P.wy[i] = s.y;
+    P.wz[i] = s.z;
+    s.kx = voxel_coord(s.x, P.voxel, inv_voxel);
+    s.ky = voxel_coord(s.y, P.voxel, inv_voxel);
+    s.kz = voxel_coord(s.z, P.voxel, inv_voxel);
+    if (coord_in_range(s.kx) && coord_in_range(s.ky) && coord_in_range(s.kz)) {
+      const SlotAddr ad = slot_addr(pack_key(s.kx, s.ky, s.kz), P.n_slots);
+      s.home = ad.home;
+      s.tag = ad.tag;
+    }
+  };
+  auto load_pos = [&](unsigned tile, double& rx, double& ry, double& rz) {
+    const unsigned i = tile * 32u + lane;
+    rx = ry = rz = 0.0;
+    if (tile < n_tiles && i < P.n) {
+      rx = first ? __ldcs(sx + i) : __ldcg(sx + i);
+      ry = first ? __ldcs(sy + i) : __ldcg(sy + i);
+      rz = first ? __ldcs(sz + i) : __ldcg(sz + i);
+    }
+  };
+  // finish the tag scan of s given its first group w (rarely needs more groups)
+  auto finish_scan = [&](PtState& s, uint4 w) {
+    if (s.tag == 0u) return;
+    uint32_t h = s.home;
+    uint32_t r = scan_tag_group(w, h, s.tag);
+    uint32_t scanned = 8u - (h & 7u);
+    while (r == kMore && scanned < P.n_slots) {
+      h = (h & ~7u) + 8u == P.n_slots ? 0u : (h & ~7u) + 8u;
+      r = scan_tag_group(__ldg(reinterpret_cast<const uint4*>(P.tags + h)), h, s.tag);
+      scanned += 8u;
+    }
+    if (r != kNoCand && r != kMore) {
+      s.cand = r;
+      prefetch_record(P.slots + r);
+    }
+  };
+
+  double acc = 0.0;
+  // ---- prologue: cur = tile0 (scanned), nxt = tile1 (transformed)
+  PtState cur, nxt;
+  {
+    double rx, ry, rz, qx, qy, qz;
+    load_pos(wglobal, rx, ry, rz);
+    load_pos(wglobal + wstride, qx, qy, qz);
+    xform(wglobal, rx, ry, rz, cur);
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (cur.tag != 0u) w = __ldg(reinterpret_cast<const uint4*>(P.tags + (cur.home & ~7u)));
+    finish_scan(cur, w);
+    xform(wglobal + wstride, qx, qy, qz, nxt);
+  }
+  for (unsigned tile = wglobal; tile < n_tiles; tile += wstride) {
+    const unsigned i = tile * 32u + lane;
+    // ---- issue: three independent groups of loads
+    double rx, ry, rz;
+    load_pos(tile + 2u * wstride, rx, ry, rz);
+    uint4 tagw = make_uint4(0u, 0u, 0u, 0u);
+    if (nxt.tag != 0u) tagw = __ldg(reinterpret_cast<const uint4*>(P.tags + (nxt.home & ~7u)));
+    uint4 r0 = make_uint4(0u, 0u, 0u, 0u);
+    float4 pa, pc, pd, s4;
+    float2 s2;
+    const bool has_cand = cur.cand != kNoCand;
+    if (has_cand) {
+      const VoxelSlot* rec = P.slots + cur.cand;
+      r0 = __ldg(reinterpret_cast<const uint4*>(rec));       // key, count
+      pa = __ldg(reinterpret_cast<const float4*>(rec) + 1);  // mx my mz -
+      pc = __ldg(reinterpret_cast<const float4*>(rec) + 2);  // c00 c01 c02 c11
+      pd = __ldg(reinterpret_cast<const float4*>(rec) + 3);  // c12 c22 - -
+      s4 = __ldcs(P.c4 + i);
+      s2 = __ldcs(P.c2 + i);
+    }
+    // ---- consume
+    finish_scan(nxt, tagw);
+    F v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = F(0);
+    bool hit = false;
+    if (has_cand) {
+      const uint64_t key = pack_key(cur.kx, cur.ky, cur.kz);
+      hit = ((static_cast<uint64_t>(r0.y) << 32) | r0.x) == key;
+      if (!hit) {
+        // 16-bit tag collision (1/65536 per occupied probe): walk on, slowly
+        SlotAddr rest;
+        rest.home = next_slot(cur.cand, P.n_slots);
+        rest.tag = static_cast<tag_t>(cur.tag);
+        const VoxelSlot* rec = resolve_probe(P.tags, P.slots, P.n_slots, key, rest, __ldg(P.tags + rest.home));
+        if (rec != nullptr) {
+          hit = true;
+          pa = __ldg(reinterpret_cast<const float4*>(rec) + 1);
+          pc = __ldg(reinterpret_cast<const float4*>(rec) + 2);
+          pd = __ldg(reinterpret_cast<const float4*>(rec) + 3);
+        }
+      }
+    }
+    if (write_hit && i < P.n) P.hit[i] = hit ? 1 : 0;
+    if (hit) {
+      F cr[6];
+      rotate_sym<F>(sR, F(s4.x), F(s4.y), F(s4.z), F(s4.w), F(s2.x), F(s2.y), cr);
+      // residual against the voxel mean, formed relative to the voxel centre
+      const double cx = __dmul_rn(static_cast<double>(cur.kx) + 0.5, P.voxel);
+      const double cy = __dmul_rn(static_cast<double>(cur.ky) + 0.5, P.voxel);
+      const double cz = __dmul_rn(static_cast<double>(cur.kz) + 0.5, P.voxel);
+      const F ex = F(cur.x - cx) - F(pa.x), ey = F(cur.y - cy) - F(pa.y), ez = F(cur.z - cz) - F(pa.z);
+      point_terms<F>(F(cur.x), F(cur.y), F(cur.z), ex, ey, ez, cr[0] + F(pc.x), cr[1] + F(pc.y),
+                     cr[2] + F(pc.z), cr[3] + F(pc.w), cr[4] + F(pd.x), cr[5] + F(pd.y), v);
+    }
+    acc += static_cast<double>(warp_reduce_scatter32<F>(v, lane));
+    cur = nxt;
+    xform(tile + 2u * wstride, rx, ry, rz, nxt);
   }
   return acc;
 }
@@ -317,8 +529,20 @@ __device__ __forceinline__ void final_reduce(const double* partials, unsigned G,
                                              double (*s_part)[32], double* s_sum) {
   const unsigned term = threadIdx.x & 31, grp = threadIdx.x >> 5;
   double s = 0.0;
-  if (term < kAcc)
-    for (unsigned bb = grp; bb < G; bb += kW) s += ld_cg(partials + static_cast<size_t>(bb) * kAcc + term);
+  if (term < kAcc) {
+    // 8 independent loads in flight per thread (a dependent chain of ~G/8 L2
+    // round trips used to cost ~20 us per iteration)
+    for (unsigned bb = grp; bb < G; bb += kW * 8) {
+      double v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const unsigned b2 = bb + kW * k;
+        v[k] = b2 < G ? ld_cg(partials + static_cast<size_t>(b2) * kAcc + term) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[k];
+    }
+  }
   s_part[grp][term] = s;
   __syncthreads();
   if (threadIdx.x < kAcc) {
@@ -532,7 +756,9 @@ __global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
                                   : (sizeof(F) == 8 ? F(ld_cg(&st->T_total[t])) : F(ld_cg(&st->Rf[t])));
     __syncthreads();
 
-    const double acc = accumulate_points<F, U, NN>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0);
+    const double acc = (NN == 1 && U == 1 && ESKF_PIPELINED)
+                           ? accumulate_points_pipelined<F>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0)
+                           : accumulate_points<F, U, NN>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0);
     block_reduce_store(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
 
     // last CTA to arrive reduces the partials and solves
@@ -589,7 +815,9 @@ __global__ void __launch_bounds__(kT, MINB) linearize_pass_kernel(AlignParams P,
   if (t < 12) s_T[t] = (it == 0) ? P.guess[t] : ld_cg(&st->T_step[t]);
   if (t < 9) s_R[t] = (it == 0) ? F(P.guess[t]) : F(ld_cg(&st->Rf[t]));
   __syncthreads();
-  const double acc = accumulate_points<F, U, NN>(P, s_T, s_R, it == 0, false);
+  const double acc = (NN == 1 && U == 1 && ESKF_PIPELINED)
+                         ? accumulate_points_pipelined<F>(P, s_T, s_R, it == 0, false)
+                         : accumulate_points<F, U, NN>(P, s_T, s_R, it == 0, false);
   block_reduce_store(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
   if (t == 0) {
     const unsigned ticket = atomicAdd(&st->block_counter, 1u);
@@ -679,8 +907,9 @@ int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, T
   ESKF_TRY(ctx->astate.ensure(L->total));
   char* base = ctx->astate.as<char>();
   std::memset(P, 0, sizeof *P);
+  P->tags = m->tags;
   P->slots = m->slots;
-  P->mask = m->n_slots - 1;
+  P->n_slots = static_cast<uint32_t>(m->n_slots);
   P->voxel = m->voxel;
   P->x0 = c->x();
   P->y0 = c->y();
@@ -775,6 +1004,25 @@ int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align
   int G = 1;
   ESKF_TRY(fill_params(ctx, a, max_it, &P, &L, &G));
   ESKF_CUDA(cudaMemsetAsync(ctx->astate.p, 0, L.o_H, ctx->stream));
+  // keep the probed tag array resident in L2 across iterations (the position /
+  // covariance streams would otherwise evict it every pass)
+  static const int persist = [] {
+    const char* e = getenv("ESKF_L2_PERSIST");
+    return e ? atoi(e) : 1;
+  }();
+  if (persist && ctx->l2_persist_bytes > 0) {
+    cudaStreamAttrValue attr;
+    std::memset(&attr, 0, sizeof attr);
+    size_t bytes = static_cast<size_t>(a.map->n_slots) * sizeof(tag_t);
+    if (bytes > ctx->l2_window_max) bytes = ctx->l2_window_max;
+    attr.accessPolicyWindow.base_ptr = a.map->tags;
+    attr.accessPolicyWindow.num_bytes = bytes;
+    const double ratio = static_cast<double>(ctx->l2_persist_bytes) / static_cast<double>(bytes);
+    attr.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : static_cast<float>(ratio);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ESKF_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+  }
   void* args[] = {&P};
   void* fn = g_variants[variant_index(a)].align;
   ESKF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(kT), args, 0, ctx->stream));

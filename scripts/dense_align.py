@@ -29,7 +29,7 @@ def main():
     ctx = capi.Context(0)
     rng = np.random.default_rng(44)
     scene = S.block_scene()
-    gmap = capi.Map(ctx, a.voxel, 1000, 1 << 24)
+    gmap = capi.Map(ctx, a.voxel, 1000, 9_000_000)
     chunk = 2_500_000
     left = a.map
     while left > 0:
