@@ -1,0 +1,155 @@
+// LocalMap.hpp — drop-in for include/ESKF_LIO/LocalMap.hpp + src/LocalMap.cpp
+// of the reference: same public names and argument meaning, the voxel map
+// itself lives in HBM behind the C ABI (include/eskf_gpu.h).
+// Out of scope: visualiser, save(), raw per-voxel points.
+#ifndef ESKF_LIO_B200_LOCAL_MAP_HPP_
+#define ESKF_LIO_B200_LOCAL_MAP_HPP_
+
+#include <chrono>
+#include <functional>
+#include <iostream>
+#include <limits>
+#include <tuple>
+
+#include "ESKF_LIO/GpuContext.hpp"
+#include "ESKF_LIO/Types.hpp"
+
+namespace ESKF_LIO
+{
+class LocalMap
+{
+public:
+  using PointVector = typename std::vector<Vector3d>;
+  using CovarianceVector = typename std::vector<Matrix3d>;
+  using Correspondence = typename std::tuple<PointVector, CovarianceVector, PointVector,
+      CovarianceVector>;
+
+  // LocalMap(const YAML::Node &, ...) (LocalMap.hpp:28-52)
+  explicit LocalMap(const Config & config, bool visualize = false)
+  : voxelSize_(config.local_map.voxel_size)
+    , maxNumPointsPerVoxel_(config.local_map.max_num_points_per_voxel)
+    , translationSquaredThreshold_(config.local_map.update.translation_sq_threshold)
+    , cosineThreshold_(config.local_map.update.cosine_threshold)
+    , removeDistantPoints_(config.local_map.remove_distant_points.enabled)
+    , distanceThreshold_(config.local_map.remove_distant_points.distance_threshold)
+    , removePeriod_(config.local_map.remove_distant_points.removing_period)
+  {
+    (void)visualize;
+    create();
+  }
+
+  // LocalMap(double voxelSize, size_t maxNumPointsPerVoxel, bool visualize = false)
+  // (LocalMap.hpp:54-61; the reference leaves the update / removal members
+  // uninitialised here — they get the YAML defaults instead)
+  LocalMap(double voxelSize, std::size_t maxNumPointsPerVoxel, bool visualize = false)
+  : voxelSize_(voxelSize), maxNumPointsPerVoxel_(maxNumPointsPerVoxel)
+  {
+    (void)visualize;
+    create();
+  }
+
+  ~LocalMap() {eskf_map_destroy(map_);}
+  LocalMap(const LocalMap &) = delete;
+  LocalMap & operator=(const LocalMap &) = delete;
+
+  // LocalMap::updateLocalMap (src/LocalMap.cpp:10-76)
+  void updateLocalMap(PointCloudPtr cloud, const Isometry3d & transform, bool initialize = false)
+  {
+    if (initialize == false && needsMapUpdate(transform) == false) {
+      cloud->Transform(transform);  // :15 — the caller's cloud always ends up in the world frame
+      prevTransform_ = transform;   // :40
+      return;
+    }
+    const auto T = transform.matrix();
+    gpuCheck(
+      eskf_map_insert(
+        map_, reinterpret_cast<const double *>(cloud->points_.data()),
+        reinterpret_cast<const double *>(cloud->covariances_.data()), cloud->points_.size(),
+        T.data()), "eskf_map_insert");
+    cloud->Transform(transform);
+    const double now = clock_();
+    if (removeDistantPoints_ && now - currentRemoveTime_ > removePeriod_) {  // :60
+      uint64_t removed = 0;
+      gpuCheck(eskf_map_evict(map_, transform.t.v, distanceThreshold_, &removed), "eskf_map_evict");
+      currentRemoveTime_ = now;
+      std::cout << "removed " << removed << " voxels\n";  // :71
+    }
+    prevTransform_ = transform;  // :74
+  }
+
+  // LocalMap::correspondenceMatching (src/LocalMap.cpp:78-112); output in
+  // ascending source index (the reference's order is OpenMP arrival order)
+  Correspondence correspondenceMatching(
+    const PointVector & points, const CovarianceVector & covariances) const
+  {
+    Correspondence correspondence;
+    auto & [srcPoints, srcCovs, mapPoints, mapCovs] = correspondence;
+    const std::size_t n = points.size();
+    std::vector<uint8_t> hit(n);
+    std::vector<double> mean(3 * n), cov(9 * n);
+    gpuCheck(
+      eskf_map_query(
+        map_, reinterpret_cast<const double *>(points.data()), n, nullptr, hit.data(), nullptr,
+        mean.data(), cov.data()), "eskf_map_query");
+    for (std::size_t i = 0; i < n; ++i) {
+      if (!hit[i]) {continue;}
+      srcPoints.push_back(points[i]);
+      srcCovs.push_back(covariances[i]);
+      mapPoints.emplace_back(mean[3 * i], mean[3 * i + 1], mean[3 * i + 2]);
+      Matrix3d C;
+      for (int k = 0; k < 9; ++k) {C.m[k] = cov[9 * i + k];}
+      mapCovs.push_back(C);
+    }
+    return correspondence;
+  }
+
+  // ---- not in the reference: handles / test seams
+  eskf_map * handle() const {return map_;}
+  std::size_t size() const
+  {
+    uint64_t n = 0;
+    gpuCheck(eskf_map_size(map_, &n), "eskf_map_size");
+    return n;
+  }
+  // the eviction period is tested against omp_get_wtime() in the reference
+  // (:60,70); inject a clock to make runs reproducible
+  void setClock(std::function<double()> clock) {clock_ = std::move(clock);}
+
+private:
+  void create()
+  {
+    gpuCheck(
+      eskf_map_create(
+        GpuContext::get(), voxelSize_, static_cast<uint32_t>(maxNumPointsPerVoxel_), 1u << 16,
+        &map_), "eskf_map_create");
+    clock_ = [] {
+        return std::chrono::duration<double>(
+          std::chrono::steady_clock::now().time_since_epoch()).count();
+      };
+  }
+
+  // LocalMap::needsMapUpdate (src/LocalMap.cpp:132-147), vs the previous FRAME
+  bool needsMapUpdate(const Isometry3d & transform) const
+  {
+    const Isometry3d moved = prevTransform_.inverse() * transform;
+    const double cosine = 0.5 * (moved.R.trace() - 1.0);
+    if (cosine < cosineThreshold_) {return true;}
+    if (moved.t.squaredNorm() > translationSquaredThreshold_) {return true;}
+    return false;
+  }
+
+  double voxelSize_;
+  std::size_t maxNumPointsPerVoxel_;
+  double translationSquaredThreshold_ = 1.0e-2;
+  double cosineThreshold_ = 0.985;
+  bool removeDistantPoints_ = true;
+  double distanceThreshold_ = 100.0;
+  double removePeriod_ = 10.0;
+  double currentRemoveTime_ = std::numeric_limits<double>::lowest();  // LocalMap.hpp:40
+  Isometry3d prevTransform_;  // uninitialised in the reference; identity here
+  std::function<double()> clock_;
+  eskf_map * map_ = nullptr;
+};
+}  // namespace ESKF_LIO
+
+#endif  // ESKF_LIO_B200_LOCAL_MAP_HPP_

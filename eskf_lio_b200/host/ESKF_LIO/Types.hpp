@@ -1,0 +1,211 @@
+// Types.hpp — boundary types of the hot path, restated without Eigen / Open3D
+// (neither exists in this environment).  Mirrors include/ESKF_LIO/Types.hpp:11-52
+// of the reference: PointCloud (= open3d::geometry::PointCloud: points_ +
+// covariances_ + Transform()), ImuMeasurement, LidarMeasurement, State, and
+// just enough of Eigen::Vector3d / Matrix3d / Isometry3d / Quaterniond for the
+// three class interfaces.  Memory layout of the vectors equals the reference's
+// std::vector<Eigen::Vector3d> / <Eigen::Matrix3d> (3 / 9 contiguous doubles;
+// Matrix3d is stored ROW-major here, the C ABI's convention).
+#ifndef ESKF_LIO_B200_TYPES_HPP_
+#define ESKF_LIO_B200_TYPES_HPP_
+
+#include <array>
+#include <cmath>
+#include <cstddef>
+#include <deque>
+#include <memory>
+#include <vector>
+
+namespace ESKF_LIO
+{
+struct Vector3d
+{
+  double v[3] = {0.0, 0.0, 0.0};
+  Vector3d() = default;
+  Vector3d(double x, double y, double z) : v{x, y, z} {}
+  double & operator()(int i) {return v[i];}
+  double operator()(int i) const {return v[i];}
+  double & x() {return v[0];}
+  double & y() {return v[1];}
+  double & z() {return v[2];}
+  double squaredNorm() const {return (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2];}
+  static Vector3d Zero() {return Vector3d();}
+};
+
+struct Matrix3d
+{
+  double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // row-major
+  double & operator()(int r, int c) {return m[3 * r + c];}
+  double operator()(int r, int c) const {return m[3 * r + c];}
+  double trace() const {return (m[0] + m[4]) + m[8];}
+  static Matrix3d Identity()
+  {
+    Matrix3d I;
+    I.m[0] = I.m[4] = I.m[8] = 1.0;
+    return I;
+  }
+};
+
+struct Quaterniond
+{
+  double x = 0.0, y = 0.0, z = 0.0, w = 1.0;  // Eigen coefficient order x,y,z,w
+  static Quaterniond Identity() {return Quaterniond();}
+  Matrix3d toRotationMatrix() const
+  {
+    Matrix3d R;
+    const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R.m[0] = 1.0 - (tyy + tzz); R.m[1] = txy - twz; R.m[2] = txz + twy;
+    R.m[3] = txy + twz; R.m[4] = 1.0 - (txx + tzz); R.m[5] = tyz - twx;
+    R.m[6] = txz - twy; R.m[7] = tyz + twx; R.m[8] = 1.0 - (txx + tyy);
+    return R;
+  }
+};
+
+// rigid transform; matrix() gives the row-major 4x4 the C ABI takes
+struct Isometry3d
+{
+  Matrix3d R = Matrix3d::Identity();
+  Vector3d t;
+  static Isometry3d Identity() {return Isometry3d();}
+  Matrix3d & linear() {return R;}
+  const Matrix3d & linear() const {return R;}
+  Vector3d & translation() {return t;}
+  const Vector3d & translation() const {return t;}
+  std::array<double, 16> matrix() const
+  {
+    return {R.m[0], R.m[1], R.m[2], t.v[0], R.m[3], R.m[4], R.m[5], t.v[1],
+      R.m[6], R.m[7], R.m[8], t.v[2], 0.0, 0.0, 0.0, 1.0};
+  }
+  static Isometry3d fromMatrix(const double * T)
+  {
+    Isometry3d a;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) {a.R.m[3 * i + j] = T[4 * i + j];}
+      a.t.v[i] = T[4 * i + 3];
+    }
+    return a;
+  }
+  // Eigen Isometry3d * Isometry3d: linear = La*Lb ; translation = La*tb + ta
+  Isometry3d operator*(const Isometry3d & b) const
+  {
+    Isometry3d r;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) {
+        r.R.m[3 * i + j] = (R.m[3 * i] * b.R.m[j] + R.m[3 * i + 1] * b.R.m[3 + j]) +
+          R.m[3 * i + 2] * b.R.m[6 + j];
+      }
+      r.t.v[i] = ((R.m[3 * i] * b.t.v[0] + R.m[3 * i + 1] * b.t.v[1]) + R.m[3 * i + 2] * b.t.v[2]) +
+        t.v[i];
+    }
+    return r;
+  }
+  Isometry3d inverse() const
+  {
+    Isometry3d r;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) {r.R.m[3 * i + j] = R.m[3 * j + i];}
+    }
+    for (int i = 0; i < 3; ++i) {
+      r.t.v[i] = -((r.R.m[3 * i] * t.v[0] + r.R.m[3 * i + 1] * t.v[1]) + r.R.m[3 * i + 2] * t.v[2]);
+    }
+    return r;
+  }
+};
+
+// open3d::geometry::PointCloud as far as the hot path uses it
+struct PointCloud
+{
+  std::vector<Vector3d> points_;
+  std::vector<Matrix3d> covariances_;
+  bool HasCovariances() const {return !points_.empty() && covariances_.size() == points_.size();}
+  // Open3D PointCloud::Transform: p <- T p ; C <- R C R^T  (host-side, same
+  // evaluation order as the device kernels: ((a0 b0 + a1 b1) + a2 b2) + t)
+  PointCloud & Transform(const Isometry3d & T)
+  {
+    const double * R = T.R.m;
+    for (auto & p : points_) {
+      const double x = p.v[0], y = p.v[1], z = p.v[2];
+      p.v[0] = ((R[0] * x + R[1] * y) + R[2] * z) + T.t.v[0];
+      p.v[1] = ((R[3] * x + R[4] * y) + R[5] * z) + T.t.v[1];
+      p.v[2] = ((R[6] * x + R[7] * y) + R[8] * z) + T.t.v[2];
+    }
+    for (auto & C : covariances_) {
+      double A[9];
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+          A[3 * i + j] = (R[3 * i] * C.m[j] + R[3 * i + 1] * C.m[3 + j]) + R[3 * i + 2] * C.m[6 + j];
+        }
+      }
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+          C.m[3 * i + j] = (A[3 * i] * R[3 * j] + A[3 * i + 1] * R[3 * j + 1]) +
+            A[3 * i + 2] * R[3 * j + 2];
+        }
+      }
+    }
+    return *this;
+  }
+};
+using PointCloudPtr = std::shared_ptr<PointCloud>;
+
+struct ImuMeasurement
+{
+  double timestamp;
+  Vector3d angularVelocity;
+  Vector3d acceleration;
+};
+using ImuMeasurementPtr = std::shared_ptr<ImuMeasurement>;
+
+struct LidarMeasurement
+{
+  PointCloudPtr cloud;
+  std::vector<double> pointTime;
+  double startTime;
+  double endTime;
+};
+using LidarMeasurementPtr = std::shared_ptr<LidarMeasurement>;
+
+// the nominal state; the 18x18 covariance P of the reference is host-ESKF
+// business and is not needed by the hot path
+struct State
+{
+  double timestamp = 0.0;
+  Vector3d position;
+  Vector3d velocity;
+  Quaterniond attitude;
+  Vector3d biasAccel;
+  Vector3d biasGyro;
+  Vector3d gravity;
+};
+
+// plain-struct stand-in for the YAML::Node the reference's constructors take
+// (config/hilti_config.yaml; yaml-cpp is not available here).  Same keys, same
+// defaults.
+struct Config
+{
+  struct {
+    int max_iteration = 100;
+    double translation_sq_threshold = 1.0e-6;
+    double cosine_threshold = 0.9999;
+    int neighbor_mode = 1;  // extension: 7 = DIRECT7
+  } registration;
+  struct {
+    double voxel_size = 0.3;
+    std::size_t max_num_points_per_voxel = 1000;
+    struct {double translation_sq_threshold = 1.0e-2; double cosine_threshold = 0.985;} update;
+    struct {bool enabled = true; double distance_threshold = 100.0; double removing_period = 10.0;}
+    remove_distant_points;
+  } local_map;
+  struct {double voxel_size = 0.3;} cloud_preprocessor;
+  struct {
+    double quaternion[4] = {0.7071068, -0.7071068, 0.0, 0.0};  // x,y,z,w
+    double translation[3] = {-0.001, -0.00855, 0.055};
+  } lidar_extrinsics;
+};
+
+}  // namespace ESKF_LIO
+
+#endif  // ESKF_LIO_B200_TYPES_HPP_
