@@ -44,7 +44,7 @@ struct AlignState {
   unsigned block_counter;
   unsigned epoch;
   unsigned error;
-  unsigned pad1;
+  unsigned tile_counter;  // dynamic tile scheduling (reset by the solver every iteration)
 };
 
 struct AlignParams {
@@ -68,7 +68,7 @@ struct AlignParams {
   double trans_sq_thr;
   double cos_thr;
   int fixed_iterations;
-  int pad;
+  int dynamic_tiles;  // 1: warps pull tiles from a counter (load-balanced, summation order varies)
   AlignState* st;
   double* partials;  // [G][kAcc]
   double* sums;      // [kAcc] (single_pass output / solve input)
@@ -151,6 +151,15 @@ __device__ __forceinline__ F warp_reduce_scatter32(F* v, unsigned lane) {
     }
   }
   return v[0];
+}
+
+// ticket / epoch hand-off primitives: the CTA's partial sums are published by
+// bar.sync + ONE acq_rel atomic of thread 0 (cumulative release), consumed by
+// the last CTA through the same atomic (acquire) + bar.sync.
+__device__ __forceinline__ unsigned atom_add_acq_rel(unsigned* p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
 }
 
 __constant__ int c_off7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0},
@@ -435,23 +444,38 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
   };
 
   double acc = 0.0;
-  // ---- prologue: cur = tile0 (scanned), nxt = tile1 (transformed)
+  // tiles: a fixed stride per warp (deterministic summation order), or pulled
+  // from a global counter (balances the tail of every iteration)
+  unsigned static_next = wglobal;
+  auto next_tile = [&]() -> unsigned {
+    if (!P.dynamic_tiles) {
+      const unsigned t = static_next;
+      static_next = t < n_tiles ? t + wstride : t;
+      return t;
+    }
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(&P.st->tile_counter, 1u);
+    return __shfl_sync(0xffffffffu, t, 0);
+  };
+  // ---- prologue: cur = first tile (scanned), nxt = second tile (transformed)
   PtState cur, nxt;
+  unsigned tile = next_tile(), tile_n = next_tile();
   {
     double rx, ry, rz, qx, qy, qz;
-    load_pos(wglobal, rx, ry, rz);
-    load_pos(wglobal + wstride, qx, qy, qz);
-    xform(wglobal, rx, ry, rz, cur);
+    load_pos(tile, rx, ry, rz);
+    load_pos(tile_n, qx, qy, qz);
+    xform(tile, rx, ry, rz, cur);
     uint4 w = make_uint4(0u, 0u, 0u, 0u);
     if (cur.tag != 0u) w = __ldg(reinterpret_cast<const uint4*>(P.tags + (cur.home & ~7u)));
     finish_scan(cur, w);
-    xform(wglobal + wstride, qx, qy, qz, nxt);
+    xform(tile_n, qx, qy, qz, nxt);
   }
-  for (unsigned tile = wglobal; tile < n_tiles; tile += wstride) {
+  while (tile < n_tiles) {
     const unsigned i = tile * 32u + lane;
+    const unsigned tile_r = next_tile();
     // ---- issue: three independent groups of loads
     double rx, ry, rz;
-    load_pos(tile + 2u * wstride, rx, ry, rz);
+    load_pos(tile_r, rx, ry, rz);
     uint4 tagw = make_uint4(0u, 0u, 0u, 0u);
     if (nxt.tag != 0u) tagw = __ldg(reinterpret_cast<const uint4*>(P.tags + (nxt.home & ~7u)));
     uint4 r0 = make_uint4(0u, 0u, 0u, 0u);
@@ -504,7 +528,9 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
     }
     acc += static_cast<double>(warp_reduce_scatter32<F>(v, lane));
     cur = nxt;
-    xform(tile + 2u * wstride, rx, ry, rz, nxt);
+    xform(tile_r, rx, ry, rz, nxt);
+    tile = tile_n;
+    tile_n = tile_r;
   }
   return acc;
 }
@@ -519,7 +545,6 @@ __device__ __forceinline__ void block_reduce_store(double acc, double (*s_part)[
 #pragma unroll
     for (int i = 0; i < kW; ++i) s += s_part[i][threadIdx.x];
     out[threadIdx.x] = s;
-    __threadfence();
   }
   __syncthreads();
 }
@@ -733,9 +758,120 @@ __device__ __noinline__ void solve_and_update(const AlignParams& P, const double
   st->n_corr = static_cast<unsigned long long>(S[27]);
   st->iter = it + 1;
   st->converged = conv;
+  st->tile_counter = 0u;
   const int done = P.fixed_iterations > 0 ? (it + 1 >= P.fixed_iterations)
                                           : (conv || it + 1 >= P.max_iteration);
   st->done = done;
+}
+
+// Warp-cooperative version of the per-iteration solve (called by the 32 lanes
+// of ONE warp; `sm` is >= 96 doubles of shared scratch).  Same mathematics as
+// solve_and_update below; the 6x6 LDL^T runs in shared memory with the rank-1
+// updates spread over lanes, the triangular solves use shuffles.  Falls back
+// to the serial pivoted path (lane 0) when a pivot is not safely positive.
+__device__ __noinline__ void solve_and_update(const AlignParams& P, const double* S, int it);
+
+// H(6x6, row-major) entry -> index of its unique term in the 27 sums
+__constant__ unsigned char c_hmap[36] = {0, 1, 2,  6,  7,  8,  1, 3,  4,  9,  10, 11,
+                                         2, 4, 5,  12, 13, 14, 6, 9,  12, 15, 16, 17,
+                                         7, 10, 13, 16, 18, 19, 8, 11, 14, 17, 19, 20};
+
+__device__ __noinline__ void solve_and_update_warp(const AlignParams& P, const double* S, int it,
+                                                   double* sm) {
+  const unsigned lane = threadIdx.x & 31;
+  double* A = sm;          // 36: H, overwritten by L (below diagonal)
+  double* stp = sm + 36;   // 12: step
+  double* old = sm + 48;   // 12: previous total
+  double* tot = sm + 60;   // 12: new total
+  double* Dg = sm + 72;    // 6
+  AlignState* st = P.st;
+  // unpack S -> full symmetric H (lanes cover the 36 entries)
+  for (int e = lane; e < 36; e += 32) {
+    const double v = S[c_hmap[e]];
+    A[e] = v;
+    if (P.trace_H) P.trace_H[36 * it + e] = v;
+  }
+  if (lane < 12) old[lane] = (it == 0) ? P.guess[lane] : st->T_total[lane];
+  if (lane < 6 && P.trace_b) P.trace_b[6 * it + lane] = S[21 + lane];
+  __syncwarp();
+  double maxd = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) maxd = fmax(maxd, fabs(A[7 * i]));
+  const double tol = maxd * 1e-12;
+  bool ok = maxd > 0.0;
+  for (int k = 0; k < 6; ++k) {
+    const double d = A[7 * k];
+    ok = ok && (d > tol);
+    const int m = 5 - k;
+    if (static_cast<int>(lane) < m * m) {
+      const int i = k + 1 + static_cast<int>(lane) / m, j = k + 1 + static_cast<int>(lane) % m;
+      A[6 * i + j] -= A[6 * i + k] * A[6 * j + k] / d;
+    }
+    __syncwarp();
+    if (static_cast<int>(lane) > k && lane < 6) A[6 * lane + k] /= d;
+    if (lane == 0) Dg[k] = d;
+    __syncwarp();
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (!ok) {  // singular / indefinite system: the Eigen-style pivoted path decides
+    if (lane == 0) solve_and_update(P, S, it);
+    __syncwarp();
+    return;
+  }
+  // L y = -b ; D z = y ; L^T x = z   (lane i < 6 owns component i)
+  double y = lane < 6 ? -S[21 + lane] : 0.0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const double yj = __shfl_sync(0xffffffffu, y, j);
+    if (static_cast<int>(lane) > j && lane < 6) y -= A[6 * lane + j] * yj;
+  }
+  if (lane < 6) y /= Dg[lane];
+#pragma unroll
+  for (int j = 5; j >= 0; --j) {
+    const double xj = __shfl_sync(0xffffffffu, y, j);
+    if (static_cast<int>(lane) < j) y -= A[6 * j + lane] * xj;
+  }
+  if (lane < 6) Dg[lane] = y;  // se3
+  __syncwarp();
+  if (lane == 0) {
+    double se3[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) se3[i] = Dg[i];
+    double s12[12];
+    se3_to_SE3(se3, s12);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) stp[i] = s12[i];
+  }
+  __syncwarp();
+  // totalTransform = transformIter * totalTransform (Registration.cpp:20)
+  if (lane < 9) {
+    const int i = lane / 3, j = lane % 3;
+    tot[lane] = stp[3 * i] * old[j] + stp[3 * i + 1] * old[3 + j] + stp[3 * i + 2] * old[6 + j];
+  } else if (lane < 12) {
+    const int i = lane - 9;
+    tot[lane] = (stp[3 * i] * old[9] + stp[3 * i + 1] * old[10] + stp[3 * i + 2] * old[11]) + stp[9 + i];
+  }
+  __syncwarp();
+  if (lane < 12) {
+    st->T_total[lane] = tot[lane];
+    st->T_step[lane] = stp[lane];
+    if (P.trace_step) P.trace_step[12 * it + lane] = stp[lane];
+  }
+  if (lane < 9) st->Rf[lane] = static_cast<float>(tot[lane]);
+  if (lane == 0) {
+    // convergenceCheck (Registration.cpp:37-50)
+    const double cosine = 0.5 * (((stp[0] + stp[4]) + stp[8]) - 1.0);
+    const double tsq = stp[9] * stp[9] + stp[10] * stp[10] + stp[11] * stp[11];
+    const int conv = (cosine >= P.cos_thr && tsq <= P.trans_sq_thr) ? 1 : 0;
+    if (P.trace_ncorr) P.trace_ncorr[it] = static_cast<unsigned long long>(S[27]);
+    st->n_corr = static_cast<unsigned long long>(S[27]);
+    st->iter = it + 1;
+    st->converged = conv;
+    st->tile_counter = 0u;
+    st->done = P.fixed_iterations > 0 ? (it + 1 >= P.fixed_iterations)
+                                      : (conv || it + 1 >= P.max_iteration);
+  }
+  __syncwarp();
 }
 
 template <typename F, int U, int NN, int MINB>
@@ -744,6 +880,7 @@ __global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
   __shared__ F s_R[9];
   __shared__ double s_part[kW][32];
   __shared__ double s_sum[kAcc];
+  __shared__ double s_solve[96];
   __shared__ int s_last, s_done;
   const unsigned G = gridDim.x, t = threadIdx.x;
   AlignState* st = P.st;
@@ -763,17 +900,16 @@ __global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
 
     // last CTA to arrive reduces the partials and solves
     if (t == 0) {
-      const unsigned ticket = atomicAdd(&st->block_counter, 1u);
+      const unsigned ticket = atom_add_acq_rel(&st->block_counter, 1u);
       s_last = (ticket == G * static_cast<unsigned>(it + 1) - 1u) ? 1 : 0;
     }
     __syncthreads();
     if (s_last) {
-      __threadfence();
       final_reduce(P.partials, G, s_part, s_sum);
-      if (t == 0) {
-        solve_and_update(P, s_sum, it);
-        __threadfence();
-        st_release_u32(&st->epoch, static_cast<unsigned>(it + 1));
+      if (t < 32) {
+        solve_and_update_warp(P, s_sum, it, s_solve);
+        __syncwarp();
+        if (t == 0) st_release_u32(&st->epoch, static_cast<unsigned>(it + 1));
       }
     }
     // everyone waits for the solver (bounded spin)
@@ -788,7 +924,6 @@ __global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
           break;
         }
       }
-      __threadfence();
       s_done = ok ? ld_cg(&st->done) : 1;
     }
     __syncthreads();
@@ -798,7 +933,11 @@ __global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
 
 // sharded mode, after the caller's all-reduce of `sums`: one thread solves
 __global__ void solve_kernel(AlignParams P, int it) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) solve_and_update(P, P.sums, it);
+  __shared__ double s_solve[96];
+  __shared__ double s_in[kAcc];
+  if (threadIdx.x < kAcc) s_in[threadIdx.x] = P.sums[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x < 32) solve_and_update_warp(P, s_in, it, s_solve);
 }
 
 // sharded mode: ONE linearisation of this rank's point range; the 28 sums go
@@ -820,12 +959,11 @@ __global__ void __launch_bounds__(kT, MINB) linearize_pass_kernel(AlignParams P,
                          : accumulate_points<F, U, NN>(P, s_T, s_R, it == 0, false);
   block_reduce_store(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
   if (t == 0) {
-    const unsigned ticket = atomicAdd(&st->block_counter, 1u);
+    const unsigned ticket = atom_add_acq_rel(&st->block_counter, 1u);
     s_flag = (ticket == G * static_cast<unsigned>(it + 1) - 1u) ? 1 : 0;
   }
   __syncthreads();
   if (s_flag) {
-    __threadfence();
     final_reduce(P.partials, G, s_part, s_sum);
     if (t < kAcc) P.sums[t] = s_sum[t];
   }
@@ -929,6 +1067,13 @@ int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, T
   P->trans_sq_thr = a.trans_sq_thr;
   P->cos_thr = a.cos_thr;
   P->fixed_iterations = a.fixed_iterations;
+  {
+    static const int dyn = [] {
+      const char* e = getenv("ESKF_ALIGN_DYNAMIC");
+      return e ? atoi(e) : 0;
+    }();
+    P->dynamic_tiles = dyn;
+  }
   P->st = reinterpret_cast<AlignState*>(base + L->o_state);
   P->partials = ctx->partials.as<double>();
   P->sums = reinterpret_cast<double*>(base + L->o_sums);
