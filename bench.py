@@ -3,27 +3,29 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Metric (BASELINE.json): ms/frame for a 64k-point scan going through
-preprocess (T_il + voxel downsample + 30-NN covariances) -> VGICP align
-against the local voxel map -> map update.  A "step" is one frame.
+Metric (BASELINE.json): ms/frame on configs[1], the synthetic odometry
+sequence (10 Hz 64k-point sweeps + 400 Hz IMU).  A "step" is one LiDAR frame
+through the three stages the reference times (src/Odometry.cpp:73-87):
+CloudPreprocessor::process -> ErrorStateKF::update{ICP::align} ->
+LocalMap::updateLocalMap, driven by the ROS-free Odometry / ErrorStateKF host
+classes (eskf_lio_b200/host/ESKF_LIO) with the hot path on the B200.
 
-  value     device-resident: every raw scan is already in HBM when the timed
-            region starts; per frame the host only receives the pose.
-  e2e       the same frames through the public API with HOST inputs: the raw
-            scan is copied from pinned host memory (H2D) and the pose is read
-            back (D2H) inside the timed region.
+  value     sweeps already resident in HBM; CUDA events around the three stages
+            of every timed frame, summed.
+  e2e       sweeps in pinned host memory (float32 wire format): H2D at
+            delivery + the three stages + pose read-back, wall clock.
   roofline  the correspondence/linearise kernel (align_kernel) on the dense
             config (BASELINE.json configs[2]: 2M-point source vs a 10M-point
             map at 0.1 m voxels, fixed 10 GN iterations), where the path is
-            HBM-bound; the 64k-point frame itself is L2-resident and
-            latency-bound (north_star), reported under "frame_kernel".
+            HBM-bound; a 64k-point frame is L2-resident and latency-bound.
   cpu_baseline / --impl reference
             the CPU oracle (dependency-free restatement of the reference's
-            OpenMP path; the reference itself cannot be built here) on the
-            host cores, same frames.
+            OpenMP path, its ErrorStateKF and Odometry::run call order; the
+            reference itself cannot be built here) on the host cores, same log.
 
-N > 1 (torchrun): one independent frame sequence per GPU (the single-scan
-path does not shard: replicas, weak scaling), no data-path collective.
+N > 1 (torchrun): one independent sequence per GPU (a single frame does not
+shard: replicas, weak scaling), no data-path collective.  The sharded dense
+registration is measured by scripts/dense_sharded.py.
 """
 from __future__ import annotations
 
@@ -43,33 +45,50 @@ if ROOT not in sys.path:
 
 from eskf_lio_b200 import synth as S  # noqa: E402
 
-VOXEL = 0.5
-MAP_SCANS = 20
 ALG_BYTES_PER_POINT_ITER = 136  # 24 pos rd + 24 pos wr + 24 src cov + 64 voxel slot
 DENSE_SRC = 2_000_000
 DENSE_MAP = 10_000_000
 DENSE_VOXEL = 0.1
 DENSE_ITERS = 10
+# configs[1]: reference defaults (config/hilti_config.yaml): 0.3 m voxels, cap 1000, ICP 100 / 1e-6 / 0.9999
+VOXEL = 0.3
+# untimed lead-in: frame 0 initialises the map, the trajectory starts from rest (the keyframe gate of
+# LocalMap.cpp:132-147 only opens at ~1 m/s), so ~35 frames put >= 20 scans into the local map
+LEAD_IN = 35
+CACHE_DIR = os.environ.get("ESKF_BENCH_CACHE", "/tmp/eskf_lio_b200_cache")
 
 
-def loop_trajectory(n, radius=7.0, centre=(5.0, -1.0), step=0.5, z=1.5):
-    """Body poses `step` m apart on a circle inside the hall (config 1/2 scene)."""
-    poses = []
-    dth = step / radius
-    for k in range(n):
-        th = k * dth
-        x = centre[0] + radius * np.cos(th)
-        y = centre[1] + radius * np.sin(th)
-        poses.append(S.pose([x, y, z], [0.0, 0.0, th + np.pi / 2]))
-    return poses
+def make_log(n_frames, seed):
+    """The synthetic sensor log of configs[1]: 400x30x10 m corridor,
+    10 Hz motion-distorted 32x2000 sweeps + 400 Hz IMU from an analytic trajectory (~1.2 m/s).
+    Cached on disk so the reference arm (a separate process) replays the identical log."""
+    path = os.path.join(CACHE_DIR, f"corridor_v1_{n_frames}_{seed}.npz")
+    if os.path.exists(path):
+        try:
+            z = np.load(path)
+            n = z["n"]
+            xyz, t = z["xyz"], z["t"]
+            off = np.concatenate([[0], np.cumsum(n)])
+            scans = [(xyz[off[i]:off[i + 1]].astype(np.float64), t[off[i]:off[i + 1]].copy())
+                     for i in range(len(n))]
+            return scans, z["imu"]
+        except Exception:
+            pass
+    scans, imu = S.make_sequence(S.corridor_scene(), S.corridor_trajectory(), n_frames, seed, chunk=100)
+    try:
+        os.makedirs(CACHE_DIR, exist_ok=True)
+        tmp = path + f".{os.getpid()}.tmp.npz"
+        np.savez(tmp, n=np.array([len(x) for x, _ in scans]),
+                 xyz=np.concatenate([x for x, _ in scans]).astype(np.float32),
+                 t=np.concatenate([t for _, t in scans]), imu=imu)
+        os.replace(tmp, path)
+    except Exception:
+        pass
+    return scans, imu
 
 
-def make_frames(n_frames, seed):
-    rng = np.random.default_rng(seed)
-    scene = S.hall_scene()
-    poses = loop_trajectory(n_frames)
-    scans = [S.make_scan(scene, T, rng) for T in poses]
-    return poses, scans
+def odom_overrides():
+    return dict(map_voxel_size=VOXEL, preprocess_voxel_size=VOXEL)
 
 
 def peaks():
@@ -136,52 +155,89 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ----------------------------------------------------------------- CPU arm
-def run_reference_frames(poses, scans, warmup, steps, threads=None):
-    """The CPU oracle on the same frame sequence.  Returns ms/frame stats."""
+# ----------------------------------------------------------------- driving
+def replay(odom, scans, imu, feed, first_timed, on_timed_start=None):
+    """Deliver the log the way the two sensor callbacks would (IMU samples in time order, a sweep
+    once its last point is measured, one spin per delivery) and time, per frame from `first_timed`
+    on, the delivery of the sweep + the spin that consumes it (wall clock)."""
+    k = 0
+    n_imu = imu.shape[0]
+    wall = 0.0
+    poses, iters = [], []
+    for i, (xyz, t) in enumerate(scans):
+        if i == first_timed and on_timed_start:
+            on_timed_start()
+        end = t[-1]
+        while k < n_imu and imu[k, 0] <= end:
+            odom.feed_imu(imu[k, 0], imu[k, 1:4], imu[k, 4:7])
+            k += 1
+            odom.spin_once()
+        # the first IMU sample past the sweep end makes the frame eligible (Odometry.cpp:65-69)
+        if k < n_imu:
+            odom.feed_imu(imu[k, 0], imu[k, 1:4], imu[k, 4:7])
+            k += 1
+        t0 = time.perf_counter()
+        feed(i)
+        done = odom.spin_once()
+        pose = odom.pose()
+        t1 = time.perf_counter()
+        if not done:
+            raise RuntimeError("frame not consumed: IMU stream too short")
+        if i >= first_timed:
+            wall += t1 - t0
+            iters.append(odom.info().last_iterations)
+        poses.append(pose)
+    return wall, poses, iters
+
+
+def run_oracle(scans, imu, first_timed, threads=None):
+    """The CPU oracle (restatement of the reference's OpenMP path incl. its ErrorStateKF and the call
+    order of Odometry::run) on the same log; ms/frame = the reference's own three stage timers
+    (src/Odometry.cpp:73-87), summed over the frames from `first_timed` on."""
     import oracle as O
+    O.build()
     if threads:
         O.set_num_threads(threads)
-    T_il = S.default_T_il()
-    pert = S.perturbation()
-    omap = O.Map(VOXEL, 1000)
-    omap.set_update_params(1e-2, 0.985, False, 100.0, 10.0)
-    stage = {"preprocess": 0.0, "align": 0.0, "map_update": 0.0}
-    t_total = 0.0
-    done = 0
-    iters = []
-    for i, ((xyz, t), T) in enumerate(zip(scans, poses)):
-        timed = i >= MAP_SCANS + warmup
-        t0 = time.perf_counter()
-        p, c, _ = O.preprocess(xyz, t, T_il, None, VOXEL)
-        t1 = time.perf_counter()
-        if i < MAP_SCANS:
-            pose = T
-        else:
-            r = omap.align(p, c, T @ pert)
-            pose = r["T"]
-            iters.append(r["iterations"])
-        t2 = time.perf_counter()
-        omap.update(p, c, pose, initialize=(i < MAP_SCANS))
-        t3 = time.perf_counter()
-        if timed:
-            stage["preprocess"] += t1 - t0
-            stage["align"] += t2 - t1
-            stage["map_update"] += t3 - t2
-            t_total += t3 - t0
-            done += 1
-            if done >= steps:
-                break
-    return {"ms_per_frame": 1e3 * t_total / max(done, 1), "frames": done,
-            "stage_ms": {k: 1e3 * v / max(done, 1) for k, v in stage.items()},
-            "cores": O.num_threads(), "gn_iterations_mean": float(np.mean(iters)) if iters else 0.0}
+    od = O.Odometry(O.odom_default_config(**odom_overrides()))
+    base = [None]
+
+    def snap():
+        inf = od.info()
+        return np.array(inf.stage_avg_ms) * inf.frames, inf.frames
+
+    _, poses, iters = replay(od, scans, imu, lambda i: od.feed_lidar(scans[i][0], scans[i][1]),
+                             first_timed, lambda: base.__setitem__(0, snap()))
+    s1, f1 = snap()
+    s0, f0 = base[0]
+    n = f1 - f0
+    stage = (s1 - s0) / max(n, 1)
+    return {"ms_per_frame": float(stage.sum()), "frames": int(n), "cores": O.num_threads(),
+            "stage_ms": {"preprocess": float(stage[0]), "filter_update": float(stage[1]),
+                         "map_update": float(stage[2])},
+            "gn_iterations_mean": float(np.mean(iters)) if iters else 0.0, "poses": poses}
+
+
+def workload_config():
+    return {"workload": "BASELINE.json configs[1]: synthetic odometry sequence, 10 Hz 32-beam x 2000-col "
+                        "(64k-pt) motion-distorted sweeps + 400 Hz IMU in a 400x30x10 m corridor (~1.2 m/s); "
+                        "per frame: preprocess (T_il, deskew against the filter states, 0.3 m downsample, "
+                        "30-NN covariances) -> host ErrorStateKF::update {VGICP align from the IMU-predicted "
+                        "pose} -> LocalMap insert/evict; ms/frame = the three stages the reference times "
+                        "(src/Odometry.cpp:73-87); the 400 Hz IMU propagation between frames is host work in "
+                        "both arms and reported separately",
+            "voxel_size": VOXEL, "lead_in_frames": LEAD_IN,
+            "registration": "max_iteration=100, translation_sq_threshold=1e-6, cosine_threshold=0.9999, "
+                            "1-neighbour (config/hilti_config.yaml)",
+            "l2": "frame working set (~4 MB) is L2-resident by nature and every frame is a different sweep; "
+                  "the roofline leg's working set (~0.6 GB) exceeds the 126 MB L2"}
 
 
 def impl_reference(args, rank, world):
     if rank != 0:
         return
-    poses, scans = make_frames(MAP_SCANS + args.warmup + args.steps, seed=43)
-    r = run_reference_frames(poses, scans, args.warmup, args.steps)
+    n_frames = 1 + LEAD_IN + args.warmup + args.steps
+    scans, imu = make_log(n_frames, seed=43)
+    r = run_oracle(scans, imu, 1 + LEAD_IN + args.warmup)
     line = {
         "impl": "reference", "metric": "ms_per_frame", "value": r["ms_per_frame"], "unit": "ms",
         "n_gpus": args.gpus, "steps": r["frames"], "warmup": args.warmup,
@@ -189,95 +245,78 @@ def impl_reference(args, rank, world):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(),
         "cpu_baseline": {"value": r["ms_per_frame"], "unit": "ms", "cores": r["cores"], "kind": "port",
-                         "sample": f"{r['frames']} frames of the same sequence (oracle: dependency-free "
-                                   "restatement of the reference's OpenMP path; the reference itself "
-                                   "needs Eigen/Open3D/yaml-cpp/rclcpp and cannot be built here)",
-                         "stage_ms": r["stage_ms"]},
+                         "sample": f"{r['frames']} frames of the same log after the {LEAD_IN}-frame lead-in "
+                                   "(oracle: dependency-free restatement of the reference's OpenMP path; the "
+                                   "reference itself needs Eigen/Open3D/yaml-cpp/rclcpp and cannot be built here)",
+                         "stage_ms": r["stage_ms"], "gn_iterations_mean": r["gn_iterations_mean"]},
         "e2e": {"value": r["ms_per_frame"], "unit": "ms", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config():
-    return {"workload": "BASELINE.json configs[1]-style frame sequence (configs[0] scene): synthetic "
-                        "32-beam x 2000-col (64k-pt) scans on a 7 m loop in the 60x40x10 m hall, "
-                        "0.5 m voxels, 20-scan local map, per frame preprocess + VGICP align from a "
-                        "(0.10,-0.05,0.03) m / 1.0 deg perturbed pose + map insert; host ESKF not in "
-                        "the loop yet",
-            "voxel_size": VOXEL, "map_scans": MAP_SCANS, "registration": "max_iteration=100, "
-            "translation_sq_threshold=1e-6, cosine_threshold=0.9999, 1-neighbour",
-            "l2": "frame working set (~2 MB) is L2-resident by nature; every frame is a different "
-                  "scan; the roofline leg's working set (~0.6 GB) exceeds the 126 MB L2"}
-
-
 # ----------------------------------------------------------------- GPU arm
-def gpu_frames(ctx, capi, poses, scans, warmup, steps, mode):
-    """mode 'resident': raw scans pre-uploaded; 'e2e': per-frame upload from pinned host."""
-    T_il = S.default_T_il()
-    pert = S.perturbation()
-    gmap = capi.Map(ctx, VOXEL, 1000, 1 << 17)
-    ds = capi.Cloud(ctx, 70000)
-    n_frames = len(scans)
-    raws = []
-    pinned = []
+def gpu_sequence(capi, odometry, device, scans, imu, first_timed, mode):
+    """mode 'resident': every raw sweep is uploaded to HBM before the timed region (the frames are
+    fed as device clouds); 'e2e': sweeps sit in pinned host memory in the float32 wire format and
+    are copied to the device when they are delivered, the pose is read back every frame."""
+    import ctypes as C
+    od = odometry.Odometry(odometry.default_config(device_resident=1, **odom_overrides()), device)
+    ctx = od.context()
+    keep = []
     if mode == "resident":
-        for xyz, _ in scans:
-            raws.append(capi.Cloud(ctx, len(xyz)).upload(xyz))
+        clouds = [capi.Cloud(ctx, len(x)).upload_f32(x) for x, _ in scans]
+        ctx.sync()
+
+        def feed(i):
+            od.feed_lidar_cloud(clouds[i], scans[i][1])
     else:
-        import ctypes as C
-        for xyz, _ in scans:
-            ptr = C.c_void_p()
-            capi.check(capi.lib().eskf_host_alloc(C.c_size_t(xyz.nbytes), C.byref(ptr)))
-            C.memmove(ptr, xyz.ctypes.data, xyz.nbytes)
-            pinned.append((ptr, len(xyz)))
-        raw_e2e = capi.Cloud(ctx, 70000)
+        pinned = []
+        for x, t in scans:
+            x32 = np.ascontiguousarray(x, dtype=np.float32)
+            px, pt = C.c_void_p(), C.c_void_p()
+            capi.check(capi.lib().eskf_host_alloc(C.c_size_t(x32.nbytes), C.byref(px)))
+            capi.check(capi.lib().eskf_host_alloc(C.c_size_t(t.nbytes), C.byref(pt)))
+            C.memmove(px, x32.ctypes.data, x32.nbytes)
+            C.memmove(pt, t.ctypes.data, t.nbytes)
+            pinned.append((px, pt, len(t)))
+        keep = pinned
+
+        def feed(i):
+            px, pt, n = pinned[i]
+            od.feed_lidar_ptr(px.value, pt.value, n)
+
+    state = {}
+
+    def start():
+        ctx.sync()
+        inf = od.info()
+        state["dev0"] = inf.device_frame_ms_sum
+        state["stage0"] = np.array(inf.stage_sum_ms)
+        state["frames0"] = inf.frames
+        state["launch0"] = od.launch_count()
+        state["sampler"] = ClockSampler(device)
+        state["sampler"].start()
+        state["t0"] = time.perf_counter()
+
+    wall, poses, iters = replay(od, scans, imu, feed, first_timed, start)
     ctx.sync()
-    h2d = d2h = 0
-    iters, npts = [], []
-    launches0 = t_wall0 = None
-    gpu_ms = None
-    sampler = None
-    for i in range(n_frames):
-        if i == MAP_SCANS + warmup:
-            ctx.sync()
-            sampler = ClockSampler(ctx.device)
-            sampler.start()
-            launches0 = ctx.launch_count()
-            ctx.timer_start()
-            t_wall0 = time.perf_counter()
-        timed = i >= MAP_SCANS + warmup
-        if mode == "resident":
-            raw = raws[i]
-        else:
-            ptr, n = pinned[i]
-            raw_e2e.upload_ptr(ptr.value, None, n)
-            raw = raw_e2e
-            if timed:
-                h2d += n * 24
-        raw.preprocess_into(ds, None, T_il, None, VOXEL)
-        if i < MAP_SCANS:
-            pose = poses[i]
-        else:
-            r = gmap.align_cloud(ds, poses[i] @ pert)
-            pose = r["T"]
-            if timed:
-                d2h += 16 * 8
-                iters.append(r["iterations"])
-                npts.append(ds.size())
-        gmap.insert_cloud(ds, pose)
-    gpu_ms = ctx.timer_stop()
-    wall_ms = 1e3 * (time.perf_counter() - t_wall0)
-    clocks = sampler.stop()
-    launches = ctx.launch_count() - launches0
-    n_vox = gmap.size()
-    if mode != "resident":
-        for ptr, _ in pinned:
-            capi.lib().eskf_host_free(ptr)
-    return {"gpu_ms": gpu_ms, "wall_ms": wall_ms, "frames": steps, "launches": launches,
-            "h2d": h2d // max(steps, 1), "d2h": d2h // max(steps, 1), "clocks": clocks,
-            "gn_iterations_mean": float(np.mean(iters)), "n_ds_mean": float(np.mean(npts)),
-            "map_voxels": n_vox, "last_pose": pose}
+    total_wall = time.perf_counter() - state["t0"]
+    clocks = state["sampler"].stop()
+    inf = od.info()
+    n = int(inf.frames - state["frames0"])
+    res = {"frames": n, "device_ms": inf.device_frame_ms_sum - state["dev0"],
+           "stage_ms": ((np.array(inf.stage_sum_ms) - state["stage0"]) / max(n, 1)).tolist(),
+           "wall_ms": 1e3 * wall, "replay_wall_ms": 1e3 * total_wall,
+           "launches": od.launch_count() - state["launch0"], "clocks": clocks,
+           "gn_iterations_mean": float(np.mean(iters)), "map_voxels": int(inf.map_voxels),
+           "n_states": int(inf.n_states), "poses": poses,
+           "h2d": int(np.mean([len(t) * 12 for _, t in scans[first_timed:]])), "d2h": 16 * 8 + 64}
+    od.close()
+    for px, pt, _ in keep:
+        capi.lib().eskf_host_free(px)
+        capi.lib().eskf_host_free(pt)
+    return res
 
 
 def dense_roofline(ctx, capi, peak_gbs, peak_src):
@@ -296,16 +335,18 @@ def dense_roofline(ctx, capi, peak_gbs, peak_src):
     for _ in range(3):  # warm-up
         gmap.align_cloud_fixed(src, guess, DENSE_ITERS)
     times = []
-    ncorr = 0
+    ncorr = []
     for _ in range(5):
         ctx.sync()
         ctx.timer_start()
         r = gmap.align_cloud_fixed(src, guess, DENSE_ITERS, trace=True)
         times.append(ctx.timer_stop())
-        ncorr = int(r["ncorr"][-1])
+        ncorr = [int(v) for v in r["ncorr"]]
     ms = float(np.median(times))
     bytes_launch = DENSE_SRC * ALG_BYTES_PER_POINT_ITER * DENSE_ITERS
     achieved = bytes_launch / (ms * 1e-3) / 1e9
+    # a point whose voxel is empty needs neither the 64 B record nor its 24 B source covariance
+    hit_bytes = sum(48 * DENSE_SRC + 88 * h for h in ncorr)
     return {
         "bound": "hbm", "kernel": "align_kernel<float> (fused transform + voxel lookup + "
                                   "J^T W J / J^T W r + reduction + on-device solve)",
@@ -313,13 +354,31 @@ def dense_roofline(ctx, capi, peak_gbs, peak_src):
                     f"{DENSE_VOXEL} m voxels ({n_vox} voxels), {DENSE_ITERS} GN iterations per launch",
         "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
         "peak_source": peak_src, "frac_of_8TBs_spec": achieved / 8000.0,
-        "traffic": None,
+        "traffic": DENSE_TRAFFIC_BYTES,
+        "traffic_source": DENSE_TRAFFIC_SOURCE,
         "algorithmic_bytes_per_launch": bytes_launch,
+        "hit_weighted": {"note": "only the points that find a voxel need the 64 B record and the 24 B "
+                                 "source covariance; bytes = 48 N + 88 hits per iteration",
+                         "bytes_per_launch": hit_bytes, "achieved": hit_bytes / (ms * 1e-3) / 1e9,
+                         "frac": hit_bytes / (ms * 1e-3) / 1e9 / peak_gbs,
+                         "hit_rate": float(np.mean(ncorr)) / DENSE_SRC},
         "ms_per_launch": ms, "ms_per_gn_iteration": ms / DENSE_ITERS,
         "mpts_per_s_per_gn_iteration": DENSE_SRC / (ms / DENSE_ITERS * 1e-3) / 1e6,
-        "correspondences_last_iter": ncorr,
+        "correspondences_last_iter": ncorr[-1],
         "timing": "CUDA events on the launching stream (eskf_ctx_timer_*), median of 5 after 3 warm-ups",
     }
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE align_kernel launch of this very workload from the
+# committed `ncu --set full` capture (profiles/); None until a capture of the current kernel exists
+DENSE_TRAFFIC_BYTES = 1_745_224_000 + 535_775_000
+DENSE_TRAFFIC_SOURCE = "profiles/r1_prof_align_ncu.md (ncu --set full, one launch)"
+
+
+def pose_delta(A, B):
+    E = np.linalg.inv(A) @ B
+    return (float(np.linalg.norm(E[:3, 3])),
+            float(np.arccos(np.clip(0.5 * (np.trace(E[:3, :3]) - 1.0), -1.0, 1.0))))
 
 
 def main():
@@ -330,6 +389,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=5,
+                    help="timed frames of the cpu_baseline leg (after the same lead-in)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -341,7 +402,7 @@ def main():
         impl_reference(args, rank, world)
         return
 
-    from eskf_lio_b200 import capi
+    from eskf_lio_b200 import capi, odometry
     import torch
     dist = None
     if world > 1:
@@ -349,9 +410,9 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    ctx = capi.Context(local_rank)
-    n_frames = MAP_SCANS + args.warmup + args.steps
-    poses, scans = make_frames(n_frames, seed=43 + rank)
+    first_timed = 1 + LEAD_IN + args.warmup
+    n_frames = first_timed + args.steps
+    scans, imu = make_log(n_frames, seed=43 + rank)
 
     def barrier():
         if dist is not None:
@@ -359,12 +420,12 @@ def main():
         torch.cuda.synchronize()
 
     barrier()
-    res = gpu_frames(ctx, capi, poses, scans, args.warmup, args.steps, "resident")
+    res = gpu_sequence(capi, odometry, local_rank, scans, imu, first_timed, "resident")
     barrier()
-    e2e = gpu_frames(ctx, capi, poses, scans, args.warmup, args.steps, "e2e")
+    e2e = gpu_sequence(capi, odometry, local_rank, scans, imu, first_timed, "e2e")
     barrier()
 
-    ms = res["gpu_ms"]
+    ms = res["device_ms"]
     ms_e2e = e2e["wall_ms"]
     if dist is not None:
         t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -377,36 +438,47 @@ def main():
     line = None
     if rank == 0:
         peak, peak_src, _ = peaks()
-        n_ds = res["n_ds_mean"]
-        its = res["gn_iterations_mean"]
+        dts, drs = zip(*[pose_delta(a, b) for a, b in zip(res["poses"], e2e["poses"])])
         line = {
             "metric": "ms_per_frame", "value": value, "unit": "ms", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 positions/keys + f32 per-point algebra + f64 accumulation",
             "data": "synthetic", "config": workload_config(),
+            "timing": "value: CUDA events on the context's stream around the three stages of every timed "
+                      "frame (sweeps resident in HBM), summed; e2e: wall clock around sweep delivery "
+                      "(float32 H2D from pinned memory) + the three stages + pose read-back, summed",
             "e2e": {"value": e2e_value, "unit": "ms", "h2d_bytes_per_step": e2e["h2d"],
                     "d2h_bytes_per_step": e2e["d2h"],
-                    "note": "wall clock over the public device-cloud API: raw scan H2D from pinned "
-                            "memory + preprocess + align + map insert + pose D2H every frame"},
+                    "stage_ms": dict(zip(("preprocess", "filter_update", "map_update"), e2e["stage_ms"])),
+                    "replay_wall_ms_per_frame_incl_imu_propagation": e2e["replay_wall_ms"] / args.steps},
             "gpu_launches": res["launches"], "clocks": res["clocks"],
             "frames_per_s": 1e3 / value,
+            "stage_ms": dict(zip(("preprocess", "filter_update", "map_update"), res["stage_ms"])),
             "wall_ms_per_frame_resident": res["wall_ms"] / args.steps,
-            "gn_iterations_mean": its, "n_downsampled_mean": n_ds, "map_voxels": res["map_voxels"],
+            "replay_wall_ms_per_frame_incl_imu_propagation": res["replay_wall_ms"] / args.steps,
+            "gn_iterations_mean": res["gn_iterations_mean"], "map_voxels": res["map_voxels"],
+            "filter_states": res["n_states"],
+            "resident_vs_e2e_pose_delta": {"max_m": max(dts), "max_rad": max(drs)},
             "frame_kernel": {
-                "note": "64k-pt frame is L2-resident and latency-bound (north_star): HBM fraction "
-                        "is not the figure of merit here",
-                "mpts_per_s_per_gn_iteration_upper_bound": None},
+                "note": "a 64k-pt frame is L2-resident and latency-bound (north_star): the HBM "
+                        "fraction is reported on the dense configs[2] leg below"},
         }
         if not args.no_roofline:
-            line["roofline"] = dense_roofline(ctx, capi, peak, peak_src)
+            dctx = capi.Context(local_rank)
+            line["roofline"] = dense_roofline(dctx, capi, peak, peak_src)
+            dctx.close()
         if not args.no_cpu_baseline:
-            r = run_reference_frames(poses, scans, 1, 5)
+            n_cpu = first_timed + args.cpu_frames
+            r = run_oracle(scans[:n_cpu], imu, first_timed)
+            od, oe = zip(*[pose_delta(a, b) for a, b in zip(r["poses"], res["poses"][:n_cpu])])
             line["cpu_baseline"] = {
                 "value": r["ms_per_frame"], "unit": "ms", "cores": r["cores"], "kind": "port",
-                "sample": "5 frames of the same sequence after the 20-scan map build (oracle = "
-                          "dependency-free restatement of the reference's OpenMP path)",
+                "sample": f"{r['frames']} timed frames of the same log after the same {first_timed}-frame "
+                          "lead-in (oracle = dependency-free restatement of the reference's OpenMP path, "
+                          "its ErrorStateKF and the call order of Odometry::run)",
                 "stage_ms": r["stage_ms"], "gn_iterations_mean": r["gn_iterations_mean"]}
+            line["trajectory_match_vs_cpu"] = {"frames": n_cpu, "max_m": max(od), "max_rad": max(oe)}
     barrier()
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -12,7 +12,7 @@ class CloudPreprocessor
 {
 public:
   explicit CloudPreprocessor(const Config & config)
-  : voxelSize_(config.cloud_preprocessor.voxel_size)
+  : voxelSize_(config.cloud_preprocessor.voxel_size), deviceResident_(config.device_resident)
   {
     Quaterniond q;
     q.x = config.lidar_extrinsics.quaternion[0];
@@ -29,14 +29,29 @@ public:
   // lidarMeas->cloud in place and frees pointTime, like the reference
   void process(const std::deque<State> & states, LidarMeasurementPtr lidarMeas) const
   {
-    std::vector<eskf_state> st(states.size());
-    for (std::size_t i = 0; i < states.size(); ++i) {
-      st[i].timestamp = states[i].timestamp;
-      for (int k = 0; k < 3; ++k) {st[i].position[k] = states[i].position.v[k];}
-      st[i].attitude_xyzw[0] = states[i].attitude.x;
-      st[i].attitude_xyzw[1] = states[i].attitude.y;
-      st[i].attitude_xyzw[2] = states[i].attitude.z;
-      st[i].attitude_xyzw[3] = states[i].attitude.w;
+    // deskew (:25-74) walks the state deque from its begin, but a state whose
+    // stamp is <= the first point time consumes no point (:54-65): only the
+    // states from the last such one onwards are handed to the device path, so
+    // the per-frame cost does not grow with the (never trimmed) history.
+    std::size_t first = 0;
+    if (!states.empty() && !lidarMeas->pointTime.empty()) {
+      const double t0 = lidarMeas->pointTime.front();
+      std::size_t lo = 0, hi = states.size();  // first state with timestamp > t0
+      while (lo < hi) {
+        const std::size_t mid = (lo + hi) / 2;
+        if (states[mid].timestamp <= t0) {lo = mid + 1;} else {hi = mid;}
+      }
+      first = lo > 0 ? lo - 1 : 0;
+    }
+    std::vector<eskf_state> st(states.size() - first);
+    for (std::size_t i = first; i < states.size(); ++i) {
+      eskf_state & o = st[i - first];
+      o.timestamp = states[i].timestamp;
+      for (int k = 0; k < 3; ++k) {o.position[k] = states[i].position.v[k];}
+      o.attitude_xyzw[0] = states[i].attitude.x;
+      o.attitude_xyzw[1] = states[i].attitude.y;
+      o.attitude_xyzw[2] = states[i].attitude.z;
+      o.attitude_xyzw[3] = states[i].attitude.w;
     }
     const auto T = T_il_.matrix();
     run(*lidarMeas->cloud, lidarMeas->pointTime.data(), T.data(), st.data(), st.size());
@@ -57,6 +72,26 @@ private:
     PointCloud & cloud, const double * pointTime, const double * T_il, const eskf_state * states,
     std::size_t nStates) const
   {
+    if (deviceResident_) {
+      // raw scan: already in HBM (uploaded on arrival) or uploaded now
+      std::shared_ptr<eskf_cloud> raw = cloud.device_;
+      if (!raw) {
+        raw = rawPool_.acquire(cloud.points_.size());
+        gpuCheck(
+          eskf_cloud_upload(
+            raw.get(), reinterpret_cast<const double *>(cloud.points_.data()), nullptr,
+            cloud.points_.size()), "eskf_cloud_upload");
+      }
+      std::shared_ptr<eskf_cloud> out = outPool_.acquire(1u << 16);
+      gpuCheck(
+        eskf_preprocess_cloud(
+          GpuContext::get(), raw.get(), pointTime, T_il, states, nStates, voxelSize_, out.get()),
+        "eskf_preprocess_cloud");
+      cloud.device_ = std::move(out);
+      cloud.points_.clear();
+      cloud.covariances_.clear();
+      return;
+    }
     const std::size_t n = cloud.points_.size();
     std::vector<Vector3d> pointsDown(n);
     std::vector<Matrix3d> covs(n);
@@ -73,7 +108,9 @@ private:
   }
 
   double voxelSize_;
+  bool deviceResident_;
   Isometry3d T_il_;
+  mutable DeviceCloudPool rawPool_, outPool_;
 };
 }  // namespace ESKF_LIO
 

@@ -55,24 +55,36 @@ public:
   // LocalMap::updateLocalMap (src/LocalMap.cpp:10-76)
   void updateLocalMap(PointCloudPtr cloud, const Isometry3d & transform, bool initialize = false)
   {
+    const auto T = transform.matrix();
+    lastInserted_ = false;
     if (initialize == false && needsMapUpdate(transform) == false) {
-      cloud->Transform(transform);  // :15 — the caller's cloud always ends up in the world frame
+      // :15 — the caller's cloud always ends up in the world frame
+      if (cloud->device_) {
+        gpuCheck(eskf_cloud_transform(cloud->device_.get(), T.data()), "eskf_cloud_transform");
+      } else {
+        cloud->Transform(transform);
+      }
       prevTransform_ = transform;   // :40
       return;
     }
-    const auto T = transform.matrix();
-    gpuCheck(
-      eskf_map_insert(
-        map_, reinterpret_cast<const double *>(cloud->points_.data()),
-        reinterpret_cast<const double *>(cloud->covariances_.data()), cloud->points_.size(),
-        T.data()), "eskf_map_insert");
-    cloud->Transform(transform);
+    lastInserted_ = true;
+    if (cloud->device_) {  // frame already in HBM: transformed in place on the device
+      gpuCheck(eskf_map_insert_cloud(map_, cloud->device_.get(), T.data()), "eskf_map_insert_cloud");
+    } else {
+      gpuCheck(
+        eskf_map_insert(
+          map_, reinterpret_cast<const double *>(cloud->points_.data()),
+          reinterpret_cast<const double *>(cloud->covariances_.data()), cloud->points_.size(),
+          T.data()), "eskf_map_insert");
+      cloud->Transform(transform);
+    }
     const double now = clock_();
     if (removeDistantPoints_ && now - currentRemoveTime_ > removePeriod_) {  // :60
       uint64_t removed = 0;
       gpuCheck(eskf_map_evict(map_, transform.t.v, distanceThreshold_, &removed), "eskf_map_evict");
       currentRemoveTime_ = now;
-      std::cout << "removed " << removed << " voxels\n";  // :71
+      lastRemoved_ = removed;
+      if (verbose_) {std::cout << "removed " << removed << " voxels\n";}  // :71
     }
     prevTransform_ = transform;  // :74
   }
@@ -114,6 +126,9 @@ public:
   // the eviction period is tested against omp_get_wtime() in the reference
   // (:60,70); inject a clock to make runs reproducible
   void setClock(std::function<double()> clock) {clock_ = std::move(clock);}
+  void setVerbose(bool v) {verbose_ = v;}
+  bool lastInserted() const {return lastInserted_;}
+  uint64_t lastRemoved() const {return lastRemoved_;}
 
 private:
   void create()
@@ -148,6 +163,9 @@ private:
   double currentRemoveTime_ = std::numeric_limits<double>::lowest();  // LocalMap.hpp:40
   Isometry3d prevTransform_;  // uninitialised in the reference; identity here
   std::function<double()> clock_;
+  bool verbose_ = true;
+  bool lastInserted_ = false;
+  uint64_t lastRemoved_ = 0;
   eskf_map * map_ = nullptr;
 };
 }  // namespace ESKF_LIO

@@ -30,11 +30,18 @@ public:
     eskf_align_info info = {};
     double T[16];
     const auto G = guess.matrix();
-    gpuCheck(
-      eskf_align(
+    if (cloud.device_) {  // frame already in HBM (Config::device_resident)
+      gpuCheck(
+        eskf_align_cloud(
+          GpuContext::get(), localMap.handle(), cloud.device_.get(), G.data(), &prm, T, &info),
+        "eskf_align_cloud");
+    } else {
+      gpuCheck(
+        eskf_align(
         GpuContext::get(), localMap.handle(), reinterpret_cast<const double *>(cloud.points_.data()),
         reinterpret_cast<const double *>(cloud.covariances_.data()), cloud.points_.size(), G.data(),
-        &prm, T, &info), "eskf_align");
+          &prm, T, &info), "eskf_align");
+    }
     lastIterations_ = info.iterations;
     if (info.converged) {converged_ = true;}
     if (!converged_) {std::cout << "ICP not converged!\n";}

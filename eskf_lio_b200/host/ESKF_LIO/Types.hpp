@@ -16,6 +16,8 @@
 #include <memory>
 #include <vector>
 
+struct eskf_cloud;  // include/eskf_gpu.h: device-resident cloud handle
+
 namespace ESKF_LIO
 {
 struct Vector3d
@@ -120,6 +122,11 @@ struct PointCloud
 {
   std::vector<Vector3d> points_;
   std::vector<Matrix3d> covariances_;
+  // Not in the reference: HBM mirror of this cloud.  With Config::device_resident
+  // the three classes hand the frame to each other through this handle and the
+  // host vectors stay empty (no PCIe round trip between process / align /
+  // updateLocalMap); otherwise it is unused and the host vectors are the cloud.
+  std::shared_ptr<eskf_cloud> device_;
   bool HasCovariances() const {return !points_.empty() && covariances_.size() == points_.size();}
   // Open3D PointCloud::Transform: p <- T p ; C <- R C R^T  (host-side, same
   // evaluation order as the device kernels: ((a0 b0 + a1 b1) + a2 b2) + t)
@@ -168,8 +175,8 @@ struct LidarMeasurement
 };
 using LidarMeasurementPtr = std::shared_ptr<LidarMeasurement>;
 
-// the nominal state; the 18x18 covariance P of the reference is host-ESKF
-// business and is not needed by the hot path
+// ESKF_LIO::State (Types.hpp:29-40): nominal state + the 18x18 error-state
+// covariance P (row-major here), initialised to 1e-3 * Identity
 struct State
 {
   double timestamp = 0.0;
@@ -179,6 +186,14 @@ struct State
   Vector3d biasAccel;
   Vector3d biasGyro;
   Vector3d gravity;
+  std::array<double, 18 * 18> P = identityP();
+
+  static std::array<double, 18 * 18> identityP()
+  {
+    std::array<double, 18 * 18> p{};
+    for (int i = 0; i < 18; ++i) {p[19 * i] = 1e-3;}
+    return p;
+  }
 };
 
 // plain-struct stand-in for the YAML::Node the reference's constructors take
@@ -204,6 +219,20 @@ struct Config
     double quaternion[4] = {0.7071068, -0.7071068, 0.0, 0.0};  // x,y,z,w
     double translation[3] = {-0.001, -0.00855, 0.055};
   } lidar_extrinsics;
+  struct {  // sensors.imu (hilti_config.yaml:2-17)
+    double update_rate = 400.0;
+    double bias_a[3] = {0.06080652138668933, 0.08353074835853214, 0.057072968234636895};
+    double bias_g[3] = {-0.0015351229643790084, -0.0013449146576507546, 0.00030127855524786183};
+    double gravity[3] = {0.01165152782783894, -0.008749296634685332, 9.804989173462031};
+    double accel_noise_density[3] = {105.0, 105.0, 135.0};
+    double accel_zero_g_offset = 20.0;
+    double gyro_noise_density = 0.014;
+    double gyro_zero_rate_offset = 1.0;
+  } imu;
+  struct {double translation_noise = 1.0e-6; double rotation_noise = 1.0e-6;} kalman_filter;
+  // Not in the reference: keep each frame in HBM between process / align /
+  // updateLocalMap (PointCloud::device_) instead of round-tripping host vectors.
+  bool device_resident = false;
 };
 
 }  // namespace ESKF_LIO

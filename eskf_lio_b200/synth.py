@@ -204,11 +204,12 @@ def beam_dirs():
     return d.reshape(-1, 3)
 
 
-def make_scan(scene, T_wb, rng, T_il=None, t0=0.0, pose_fn=None):
+def make_scan(scene, T_wb, rng, T_il=None, t0=0.0, pose_fn=None, chunk=50):
     """One 64,000-ray sweep.
 
     T_wb: IMU-body pose in the world used for every ray, unless ``pose_fn(t)``
-    is given (motion-distorted sweep: each column is cast from pose_fn(t_col)).
+    is given (motion-distorted sweep: every block of `chunk` columns is cast
+    from pose_fn at the block's mid time).
     Returns (xyz_lidar float64[N,3] (float32-rounded), point_time float64[N]).
     """
     T_il = default_T_il() if T_il is None else T_il
@@ -220,7 +221,6 @@ def make_scan(scene, T_wb, rng, T_il=None, t0=0.0, pose_fn=None):
         t_hit, _ = scene.raycast(T_wl[:3, 3], dirs_l @ T_wl[:3, :3].T)
     else:
         t_hit = np.empty(dirs_l.shape[0])
-        chunk = 50  # columns per pose sample
         for c0 in range(0, N_COLS, chunk):
             sl = slice(c0 * N_BEAMS, (c0 + chunk) * N_BEAMS)
             T_wl = pose_fn(t0 + SWEEP_S * (c0 + 0.5 * chunk) / N_COLS) @ T_il
@@ -257,3 +257,110 @@ def dense_cloud(scene, n, rng, sigma=RANGE_SIGMA):
     p = p + nn * rng.normal(0.0, sigma, size=(n, 1))
     cov = np.eye(3)[None, :, :] - 0.99 * nn[:, :, None] * nn[:, None, :]
     return np.ascontiguousarray(p), np.ascontiguousarray(cov)
+
+
+# ---------------------------------------------------------------- sequences
+# BASELINE.json configs[1]: 10 Hz LiDAR + 400 Hz IMU
+# from an analytic C^inf trajectory.  World frame = IMU body frame at t = 0
+# (the reference inserts its first scan at Identity, src/Odometry.cpp:61, and
+# starts the filter at rest, include/ESKF_LIO/Types.hpp:34-36), so the
+# trajectory starts at the identity pose with zero velocity and acceleration.
+IMU_RATE = 400.0
+GRAVITY_STATE = np.array([0.01165152782783894, -0.008749296634685332, 9.804989173462031])
+BIAS_A = np.array([0.06080652138668933, 0.08353074835853214, 0.057072968234636895])
+BIAS_G = np.array([-0.0015351229643790084, -0.0013449146576507546, 0.00030127855524786183])
+
+
+@dataclass
+class Trajectory:
+    """p(t), R(t) = Rz(yaw) Ry(pitch) Rx(roll), every component A sin(k u(t))
+    (x: v u) with the smooth start u(t) = t - tau tanh(t / tau)."""
+    v: float = 1.2            # cruise speed along +x [m/s] (0.12 m per frame > the 0.1 m map-update gate)
+    tau: float = 1.0
+    amp: tuple = (0.0, 1.5, 0.10, 0.25, 0.03, 0.02)     # x(unused) y z yaw pitch roll
+    freq: tuple = (0.0, 0.20, 0.50, 0.30, 0.70, 0.90)   # rad per metre-of-u
+    T_scene_world: np.ndarray = field(default_factory=lambda: np.eye(4))
+
+    def _u(self, t):
+        th = np.tanh(t / self.tau)
+        return t - self.tau * th, th * th, 2.0 * th * (1.0 - th * th) / self.tau
+
+    def _comp(self, i, t):
+        u, du, ddu = self._u(t)
+        if i == 0:
+            return self.v * u, self.v * du, self.v * ddu
+        A, k = self.amp[i], self.freq[i]
+        s, c = np.sin(k * u), np.cos(k * u)
+        return A * s, A * k * c * du, -A * k * k * s * du * du + A * k * c * ddu
+
+    def rotation(self, t):
+        psi, th, ph = self._comp(3, t)[0], self._comp(4, t)[0], self._comp(5, t)[0]
+        cz, sz, cy, sy, cx, sx = np.cos(psi), np.sin(psi), np.cos(th), np.sin(th), np.cos(ph), np.sin(ph)
+        Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1.0]])
+        Ry = np.array([[cy, 0, sy], [0, 1.0, 0], [-sy, 0, cy]])
+        Rx = np.array([[1.0, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        return Rz @ Ry @ Rx
+
+    def pose_world(self, t):
+        T = np.eye(4)
+        T[:3, :3] = self.rotation(t)
+        T[:3, 3] = [self._comp(i, t)[0] for i in range(3)]
+        return T
+
+    def pose_scene(self, t):
+        return self.T_scene_world @ self.pose_world(t)
+
+    def velocity(self, t):
+        return np.array([self._comp(i, t)[1] for i in range(3)])
+
+    def imu(self, t, rng=None, gyro_sigma=0.0, accel_sigma=0.0):
+        """(gyro, accel) the reference's model would read at time t:
+        a_world = R (acc - b_a) + gravity, attitude <- attitude * Exp((w - b_g) dt)
+        (src/ErrorStateKF.cpp:86-96)."""
+        a_w = np.array([self._comp(i, t)[2] for i in range(3)])
+        (psi, dpsi, _), (th, dth, _), (ph, dph, _) = self._comp(3, t), self._comp(4, t), self._comp(5, t)
+        w_b = np.array([dph - dpsi * np.sin(th),
+                        dth * np.cos(ph) + dpsi * np.sin(ph) * np.cos(th),
+                        -dth * np.sin(ph) + dpsi * np.cos(ph) * np.cos(th)])
+        f_b = self.rotation(t).T @ (a_w - GRAVITY_STATE)
+        gyro, acc = w_b + BIAS_G, f_b + BIAS_A
+        if rng is not None:
+            gyro = gyro + rng.normal(0.0, gyro_sigma, 3)
+            acc = acc + rng.normal(0.0, accel_sigma, 3)
+        return gyro, acc
+
+
+def corridor_trajectory():
+    """Config 2: start 50 m from the corridor's -x end wall, 1.5 m above the floor."""
+    return Trajectory(T_scene_world=pose([-150.0, 0.0, 1.5]))
+
+
+def hall_trajectory():
+    """Short sequences (tests, default bench): the config-1 hall."""
+    return Trajectory(amp=(0.0, 1.0, 0.10, 0.25, 0.03, 0.02), T_scene_world=pose([-20.0, -2.0, 1.5]))
+
+
+def make_sequence(scene, traj, n_frames, seed, imu_noise=True, chunk=50):
+    """n_frames motion-distorted sweeps + the IMU stream covering them.
+
+    Returns (scans, imu) with scans[i] = (xyz_lidar[N,3], point_time[N]) for the
+    sweep starting at 0.1 i s, and imu = float64[M, 7] rows (t, gyro xyz, accel xyz)
+    at 400 Hz from t = 0 to 0.1 n_frames + 0.05 s.
+    """
+    rng = np.random.default_rng(seed)
+    T_il = default_T_il()
+    scans = []
+    for i in range(n_frames):
+        scans.append(make_scan(scene, None, rng, T_il, t0=SWEEP_S * i, pose_fn=traj.pose_scene, chunk=chunk))
+    n_imu = int(round((SWEEP_S * n_frames + 0.05) * IMU_RATE)) + 1
+    imu = np.empty((n_imu, 7))
+    # noise densities of config/hilti_config.yaml:13-16 at 400 Hz
+    gs = 0.014 * np.sqrt(IMU_RATE) * np.pi / 180.0 if imu_noise else 0.0
+    as_ = 120e-6 * 9.81 * np.sqrt(IMU_RATE) if imu_noise else 0.0
+    for k in range(n_imu):
+        t = k / IMU_RATE
+        g, a = traj.imu(t, rng if imu_noise else None, gs, as_)
+        imu[k, 0] = t
+        imu[k, 1:4] = g
+        imu[k, 4:7] = a
+    return scans, imu

@@ -19,7 +19,7 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 def build(force: bool = False) -> str:
     """Compile liboracle.so with the committed Makefile (g++ only)."""
-    src = [os.path.join(_HERE, f) for f in ("eskf_oracle.cpp", "eskf_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("eskf_oracle.cpp", "odom_oracle.cpp", "eskf_oracle.h", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
     if force or stale:
@@ -339,3 +339,133 @@ def preprocess(xyz, point_time, T_il, states, voxel_size):
     if m < 0:
         raise RuntimeError("preprocess: deskew failed")
     return oxyz[:m].copy(), ocov[:m].reshape(m, 3, 3).copy(), osrc[:m].copy()
+
+
+# ------------------------------------------- ErrorStateKF + Odometry::run
+class OdomConfig(C.Structure):
+    """orc_odom_config: the keys of config/hilti_config.yaml the path reads."""
+    _fields_ = [("imu_update_rate", C.c_double), ("bias_a", C.c_double * 3),
+                ("bias_g", C.c_double * 3), ("gravity", C.c_double * 3),
+                ("accel_noise_density", C.c_double * 3), ("accel_zero_g_offset", C.c_double),
+                ("gyro_noise_density", C.c_double), ("gyro_zero_rate_offset", C.c_double),
+                ("translation_noise", C.c_double), ("rotation_noise", C.c_double),
+                ("lidar_quaternion_xyzw", C.c_double * 4), ("lidar_translation", C.c_double * 3),
+                ("map_voxel_size", C.c_double), ("max_points_per_voxel", C.c_uint64),
+                ("update_translation_sq_threshold", C.c_double),
+                ("update_cosine_threshold", C.c_double), ("remove_enabled", C.c_int32),
+                ("remove_distance_threshold", C.c_double), ("remove_period", C.c_double),
+                ("preprocess_voxel_size", C.c_double), ("max_iteration", C.c_int32),
+                ("neighbor_mode", C.c_int32), ("icp_translation_sq_threshold", C.c_double),
+                ("icp_cosine_threshold", C.c_double)]
+
+
+class OdomInfo(C.Structure):
+    _fields_ = [("frames", C.c_uint64), ("n_states", C.c_uint64), ("map_voxels", C.c_uint64),
+                ("last_kept", C.c_uint64), ("last_removed", C.c_uint64),
+                ("last_iterations", C.c_int32), ("last_inserted", C.c_int32),
+                ("stage_avg_ms", C.c_double * 3), ("stage_max_ms", C.c_double * 3)]
+
+
+def odom_default_config(**overrides) -> OdomConfig:
+    cfg = OdomConfig()
+    lib().orc_odom_default_config(C.byref(cfg))
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+class Odometry:
+    """ErrorStateKF (src/ErrorStateKF.cpp) driven in the call order of
+    Odometry::run (src/Odometry.cpp:16-98), on the CPU oracle's hot path."""
+
+    def __init__(self, cfg: OdomConfig | None = None):
+        L = lib()
+        L.orc_odom_create.restype = C.c_void_p
+        L.orc_odom_map.restype = C.c_void_p
+        self.cfg = cfg or odom_default_config()
+        self._h = C.c_void_p(L.orc_odom_create(C.byref(self.cfg)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_odom_destroy(self._h)
+            self._h = None
+
+    def feed_imu(self, t, gyro, acc):
+        lib().orc_odom_feed_imu(self._h, C.c_double(t), _d(_f64(gyro)), _d(_f64(acc)))
+
+    def feed_lidar(self, xyz, point_time):
+        xyz = _f64(xyz, (-1, 3))
+        t = _f64(point_time)
+        lib().orc_odom_feed_lidar(self._h, _d(xyz), _d(t), C.c_size_t(xyz.shape[0]),
+                                  C.c_double(t[0]), C.c_double(t[-1]))
+
+    def spin_once(self) -> int:
+        rc = lib().orc_odom_spin_once(self._h)
+        if rc < 0:
+            raise RuntimeError("odometry: deskew failed")
+        return rc
+
+    def kf_process(self, t, gyro, acc):
+        lib().orc_kf_process(self._h, C.c_double(t), _d(_f64(gyro)), _d(_f64(acc)))
+
+    def kf_update_with_observation(self, lidar_end, obs):
+        guess = np.zeros(16)
+        T = np.zeros(16)
+        lib().orc_kf_update_with_observation(self._h, C.c_double(lidar_end), _d(_f64(obs)),
+                                             _d(guess), _d(T))
+        return guess.reshape(4, 4), T.reshape(4, 4)
+
+    def pose(self):
+        T = np.zeros(16)
+        lib().orc_odom_last_pose(self._h, _d(T))
+        return T.reshape(4, 4)
+
+    def info(self) -> OdomInfo:
+        out = OdomInfo()
+        lib().orc_odom_info(self._h, C.byref(out))
+        return out
+
+    def last_state(self, with_P=False):
+        s = np.zeros(20)
+        P = np.zeros(324) if with_P else None
+        lib().orc_odom_last_state(self._h, _d(s), _d(P) if with_P else None)
+        d = {"t": s[0], "p": s[1:4].copy(), "v": s[4:7].copy(), "q": s[7:11].copy(),
+             "ba": s[11:14].copy(), "bg": s[14:17].copy(), "g": s[17:20].copy()}
+        if with_P:
+            d["P"] = P.reshape(18, 18)
+        return d
+
+
+def rotation_matrix_to_vector(R):
+    out = np.zeros(3)
+    lib().orc_rotation_matrix_to_vector(_d(_f64(R)), _d(out))
+    return out
+
+
+def run_sequence(odom, scans, imu, on_frame=None):
+    """Feed a synthetic sequence the way the two ROS callbacks would: IMU samples
+    in time order, each sweep when its last point has been measured; one
+    spin_once per sample.  Returns the list of per-frame poses (frame 0 = init)."""
+    poses = []
+    k = 0
+    n_imu = imu.shape[0]
+    for xyz, t in scans:
+        end = t[-1]
+        while k < n_imu and imu[k, 0] <= end:
+            odom.feed_imu(imu[k, 0], imu[k, 1:4], imu[k, 4:7])
+            k += 1
+            odom.spin_once()
+        odom.feed_lidar(xyz, t)
+        done = odom.spin_once()
+        while not done and k < n_imu:
+            odom.feed_imu(imu[k, 0], imu[k, 1:4], imu[k, 4:7])
+            k += 1
+            done = odom.spin_once()
+        if not done:
+            raise RuntimeError("IMU stream ended before the sweep could be processed")
+        poses.append(odom.pose())
+        if on_frame:
+            on_frame(len(poses) - 1, odom)
+    return poses

@@ -161,6 +161,50 @@ long orc_preprocess(double* xyz, const double* point_time, size_t n, const doubl
                     const orc_state* states, size_t n_states, double voxel_size,
                     double* out_xyz, double* out_cov, uint32_t* out_src_index);
 
+/* ---- callers either side of the hot path (oracle/odom_oracle.cpp) -------
+ * ErrorStateKF (src/ErrorStateKF.cpp) + the call order of Odometry::run
+ * (src/Odometry.cpp:16-98), ROS-free.  Keys/defaults of config/hilti_config.yaml. */
+typedef struct orc_odom orc_odom;
+typedef struct {
+  double imu_update_rate;          /* sensors.imu.update_rate            */
+  double bias_a[3], bias_g[3], gravity[3];
+  double accel_noise_density[3];
+  double accel_zero_g_offset, gyro_noise_density, gyro_zero_rate_offset;
+  double translation_noise, rotation_noise;      /* kalman_filter.update */
+  double lidar_quaternion_xyzw[4], lidar_translation[3]; /* sensors.lidar.extrinsics */
+  double map_voxel_size;           /* local_map.*                        */
+  uint64_t max_points_per_voxel;
+  double update_translation_sq_threshold, update_cosine_threshold;
+  int32_t remove_enabled;
+  double remove_distance_threshold, remove_period;
+  double preprocess_voxel_size;    /* cloud_preprocessor.voxel_size      */
+  int32_t max_iteration, neighbor_mode;          /* registration.*       */
+  double icp_translation_sq_threshold, icp_cosine_threshold;
+} orc_odom_config;
+typedef struct {
+  uint64_t frames, n_states, map_voxels, last_kept, last_removed;
+  int32_t last_iterations, last_inserted;
+  double stage_avg_ms[3], stage_max_ms[3]; /* preprocess, filter update, map update (Odometry.cpp:99-109) */
+} orc_odom_info_t;
+void orc_odom_default_config(orc_odom_config* c);
+orc_odom* orc_odom_create(const orc_odom_config* cfg);
+void orc_odom_destroy(orc_odom* o);
+void orc_odom_feed_imu(orc_odom* o, double t, const double gyro[3], const double acc[3]);
+void orc_odom_feed_lidar(orc_odom* o, const double* xyz, const double* point_time, size_t n,
+                         double start_time, double end_time);
+/* one trip of the loop of Odometry::run: 1 = a LiDAR frame was consumed */
+int orc_odom_spin_once(orc_odom* o);
+void orc_odom_last_pose(const orc_odom* o, double T16[16]);
+void orc_odom_info(const orc_odom* o, orc_odom_info_t* out);
+/* newest state: t, p, v, q(xyzw), ba, bg, g = 20 doubles; P324 nullable */
+void orc_odom_last_state(const orc_odom* o, double out20[20], double* P324);
+const orc_map* orc_odom_map(const orc_odom* o);
+void orc_kf_process(orc_odom* o, double t, const double gyro[3], const double acc[3]); /* ErrorStateKF.cpp:76-113 */
+void orc_rotation_matrix_to_vector(const double R9[9], double r3[3]);                  /* Utils.cpp:22-26 */
+/* ErrorStateKF::update (ErrorStateKF.cpp:115-162) with the ICP pose given by the caller */
+void orc_kf_update_with_observation(orc_odom* o, double lidar_end, const double obs16[16],
+                                    double guess16_out[16], double T_out16[16]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,3 +45,20 @@ def test_fails_loudly_without_gpu(built):
         capi.Context(0)
     assert e.value.status == 3  # ESKF_ERR_NO_DEVICE
     assert "no CPU fallback" in str(e.value)
+
+
+def test_host_driver_symbols_all_exported(built):
+    """libeskf_host.so (include/eskf_host.h): Odometry + ErrorStateKF host classes."""
+    from eskf_lio_b200 import odometry
+    hdr = open(os.path.join(ROOT, "include", "eskf_host.h")).read()
+    declared = sorted(set(re.findall(r"^(?:int|void|const char\*) (eskf_[a-z0-9_]+)\(", hdr, flags=re.M)))
+    assert sorted(odometry.SYMBOLS) == declared
+    L = odometry.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    cfg = odometry.default_config()
+    assert cfg.map_voxel_size == 0.3 and cfg.max_iteration == 100 and cfg.imu_update_rate == 400.0
+    if capi.device_count() == 0:
+        with pytest.raises(RuntimeError) as e:
+            odometry.Odometry(cfg)
+        assert "no CPU fallback" in str(e.value)

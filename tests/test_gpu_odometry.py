@@ -1,0 +1,70 @@
+"""BASELINE.json configs[1]: the ROS-free Odometry + host ErrorStateKF (product,
+eskf_lio_b200/host/ESKF_LIO/{Odometry,ErrorStateKF}.hpp, hot path on the B200)
+against the CPU oracle's restatement of src/Odometry.cpp + src/ErrorStateKF.cpp
+on the same synthetic 10 Hz LiDAR + 400 Hz IMU log."""
+import numpy as np
+import pytest
+
+from eskf_lio_b200 import synth as S
+from gpu_common import pose_err
+
+pytestmark = pytest.mark.gpu
+
+N_FRAMES = 30
+
+
+@pytest.fixture(scope="module")
+def log():
+    tr = S.hall_trajectory()
+    scans, imu = S.make_sequence(S.hall_scene(), tr, N_FRAMES, seed=17)
+    return tr, scans, imu
+
+
+@pytest.fixture(scope="module")
+def oracle_run(oracle, log):
+    _, scans, imu = log
+    od = oracle.Odometry(oracle.odom_default_config(map_voxel_size=0.5, preprocess_voxel_size=0.5))
+    rec = []
+    poses = oracle.run_sequence(od, scans, imu, lambda i, o: rec.append(
+        (o.info().last_iterations, o.info().last_inserted, o.info().map_voxels, o.info().n_states)))
+    return poses, rec, od.last_state(with_P=True)
+
+
+@pytest.mark.parametrize("device_resident", [1, 0])
+def test_sequence_matches_oracle(log, oracle_run, device_resident):
+    from eskf_lio_b200 import odometry
+    _, scans, imu = log
+    o_poses, o_rec, o_state = oracle_run
+    cfg = odometry.default_config(map_voxel_size=0.5, preprocess_voxel_size=0.5,
+                                  device_resident=device_resident)
+    od = odometry.Odometry(cfg)
+    rec = []
+    poses = odometry.run_sequence(od, scans, imu, lambda i, o: rec.append(
+        (o.info().last_iterations, o.info().last_inserted, o.info().map_voxels, o.info().n_states)))
+    assert len(poses) == N_FRAMES
+    dts, drs = zip(*[pose_err(a, b) for a, b in zip(o_poses, poses)])
+    # north_star: final poses within 1e-5 m / 1e-5 rad of the reference path, every frame
+    assert max(dts) < 1e-5 and max(drs) < 1e-5, (max(dts), max(drs))
+    assert [r[0] for r in rec] == [r[0] for r in o_rec]          # Gauss-Newton iteration counts
+    assert [r[1] for r in rec] == [r[1] for r in o_rec]          # keyframe gate decisions
+    assert [r[3] for r in rec] == [r[3] for r in o_rec]          # filter state history length
+    # occupancy: identical while the poses agree to ~1e-9 m, bar a voxel-face flip
+    assert all(abs(int(a[2]) - int(b[2])) <= 3 for a, b in zip(rec, o_rec))
+    st = od.last_state(with_P=True)
+    assert np.linalg.norm(st["p"] - o_state["p"]) < 1e-5 and np.linalg.norm(st["v"] - o_state["v"]) < 1e-3
+    assert np.linalg.norm(st["P"] - o_state["P"]) / np.linalg.norm(o_state["P"]) < 1e-6
+    info = od.info()
+    assert info.frames == N_FRAMES - 1 and od.launch_count() > 0
+    od.close()
+
+
+def test_sequence_tracks_ground_truth(log):
+    from eskf_lio_b200 import odometry
+    tr, scans, imu = log
+    od = odometry.Odometry(odometry.default_config(map_voxel_size=0.5, preprocess_voxel_size=0.5))
+    poses = odometry.run_sequence(od, scans, imu)
+    G0 = tr.pose_world(scans[0][1][-1])
+    for i in range(1, N_FRAMES):
+        dt, dr = pose_err(np.linalg.inv(G0) @ tr.pose_world(scans[i][1][-1]), poses[i])
+        assert dt < 0.05 and dr < 0.01, (i, dt, dr)
+    od.close()

@@ -14,22 +14,61 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "cpp", "test_host_classes.cpp")
 
 
-def _compile(out, syntax_only=False):
+def _compile(out, syntax_only=False, src=SRC):
     cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Wextra",
            f"-I{ROOT}/include", f"-I{ROOT}/eskf_lio_b200/host"]
     if syntax_only:
-        cmd += ["-fsyntax-only", SRC]
+        cmd += ["-fsyntax-only", src]
     else:
-        cmd += ["-o", out, SRC, f"-L{_build.LIB_DIR}", "-leskf_gpu", f"-Wl,-rpath,{_build.LIB_DIR}"]
+        cmd += ["-o", out, src, f"-L{_build.LIB_DIR}", "-leskf_gpu", f"-Wl,-rpath,{_build.LIB_DIR}"]
     subprocess.check_call(cmd)
 
 
 def test_host_classes_compile():
     """CPU: the headers are self-contained C++17 over include/eskf_gpu.h only."""
     _compile(None, syntax_only=True)
-    for h in ("Types.hpp", "LocalMap.hpp", "Registration.hpp", "CloudPreprocessor.hpp"):
+    _compile(None, syntax_only=True, src=os.path.join(ROOT, "eskf_lio_b200", "host", "odometry_capi.cpp"))
+    for h in ("Types.hpp", "LocalMap.hpp", "Registration.hpp", "CloudPreprocessor.hpp",
+              "ErrorStateKF.hpp", "Odometry.hpp", "SynchronizedQueue.hpp", "GpuContext.hpp"):
         src = open(os.path.join(ROOT, "eskf_lio_b200", "host", "ESKF_LIO", h)).read()
         assert "Eigen/" not in src and "open3d" not in src.replace("open3d::", "") and "oracle" not in src
+
+
+def test_host_eskf_process_matches_oracle(tmp_path, oracle):
+    """CPU: the product's host ErrorStateKF::process (src/ErrorStateKF.cpp:76-113) against the
+    oracle's restatement on the same IMU stream (no GPU call is involved in propagation)."""
+    _build.build()
+    exe = str(tmp_path / "test_eskf_host")
+    _compile(exe, src=os.path.join(ROOT, "tests", "cpp", "test_eskf_host.cpp"))
+    tr = S.hall_trajectory()
+    rng = np.random.default_rng(9)
+    rows = []
+    for k in range(1, 301):
+        g, a = tr.imu(k / 400.0, rng, 0.005, 0.02)
+        rows.append([k / 400.0, *g, *a])
+    rows.insert(100, [0.1, 0, 0, 0, 0, 0, 0])   # a stale sample: dt < 0 -> ignored (:80-82)
+    rows = np.array(rows)
+    path = str(tmp_path / "imu.bin")
+    with open(path, "wb") as f:
+        f.write(struct.pack("<Q", len(rows)))
+        f.write(rows.tobytes())
+    out = subprocess.check_output([exe, path], text=True).strip().splitlines()
+    od = oracle.Odometry()
+    for r in rows:
+        od.kf_process(r[0], r[1:4], r[4:7])
+    st = od.last_state(with_P=True)
+    assert int(out[0].split()[1]) == od.info().n_states == 301
+    got = np.array([float(v) for v in out[1].split()[1:]])
+    want = np.concatenate([[st["t"]], st["p"], st["v"], st["q"]])
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
+    P = np.array([float(v) for v in out[2].split()[1:]]).reshape(18, 18)
+    assert np.linalg.norm(P - st["P"]) / np.linalg.norm(st["P"]) < 1e-12
+    from scipy.spatial.transform import Rotation
+    ax = np.array([0.2, -0.5, 0.84])
+    ax /= np.linalg.norm(ax)
+    for line, ang in zip(out[3:5], (0.3, 2.9)):
+        rv = np.array([float(v) for v in line.split()[1:]])
+        np.testing.assert_allclose(rv, Rotation.from_rotvec(ang * ax).as_rotvec(), atol=1e-12)
 
 
 @pytest.mark.gpu
