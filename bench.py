@@ -377,8 +377,9 @@ DENSE_TRAFFIC_SOURCE = "profiles/r1_prof_align_ncu.md (ncu --set full, one launc
 
 def pose_delta(A, B):
     E = np.linalg.inv(A) @ B
-    return (float(np.linalg.norm(E[:3, 3])),
-            float(np.arccos(np.clip(0.5 * (np.trace(E[:3, :3]) - 1.0), -1.0, 1.0))))
+    R = E[:3, :3]
+    sin = 0.5 * np.linalg.norm([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    return float(np.linalg.norm(E[:3, 3])), float(np.arctan2(sin, 0.5 * (np.trace(R) - 1.0)))
 
 
 def main():

@@ -255,7 +255,7 @@ int eskf_ctx_destroy(eskf_ctx* ctx) {
   }
   eskf::DevBuf* bufs[] = {&ctx->stage, &ctx->sortbuf, &ctx->hist, &ctx->hdr, &ctx->runs,
                           &ctx->sorted_xyz, &ctx->segs, &ctx->work, &ctx->partials, &ctx->astate,
-                          &ctx->misc};
+                          &ctx->misc, &ctx->knn_levels, &ctx->knn_nbr};
   for (auto* b : bufs) b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -143,6 +143,53 @@ __host__ __device__ __forceinline__ uint64_t morton3(uint32_t x, uint32_t y, uin
   return (spread3(x) << 2) | (spread3(y) << 1) | spread3(z);
 }
 
+// ----------------------------------------------- k-NN block-range tables
+// After the Morton sort an aligned block of 2^L voxels per axis is ONE
+// contiguous range of the sorted scan.  For the levels the 30-NN search visits
+// most (L < kKnnHashLevels) the voxelize kernel records every occupied block's
+// [start, end) in a small open-addressing table, so a neighbour-block lookup
+// costs one or two 16 B loads instead of two 16-step binary searches.
+// Entry (uint4): x,y = block key (Morton >> 3L) lo/hi, z = start, w = end;
+// all-ones = empty.  Level L's table starts at L * level_stride entries and
+// uses knn_level_slots() of them (a power of two >= 2 x the blocks it can hold).
+constexpr int kKnnHashLevels = 6;
+
+__host__ __device__ __forceinline__ unsigned knn_level_slots(unsigned n, unsigned bits, int L) {
+  const unsigned b = bits > static_cast<unsigned>(L) ? bits - static_cast<unsigned>(L) : 0u;
+  unsigned long long most = n;  // occupied blocks <= min(n, 8^b)
+  if (b < 10u && (1ull << (3u * b)) < most) most = 1ull << (3u * b);
+  unsigned s = 8u;
+  while (static_cast<unsigned long long>(s) < 2ull * most) s <<= 1;
+  return s;
+}
+
+__device__ __forceinline__ uint4* knn_level_claim(uint4* tab, unsigned mask, uint64_t bk) {
+  unsigned h = static_cast<unsigned>(hash_key(bk)) & mask;
+  for (;;) {
+    unsigned long long* kp = reinterpret_cast<unsigned long long*>(tab + h);
+    const unsigned long long old = atomicCAS(kp, ~0ull, static_cast<unsigned long long>(bk));
+    if (old == ~0ull || old == bk) return tab + h;
+    h = (h + 1u) & mask;
+  }
+}
+
+__device__ __forceinline__ bool knn_level_find(const uint4* tab, unsigned mask, uint64_t bk,
+                                               unsigned& start, unsigned& end) {
+  unsigned h = static_cast<unsigned>(hash_key(bk)) & mask;
+  for (unsigned probe = 0; probe <= mask; ++probe) {
+    const uint4 e = __ldg(tab + h);
+    const uint64_t k = (static_cast<uint64_t>(e.y) << 32) | e.x;
+    if (k == bk) {
+      start = e.z;
+      end = e.w;
+      return true;
+    }
+    if (k == ~0ull) return false;
+    h = (h + 1u) & mask;
+  }
+  return false;
+}
+
 // --------------------------------------------------------- cache-global IO
 template <typename T>
 __device__ __forceinline__ T ld_cg(const T* p) {

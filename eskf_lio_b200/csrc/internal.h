@@ -116,6 +116,8 @@ struct eskf_ctx {
   eskf::DevBuf hdr;        // VoxelHeader
   eskf::DevBuf runs;       // run_start / keep_flag / kept_src / kept_pos
   eskf::DevBuf sorted_xyz; // positions gathered in sorted order (kNN)
+  eskf::DevBuf knn_levels; // block-range tables of the k-NN search (kKnnHashLevels x stride uint4)
+  eskf::DevBuf knn_nbr;    // neighbour lists handed from the search to the finish kernel
   eskf::DevBuf segs;       // deskew segments
   eskf::DevBuf work;       // align working positions (SoA)
   eskf::DevBuf partials;   // align per-block partial sums
@@ -154,6 +156,13 @@ struct eskf_map {
   double* master = nullptr;            // [n_slots][12]
   unsigned long long* d_count = nullptr;  // occupied voxels (+1 word: table-full error)
   uint64_t count_upper = 0;            // host-side upper bound of *d_count
+  // the table the last same-size rebuild (eviction sweep) moved out of: the
+  // next sweep moves back into it, so steady-state eviction never calls
+  // cudaMalloc / cudaFree
+  eskf::tag_t* spare_tags = nullptr;
+  eskf::VoxelSlot* spare_slots = nullptr;
+  double* spare_master = nullptr;
+  uint64_t spare_n = 0;
 };
 
 namespace eskf {
@@ -199,6 +208,8 @@ struct SortView {
   double* sy;
   double* sz;
   VoxelHeader* hdr;
+  uint4* levels;          // mode 1: k-NN block-range tables
+  unsigned level_stride;  // entries between consecutive level tables
 };
 SortView sort_view(eskf_ctx* ctx, unsigned n);
 

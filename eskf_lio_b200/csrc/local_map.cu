@@ -320,7 +320,21 @@ int rebuild(eskf_map* m, uint64_t new_slots, int evict, const double* pos, doubl
   tag_t* nt = nullptr;
   VoxelSlot* ns = nullptr;
   double* nm = nullptr;
-  ESKF_TRY(alloc_table(ctx, new_slots, &nt, &ns, &nm));
+  if (m->spare_n == new_slots && m->spare_tags) {
+    nt = m->spare_tags;
+    ns = m->spare_slots;
+    nm = m->spare_master;
+    m->spare_tags = nullptr;
+    m->spare_slots = nullptr;
+    m->spare_master = nullptr;
+    m->spare_n = 0;
+    const unsigned cb = static_cast<unsigned>((new_slots + 255) / 256);
+    clear_slots_kernel<<<cb, 256, 0, ctx->stream>>>(ns, nt, new_slots);
+    ESKF_CUDA(cudaGetLastError());
+    count_launch(ctx);
+  } else {
+    ESKF_TRY(alloc_table(ctx, new_slots, &nt, &ns, &nm));
+  }
   ESKF_CUDA(cudaMemsetAsync(m->d_count, 0, 4 * sizeof(unsigned long long), ctx->stream));
   RehashParams P;
   P.old_tags = m->tags;
@@ -347,9 +361,25 @@ int rebuild(eskf_map* m, uint64_t new_slots, int evict, const double* pos, doubl
   ESKF_CUDA(cudaMemcpyAsync(h, m->d_count, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                             ctx->stream));
   ESKF_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(m->tags);
-  cudaFree(m->slots);
-  cudaFree(m->master);
+  if (m->spare_tags) {  // a spare of another size is of no use any more
+    cudaFree(m->spare_tags);
+    cudaFree(m->spare_slots);
+    cudaFree(m->spare_master);
+    m->spare_tags = nullptr;
+    m->spare_slots = nullptr;
+    m->spare_master = nullptr;
+    m->spare_n = 0;
+  }
+  if (m->n_slots == new_slots) {  // same-size sweep: keep the old table for the next one
+    m->spare_tags = m->tags;
+    m->spare_slots = m->slots;
+    m->spare_master = m->master;
+    m->spare_n = m->n_slots;
+  } else {
+    cudaFree(m->tags);
+    cudaFree(m->slots);
+    cudaFree(m->master);
+  }
   m->tags = nt;
   m->slots = ns;
   m->master = nm;
@@ -376,7 +406,9 @@ int map_reserve(eskf_map* m, uint64_t incoming) {
   ESKF_CUDA(cudaStreamSynchronize(ctx->stream));
   m->count_upper = h[0];
   if ((m->count_upper + incoming) * 2 <= m->n_slots) return ESKF_OK;
-  return rebuild(m, table_size_for((m->count_upper + incoming) * 5 / 4), 0, nullptr, 0.0, nullptr);
+  // grow geometrically: a rebuild allocates and frees device memory (milliseconds of host time),
+  // so it must stay rare on a map that gains ~1k voxels per frame
+  return rebuild(m, table_size_for(2 * (m->count_upper + incoming)), 0, nullptr, 0.0, nullptr);
 }
 
 }  // namespace eskf
@@ -422,6 +454,11 @@ int eskf_map_destroy(eskf_map* m) {
   cudaFree(m->tags);
   cudaFree(m->slots);
   cudaFree(m->master);
+  if (m->spare_tags) {
+    cudaFree(m->spare_tags);
+    cudaFree(m->spare_slots);
+    cudaFree(m->spare_master);
+  }
   cudaFree(m->d_count);
   delete m;
   return ESKF_OK;

@@ -8,16 +8,29 @@
 //                         first-point-per-voxel == run heads of the stable
 //                         radix sort; 30-NN covariance = K4 below
 //
-// K4: one warp per kept point.  The points are sorted by the Morton code of
-// their voxel, so an aligned 2^L-voxel block is ONE contiguous range of the
-// sorted array.  The warp searches the 3x3x3 blocks around the query at level
-// L (27 lanes binary-search the 27 ranges at once), keeps an exact top-30 in
-// registers (one entry per lane, shuffle insertion), and stops when the 30th
-// distance is inside the searched neighbourhood; otherwise L += 1.  That is an
-// exact k-NN (same set as the reference's KD-tree, Open3D KDTreeFlann with
-// KDTreeSearchParamKNN() => k = 30) with bounded work in sparse regions.
+// K4a knn_search_kernel: one warp per kept point.  The points are sorted by the
+// Morton code of their voxel, so an aligned 2^L-voxel block is ONE contiguous
+// range of the sorted array.  The warp looks up the 3x3x3 blocks around the
+// query at level L (27 lanes, block-range tables built by the voxelize kernel;
+// binary search only above kKnnHashLevels), selects the exact 30 nearest of
+// their points and stops when the 30th distance is inside the searched
+// neighbourhood; otherwise L += 1.  That is an exact k-NN (same set as the
+// reference's KD-tree, Open3D KDTreeFlann with KDTreeSearchParamKNN() => k =
+// 30) with bounded work in sparse regions.
+// Selection without a serial insertion per candidate: pass 1 streams the
+// candidates once keeping the two smallest distances of every lane; the 32nd
+// smallest of those 64 values bounds the 30th nearest distance from above;
+// pass 2 compacts the (few) candidates under the bound into shared memory and
+// a rank-count sort on (distance, index) orders them.  The serial shuffle
+// insertion is kept as the overflow path.
+// K4b knn_finish_kernel: one THREAD per kept point: cumulants in distance
+// order (bit-exact with the oracle), Jacobi eigen-decomposition,
+// U diag(1,1,0.01) U^T, outputs.
 #include <cmath>
+#include <cstdlib>
+#include <algorithm>
 #include <limits>
+#include <type_traits>
 
 #include "internal.h"
 
@@ -49,6 +62,11 @@ struct KnnParams {
   uint32_t* osrc;
   float4* oc4;
   float2* oc2;
+  const uint4* levels;    // block-range tables (common.cuh)
+  unsigned level_stride;
+  uint32_t* nbr;          // [kKnn][nbr_pitch] neighbour source indices, ascending distance
+  uint32_t* nbr_cnt;      // [n_kept]
+  size_t nbr_pitch;
 };
 
 __device__ __forceinline__ unsigned lower_bound_u64(const uint64_t* a, unsigned lo, unsigned hi,
@@ -309,6 +327,366 @@ __global__ void __launch_bounds__(128) knn_cov_kernel(KnnParams P) {
   }
 }
 
+// ===================================================================== K4a
+constexpr int kSearchThreads = 128;
+constexpr int kSearchWarps = kSearchThreads / 32;
+constexpr int kBuf = 128;  // survivors of pass 2 per warp (typically 35..70)
+
+// the 27 neighbour ranges of a query, one per lane (lanes 27..31 hold len 0)
+struct Ranges {
+  unsigned start;
+  unsigned len;
+  double box2;  // squared distance from the query to the block's AABB
+};
+
+// Enumerates the points of the lanes' ranges [start, start + len) as ONE
+// flattened candidate list, 32 candidates a step: candidate c belongs to the
+// first range whose inclusive length prefix exceeds c.  f(valid, d2, id, j).
+template <typename F>
+__device__ __forceinline__ void for_each_candidate(const KnnParams& P, const uint32_t* sidx,
+                                                   unsigned start, unsigned len, double qx, double qy,
+                                                   double qz, unsigned lane, F&& f) {
+  unsigned off = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned u = __shfl_up_sync(0xffffffffu, off, o);
+    if (lane >= static_cast<unsigned>(o)) off += u;
+  }
+  const unsigned total = __shfl_sync(0xffffffffu, off, 31);
+  const unsigned excl = off - len;
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+  for (unsigned c0 = 0; c0 < total; c0 += 32) {
+    const unsigned c = c0 + lane;
+    unsigned pos = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      const unsigned v = __shfl_sync(0xffffffffu, off, pos + step - 1);
+      if (v <= c) pos += step;
+    }
+    const unsigned s_t = __shfl_sync(0xffffffffu, start, pos & 31u);
+    const unsigned e_t = __shfl_sync(0xffffffffu, excl, pos & 31u);
+    const bool valid = c < total;
+    double d = kInf;
+    int id = -1;
+    if (valid) {
+      const unsigned j = s_t + (c - e_t);
+      const double dx = P.sx[j] - qx, dy = P.sy[j] - qy, dz = P.sz[j] - qz;
+      d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+      id = static_cast<int>(__ldg(sidx + j));
+    }
+    f(valid, d, id);
+  }
+}
+
+// ascending bitonic sort of one non-negative double per lane (bit patterns of
+// non-negative doubles order like unsigned integers)
+__device__ __forceinline__ unsigned long long warp_sort_u64(unsigned long long v, unsigned lane) {
+#pragma unroll
+  for (unsigned k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (unsigned j = k >> 1; j > 0; j >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool up = (lane & k) == 0u || k == 32u;
+      const bool lower = (lane & j) == 0u;
+      const unsigned long long mn = v < o ? v : o, mx = v < o ? o : v;
+      v = (lower == up) ? mn : mx;
+    }
+  }
+  return v;
+}
+
+// upper bound of the K-th (K <= 32) smallest candidate distance from the two
+// smallest distances every lane has seen: the 32nd smallest of the 64 values
+__device__ __forceinline__ double bound_from_minima(double m1, double m2, unsigned lane) {
+  const unsigned long long a = warp_sort_u64(static_cast<unsigned long long>(__double_as_longlong(m1)), lane);
+  const unsigned long long b = warp_sort_u64(static_cast<unsigned long long>(__double_as_longlong(m2)), lane);
+  const unsigned long long br = __shfl_sync(0xffffffffu, b, 31u - lane);
+  unsigned long long c = a < br ? a : br;  // the 32 smallest of the union (bitonic)
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const unsigned long long x = __shfl_xor_sync(0xffffffffu, c, o);
+    c = c > x ? c : x;
+  }
+  return __longlong_as_double(static_cast<long long>(c));
+}
+
+// Overflow path (and the reference behaviour the selection above must equal):
+// exact top-K of the given ranges by shuffle insertion, one entry per lane,
+// (d2, index) lexicographic order like the oracle's heap.
+struct SerialTop {
+  double ld2;
+  int lid;
+  int cnt;
+  double kth;
+};
+
+__device__ __forceinline__ void serial_scan(const KnnParams& P, const uint32_t* sidx, unsigned start,
+                                            unsigned len, double qx, double qy, double qz,
+                                            unsigned lane, int K, SerialTop& T) {
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+  for_each_candidate(P, sidx, start, len, qx, qy, qz, lane, [&](bool valid, double d0, int id0) {
+    unsigned bal = __ballot_sync(0xffffffffu, valid && d0 <= T.kth);
+    while (bal) {
+      const int src = __ffs(bal) - 1;
+      bal &= bal - 1;
+      const double cd = __shfl_sync(0xffffffffu, d0, src);
+      const int cid = __shfl_sync(0xffffffffu, id0, src);
+      const int pos = __popc(__ballot_sync(0xffffffffu, T.ld2 < cd || (T.ld2 == cd && T.lid < cid)));
+      if (pos < K) {
+        const double up_d = __shfl_up_sync(0xffffffffu, T.ld2, 1);
+        const int up_i = __shfl_up_sync(0xffffffffu, T.lid, 1);
+        if (static_cast<int>(lane) > pos) {
+          T.ld2 = up_d;
+          T.lid = up_i;
+        } else if (static_cast<int>(lane) == pos) {
+          T.ld2 = cd;
+          T.lid = cid;
+        }
+        if (static_cast<int>(lane) >= K) {
+          T.ld2 = kInf;
+          T.lid = -1;
+        }
+        if (T.cnt < K) ++T.cnt;
+        T.kth = __shfl_sync(0xffffffffu, T.ld2, K - 1);
+      }
+    }
+  });
+}
+
+__global__ void __launch_bounds__(kSearchThreads) knn_search_kernel(KnnParams P) {
+  __shared__ double s_d[kSearchWarps][kBuf];
+  __shared__ int s_i[kSearchWarps][kBuf];
+  __shared__ unsigned s_mask[kKnnHashLevels];
+  const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  if (threadIdx.x < kKnnHashLevels)
+    s_mask[threadIdx.x] = knn_level_slots(P.n, P.hdr->bits, static_cast<int>(threadIdx.x)) - 1u;
+  __syncthreads();
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned n_kept = P.hdr->n_out;
+  const unsigned sel = P.hdr->sel;
+  const uint64_t* keys = P.key[sel];
+  const uint32_t* sidx = P.sidx[sel];
+  const int m0 = P.hdr->mn[0], m1 = P.hdr->mn[1], m2 = P.hdr->mn[2];
+  const int M0 = -P.hdr->nmx[0] - m0, M1 = -P.hdr->nmx[1] - m1, M2 = -P.hdr->nmx[2] - m2;
+  const unsigned n = P.n;
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+  const int K = kKnn < static_cast<int>(n) ? kKnn : static_cast<int>(n);
+  double* bd = s_d[wib];
+  int* bi = s_i[wib];
+
+  for (unsigned r = warp; r < n_kept; r += nwarps) {
+    const unsigned j0 = P.kept_pos[r];
+    const double qx = P.sx[j0], qy = P.sy[j0], qz = P.sz[j0];
+    const uint64_t mk = __ldg(keys + j0);
+    const int cx = static_cast<int>(compact3(mk >> 2));
+    const int cy = static_cast<int>(compact3(mk >> 1));
+    const int cz = static_cast<int>(compact3(mk));
+    int my_id = -1;  // lane l: source index of the l-th nearest neighbour
+    int cnt = 0;
+    for (int L = 0; L <= kKeyBits; ++L) {
+      const int bx = cx >> L, by = cy >> L, bz = cz >> L;
+      const double span = static_cast<double>(1 << L);
+      unsigned start = 0, end = 0;
+      double box2 = kInf;
+      if (lane < 27) {
+        const int nx = bx + static_cast<int>(lane % 3) - 1;
+        const int ny = by + static_cast<int>((lane / 3) % 3) - 1;
+        const int nz = bz + static_cast<int>(lane / 9) - 1;
+        if (nx >= 0 && ny >= 0 && nz >= 0 && nx <= (M0 >> L) && ny <= (M1 >> L) && nz <= (M2 >> L)) {
+          const uint64_t bk = morton3(nx, ny, nz);
+          if (L < kKnnHashLevels) {
+            if (!knn_level_find(P.levels + static_cast<size_t>(L) * P.level_stride, s_mask[L], bk, start, end))
+              start = end = 0;
+          } else {
+            const uint64_t lo = bk << (3 * L);
+            start = lower_bound_u64(keys, 0, n, lo);
+            end = lower_bound_u64(keys, start, n, lo + (1ull << (3 * L)));
+          }
+          const double x0 = (static_cast<double>(m0) + static_cast<double>(nx) * span) * P.voxel;
+          const double y0 = (static_cast<double>(m1) + static_cast<double>(ny) * span) * P.voxel;
+          const double z0 = (static_cast<double>(m2) + static_cast<double>(nz) * span) * P.voxel;
+          const double w = span * P.voxel;
+          const double ex = fmax(fmax(x0 - qx, qx - (x0 + w)) - 1e-9, 0.0);
+          const double ey = fmax(fmax(y0 - qy, qy - (y0 + w)) - 1e-9, 0.0);
+          const double ez = fmax(fmax(z0 - qz, qz - (z0 + w)) - 1e-9, 0.0);
+          box2 = ex * ex + ey * ey + ez * ez;
+        }
+      }
+      const unsigned len = end - start;
+      const unsigned total = warp_reduce_add(len);
+      const bool all = (M0 >> L) == 0 && (M1 >> L) == 0 && (M2 >> L) == 0;
+      // Too few candidates to finish here.  (K is the hard limit; below ~2K
+      // the K-th neighbour almost never lies inside the inscribed ball, and
+      // starting one level up is cheaper than a failed attempt.)
+      if (total < static_cast<unsigned>(2 * K) && !all) continue;
+
+      // ---- pass 1: two smallest distances per lane, own block first
+      double mn1 = kInf, mn2 = kInf;
+      auto track = [&](bool valid, double d, int) {
+        if (valid) {
+          if (d < mn1) {
+            mn2 = mn1;
+            mn1 = d;
+          } else if (d < mn2) {
+            mn2 = d;
+          }
+        }
+      };
+      const unsigned own_len = __shfl_sync(0xffffffffu, len, 13);
+      for_each_candidate(P, sidx, start, lane == 13 ? len : 0u, qx, qy, qz, lane, track);
+      double b0 = kInf;  // 32 distinct candidates are <= max(mn1) once every lane has one
+      if (own_len >= 32u) {
+        b0 = mn1;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) b0 = fmax(b0, __shfl_xor_sync(0xffffffffu, b0, o));
+      }
+      const unsigned len1b = (lane != 13 && box2 <= b0) ? len : 0u;
+      for_each_candidate(P, sidx, start, len1b, qx, qy, qz, lane, track);
+      // with no more than 2 x 32 candidates everything fits the rank sort below: no bound needed
+      const double b1 = own_len + warp_reduce_add(len1b) > 64u ? bound_from_minima(mn1, mn2, lane) : kInf;
+
+      // ---- pass 2: compact the candidates under the bound
+      unsigned S = 0;
+      for_each_candidate(P, sidx, start, (lane == 13 || box2 <= b1) ? len : 0u, qx, qy, qz, lane,
+                         [&](bool valid, double d, int id) {
+                           const bool keep = valid && d <= b1;
+                           const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                           const unsigned at = S + __popc(bal & ((1u << lane) - 1u));
+                           if (keep && at < static_cast<unsigned>(kBuf)) {
+                             bd[at] = d;
+                             bi[at] = id;
+                           }
+                           S += __popc(bal);
+                         });
+      __syncwarp();
+      double kth = kInf;
+      if (S <= static_cast<unsigned>(kBuf)) {
+        // rank-count sort: entry e goes to position #{o : (d_o, id_o) < (d_e, id_e)}
+        double ed[kBuf / 32];
+        int ei[kBuf / 32], rk[kBuf / 32];
+#pragma unroll
+        for (int t = 0; t < kBuf / 32; ++t) {
+          const unsigned e = lane + 32u * t;
+          ed[t] = e < S ? bd[e] : kInf;
+          ei[t] = e < S ? bi[e] : 0x7fffffff;
+          rk[t] = 0;
+        }
+        auto rank_pass = [&](auto nt_tag) {
+          constexpr int NT = decltype(nt_tag)::value;
+#pragma unroll 4
+          for (unsigned o = 0; o < S; ++o) {
+            const double od = bd[o];
+            const int oi = bi[o];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) rk[t] += (od < ed[t] || (od == ed[t] && oi < ei[t])) ? 1 : 0;
+          }
+        };
+        if (S <= 32u) rank_pass(std::integral_constant<int, 1>());
+        else if (S <= 64u) rank_pass(std::integral_constant<int, 2>());
+        else rank_pass(std::integral_constant<int, kBuf / 32>());
+        __syncwarp();
+        cnt = static_cast<int>(S) < K ? static_cast<int>(S) : K;
+        // hand entry of rank l to lane l through the (now free) buffer
+#pragma unroll
+        for (int t = 0; t < kBuf / 32; ++t) {
+          const unsigned e = lane + 32u * t;
+          if (e < S && rk[t] < K) {
+            bd[rk[t]] = ed[t];
+            bi[rk[t]] = ei[t];
+          }
+        }
+        __syncwarp();
+        my_id = static_cast<int>(lane) < cnt ? bi[lane] : -1;
+        if (cnt == K) kth = bd[K - 1];
+        __syncwarp();
+      } else {
+        SerialTop T;
+        T.ld2 = kInf;
+        T.lid = -1;
+        T.cnt = 0;
+        T.kth = kInf;
+        serial_scan(P, sidx, start, lane == 13 ? len : 0u, qx, qy, qz, lane, K, T);
+        serial_scan(P, sidx, start, (lane != 13 && box2 <= T.kth) ? len : 0u, qx, qy, qz, lane, K, T);
+        my_id = T.lid;
+        cnt = T.cnt;
+        kth = T.cnt == K ? T.kth : kInf;
+      }
+      // the 3x3x3 neighbourhood already holds every point?
+      if (all) break;
+      if (cnt == K) {
+        const double ax = (static_cast<double>(m0) + static_cast<double>(bx) * span);
+        const double ay = (static_cast<double>(m1) + static_cast<double>(by) * span);
+        const double az = (static_cast<double>(m2) + static_cast<double>(bz) * span);
+        double bound = fmin(qx - (ax - span) * P.voxel, (ax + 2.0 * span) * P.voxel - qx);
+        bound = fmin(bound, fmin(qy - (ay - span) * P.voxel, (ay + 2.0 * span) * P.voxel - qy));
+        bound = fmin(bound, fmin(qz - (az - span) * P.voxel, (az + 2.0 * span) * P.voxel - qz));
+        bound -= 1e-9;
+        if (bound > 0.0 && kth <= bound * bound) break;
+      }
+    }
+    if (static_cast<int>(lane) < cnt) P.nbr[static_cast<size_t>(lane) * P.nbr_pitch + r] = static_cast<uint32_t>(my_id);
+    if (lane == 0) P.nbr_cnt[r] = static_cast<uint32_t>(cnt);
+  }
+}
+
+// ===================================================================== K4b
+__global__ void __launch_bounds__(64) knn_finish_kernel(KnnParams P) {
+  const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P.hdr->n_out) return;
+  const unsigned j0 = P.kept_pos[r];
+  const int cnt = static_cast<int>(P.nbr_cnt[r]);
+  // Open3D utility::ComputeCovariance over the neighbours in ascending
+  // distance order, exact ops (src/CloudPreprocessor.cpp:111-118)
+  double C[9];
+  if (cnt >= 3) {
+    double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int l = 0; l < cnt; ++l) {
+      const uint32_t id = P.nbr[static_cast<size_t>(l) * P.nbr_pitch + r];
+      const double x = P.px[id], y = P.py[id], z = P.pz[id];
+      c[0] = __dadd_rn(c[0], x);
+      c[1] = __dadd_rn(c[1], y);
+      c[2] = __dadd_rn(c[2], z);
+      c[3] = __dadd_rn(c[3], __dmul_rn(x, x));
+      c[4] = __dadd_rn(c[4], __dmul_rn(x, y));
+      c[5] = __dadd_rn(c[5], __dmul_rn(x, z));
+      c[6] = __dadd_rn(c[6], __dmul_rn(y, y));
+      c[7] = __dadd_rn(c[7], __dmul_rn(y, z));
+      c[8] = __dadd_rn(c[8], __dmul_rn(z, z));
+    }
+    const double nn = static_cast<double>(cnt);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) c[k] = __ddiv_rn(c[k], nn);
+    C[0] = __dadd_rn(c[3], -__dmul_rn(c[0], c[0]));
+    C[4] = __dadd_rn(c[6], -__dmul_rn(c[1], c[1]));
+    C[8] = __dadd_rn(c[8], -__dmul_rn(c[2], c[2]));
+    C[1] = C[3] = __dadd_rn(c[4], -__dmul_rn(c[0], c[1]));
+    C[2] = C[6] = __dadd_rn(c[5], -__dmul_rn(c[0], c[2]));
+    C[5] = C[7] = __dadd_rn(c[7], -__dmul_rn(c[1], c[2]));
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) C[k] = (k % 4 == 0) ? 1.0 : 0.0;
+  }
+  // regularise: U diag(1,1,1e-2) V^T (src/CloudPreprocessor.cpp:120-123);
+  // U == V for a symmetric PSD matrix
+  double wv[3], V[9], R[9];
+  eig_sym3(C, wv, V);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      R[3 * i + j] = (V[3 * i] * V[3 * j] + V[3 * i + 1] * V[3 * j + 1]) + 1e-2 * (V[3 * i + 2] * V[3 * j + 2]);
+  P.ox[r] = P.sx[j0];
+  P.oy[r] = P.sy[j0];
+  P.oz[r] = P.sz[j0];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) P.ocov[k * P.opitch + r] = R[k];
+  P.osrc[r] = P.kept_src[r];
+  P.oc4[r] = make_float4(static_cast<float>(R[0]), static_cast<float>(R[1]), static_cast<float>(R[2]),
+                         static_cast<float>(R[4]));
+  P.oc2[r] = make_float2(static_cast<float>(R[5]), static_cast<float>(R[8]));
+}
+
 // ------------------------------------------------------------ host helpers
 struct HIso {
   double R[9];
@@ -504,10 +882,33 @@ int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
   P.osrc = out->src;
   P.oc4 = out->c4;
   P.oc2 = out->c2;
-  const unsigned blocks = std::min<unsigned>((n + 3) / 4, static_cast<unsigned>(ctx->sm_count) * 16u);
-  knn_cov_kernel<<<blocks, 128, 0, ctx->stream>>>(P);
-  ESKF_CUDA(cudaGetLastError());
-  count_launch(ctx);
+  P.levels = v.levels;
+  P.level_stride = v.level_stride;
+  const size_t pitch = (static_cast<size_t>(n) + 63) / 64 * 64;
+  ESKF_TRY(ctx->knn_nbr.ensure((static_cast<size_t>(kKnn) + 1) * pitch * sizeof(uint32_t)));
+  P.nbr = ctx->knn_nbr.as<uint32_t>();
+  P.nbr_cnt = P.nbr + static_cast<size_t>(kKnn) * pitch;
+  P.nbr_pitch = pitch;
+  static const int legacy = [] {
+    const char* e = getenv("ESKF_KNN_LEGACY");  // A/B knob: the one-kernel shuffle-insertion search
+    return e ? atoi(e) : 0;
+  }();
+  if (legacy) {
+    const unsigned blocks = std::min<unsigned>((n + 3) / 4, static_cast<unsigned>(ctx->sm_count) * 16u);
+    knn_cov_kernel<<<blocks, 128, 0, ctx->stream>>>(P);
+    ESKF_CUDA(cudaGetLastError());
+    count_launch(ctx);
+  } else {
+    // the number of kept points is only known on the device: size the grids
+    // for the worst case (every point kept); surplus warps / threads exit at once
+    const unsigned sblocks = std::min<unsigned>((n + kSearchWarps - 1) / kSearchWarps,
+                                                static_cast<unsigned>(ctx->sm_count) * 16u);
+    knn_search_kernel<<<sblocks, kSearchThreads, 0, ctx->stream>>>(P);
+    ESKF_CUDA(cudaGetLastError());
+    knn_finish_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(P);
+    ESKF_CUDA(cudaGetLastError());
+    count_launch(ctx, 2);
+  }
   unsigned n_out = 0;
   ESKF_TRY(check_header(ctx, &n_out));
   out->n = n_out;

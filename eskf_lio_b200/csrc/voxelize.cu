@@ -43,6 +43,8 @@ struct VoxParams {
   double* sx;
   double* sy;
   double* sz;
+  uint4* levels;          // mode 1: k-NN block-range tables (common.cuh)
+  unsigned level_stride;
   unsigned chunk;  // elements per CTA, multiple of kT
 };
 
@@ -165,6 +167,16 @@ __global__ void __launch_bounds__(kT) voxelize_kernel(VoxParams P) {
     P.idx[0][i] = i;
   }
   if (b == 0 && t == 0) P.hdr->bits = bits;
+  if (P.a.mode == 1) {
+    // empty the k-NN block-range tables (filled after the sort; at least one
+    // grid barrier lies in between)
+    const uint4 empty = make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (int L = 0; L < kKnnHashLevels; ++L) {
+      const unsigned slots = knn_level_slots(n, bits, L);
+      uint4* tab = P.levels + static_cast<size_t>(L) * P.level_stride;
+      for (unsigned k = b * kT + t; k < slots; k += G * kT) tab[k] = empty;
+    }
+  }
   __syncthreads();
 
   // ------------------------------------------------------- LSD radix passes
@@ -177,9 +189,13 @@ __global__ void __launch_bounds__(kT) voxelize_kernel(VoxParams P) {
     // A: per-warp digit histograms of the warp's contiguous sub-chunk
     for (unsigned k = t; k < kW * 256; k += kT) (&s_whist[0][0])[k] = 0;
     __syncthreads();
-    for (unsigned j = wbeg + lane; j < wend; j += 32) {
-      const unsigned d = static_cast<unsigned>(ld_cg(sk + j) >> shift) & 255u;
-      atomicAdd(&s_whist[w][d], 1u);
+    for (unsigned j0 = wbeg + lane; j0 < wend; j0 += 128) {
+      uint64_t kk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) kk[u] = j0 + 32u * u < wend ? ld_cg(sk + j0 + 32u * u) : 0ull;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + 32u * u < wend) atomicAdd(&s_whist[w][static_cast<unsigned>(kk[u] >> shift) & 255u], 1u);
     }
     __syncthreads();
     unsigned* histp = P.hist + static_cast<size_t>(p & 1u) * G * 256u;
@@ -191,12 +207,18 @@ __global__ void __launch_bounds__(kT) voxelize_kernel(VoxParams P) {
     }
     if (!grid_sync(gb, G)) return;
     // B: global digit offsets for this CTA (every CTA redoes the tiny scan)
+    // (16 independent loads in flight per thread: this scan is one L2 round
+    // trip per batch, and it sits on the critical path of every pass)
     unsigned total = 0, pre = 0;
-#pragma unroll 4
-    for (unsigned bb = 0; bb < G; ++bb) {
-      const unsigned v = ld_cg(&histp[bb * 256u + t]);
-      if (bb < b) pre += v;
-      total += v;
+    for (unsigned b0 = 0; b0 < G; b0 += 16) {
+      unsigned v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = b0 + k < G ? ld_cg(&histp[(b0 + k) * 256u + t]) : 0u;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        if (b0 + k < b) pre += v[k];
+        total += v[k];
+      }
     }
     // a digit shared by every key makes the pass the identity: skip it
     // (decision is identical in every CTA; hist is double-buffered so the
@@ -215,13 +237,19 @@ __global__ void __launch_bounds__(kT) voxelize_kernel(VoxParams P) {
     // C: stable scatter, one warp per contiguous sub-chunk, 32 keys a step
     uint64_t* dk = P.key[sel ^ 1u];
     uint32_t* di = P.idx[sel ^ 1u];
+    uint64_t nkey = wbeg + lane < wend ? ld_cg(sk + wbeg + lane) : 0ull;
+    uint32_t nid = wbeg + lane < wend ? ld_cg(si + wbeg + lane) : 0u;
     for (unsigned j0 = wbeg; j0 < wend; j0 += 32) {
       const unsigned j = j0 + lane;
       const bool valid = j < wend;
       const unsigned am = __ballot_sync(0xffffffffu, valid);
+      const uint64_t key = nkey;
+      const uint32_t id = nid;
+      if (j + 32u < wend) {  // next step's loads overlap this step's ranking
+        nkey = ld_cg(sk + j + 32u);
+        nid = ld_cg(si + j + 32u);
+      }
       if (valid) {
-        const uint64_t key = ld_cg(sk + j);
-        const uint32_t id = ld_cg(si + j);
         const unsigned d = static_cast<unsigned>(key >> shift) & 255u;
         const unsigned mask = __match_any_sync(am, d);
         const unsigned leader = __ffs(mask) - 1;
@@ -300,6 +328,30 @@ __global__ void __launch_bounds__(kT) voxelize_kernel(VoxParams P) {
   }
 }
 
+// k-NN block-range tables (common.cuh): one thread per sorted element; the
+// first / last element of every occupied block of level L records the block's
+// start / end.  A separate launch with n threads: inside the persistent kernel
+// (4 elements per thread, up to 6 dependent L2 atomics each) it cost ~35 us.
+__global__ void __launch_bounds__(256) knn_levels_kernel(const uint64_t* key0, const uint64_t* key1,
+                                                         const VoxelHeader* hdr, uint4* levels,
+                                                         unsigned level_stride, unsigned n) {
+  const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint64_t* sk = hdr->sel ? key1 : key0;
+  const unsigned bits = hdr->bits;
+  const uint64_t cur = __ldg(sk + j);
+  const uint64_t dprev = j == 0 ? ~0ull : (__ldg(sk + j - 1) ^ cur);
+  const uint64_t dnext = j + 1 == n ? ~0ull : (__ldg(sk + j + 1) ^ cur);
+  for (int L = 0; L < kKnnHashLevels; ++L) {
+    const bool head = (dprev >> (3 * L)) != 0, tail = (dnext >> (3 * L)) != 0;
+    if (!head && !tail) break;  // inside a block of level L => inside all coarser ones
+    uint4* e = knn_level_claim(levels + static_cast<size_t>(L) * level_stride,
+                               knn_level_slots(n, bits, L) - 1u, cur >> (3 * L));
+    if (head) e->z = j;
+    if (tail) e->w = j + 1u;
+  }
+}
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
@@ -321,6 +373,8 @@ SortView sort_view(eskf_ctx* ctx, unsigned n) {
   v.sy = v.sx + nn;
   v.sz = v.sx + 2 * nn;
   v.hdr = ctx->hdr.as<VoxelHeader>();
+  v.levels = ctx->knn_levels.as<uint4>();
+  v.level_stride = knn_level_slots(n, kKeyBits, 0);
   return v;
 }
 
@@ -331,7 +385,11 @@ int voxelize(eskf_ctx* ctx, const VoxelizeArgs& a) {
   const size_t nn = align_up(static_cast<size_t>(n) + 1, 64);
   ESKF_TRY(ctx->sortbuf.ensure(nn * (8 + 8 + 4 + 4)));
   ESKF_TRY(ctx->runs.ensure(nn * 4 * 4));
-  if (a.mode == 1) ESKF_TRY(ctx->sorted_xyz.ensure(nn * 3 * 8));
+  if (a.mode == 1) {
+    ESKF_TRY(ctx->sorted_xyz.ensure(nn * 3 * 8));
+    ESKF_TRY(ctx->knn_levels.ensure(static_cast<size_t>(kKnnHashLevels) * knn_level_slots(n, kKeyBits, 0) *
+                                    sizeof(uint4)));
+  }
   ESKF_TRY(ctx->hdr.ensure(sizeof(VoxelHeader)));
 
   // elements per CTA: small enough that a 64k-point scan spreads over ~64 SMs
@@ -363,6 +421,8 @@ int voxelize(eskf_ctx* ctx, const VoxelizeArgs& a) {
   P.sx = v.sx;
   P.sy = v.sy;
   P.sz = v.sz;
+  P.levels = v.levels;
+  P.level_stride = v.level_stride;
   P.chunk = static_cast<unsigned>(align_up((n + G - 1) / G, kT));
 
   // header: min/max words to 0x7F7F7F7F (+inf for in-range ints), rest zero
@@ -373,6 +433,12 @@ int voxelize(eskf_ctx* ctx, const VoxelizeArgs& a) {
   ESKF_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(voxelize_kernel), dim3(G), dim3(kT),
                                         args, 0, ctx->stream));
   count_launch(ctx);
+  if (a.mode == 1) {
+    knn_levels_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(v.key[0], v.key[1], v.hdr, v.levels,
+                                                                v.level_stride, n);
+    ESKF_CUDA(cudaGetLastError());
+    count_launch(ctx);
+  }
   return ESKF_OK;
 }
 

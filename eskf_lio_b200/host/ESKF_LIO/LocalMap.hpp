@@ -33,6 +33,7 @@ public:
     , removeDistantPoints_(config.local_map.remove_distant_points.enabled)
     , distanceThreshold_(config.local_map.remove_distant_points.distance_threshold)
     , removePeriod_(config.local_map.remove_distant_points.removing_period)
+    , capacityHint_(config.local_map.capacity_hint)
   {
     (void)visualize;
     create();
@@ -135,7 +136,7 @@ private:
   {
     gpuCheck(
       eskf_map_create(
-        GpuContext::get(), voxelSize_, static_cast<uint32_t>(maxNumPointsPerVoxel_), 1u << 16,
+        GpuContext::get(), voxelSize_, static_cast<uint32_t>(maxNumPointsPerVoxel_), capacityHint_,
         &map_), "eskf_map_create");
     clock_ = [] {
         return std::chrono::duration<double>(
@@ -160,6 +161,7 @@ private:
   bool removeDistantPoints_ = true;
   double distanceThreshold_ = 100.0;
   double removePeriod_ = 10.0;
+  std::size_t capacityHint_ = std::size_t(1) << 16;
   double currentRemoveTime_ = std::numeric_limits<double>::lowest();  // LocalMap.hpp:40
   Isometry3d prevTransform_;  // uninitialised in the reference; identity here
   std::function<double()> clock_;

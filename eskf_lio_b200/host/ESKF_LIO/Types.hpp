@@ -213,6 +213,10 @@ struct Config
     struct {double translation_sq_threshold = 1.0e-2; double cosine_threshold = 0.985;} update;
     struct {bool enabled = true; double distance_threshold = 100.0; double removing_period = 10.0;}
     remove_distant_points;
+    // Not in the reference: voxels the HBM table is sized for up front (2 slots per voxel,
+    // 162 B per slot => 340 MB); it doubles by itself when it fills up, but a rebuild
+    // allocates device memory and costs milliseconds, so the default covers a 100 m window.
+    std::size_t capacity_hint = std::size_t(1) << 20;
   } local_map;
   struct {double voxel_size = 0.3;} cloud_preprocessor;
   struct {

@@ -36,10 +36,10 @@ def launches(tag):
              .replace("unnamed>::", ""), r["Grid Size"])].append(us(r))
     tot = sum(sum(v) for v in agg.values())
     with open(os.path.join(P, f"{tag}_launch_summary.md"), "w") as f:
-        f.write(f"# {tag}: ncu launch list of `bench.py --steps 3 --warmup 3 --no-cpu-baseline`\n\n"
+        f.write(f"# {tag}: ncu launch list of a short `bench.py` run\n\n"
                 "`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: compare "
-                "SHARES, not absolutes). Frame-phase kernels have small grids; the (444|592|1184)-CTA rows "
-                "are the dense roofline leg and its 10M-point map build.\n\n"
+                "SHARES, not absolutes). Frame-phase kernels have small grids; (444|592|1184)-CTA rows, when "
+                "present, are the dense roofline leg and its 10M-point map build.\n\n"
                 "| kernel | grid | launches | median us | total us | share |\n|---|---|---|---|---|---|\n")
         for (k, g), v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             f.write(f"| {k} | {g} | {len(v)} | {statistics.median(v):.1f} | {sum(v):.0f} | {sum(v)/tot:.3f} |\n")
@@ -99,6 +99,10 @@ def main():
     launches(tag)
     ncu_rep(tag, "prof_align", "align_kernel on the dense config (2M pts vs 10M-pt map @0.1 m, 10 GN iterations)")
     ncu_rep(tag, "prof_knn", "knn_cov_kernel on a 64k-point frame")
+    ncu_rep(tag, "prof_knns", "knn_search_kernel on a 64k-point frame (0.3 m voxels, ~20k kept points)")
+    ncu_rep(tag, "prof_knnf", "knn_finish_kernel on a 64k-point frame")
+    ncu_rep(tag, "prof_vox", "voxelize_kernel on a 64k-point frame")
+    ncu_rep(tag, "prof_ins", "insert_runs_kernel on one frame")
     for n in (f"bench_{tag}.json", f"bench_ref_{tag}.json"):
         s = os.path.join(G, n)
         if os.path.exists(s):

@@ -42,5 +42,7 @@ def rel_err(a, b):
 
 def pose_err(A, B):
     E = np.linalg.inv(A) @ B
-    ang = np.arccos(np.clip(0.5 * (np.trace(E[:3, :3]) - 1.0), -1.0, 1.0))
-    return float(np.linalg.norm(E[:3, 3])), float(ang)
+    R = E[:3, :3]
+    # atan2 form: arccos loses half the digits near the identity
+    sin = 0.5 * np.linalg.norm([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    return float(np.linalg.norm(E[:3, 3])), float(np.arctan2(sin, 0.5 * (np.trace(R) - 1.0)))
