@@ -208,16 +208,26 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 
 // ------------------------------------------------------------ grid barrier
 // Software grid-wide barrier for persistent kernels launched cooperatively
-// (all CTAs co-resident).  Every spin is bounded: on timeout the error word
-// is set and the caller must bail out, so a logic error can never hang the GPU.
+// (all CTAs co-resident).  One acq_rel ticket atomic per CTA and one release
+// store by the last arriver; no separate fences (bar.sync + the cumulative
+// release of thread 0 publish the whole CTA's writes).  `count` only grows:
+// barrier k owns tickets [k * nblocks, (k + 1) * nblocks).  Every spin is
+// bounded: on timeout the error word is set and the caller must bail out, so
+// a logic error can never hang the GPU.
 struct GridBarrier {
-  unsigned count;
-  unsigned gen;
+  unsigned count;  // zeroed before the launch
+  unsigned gen;    // number of completed barriers
   unsigned error;
   unsigned pad;
 };
 
-constexpr unsigned kSpinLimit = 1u << 24;  // x >= 64 ns sleeps: > 1 s
+constexpr unsigned kSpinLimit = 1u << 24;  // x >= 32 ns sleeps: > 0.5 s
+
+__device__ __forceinline__ unsigned atom_add_acq_rel_u32(unsigned* p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
 
 __device__ __forceinline__ bool grid_sync(GridBarrier* gb, unsigned nblocks) {
   __shared__ unsigned s_ok;
@@ -225,17 +235,14 @@ __device__ __forceinline__ bool grid_sync(GridBarrier* gb, unsigned nblocks) {
   if (threadIdx.x == 0) {
     unsigned ok = 1;
     if (nblocks > 1) {
-      const unsigned gen = ld_acquire_u32(&gb->gen);
-      __threadfence();
-      const unsigned arrived = atomicAdd(&gb->count, 1u);
-      if (arrived == nblocks - 1) {
-        atomicExch(&gb->count, 0u);
-        __threadfence();
-        st_release_u32(&gb->gen, gen + 1);
+      const unsigned ticket = atom_add_acq_rel_u32(&gb->count, 1u);
+      const unsigned epoch = ticket / nblocks + 1u;
+      if (ticket % nblocks == nblocks - 1u) {
+        st_release_u32(&gb->gen, epoch);
       } else {
         unsigned spins = 0;
-        while (ld_acquire_u32(&gb->gen) == gen) {
-          __nanosleep(64);
+        while (static_cast<int>(ld_acquire_u32(&gb->gen) - epoch) < 0) {
+          __nanosleep(32);
           if (++spins > kSpinLimit || ld_acquire_u32(&gb->error) != 0) {
             atomicExch(&gb->error, 1u);
             ok = 0;
@@ -243,7 +250,6 @@ __device__ __forceinline__ bool grid_sync(GridBarrier* gb, unsigned nblocks) {
           }
         }
       }
-      __threadfence();
     }
     s_ok = ok;
   }

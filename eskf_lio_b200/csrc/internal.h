@@ -97,6 +97,8 @@ struct VoxelHeader {
   unsigned sel;      // which ping-pong buffer holds the sorted (key, idx)
   unsigned n_out;    // runs (mode 0) or kept points (mode 1)
   unsigned bits;     // bits per axis of the rebased coordinates
+  unsigned knn_next; // next kept point to hand to a k-NN search warp (dynamic scheduling)
+  unsigned pad2[3];
   GridBarrier gb;
 };
 

@@ -67,6 +67,7 @@ struct KnnParams {
   uint32_t* nbr;          // [kKnn][nbr_pitch] neighbour source indices, ascending distance
   uint32_t* nbr_cnt;      // [n_kept]
   size_t nbr_pitch;
+  unsigned* knn_next;     // work counter of the search kernel (VoxelHeader::knn_next)
 };
 
 __device__ __forceinline__ unsigned lower_bound_u64(const uint64_t* a, unsigned lo, unsigned hi,
@@ -396,18 +397,19 @@ __device__ __forceinline__ unsigned long long warp_sort_u64(unsigned long long v
 }
 
 // upper bound of the K-th (K <= 32) smallest candidate distance from the two
-// smallest distances every lane has seen: the 32nd smallest of the 64 values
-__device__ __forceinline__ double bound_from_minima(double m1, double m2, unsigned lane) {
+// smallest distances every lane has seen: the K-th smallest of the 64 values
+__device__ __forceinline__ double bound_from_minima(double m1, double m2, unsigned lane, int K) {
   const unsigned long long a = warp_sort_u64(static_cast<unsigned long long>(__double_as_longlong(m1)), lane);
   const unsigned long long b = warp_sort_u64(static_cast<unsigned long long>(__double_as_longlong(m2)), lane);
   const unsigned long long br = __shfl_sync(0xffffffffu, b, 31u - lane);
-  unsigned long long c = a < br ? a : br;  // the 32 smallest of the union (bitonic)
+  unsigned long long c = a < br ? a : br;  // the 32 smallest of the union, a bitonic sequence
 #pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const unsigned long long x = __shfl_xor_sync(0xffffffffu, c, o);
-    c = c > x ? c : x;
+  for (unsigned j = 16; j > 0; j >>= 1) {  // bitonic merge -> ascending
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, c, j);
+    const unsigned long long mn = c < o ? c : o, mx = c < o ? o : c;
+    c = (lane & j) == 0u ? mn : mx;
   }
-  return __longlong_as_double(static_cast<long long>(c));
+  return __longlong_as_double(static_cast<long long>(__shfl_sync(0xffffffffu, c, K - 1)));
 }
 
 // Overflow path (and the reference behaviour the selection above must equal):
@@ -461,8 +463,6 @@ __global__ void __launch_bounds__(kSearchThreads) knn_search_kernel(KnnParams P)
   if (threadIdx.x < kKnnHashLevels)
     s_mask[threadIdx.x] = knn_level_slots(P.n, P.hdr->bits, static_cast<int>(threadIdx.x)) - 1u;
   __syncthreads();
-  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
   const unsigned n_kept = P.hdr->n_out;
   const unsigned sel = P.hdr->sel;
   const uint64_t* keys = P.key[sel];
@@ -475,7 +475,13 @@ __global__ void __launch_bounds__(kSearchThreads) knn_search_kernel(KnnParams P)
   double* bd = s_d[wib];
   int* bi = s_i[wib];
 
-  for (unsigned r = warp; r < n_kept; r += nwarps) {
+  // queries differ a lot in cost (dense near field vs sparse far field): the
+  // resident warps pull them from a counter instead of striding
+  for (;;) {
+    unsigned r = 0;
+    if (lane == 0) r = atomicAdd(P.knn_next, 1u);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= n_kept) break;
     const unsigned j0 = P.kept_pos[r];
     const double qx = P.sx[j0], qy = P.sy[j0], qz = P.sz[j0];
     const uint64_t mk = __ldg(keys + j0);
@@ -489,12 +495,23 @@ __global__ void __launch_bounds__(kSearchThreads) knn_search_kernel(KnnParams P)
       const double span = static_cast<double>(1 << L);
       unsigned start = 0, end = 0;
       double box2 = kInf;
+      // Morton spreading once per neighbour coordinate (lanes 0..8: x-1 x x+1 y-1 ... z+1)
+      unsigned long long spr = 0;
+      {
+        const int base = lane < 3 ? bx : (lane < 6 ? by : bz);
+        const int cv = base + static_cast<int>(lane % 3) - 1;
+        if (lane < 9 && cv >= 0) spr = spread3(static_cast<uint32_t>(cv));
+      }
+      const unsigned dxl = lane % 3, dyl = (lane / 3) % 3, dzl = (lane / 9) % 3;
+      const unsigned long long sprx = __shfl_sync(0xffffffffu, spr, dxl);
+      const unsigned long long spry = __shfl_sync(0xffffffffu, spr, 3u + dyl);
+      const unsigned long long sprz = __shfl_sync(0xffffffffu, spr, 6u + dzl);
       if (lane < 27) {
-        const int nx = bx + static_cast<int>(lane % 3) - 1;
-        const int ny = by + static_cast<int>((lane / 3) % 3) - 1;
-        const int nz = bz + static_cast<int>(lane / 9) - 1;
+        const int nx = bx + static_cast<int>(dxl) - 1;
+        const int ny = by + static_cast<int>(dyl) - 1;
+        const int nz = bz + static_cast<int>(dzl) - 1;
         if (nx >= 0 && ny >= 0 && nz >= 0 && nx <= (M0 >> L) && ny <= (M1 >> L) && nz <= (M2 >> L)) {
-          const uint64_t bk = morton3(nx, ny, nz);
+          const uint64_t bk = (sprx << 2) | (spry << 1) | sprz;  // morton3(nx, ny, nz)
           if (L < kKnnHashLevels) {
             if (!knn_level_find(P.levels + static_cast<size_t>(L) * P.level_stride, s_mask[L], bk, start, end))
               start = end = 0;
@@ -544,7 +561,7 @@ __global__ void __launch_bounds__(kSearchThreads) knn_search_kernel(KnnParams P)
       const unsigned len1b = (lane != 13 && box2 <= b0) ? len : 0u;
       for_each_candidate(P, sidx, start, len1b, qx, qy, qz, lane, track);
       // with no more than 2 x 32 candidates everything fits the rank sort below: no bound needed
-      const double b1 = own_len + warp_reduce_add(len1b) > 64u ? bound_from_minima(mn1, mn2, lane) : kInf;
+      const double b1 = own_len + warp_reduce_add(len1b) > 64u ? bound_from_minima(mn1, mn2, lane, K) : kInf;
 
       // ---- pass 2: compact the candidates under the bound
       unsigned S = 0;
@@ -889,6 +906,7 @@ int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
   P.nbr = ctx->knn_nbr.as<uint32_t>();
   P.nbr_cnt = P.nbr + static_cast<size_t>(kKnn) * pitch;
   P.nbr_pitch = pitch;
+  P.knn_next = &v.hdr->knn_next;
   static const int legacy = [] {
     const char* e = getenv("ESKF_KNN_LEGACY");  // A/B knob: the one-kernel shuffle-insertion search
     return e ? atoi(e) : 0;
@@ -901,8 +919,13 @@ int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
   } else {
     // the number of kept points is only known on the device: size the grids
     // for the worst case (every point kept); surplus warps / threads exit at once
+    static int per_sm = 0;
+    if (per_sm == 0) {
+      ESKF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, knn_search_kernel, kSearchThreads, 0));
+      if (per_sm < 1) per_sm = 1;
+    }
     const unsigned sblocks = std::min<unsigned>((n + kSearchWarps - 1) / kSearchWarps,
-                                                static_cast<unsigned>(ctx->sm_count) * 16u);
+                                                static_cast<unsigned>(ctx->sm_count * per_sm));
     knn_search_kernel<<<sblocks, kSearchThreads, 0, ctx->stream>>>(P);
     ESKF_CUDA(cudaGetLastError());
     knn_finish_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(P);

@@ -8,6 +8,7 @@ import sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+by_samples = len(sys.argv) > 3 and sys.argv[3] == "samples"
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                      capture_output=True, text=True).stdout
 cur_file, hdr = None, None
@@ -37,5 +38,7 @@ for r in csv.reader(out.splitlines()):
         pass
 ti, ts = sum(inst.values()) or 1, sum(samp.values()) or 1
 print(f"total warp instructions {ti:.0f}, samples {ts:.0f}")
-for k, v in inst.most_common(top):
+order = samp.most_common(top) if by_samples else inst.most_common(top)
+for k, _ in order:
+    v = inst[k]
     print(f"{k[0]}:{k[1]:<5d} inst {v / ti:6.3f}  samples {samp[k] / ts:6.3f}  {src.get(k, '')[:100]}")
