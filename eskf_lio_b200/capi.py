@@ -53,6 +53,8 @@ SYMBOLS = [
     "eskf_preprocess", "eskf_preprocess_cloud", "eskf_downsample_cov",
     "eskf_align", "eskf_align_cloud", "eskf_linearize", "eskf_align_cloud_fixed",
     "eskf_align_cloud_sharded",
+    "eskf_comm_create", "eskf_comm_destroy", "eskf_comm_local_handle", "eskf_comm_connect",
+    "eskf_align_cloud_p2p",
 ]
 
 _lib = None
@@ -303,6 +305,42 @@ class Cloud:
         return out
 
 
+class Comm:
+    """eskf_comm: peer-mapped H/b mailboxes of a registration sharded over ranks.
+
+    handles are exchanged by the caller (``all_gather`` takes a list of this rank's
+    64-byte handle and returns every rank's, in rank order)."""
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, ctx: "Context", rank: int, world: int, all_gather=None):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self._h = C.c_void_p()
+        check(lib().eskf_comm_create(ctx._h, C.c_int(rank), C.c_int(world), C.byref(self._h)))
+        if world > 1:
+            if all_gather is None:
+                raise ValueError("world > 1 needs an all_gather(bytes) -> list[bytes] callable")
+            mine = (C.c_ubyte * self.HANDLE_BYTES)()
+            check(lib().eskf_comm_local_handle(self._h, mine))
+            handles = all_gather(bytes(mine))
+            if len(handles) != world or any(len(h) != self.HANDLE_BYTES for h in handles):
+                raise ValueError("all_gather must return one 64-byte handle per rank")
+            blob = b"".join(handles)
+            check(lib().eskf_comm_connect(self._h, blob))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            if self.ctx._h.value:
+                lib().eskf_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Map:
     """eskf_map: the LocalMap voxel hash table in HBM."""
 
@@ -391,6 +429,19 @@ class Map:
         check(lib().eskf_align_cloud_fixed(self.ctx._h, self._h, cloud._h, _d(_f64(guess)),
                                            C.c_int(iterations), C.c_int(neighbor_mode), _d(T),
                                            C.byref(info)))
+        return _info_dict(T, info, bufs)
+
+    def align_cloud_p2p(self, cloud: Cloud, guess, comm: "Comm", max_iteration=100,
+                        translation_sq_threshold=1e-6, cosine_threshold=0.9999, neighbor_mode=1,
+                        fixed_iterations=0, trace=False):
+        """COLLECTIVE over comm: this rank's point range against the replicated map; the H/b
+        sums meet in NVLink peer mailboxes inside the persistent kernel."""
+        prm = IcpParams(max_iteration, neighbor_mode, translation_sq_threshold, cosine_threshold)
+        nit = fixed_iterations if fixed_iterations > 0 else max_iteration
+        info, bufs = _make_info(nit, trace)
+        T = np.zeros(16)
+        check(lib().eskf_align_cloud_p2p(self.ctx._h, self._h, cloud._h, _d(_f64(guess)), C.byref(prm),
+                                         comm._h, C.c_int(fixed_iterations), _d(T), C.byref(info)))
         return _info_dict(T, info, bufs)
 
     def align_cloud_sharded(self, cloud: Cloud, guess, allreduce, max_iteration=100,

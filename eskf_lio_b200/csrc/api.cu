@@ -565,4 +565,78 @@ int eskf_align_cloud_sharded(eskf_ctx* ctx, const eskf_map* map, const eskf_clou
   return align_sharded(ctx, a, allreduce, user, T_out, info);
 }
 
+// ---------------------------------------------------------- multi-GPU comm
+int eskf_comm_create(eskf_ctx* ctx, int rank, int world, eskf_comm** out) {
+  ESKF_REQUIRE(ctx && out, "null argument");
+  ESKF_REQUIRE(world >= 1 && world <= ESKF_MAX_WORLD, "world must be in [1, 16]");
+  ESKF_REQUIRE(rank >= 0 && rank < world, "rank out of range");
+  ESKF_CUDA(cudaSetDevice(ctx->device));
+  eskf_comm* c = new eskf_comm();
+  c->ctx = ctx;
+  c->rank = rank;
+  c->world = world;
+  const size_t bytes = static_cast<size_t>(2) * world * 32 * sizeof(double);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->local), bytes);
+  if (e == cudaSuccess) e = cudaMemset(c->local, 0, bytes);
+  if (e != cudaSuccess) {
+    set_error("mailbox allocation: %s", cudaGetErrorString(e));
+    delete c;
+    return ESKF_ERR_CUDA;
+  }
+  c->peers[rank] = c->local;
+  c->connected = world == 1;
+  *out = c;
+  return ESKF_OK;
+}
+
+int eskf_comm_destroy(eskf_comm* c) {
+  if (!c) return ESKF_OK;
+  cudaSetDevice(c->ctx->device);
+  cudaStreamSynchronize(c->ctx->stream);
+  for (int r = 0; r < c->world; ++r)
+    if (c->opened[r]) cudaIpcCloseMemHandle(c->peers[r]);
+  cudaFree(c->local);
+  delete c;
+  return ESKF_OK;
+}
+
+int eskf_comm_local_handle(eskf_comm* c, void* handle64) {
+  ESKF_REQUIRE(c && handle64, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == ESKF_COMM_HANDLE_BYTES, "IPC handle size");
+  ESKF_CUDA(cudaSetDevice(c->ctx->device));
+  cudaIpcMemHandle_t h;
+  ESKF_CUDA(cudaIpcGetMemHandle(&h, c->local));
+  std::memcpy(handle64, &h, sizeof h);
+  return ESKF_OK;
+}
+
+int eskf_comm_connect(eskf_comm* c, const void* handles) {
+  ESKF_REQUIRE(c && handles, "null argument");
+  ESKF_CUDA(cudaSetDevice(c->ctx->device));
+  const char* hp = static_cast<const char*>(handles);
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank || c->opened[r]) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, hp + static_cast<size_t>(r) * sizeof h, sizeof h);
+    void* ptr = nullptr;
+    ESKF_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peers[r] = static_cast<double*>(ptr);
+    c->opened[r] = true;
+  }
+  c->connected = true;
+  return ESKF_OK;
+}
+
+int eskf_align_cloud_p2p(eskf_ctx* ctx, const eskf_map* map, const eskf_cloud* cloud,
+                         const double guess[16], const eskf_icp_params* params, eskf_comm* comm,
+                         int fixed_iterations, double T_out[16], eskf_align_info* info) {
+  ESKF_REQUIRE(ctx && T_out && comm, "null argument");
+  AlignArgs a;
+  ESKF_TRY(fill_align_args(map, cloud, guess, params, &a));
+  a.fixed_iterations = fixed_iterations > 0 ? fixed_iterations : 0;
+  a.comm = comm;
+  if (cloud->n > 0) ESKF_TRY(cloud_build_c32(const_cast<eskf_cloud*>(cloud)));
+  return align_device(ctx, a, T_out, info);
+}
+
 }  // extern "C"

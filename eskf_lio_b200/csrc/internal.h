@@ -167,6 +167,19 @@ struct eskf_map {
   uint64_t spare_n = 0;
 };
 
+#define ESKF_MAX_WORLD 16
+
+// peer-mapped H/b mailboxes of a sharded registration (registration.cu, exchange_sums)
+struct eskf_comm {
+  eskf_ctx* ctx = nullptr;
+  int rank = 0, world = 1;
+  double* local = nullptr;                  // [2 parities][world][32] doubles, cudaMalloc'ed
+  double* peers[ESKF_MAX_WORLD] = {};       // peers[rank] == local
+  bool opened[ESKF_MAX_WORLD] = {};         // mapped with cudaIpcOpenMemHandle
+  bool connected = false;
+  unsigned seq = 0;
+};
+
 namespace eskf {
 
 // pinned scratch of at least `bytes`
@@ -234,6 +247,7 @@ struct AlignArgs {
   int fixed_iterations;  // > 0: run exactly this many, ignore convergence
   int fp64_math;
   uint8_t* d_hit;        // device, optional: hit mask of iteration 0
+  eskf_comm* comm;       // non-null + world > 1: fused NVLink exchange of the sums
 };
 int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align_info* info);
 

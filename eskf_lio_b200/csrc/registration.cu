@@ -27,6 +27,15 @@ namespace {
 constexpr int kT = 256;
 constexpr int kW = kT / 32;
 constexpr int kAcc = 28;  // A(6) B(9) D(6) b(6) + correspondence count
+constexpr int kMaxWorld = ESKF_MAX_WORLD;
+constexpr int kMailStride = 32;  // doubles per (parity, source rank): 28 sums, [28] = flag
+// measured on B200 (dense config, us per GN iteration at 0.1 m / 0.5 m voxels): FOLD 1 with
+// 3 CTAs/SM 86.7 / 160.2; FOLD 4 or 8 need 2 CTAs/SM (the partial sums stay live across the
+// load phase) 96 / 155; FOLD > 1 at 3 CTAs/SM spills: 192 / 255.
+#ifndef ESKF_ALIGN_FOLD
+#define ESKF_ALIGN_FOLD 1
+#endif
+constexpr int kFold = ESKF_ALIGN_FOLD;  // warp tiles (x 32 points) summed per lane in fp32 between reduce-scatters
 
 #ifndef ESKF_PIPELINED
 #define ESKF_PIPELINED 1
@@ -77,6 +86,13 @@ struct AlignParams {
   unsigned long long* trace_ncorr;
   double* trace_step;
   uint8_t* hit;
+  // multi-GPU (one registration sharded by point range): the 28
+  // sums of every rank meet in peer-mapped mailboxes over NVLink, see
+  // exchange_sums().  world == 1: single GPU, no exchange.
+  int world;
+  int rank;
+  unsigned seq;             // per-call sequence number (stale flags never match)
+  double* peers[kMaxWorld]; // mailbox base of every rank (peers[rank] = the local one)
 };
 
 // ------------------------------------------------------------ per point math
@@ -444,22 +460,44 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
   };
 
   double acc = 0.0;
-  // tiles: a fixed stride per warp (deterministic summation order), or pulled
-  // from a global counter (balances the tail of every iteration)
-  unsigned static_next = wglobal;
-  auto next_tile = [&]() -> unsigned {
-    if (!P.dynamic_tiles) {
-      const unsigned t = static_next;
-      static_next = t < n_tiles ? t + wstride : t;
-      return t;
-    }
-    unsigned t = 0;
-    if (lane == 0) t = atomicAdd(&P.st->tile_counter, 1u);
-    return __shfl_sync(0xffffffffu, t, 0);
+  // Tiles: a fixed stride per warp for the first 13/16 of every pass, the rest
+  // pulled from a global counter.  The spread of per-warp progress (HBM channel
+  // luck) otherwise leaves most warps waiting ~20 % of the pass at the
+  // iteration barrier for the slowest one.  A ticket is requested one trip
+  // before it is used (lane 0 keeps the raw value, the broadcast happens at the
+  // use), so the atomic's latency never stalls the pipeline.
+  // Measured: 189 -> 160 us per iteration at 0.5 m voxels (every point hits).
+  // Clouds with fewer than 8 tiles per warp, or dynamic_tiles == 0
+  // (ESKF_ALIGN_DYNAMIC=0), run fully static: bit-reproducible summation order.
+  const bool dynamic = P.dynamic_tiles != 0 && n_tiles >= 8u * wstride;  // small clouds: nothing to balance
+  const unsigned k_static = dynamic ? (n_tiles - n_tiles * 3u / 16u) / wstride : 0xffffffffu;
+  const unsigned dyn_base = dynamic ? k_static * wstride : 0u;
+  unsigned k_next = 0;
+  unsigned ticket_raw = 0;  // lane 0: result of the atomic issued one call earlier
+  auto request = [&]() {
+    if (k_next >= k_static && lane == 0) ticket_raw = atomicAdd(&P.st->tile_counter, 1u);
   };
+  auto next_tile = [&]() -> unsigned {
+    unsigned t;
+    if (k_next < k_static) {
+      t = wglobal + k_next * wstride;
+      if (t > n_tiles) t = n_tiles;  // (static mode: past the end)
+    } else {
+      t = dyn_base + __shfl_sync(0xffffffffu, ticket_raw, 0);
+      if (t > n_tiles) t = n_tiles;
+    }
+    ++k_next;
+    request();  // for the NEXT call
+    return t;
+  };
+  request();
   // ---- prologue: cur = first tile (scanned), nxt = second tile (transformed)
   PtState cur, nxt;
   unsigned tile = next_tile(), tile_n = next_tile();
+  F v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = F(0);
+  int folded = 0;
   {
     double rx, ry, rz, qx, qy, qz;
     load_pos(tile, rx, ry, rz);
@@ -493,9 +531,6 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
     }
     // ---- consume
     finish_scan(nxt, tagw);
-    F v[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = F(0);
     bool hit = false;
     if (has_cand) {
       const uint64_t key = pack_key(cur.kx, cur.ky, cur.kz);
@@ -526,12 +561,20 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
       point_terms<F>(F(cur.x), F(cur.y), F(cur.z), ex, ey, ez, cr[0] + F(pc.x), cr[1] + F(pc.y),
                      cr[2] + F(pc.z), cr[3] + F(pc.w), cr[4] + F(pd.x), cr[5] + F(pd.y), v);
     }
-    acc += static_cast<double>(warp_reduce_scatter32<F>(v, lane));
+    // the 31-shuffle reduce-scatter runs once per kFold tiles (the shuffles
+    // were ~17 % of the issue slots): lanes keep fp32 partial sums in between
+    if (++folded == kFold) {
+      acc += static_cast<double>(warp_reduce_scatter32<F>(v, lane));
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = F(0);
+      folded = 0;
+    }
     cur = nxt;
     xform(tile_r, rx, ry, rz, nxt);
     tile = tile_n;
     tile_n = tile_r;
   }
+  if (folded != 0) acc += static_cast<double>(warp_reduce_scatter32<F>(v, lane));
   return acc;
 }
 
@@ -874,6 +917,62 @@ __device__ __noinline__ void solve_and_update_warp(const AlignParams& P, const d
   __syncwarp();
 }
 
+// ---- fused H/b exchange over NVLink / NVSwitch peer memory ---------------
+// Called by the whole last CTA of a rank once its local sums sit in s_sum.
+// Every rank stores its 28 sums into slot [parity][rank] of EVERY rank's
+// mailbox (plain stores to peer-mapped memory), fences at system scope and
+// then raises the slot's flag; it then waits for the `world` flags of its own
+// mailbox and adds the contributions in rank order, so every rank forms the
+// bit-identical total (and therefore the identical step) without a collective
+// call or a host round trip: 216 B per peer per iteration is pure latency.
+// Two parities: a rank can run at most one iteration ahead of a peer (it needs
+// the peer's next contribution to go further).  Spins are bounded.
+__device__ __forceinline__ double ld_acquire_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.acquire.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_f64(double* p, double v) {
+  asm volatile("st.release.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ bool exchange_sums(const AlignParams& P, int it, double* s_sum, int* s_flag) {
+  const unsigned t = threadIdx.x;
+  const int W = P.world;
+  const size_t slot = (static_cast<size_t>(it & 1) * W + P.rank) * kMailStride;
+  const double flag = static_cast<double>(P.seq) * 65536.0 + static_cast<double>(it + 1);
+  for (unsigned k = t; k < static_cast<unsigned>(kAcc * W); k += kT)
+    P.peers[k / kAcc][slot + k % kAcc] = s_sum[k % kAcc];
+  __syncthreads();
+  if (t < static_cast<unsigned>(W)) {
+    __threadfence_system();
+    st_release_sys_f64(P.peers[t] + slot + kAcc, flag);
+  }
+  if (t == 0) *s_flag = 1;
+  __syncthreads();
+  if (t < static_cast<unsigned>(W)) {
+    const double* f = P.peers[P.rank] + (static_cast<size_t>(it & 1) * W + t) * kMailStride + kAcc;
+    unsigned spins = 0;
+    while (ld_acquire_sys_f64(f) != flag) {
+      __nanosleep(100);
+      if (++spins > 8u * kSpinLimit || ld_acquire_u32(&P.st->error) != 0) {  // several seconds
+        atomicExch(&P.st->error, 2u);
+        *s_flag = 0;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  if (t < kAcc) {
+    const double* box = P.peers[P.rank] + static_cast<size_t>(it & 1) * W * kMailStride + t;
+    double s = 0.0;
+    for (int r = 0; r < W; ++r) s += ld_acquire_sys_f64(box + static_cast<size_t>(r) * kMailStride);
+    s_sum[t] = s;
+  }
+  __syncthreads();
+  return *s_flag != 0;
+}
+
 template <typename F, int U, int NN, int MINB>
 __global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
   __shared__ double s_T[12];
@@ -881,7 +980,7 @@ __global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
   __shared__ double s_part[kW][32];
   __shared__ double s_sum[kAcc];
   __shared__ double s_solve[96];
-  __shared__ int s_last, s_done;
+  __shared__ int s_last, s_done, s_xchg;
   const unsigned G = gridDim.x, t = threadIdx.x;
   AlignState* st = P.st;
   const int max_it = P.fixed_iterations > 0 ? P.fixed_iterations : P.max_iteration;
@@ -906,9 +1005,12 @@ __global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
     __syncthreads();
     if (s_last) {
       final_reduce(P.partials, G, s_part, s_sum);
+      bool ok = true;
+      if (P.world > 1) ok = exchange_sums(P, it, s_sum, &s_xchg);
       if (t < 32) {
-        solve_and_update_warp(P, s_sum, it, s_solve);
+        if (ok) solve_and_update_warp(P, s_sum, it, s_solve);
         __syncwarp();
+        // (on an exchange timeout st->error is set: the waiters below bail out)
         if (t == 0) st_release_u32(&st->epoch, static_cast<unsigned>(it + 1));
       }
     }
@@ -924,7 +1026,7 @@ __global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
           break;
         }
       }
-      s_done = ok ? ld_cg(&st->done) : 1;
+      s_done = (ok && ld_acquire_u32(&st->error) == 0) ? ld_cg(&st->done) : 1;
     }
     __syncthreads();
     if (s_done) return;
@@ -1069,8 +1171,8 @@ int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, T
   P->fixed_iterations = a.fixed_iterations;
   {
     static const int dyn = [] {
-      const char* e = getenv("ESKF_ALIGN_DYNAMIC");
-      return e ? atoi(e) : 0;
+      const char* e = getenv("ESKF_ALIGN_DYNAMIC");  // 0: fully static tiles (bit-reproducible)
+      return e ? atoi(e) : 1;
     }();
     P->dynamic_tiles = dyn;
   }
@@ -1082,6 +1184,8 @@ int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, T
   P->trace_ncorr = reinterpret_cast<unsigned long long*>(base + L->o_nc);
   P->trace_step = reinterpret_cast<double*>(base + L->o_step);
   P->hit = a.d_hit;
+  P->world = 1;
+  P->rank = 0;
   return ESKF_OK;
 }
 
@@ -1096,7 +1200,8 @@ int read_back(eskf_ctx* ctx, const AlignArgs& a, const TraceLayout& L, int max_i
   ESKF_CUDA(cudaStreamSynchronize(ctx->stream));
   const AlignState* st = reinterpret_cast<const AlignState*>(h + L.o_state);
   if (st->error) {
-    set_error("align kernel: iteration hand-off timed out");
+    set_error(st->error == 2u ? "align kernel: a peer rank's H/b contribution did not arrive (NVLink mailbox timeout)"
+                              : "align kernel: iteration hand-off timed out");
     return ESKF_ERR_INTERNAL;
   }
   const double* Tt = st->iter > 0 ? st->T_total : nullptr;
@@ -1133,7 +1238,8 @@ int read_back(eskf_ctx* ctx, const AlignArgs& a, const TraceLayout& L, int max_i
 int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align_info* info) {
   ESKF_CUDA(cudaSetDevice(ctx->device));
   const int max_it = a.fixed_iterations > 0 ? a.fixed_iterations : a.max_iteration;
-  if (a.cloud && a.cloud->n == 0) {
+  const bool p2p = a.comm != nullptr && a.comm->world > 1;
+  if (a.cloud && a.cloud->n == 0 && !p2p) {
     // zero correspondences: zero step, "converged" after one iteration
     // (Eigen LDLT of a zero matrix solves to zero)
     for (int i = 0; i < 16; ++i) T_out[i] = a.guess[i];
@@ -1148,6 +1254,16 @@ int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align
   TraceLayout L;
   int G = 1;
   ESKF_TRY(fill_params(ctx, a, max_it, &P, &L, &G));
+  if (p2p) {
+    eskf_comm* c = a.comm;
+    ESKF_REQUIRE(c->ctx == ctx, "communicator belongs to another context");
+    ESKF_REQUIRE(c->connected, "communicator is not connected (eskf_comm_connect)");
+    ESKF_REQUIRE(max_it < 65535, "too many iterations for the exchange flag encoding");
+    P.world = c->world;
+    P.rank = c->rank;
+    P.seq = ++c->seq;
+    for (int r = 0; r < c->world; ++r) P.peers[r] = c->peers[r];
+  }
   ESKF_CUDA(cudaMemsetAsync(ctx->astate.p, 0, L.o_H, ctx->stream));
   // keep the probed tag array resident in L2 across iterations (the position /
   // covariance streams would otherwise evict it every pass)

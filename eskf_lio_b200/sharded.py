@@ -59,3 +59,29 @@ def align_sharded(gmap, cloud_shard, guess, group=None, **kw):
     import torch.distributed as dist
     cb = TorchAllReduce(group) if dist.is_initialized() and dist.get_world_size(group) > 1 else None
     return gmap.align_cloud_sharded(cloud_shard, np.asarray(guess, dtype=np.float64), cb, **kw)
+
+
+def torch_all_gather_bytes(group=None):
+    """all_gather callable for capi.Comm: exchanges the 64-byte IPC handles over the process
+    group (works with NCCL and gloo; plumbing only, called once at set-up)."""
+    import torch
+    import torch.distributed as dist
+
+    def gather(mine: bytes):
+        world = dist.get_world_size(group)
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t, group=group)
+        return [bytes(o.cpu().tolist()) for o in out]
+
+    return gather
+
+
+def make_comm(ctx, group=None):
+    """capi.Comm over the ranks of `group` (one process per GPU)."""
+    import torch.distributed as dist
+    from . import capi
+    if not dist.is_initialized():
+        return capi.Comm(ctx, 0, 1)
+    return capi.Comm(ctx, dist.get_rank(group), dist.get_world_size(group), torch_all_gather_bytes(group))

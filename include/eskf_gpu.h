@@ -48,6 +48,8 @@ typedef enum {
 typedef struct eskf_ctx eskf_ctx;
 typedef struct eskf_map eskf_map;
 typedef struct eskf_cloud eskf_cloud;
+typedef struct eskf_comm eskf_comm;
+#define ESKF_COMM_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
 
 /* registration.* keys of config/hilti_config.yaml:50-53, read by
  * include/ESKF_LIO/Registration.hpp:23-27.  neighbor_mode 1 = the reference's
@@ -212,6 +214,28 @@ int eskf_align_cloud_sharded(eskf_ctx* ctx, const eskf_map* map, const eskf_clou
                              const double guess[16], const eskf_icp_params* params,
                              eskf_allreduce_fn allreduce, void* user, int fixed_iterations,
                              double T_out[16], eskf_align_info* info);
+
+/* ------------------------------------------------ multi-GPU, fused exchange
+ * One process per GPU.  Each rank owns a small mailbox in its HBM that every
+ * peer maps through CUDA IPC (NVLink / NVSwitch peer access).  Inside the
+ * persistent Gauss-Newton kernel each rank stores its 28 partial sums straight
+ * into every peer's mailbox and sums the `world` contributions in rank order,
+ * so all ranks apply the bit-identical step with no collective call and no
+ * host round trip per iteration.  Setup: create on every rank,
+ * exchange the ESKF_COMM_HANDLE_BYTES-byte handles by any means (e.g.
+ * torch.distributed.all_gather), connect.  world <= 16. */
+int eskf_comm_create(eskf_ctx* ctx, int rank, int world, eskf_comm** out);
+int eskf_comm_destroy(eskf_comm* c);
+int eskf_comm_local_handle(eskf_comm* c, void* handle64);
+/* handles: world x ESKF_COMM_HANDLE_BYTES bytes in rank order (own entry ignored) */
+int eskf_comm_connect(eskf_comm* c, const void* handles);
+/* ICP::align with the source cloud sharded by point range: `cloud` is this
+ * rank's range (may be empty), the map is replicated.  COLLECTIVE: every rank
+ * of the communicator must call it with the same guess / params; all ranks
+ * return the same pose.  fixed_iterations > 0 ignores the convergence test. */
+int eskf_align_cloud_p2p(eskf_ctx* ctx, const eskf_map* map, const eskf_cloud* cloud,
+                         const double guess[16], const eskf_icp_params* params, eskf_comm* comm,
+                         int fixed_iterations, double T_out[16], eskf_align_info* info);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,53 @@
+"""ONE registration sharded by source point range over ranks, the
+28 H/b sums exchanged through peer-mapped mailboxes inside the persistent kernel
+(eskf_align_cloud_p2p).  Two ranks share cuda:0 here (CUDA IPC works within one
+device; the two persistent kernels time-slice), so the test runs on a 1-GPU box;
+the real NVLink numbers come from scripts/dense_sharded.py on N GPUs."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_ranks_fused_exchange_matches_unsharded():
+    port = 29600 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "scripts", "dense_sharded.py"), "--same-device", "--backend", "gloo",
+           "--src", "150001", "--map", "600000", "--voxel", "0.25", "--iters", "4", "--reps", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    r = json.loads(line)
+    assert r["world"] == 2 and r["shard_points"] == 75001
+    assert r["identical_pose_on_all_ranks"]                      # every rank applies the same steps
+    assert r["converged_iterations"] == r["unsharded_iterations"]
+    assert r["ncorr_equal"]                                      # correspondence counts per iteration
+    assert r["vs_unsharded_H_rel"] < 1e-12                       # bar: 1e-4 (north_star)
+    dt, dr = r["vs_unsharded_pose_delta"]
+    assert dt < 1e-9 and dr < 1e-9                               # bar: 1e-5 m / 1e-5 rad
+
+
+def test_single_rank_comm_is_plain_align():
+    import numpy as np
+    import oracle as O
+    from eskf_lio_b200 import capi, synth as S
+    from gpu_common import Frames, pose_err
+    O.build()
+    ctx = capi.Context(0)
+    fr = Frames(O, n_scans=4)
+    _, gm = fr.build_maps(O, capi, ctx, 3)
+    p, c = fr.ds[3]
+    cl = capi.Cloud(ctx).upload(p, c)
+    guess = fr.poses[3] @ S.perturbation()
+    comm = capi.Comm(ctx, 0, 1)
+    r1 = gm.align_cloud(cl, guess)
+    r2 = gm.align_cloud_p2p(cl, guess, comm)
+    assert r1["iterations"] == r2["iterations"]
+    np.testing.assert_array_equal(r1["T"], r2["T"])
+    comm.close()
