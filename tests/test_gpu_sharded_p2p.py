@@ -28,9 +28,10 @@ def test_two_ranks_fused_exchange_matches_unsharded():
     assert r["identical_pose_on_all_ranks"]                      # every rank applies the same steps
     assert r["converged_iterations"] == r["unsharded_iterations"]
     assert r["ncorr_equal"]                                      # correspondence counts per iteration
-    assert r["vs_unsharded_H_rel"] < 1e-12                       # bar: 1e-4 (north_star)
+    # the shard boundary regroups the 32-point fp32 tile sums: ~1e-9, bar 1e-4 (north_star)
+    assert r["vs_unsharded_H_rel"] < 1e-7
     dt, dr = r["vs_unsharded_pose_delta"]
-    assert dt < 1e-9 and dr < 1e-9                               # bar: 1e-5 m / 1e-5 rad
+    assert dt < 1e-8 and dr < 1e-8                               # bar: 1e-5 m / 1e-5 rad
 
 
 def test_single_rank_comm_is_plain_align():
