@@ -598,17 +598,17 @@ __device__ __forceinline__ void final_reduce(const double* partials, unsigned G,
   const unsigned term = threadIdx.x & 31, grp = threadIdx.x >> 5;
   double s = 0.0;
   if (term < kAcc) {
-    // 8 independent loads in flight per thread (a dependent chain of ~G/8 L2
-    // round trips used to cost ~20 us per iteration)
-    for (unsigned bb = grp; bb < G; bb += kW * 8) {
-      double v[8];
+    // 16 independent loads in flight per thread (a dependent chain of ~G/8 L2
+    // round trips used to cost ~20 us per iteration): one round trip up to 128 CTAs
+    for (unsigned bb = grp; bb < G; bb += kW * 16) {
+      double v[16];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < 16; ++k) {
         const unsigned b2 = bb + kW * k;
         v[k] = b2 < G ? ld_cg(partials + static_cast<size_t>(b2) * kAcc + term) : 0.0;
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s += v[k];
+      for (int k = 0; k < 16; ++k) s += v[k];
     }
   }
   s_part[grp][term] = s;
@@ -944,18 +944,17 @@ __device__ __forceinline__ bool exchange_sums(const AlignParams& P, int it, doub
   for (unsigned k = t; k < static_cast<unsigned>(kAcc * W); k += kT)
     P.peers[k / kAcc][slot + k % kAcc] = s_sum[k % kAcc];
   __syncthreads();
-  if (t < static_cast<unsigned>(W)) {
-    __threadfence_system();
-    st_release_sys_f64(P.peers[t] + slot + kAcc, flag);
-  }
+  // (st.release.sys orders the CTA's data stores, made visible to this thread by
+  // the bar.sync above, before the flag: no separate system fence)
+  if (t < static_cast<unsigned>(W)) st_release_sys_f64(P.peers[t] + slot + kAcc, flag);
   if (t == 0) *s_flag = 1;
   __syncthreads();
   if (t < static_cast<unsigned>(W)) {
     const double* f = P.peers[P.rank] + (static_cast<size_t>(it & 1) * W + t) * kMailStride + kAcc;
     unsigned spins = 0;
     while (ld_acquire_sys_f64(f) != flag) {
-      __nanosleep(100);
-      if (++spins > 8u * kSpinLimit || ld_acquire_u32(&P.st->error) != 0) {  // several seconds
+      __nanosleep(20);
+      if (++spins > 32u * kSpinLimit || ld_acquire_u32(&P.st->error) != 0) {  // several seconds
         atomicExch(&P.st->error, 2u);
         *s_flag = 0;
         break;
@@ -964,9 +963,15 @@ __device__ __forceinline__ bool exchange_sums(const AlignParams& P, int it, doub
   }
   __syncthreads();
   if (t < kAcc) {
-    const double* box = P.peers[P.rank] + static_cast<size_t>(it & 1) * W * kMailStride + t;
+    // the flags were acquired at system scope above (+ bar.sync): the data can be
+    // read with plain L1-bypassing loads, all of them in flight at once
+    const volatile double* box = P.peers[P.rank] + static_cast<size_t>(it & 1) * W * kMailStride + t;
+    double v[kMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r) v[r] = r < W ? box[static_cast<size_t>(r) * kMailStride] : 0.0;
     double s = 0.0;
-    for (int r = 0; r < W; ++r) s += ld_acquire_sys_f64(box + static_cast<size_t>(r) * kMailStride);
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r) s += v[r];  // rank order; absent ranks add +0.0
     s_sum[t] = s;
   }
   __syncthreads();
@@ -985,12 +990,11 @@ __global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
   AlignState* st = P.st;
   const int max_it = P.fixed_iterations > 0 ? P.fixed_iterations : P.max_iteration;
 
+  // pose of the first iteration: the guess (later ones arrive with the hand-off below)
+  if (t < 12) s_T[t] = P.guess[t];
+  if (t < 9) s_R[t] = F(P.guess[t]);
+  __syncthreads();
   for (int it = 0; it < max_it; ++it) {
-    // pose for this iteration: guess first, then the previous iteration's step
-    if (t < 12) s_T[t] = (it == 0) ? P.guess[t] : ld_cg(&st->T_step[t]);
-    if (t < 9) s_R[t] = (it == 0) ? F(P.guess[t])
-                                  : (sizeof(F) == 8 ? F(ld_cg(&st->T_total[t])) : F(ld_cg(&st->Rf[t])));
-    __syncthreads();
 
     const double acc = (NN == 1 && U == 1 && ESKF_PIPELINED)
                            ? accumulate_points_pipelined<F>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0)
@@ -1014,8 +1018,9 @@ __global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
         if (t == 0) st_release_u32(&st->epoch, static_cast<unsigned>(it + 1));
       }
     }
-    // everyone waits for the solver (bounded spin)
-    if (t == 0) {
+    // everyone waits for the solver (bounded spin): warp 0 polls the epoch word,
+    // then its lanes fetch the next pose and the done flag in ONE round trip
+    if (t < 32) {
       unsigned spins = 0;
       int ok = 1;
       while (ld_acquire_u32(&st->epoch) < static_cast<unsigned>(it + 1)) {
@@ -1026,7 +1031,10 @@ __global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
           break;
         }
       }
-      s_done = (ok && ld_acquire_u32(&st->error) == 0) ? ld_cg(&st->done) : 1;
+      ok = __all_sync(0xffffffffu, ok);
+      if (t < 12) s_T[t] = ld_cg(&st->T_step[t]);
+      else if (t < 21) s_R[t - 12] = sizeof(F) == 8 ? F(ld_cg(&st->T_total[t - 12])) : F(ld_cg(&st->Rf[t - 12]));
+      else if (t == 21) s_done = (ok && ld_acquire_u32(&st->error) == 0) ? ld_cg(&st->done) : 1;
     }
     __syncthreads();
     if (s_done) return;

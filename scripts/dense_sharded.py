@@ -42,6 +42,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--backend", default="nccl")
     ap.add_argument("--same-device", action="store_true", help="all ranks on cuda:0 (functional test)")
+    ap.add_argument("--weak", action="store_true",
+                    help="weak scaling: --src points PER RANK (each rank samples its own range; no unsharded check)")
     a = ap.parse_args()
 
     import torch
@@ -66,8 +68,13 @@ def main():
         p, c = S.dense_cloud(scene, n, rng)
         gmap.insert(p, c, np.eye(4))
         left -= n
-    p, c = S.dense_cloud(scene, a.src, rng)
-    b, e = sharded.shard_range(a.src, rank, world)
+    if a.weak:
+        p, c = S.dense_cloud(scene, a.src, np.random.default_rng(4400 + rank))
+        b, e = 0, a.src
+    else:
+        p, c = S.dense_cloud(scene, a.src, rng)
+        b, e = sharded.shard_range(a.src, rank, world)
+    total_src = a.src * world if a.weak else a.src
     shard = capi.Cloud(ctx, max(e - b, 64)).upload(p[b:e], c[b:e])
     guess = S.perturbation(dt=(0.03, -0.015, 0.01), angle_deg=0.3)
     comm = sharded.make_comm(ctx) if world > 1 else capi.Comm(ctx, 0, 1)
@@ -95,11 +102,12 @@ def main():
             ms = float(t[0])
         return ms, r
 
-    out = {"world": world, "src": a.src, "map_points": a.map, "voxel": a.voxel, "iters": a.iters,
+    out = {"world": world, "src": total_src, "scaling": "weak" if a.weak else "strong",
+           "map_points": a.map, "voxel": a.voxel, "iters": a.iters,
            "voxels": gmap.size(), "shard_points": e - b}
     ms_p2p, r_p2p = timed(lambda: gmap.align_cloud_p2p(shard, guess, comm, fixed_iterations=a.iters, trace=True))
     out["p2p_ms_per_iter"] = ms_p2p / a.iters
-    out["p2p_mpts_per_s_per_iter"] = a.src / (ms_p2p / a.iters * 1e-3) / 1e6
+    out["p2p_mpts_per_s_per_iter"] = total_src / (ms_p2p / a.iters * 1e-3) / 1e6
     if world > 1 and a.backend == "nccl":
         cb = sharded.TorchAllReduce()
         ms_nccl, r_nccl = timed(lambda: gmap.align_cloud_sharded(shard, guess, cb, fixed_iterations=a.iters))
@@ -118,7 +126,7 @@ def main():
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         same = bool(torch.equal(lo, hi))
     out["identical_pose_on_all_ranks"] = same
-    if rank == 0:
+    if rank == 0 and not a.weak:
         full = capi.Cloud(ctx, a.src).upload(p, c)
         ref = gmap.align_cloud(full, guess, trace=True)
         out["unsharded_iterations"] = ref["iterations"]
