@@ -371,7 +371,7 @@ def dense_roofline(ctx, capi, peak_gbs, peak_src):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE align_kernel launch of this very workload from the
 # committed `ncu --set full` capture (profiles/); None until a capture of the current kernel exists
-DENSE_TRAFFIC_BYTES = 1_745_224_000 + 535_775_000
+DENSE_TRAFFIC_BYTES = 2_212_161_000 + 536_666_000
 DENSE_TRAFFIC_SOURCE = "profiles/r1_prof_align_ncu.md (ncu --set full, one launch)"
 
 

@@ -25,11 +25,12 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--sort", type=int, default=0, help="1: sort the source by voxel brick on the host")
+    ap.add_argument("--hint", type=int, default=9_000_000, help="voxel capacity hint of the map")
     a = ap.parse_args()
     ctx = capi.Context(0)
     rng = np.random.default_rng(44)
     scene = S.block_scene()
-    gmap = capi.Map(ctx, a.voxel, 1000, 9_000_000)
+    gmap = capi.Map(ctx, a.voxel, 1000, a.hint)
     chunk = 2_500_000
     left = a.map
     while left > 0:
