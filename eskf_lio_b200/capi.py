@@ -45,7 +45,7 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void
 SYMBOLS = [
     "eskf_abi_version", "eskf_last_error", "eskf_device_count", "eskf_host_alloc", "eskf_host_free",
     "eskf_ctx_create", "eskf_ctx_destroy", "eskf_ctx_sync", "eskf_ctx_stream",
-    "eskf_ctx_launch_count", "eskf_ctx_timer_start", "eskf_ctx_timer_stop",
+    "eskf_ctx_launch_count", "eskf_ctx_set_option", "eskf_ctx_timer_start", "eskf_ctx_timer_stop",
     "eskf_cloud_create", "eskf_cloud_destroy", "eskf_cloud_upload", "eskf_cloud_upload_f32",
     "eskf_cloud_download", "eskf_cloud_size", "eskf_cloud_transform", "eskf_cloud_copy",
     "eskf_map_create", "eskf_map_destroy", "eskf_map_insert", "eskf_map_insert_cloud",
@@ -156,6 +156,9 @@ class Context:
         n = C.c_uint64(0)
         check(lib().eskf_ctx_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def set_option(self, name: str, value: int):
+        check(lib().eskf_ctx_set_option(self._h, name.encode(), C.c_int64(int(value))))
 
     def timer_start(self):
         check(lib().eskf_ctx_timer_start(self._h))

@@ -3,6 +3,8 @@
 // fails loudly with ESKF_ERR_NO_DEVICE.
 #include <cstdarg>
 
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace eskf {
@@ -214,6 +216,9 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
   eskf_ctx* ctx = new eskf_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  // option defaults may come from the environment (A/B runs without touching the caller)
+  if (const char* e = getenv("ESKF_ALIGN_DYNAMIC")) ctx->opt_align_dynamic = atoi(e) != 0;
+  if (const char* e = getenv("ESKF_L2_PERSIST")) ctx->opt_l2_persist = atoi(e) != 0;
   if (cuda_stream) {
     ctx->stream = static_cast<cudaStream_t>(cuda_stream);
     ctx->own_stream = false;
@@ -255,7 +260,7 @@ int eskf_ctx_destroy(eskf_ctx* ctx) {
   }
   eskf::DevBuf* bufs[] = {&ctx->stage, &ctx->sortbuf, &ctx->hist, &ctx->hdr, &ctx->runs,
                           &ctx->sorted_xyz, &ctx->segs, &ctx->work, &ctx->partials, &ctx->astate,
-                          &ctx->misc, &ctx->knn_levels, &ctx->knn_nbr};
+                          &ctx->misc, &ctx->knn_levels, &ctx->knn_nbr, &ctx->link};
   for (auto* b : bufs) b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -280,6 +285,25 @@ int eskf_ctx_stream(eskf_ctx* ctx, void** cuda_stream) {
 int eskf_ctx_launch_count(eskf_ctx* ctx, uint64_t* n) {
   ESKF_REQUIRE(ctx && n, "null argument");
   *n = ctx->launches;
+  return ESKF_OK;
+}
+
+int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
+  ESKF_REQUIRE(ctx && name, "null argument");
+  const std::string n(name);
+  if (n == "align_dynamic_tiles") {
+    ctx->opt_align_dynamic = value != 0;
+  } else if (n == "l2_persist") {
+    ctx->opt_l2_persist = value != 0;
+  } else if (n == "map_insert_sorted") {
+    ctx->opt_insert_sorted = value != 0;
+  } else if (n == "knn_buffer") {
+    ESKF_REQUIRE(value >= 1 && value <= 128, "knn_buffer must be in [1, 128]");
+    ctx->opt_knn_buffer = static_cast<int>(value);
+  } else {
+    set_error("unknown option '%s'", name);
+    return ESKF_ERR_INVALID;
+  }
   return ESKF_OK;
 }
 

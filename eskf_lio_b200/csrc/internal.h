@@ -120,6 +120,7 @@ struct eskf_ctx {
   eskf::DevBuf sorted_xyz; // positions gathered in sorted order (kNN)
   eskf::DevBuf knn_levels; // block-range tables of the k-NN search (kKnnHashLevels x stride uint4)
   eskf::DevBuf knn_nbr;    // neighbour lists handed from the search to the finish kernel
+  eskf::DevBuf link;       // next[] / slot_of[] of the sort-free map insert
   eskf::DevBuf segs;       // deskew segments
   eskf::DevBuf work;       // align working positions (SoA)
   eskf::DevBuf partials;   // align per-block partial sums
@@ -130,6 +131,10 @@ struct eskf_ctx {
   eskf_cloud* tmp_cloud[3] = {nullptr, nullptr, nullptr};  // host-buffer entry points
   int max_blocks_voxelize = 0;
   int max_blocks_align = 0;
+  int opt_align_dynamic = 1;    // eskf_ctx_set_option knobs (initialised from the environment)
+  int opt_l2_persist = 1;
+  int opt_knn_buffer = 128;
+  int opt_insert_sorted = 0;    // 1: always take the radix-sort insert path
   size_t l2_persist_bytes = 0;  // persisting-L2 carve-out (0 = unavailable)
   size_t l2_window_max = 0;     // max access-policy window
 };
@@ -161,6 +166,8 @@ struct eskf_map {
   // the table the last same-size rebuild (eviction sweep) moved out of: the
   // next sweep moves back into it, so steady-state eviction never calls
   // cudaMalloc / cudaFree
+  uint32_t* head = nullptr;            // [head_n] pending-list heads of the sort-free insert (all ~0 between batches)
+  uint64_t head_n = 0;
   eskf::tag_t* spare_tags = nullptr;
   eskf::VoxelSlot* spare_slots = nullptr;
   double* spare_master = nullptr;

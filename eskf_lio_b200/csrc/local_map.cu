@@ -175,6 +175,172 @@ __global__ void __launch_bounds__(128) insert_runs_kernel(InsertParams P) {
   }
 }
 
+// K5b: the per-frame insert (a downsampled sweep: tens of thousands of points,
+// one to a few per map voxel) without the radix sort.  link: one thread per
+// point transforms it (and its covariance) to the world frame, finds or claims
+// its voxel's slot and pushes itself on the slot's pending list (atomicExch on
+// head[slot]).  fold: the first arrival of every list (next == empty) collects
+// the list, orders it by point index and folds the points exactly like K5 —
+// same input-index order, same expression, so both paths give bit-identical
+// maps.  Two small launches (~15 us) instead of the persistent sort kernel
+// (~50 us for 20k points: 8+ grid barriers) + K5.
+constexpr uint32_t kListEnd = 0xffffffffu;
+constexpr int kListLocal = 32;
+constexpr size_t kListInsertMax = 131072;  // larger batches amortise the sort and may hold long lists
+
+struct ListInsertParams {
+  tag_t* tags;
+  VoxelSlot* slots;
+  double* master;
+  uint32_t n_slots;
+  unsigned long long* d_count;  // [0] voxels, [1] table-full, [3] key-range errors
+  uint32_t* head;               // [n_slots] pending-list heads, all kListEnd between batches
+  uint32_t* next;               // [n]
+  uint32_t* slot_of;            // [n]
+  double* x;
+  double* y;
+  double* z;
+  double* cov;
+  size_t cov_pitch;
+  unsigned n;
+  double voxel;
+  uint32_t cap_pts;
+  double T[12];
+};
+
+// find-or-claim that tolerates several threads looking for the SAME key at once:
+// a tag match whose record key is still empty belongs to a claimer that is about
+// to publish it, so wait for the key instead of walking on.
+__device__ __forceinline__ uint32_t find_or_claim_shared(tag_t* tags, VoxelSlot* slots, uint32_t n_slots,
+                                                         uint64_t key) {
+  const SlotAddr a = slot_addr(key, n_slots);
+  uint32_t h = a.home;
+  for (uint32_t probe = 0; probe < n_slots; ++probe) {
+    tag_t t = *reinterpret_cast<volatile tag_t*>(tags + h);
+    if (t == 0u) {
+      t = atomicCAS(reinterpret_cast<unsigned short*>(tags + h), static_cast<unsigned short>(0), a.tag);
+      if (t == 0u) {
+        *reinterpret_cast<volatile uint64_t*>(&slots[h].key) = key;
+        __threadfence();
+        return h;
+      }
+    }
+    if (t == a.tag) {
+      uint64_t k = *reinterpret_cast<volatile uint64_t*>(&slots[h].key);
+      for (unsigned spins = 0; k == kEmptyKey && spins < kSpinLimit; ++spins) {
+        __nanosleep(20);
+        k = *reinterpret_cast<volatile uint64_t*>(&slots[h].key);
+      }
+      if (k == key) return h;
+    }
+    h = next_slot(h, n_slots);
+  }
+  return kNoSlot;
+}
+
+__global__ void __launch_bounds__(128) link_points_kernel(ListInsertParams P) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  double x = P.x[i], y = P.y[i], z = P.z[i];
+  transform_point_rn(P.T, x, y, z);  // LocalMap.cpp:15
+  P.x[i] = x;
+  P.y[i] = y;
+  P.z[i] = z;
+  double C[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) C[k] = P.cov[k * P.cov_pitch + i];
+  rotate_cov_rn(P.T, C);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) P.cov[k * P.cov_pitch + i] = C[k];
+  const int kx = voxel_coord(x, P.voxel), ky = voxel_coord(y, P.voxel), kz = voxel_coord(z, P.voxel);
+  P.slot_of[i] = kNoSlot;
+  if (!(coord_in_range(kx) && coord_in_range(ky) && coord_in_range(kz))) {
+    atomicAdd(P.d_count + 3, 1ull);
+    return;
+  }
+  const uint32_t s = find_or_claim_shared(P.tags, P.slots, P.n_slots, pack_key(kx, ky, kz));
+  if (s == kNoSlot) {
+    atomicAdd(P.d_count + 1, 1ull);
+    return;
+  }
+  P.next[i] = atomicExch(P.head + s, i);
+  P.slot_of[i] = s;
+}
+
+__global__ void __launch_bounds__(128) fold_lists_kernel(ListInsertParams P) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  const uint32_t s = P.slot_of[i];
+  if (s == kNoSlot || P.next[i] != kListEnd) return;  // only the first arrival of a list folds it
+  const uint32_t first = P.head[s];
+  P.head[s] = kListEnd;  // ready for the next batch
+  uint32_t idx[kListLocal];
+  unsigned L = 0;
+  for (uint32_t h = first; h != kListEnd; h = P.next[h]) {
+    if (L < kListLocal) idx[L] = h;
+    ++L;
+  }
+  if (L <= kListLocal) {  // insertion sort, ascending point index (= the reference's input order)
+    for (unsigned a = 1; a < L; ++a) {
+      const uint32_t v = idx[a];
+      unsigned b = a;
+      while (b > 0 && idx[b - 1] > v) {
+        idx[b] = idx[b - 1];
+        --b;
+      }
+      idx[b] = v;
+    }
+  }
+  int kx, ky, kz;
+  unpack_key(P.slots[s].key, kx, ky, kz);
+  double* M = P.master + static_cast<size_t>(s) * kMasterStride;
+  double mean[3], C[9];
+  uint32_t cnt = P.slots[s].count;
+  if (cnt == 0) {
+    atomicAdd(P.d_count, 1ull);  // a voxel claimed by this batch
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mean[k] = M[k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) C[k] = M[3 + k];
+  }
+  const uint32_t before = cnt;
+  uint32_t last = 0;
+  for (unsigned j = 0; j < L && cnt < P.cap_pts; ++j) {
+    uint32_t p;
+    if (L <= kListLocal) {
+      p = idx[j];
+    } else {  // long list: next larger index by walking it again (rare: many points of ONE batch in one voxel)
+      p = kListEnd;
+      for (uint32_t h = first; h != kListEnd; h = P.next[h])
+        if ((j == 0 || h > last) && h < p) p = h;
+      last = p;
+    }
+    const double px = P.x[p], py = P.y[p], pz = P.z[p];
+    if (cnt == 0) {
+      mean[0] = px; mean[1] = py; mean[2] = pz;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) C[k] = P.cov[k * P.cov_pitch + p];
+    } else {
+      const double nn = static_cast<double>(cnt), n1 = static_cast<double>(cnt + 1);
+      mean[0] = __ddiv_rn(__dadd_rn(__dmul_rn(nn, mean[0]), px), n1);
+      mean[1] = __ddiv_rn(__dadd_rn(__dmul_rn(nn, mean[1]), py), n1);
+      mean[2] = __ddiv_rn(__dadd_rn(__dmul_rn(nn, mean[2]), pz), n1);
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        C[k] = __ddiv_rn(__dadd_rn(__dmul_rn(nn, C[k]), P.cov[k * P.cov_pitch + p]), n1);
+    }
+    ++cnt;
+  }
+  if (cnt != before) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) M[k] = mean[k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) M[3 + k] = C[k];
+    write_slot_payload(&P.slots[s], cnt, mean, C, kx, ky, kz, P.voxel);
+  }
+}
+
 // K6: rehash every surviving voxel of the old table into a fresh one.  With
 // evict != 0 a voxel survives iff NOT needsPointRemoval (src/LocalMap.cpp:149-154):
 //   |(k + 0.5) * voxel - pos| > dist_thresh  ->  erased.
@@ -335,7 +501,7 @@ int rebuild(eskf_map* m, uint64_t new_slots, int evict, const double* pos, doubl
   } else {
     ESKF_TRY(alloc_table(ctx, new_slots, &nt, &ns, &nm));
   }
-  ESKF_CUDA(cudaMemsetAsync(m->d_count, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  ESKF_CUDA(cudaMemsetAsync(m->d_count, 0, 3 * sizeof(unsigned long long), ctx->stream));  // [3] is sticky
   RehashParams P;
   P.old_tags = m->tags;
   P.old_slots = m->slots;
@@ -460,6 +626,7 @@ int eskf_map_destroy(eskf_map* m) {
     cudaFree(m->spare_master);
   }
   cudaFree(m->d_count);
+  if (m->head) cudaFree(m->head);
   delete m;
   return ESKF_OK;
 }
@@ -473,6 +640,48 @@ int eskf_map_insert_cloud(eskf_map* m, eskf_cloud* cloud, const double T[16]) {
   if (cloud->n == 0) return ESKF_OK;
   ESKF_REQUIRE(cloud->n < (1ull << 31), "cloud too large");
   ESKF_TRY(map_reserve(m, cloud->n));
+  if (!ctx->opt_insert_sorted && cloud->n <= kListInsertMax) {
+    // sort-free path: link every point to its voxel's pending list, fold the lists
+    if (m->head_n != m->n_slots) {
+      if (m->head) cudaFree(m->head);
+      m->head = nullptr;
+      m->head_n = 0;
+      ESKF_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->head), m->n_slots * sizeof(uint32_t)));
+      ESKF_CUDA(cudaMemsetAsync(m->head, 0xFF, m->n_slots * sizeof(uint32_t), ctx->stream));
+      m->head_n = m->n_slots;
+    }
+    const unsigned n = static_cast<unsigned>(cloud->n);
+    ESKF_TRY(ctx->link.ensure(static_cast<size_t>(n) * 2 * sizeof(uint32_t)));
+    ListInsertParams L;
+    L.tags = m->tags;
+    L.slots = m->slots;
+    L.master = m->master;
+    L.n_slots = static_cast<uint32_t>(m->n_slots);
+    L.d_count = m->d_count;
+    L.head = m->head;
+    L.next = ctx->link.as<uint32_t>();
+    L.slot_of = L.next + n;
+    L.x = cloud->x();
+    L.y = cloud->y();
+    L.z = cloud->z();
+    L.cov = cloud->cov;
+    L.cov_pitch = cloud->cap;
+    L.n = n;
+    L.voxel = m->voxel;
+    L.cap_pts = m->cap_pts;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) L.T[3 * i + j] = T[4 * i + j];
+      L.T[9 + i] = T[4 * i + 3];
+    }
+    link_points_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(L);
+    ESKF_CUDA(cudaGetLastError());
+    fold_lists_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(L);
+    ESKF_CUDA(cudaGetLastError());
+    count_launch(ctx, 2);
+    cloud->has_c32 = false;  // fp32 mirror is stale after the in-place transform
+    m->count_upper += cloud->n;
+    return ESKF_OK;
+  }
   VoxelizeArgs a;
   std::memset(&a, 0, sizeof a);
   a.in_x = cloud->x();
@@ -543,8 +752,8 @@ int eskf_map_size(eskf_map* m, uint64_t* n_voxels) {
   eskf_ctx* ctx = m->ctx;
   ESKF_CUDA(cudaSetDevice(ctx->device));
   unsigned long long* h = nullptr;
-  ESKF_TRY(ctx_pinned(ctx, 2 * sizeof(unsigned long long), reinterpret_cast<void**>(&h)));
-  ESKF_CUDA(cudaMemcpyAsync(h, m->d_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+  ESKF_TRY(ctx_pinned(ctx, 4 * sizeof(unsigned long long), reinterpret_cast<void**>(&h)));
+  ESKF_CUDA(cudaMemcpyAsync(h, m->d_count, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                             ctx->stream));
   ESKF_CUDA(cudaStreamSynchronize(ctx->stream));
   *n_voxels = h[0];
@@ -552,6 +761,10 @@ int eskf_map_size(eskf_map* m, uint64_t* n_voxels) {
   if (h[1] != 0) {
     set_error("voxel table overflowed (%llu runs dropped)", h[1]);
     return ESKF_ERR_CAPACITY;
+  }
+  if (h[3] != 0) {
+    set_error("voxel coordinate outside the 21-bit key range (%llu points dropped)", h[3]);
+    return ESKF_ERR_RANGE;
   }
   // also surface voxelize errors of the last insert
   if (ctx->hdr.p) {

@@ -68,6 +68,7 @@ struct KnnParams {
   uint32_t* nbr_cnt;      // [n_kept]
   size_t nbr_pitch;
   unsigned* knn_next;     // work counter of the search kernel (VoxelHeader::knn_next)
+  unsigned buf_limit;     // <= kBuf: survivors beyond this take the serial-insertion path
 };
 
 __device__ __forceinline__ unsigned lower_bound_u64(const uint64_t* a, unsigned lo, unsigned hi,
@@ -578,7 +579,7 @@ __global__ void __launch_bounds__(kSearchThreads) knn_search_kernel(KnnParams P)
                          });
       __syncwarp();
       double kth = kInf;
-      if (S <= static_cast<unsigned>(kBuf)) {
+      if (S <= P.buf_limit) {
         // rank-count sort: entry e goes to position #{o : (d_o, id_o) < (d_e, id_e)}
         double ed[kBuf / 32];
         int ei[kBuf / 32], rk[kBuf / 32];
@@ -907,6 +908,7 @@ int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
   P.nbr_cnt = P.nbr + static_cast<size_t>(kKnn) * pitch;
   P.nbr_pitch = pitch;
   P.knn_next = &v.hdr->knn_next;
+  P.buf_limit = static_cast<unsigned>(ctx->opt_knn_buffer);
   static const int legacy = [] {
     const char* e = getenv("ESKF_KNN_LEGACY");  // A/B knob: the one-kernel shuffle-insertion search
     return e ? atoi(e) : 0;

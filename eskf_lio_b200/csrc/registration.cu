@@ -1177,13 +1177,7 @@ int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, T
   P->trans_sq_thr = a.trans_sq_thr;
   P->cos_thr = a.cos_thr;
   P->fixed_iterations = a.fixed_iterations;
-  {
-    static const int dyn = [] {
-      const char* e = getenv("ESKF_ALIGN_DYNAMIC");  // 0: fully static tiles (bit-reproducible)
-      return e ? atoi(e) : 1;
-    }();
-    P->dynamic_tiles = dyn;
-  }
+  P->dynamic_tiles = ctx->opt_align_dynamic;
   P->st = reinterpret_cast<AlignState*>(base + L->o_state);
   P->partials = ctx->partials.as<double>();
   P->sums = reinterpret_cast<double*>(base + L->o_sums);
@@ -1275,11 +1269,7 @@ int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align
   ESKF_CUDA(cudaMemsetAsync(ctx->astate.p, 0, L.o_H, ctx->stream));
   // keep the probed tag array resident in L2 across iterations (the position /
   // covariance streams would otherwise evict it every pass)
-  static const int persist = [] {
-    const char* e = getenv("ESKF_L2_PERSIST");
-    return e ? atoi(e) : 1;
-  }();
-  if (persist && ctx->l2_persist_bytes > 0) {
+  if (ctx->opt_l2_persist && ctx->l2_persist_bytes > 0) {
     cudaStreamAttrValue attr;
     std::memset(&attr, 0, sizeof attr);
     size_t bytes = static_cast<size_t>(a.map->n_slots) * sizeof(tag_t);

@@ -108,6 +108,16 @@ int eskf_ctx_sync(eskf_ctx* ctx);
 int eskf_ctx_stream(eskf_ctx* ctx, void** cuda_stream);
 /* number of kernels launched by this context so far (bench "gpu_launches") */
 int eskf_ctx_launch_count(eskf_ctx* ctx, uint64_t* n);
+/* Tuning / test knobs (all have sensible defaults; unknown names return ESKF_ERR_INVALID):
+ *   "align_dynamic_tiles"  0 = fully static tile schedule in the registration kernel (bit-
+ *                          reproducible summation order), 1 = static + dynamic tail (default)
+ *   "l2_persist"           0 = no persisting-L2 window on the map's tag array (default 1)
+ *   "map_insert_sorted"    1 = every map insert goes through the radix-sort path (default 0:
+ *                          batches up to 131072 points take the sort-free list path; both give
+ *                          bit-identical maps)
+ *   "knn_buffer"           candidates the 30-NN selection keeps in shared memory before it falls
+ *                          back to serial insertion (1..128, default 128; tests force the fallback) */
+int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value);
 /* CUDA-event timing on the context's own stream (bench.py's roofline leg) */
 int eskf_ctx_timer_start(eskf_ctx* ctx);
 int eskf_ctx_timer_stop(eskf_ctx* ctx, float* elapsed_ms);

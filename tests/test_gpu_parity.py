@@ -144,6 +144,41 @@ def test_map_evict_matches_oracle(ctx, oracle, frames):
     assert gm2.size() == 3
 
 
+def test_insert_list_path_equals_sorted_path(ctx, oracle, frames):
+    """Per-frame batches take the sort-free insert (pending lists folded in point-index order), large
+    ones the radix-sort path: both must give bit-identical maps — and equal the oracle."""
+    rng = np.random.default_rng(8)
+    # a batch with long per-voxel lists (> 32 points of one batch in a voxel) and a cap that bites
+    pts = np.concatenate([rng.uniform(0.0, 1.0, size=(300, 3)), rng.uniform(-4.0, 4.0, size=(3000, 3))])
+    A = rng.normal(size=(len(pts), 3, 3))
+    cov = A @ A.transpose(0, 2, 1) + np.eye(3)
+    maps = []
+    for sorted_path in (0, 1):
+        ctx.set_option("map_insert_sorted", sorted_path)
+        try:
+            gm = capi.Map(ctx, 1.0, 120, 1 << 10)
+            for (p, c), T in zip(frames.ds[:3], frames.poses[:3]):
+                gm.insert(p, c, T)
+            gm.insert(pts, cov, frames.poses[1])
+            gm.insert(pts[::-1].copy(), cov[::-1].copy(), np.eye(4))
+            maps.append(gm.export())
+        finally:
+            ctx.set_option("map_insert_sorted", 0)
+    for u, v in zip(*maps):
+        np.testing.assert_array_equal(u, v)
+    om = oracle.Map(1.0, 120)
+    for (p, c), T in zip(frames.ds[:3], frames.poses[:3]):
+        om.update(p, c, T, initialize=True)
+    om.update(pts, cov, frames.poses[1], initialize=True)
+    om.update(pts[::-1].copy(), cov[::-1].copy(), np.eye(4), initialize=True)
+    ok, oc, omean, ocov = om.export()
+    np.testing.assert_array_equal(maps[0][0], ok)
+    np.testing.assert_array_equal(maps[0][1].astype(np.uint64), oc)
+    np.testing.assert_array_equal(maps[0][2], omean)
+    np.testing.assert_array_equal(maps[0][3], ocov)
+    assert oc.max() == 120
+
+
 def test_key_range_error(ctx):
     gm = capi.Map(ctx, 0.01, 10, 64)
     pts = np.array([[0.0, 0.0, 0.0], [2.0e4, 0.0, 0.0]])  # 2e6 voxels > 2^20
@@ -181,6 +216,39 @@ def test_downsample_small_and_degenerate_inputs(ctx, oracle):
     assert gsrc.tolist() == [0]
     op, oc, _ = oracle.downsample_cov(pts, 0.5)
     np.testing.assert_allclose(gc, oc, atol=1e-9)
+
+
+def test_knn_search_corner_paths(ctx, oracle):
+    """The k-NN search beyond its common path: (1) far-spread sparse points (levels above the
+    block-range tables: binary-search fallback, up to the whole-cloud level), (2) the serial-insertion
+    overflow path of the selection, (3) a dense blob next to an isolated point."""
+    rng = np.random.default_rng(12)
+    # (1) 400 points over 600 m with 0.1 m voxels: every neighbourhood needs coarse levels
+    pts = rng.uniform(-300.0, 300.0, size=(400, 3))
+    op, oc, osrc = oracle.downsample_cov(pts, 0.1)
+    gp, gc, gsrc = ctx.downsample_cov(pts, 0.1)
+    np.testing.assert_array_equal(gsrc, osrc)
+    np.testing.assert_allclose(gc, oc, atol=1e-7)
+    # (2) forced overflow: with room for only 4 candidates every query takes the serial-insertion
+    #     path; same exact neighbour sets in the same order => bit-identical covariances
+    pts = rng.normal(size=(4000, 3)) * np.array([3.0, 3.0, 0.2])
+    ref = ctx.downsample_cov(pts, 0.5)
+    ctx.set_option("knn_buffer", 4)
+    try:
+        alt = ctx.downsample_cov(pts, 0.5)
+    finally:
+        ctx.set_option("knn_buffer", 128)
+    for u, v in zip(ref, alt):
+        np.testing.assert_array_equal(u, v)
+    np.testing.assert_allclose(ref[1], oracle.downsample_cov(pts, 0.5)[1], atol=1e-7)
+    with pytest.raises(capi.EskfError):
+        ctx.set_option("no_such_option", 1)
+    # (3) blob + loner
+    pts = np.concatenate([rng.normal(size=(5000, 3)) * 0.05, [[40.0, -35.0, 3.0]]])
+    op, oc, osrc = oracle.downsample_cov(pts, 0.3)
+    gp, gc, gsrc = ctx.downsample_cov(pts, 0.3)
+    np.testing.assert_array_equal(gsrc, osrc)
+    np.testing.assert_allclose(gc, oc, atol=1e-7)
 
 
 def test_preprocess_with_deskew(ctx, oracle, frames):
