@@ -219,6 +219,7 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
   // option defaults may come from the environment (A/B runs without touching the caller)
   if (const char* e = getenv("ESKF_ALIGN_DYNAMIC")) ctx->opt_align_dynamic = atoi(e) != 0;
   if (const char* e = getenv("ESKF_L2_PERSIST")) ctx->opt_l2_persist = atoi(e) != 0;
+  if (const char* e = getenv("ESKF_TRACE")) ctx->opt_trace = atoi(e) != 0;
   if (cuda_stream) {
     ctx->stream = static_cast<cudaStream_t>(cuda_stream);
     ctx->own_stream = false;

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/eskf_gpu.h"
@@ -133,6 +134,8 @@ struct eskf_ctx {
   int max_blocks_align = 0;
   int opt_align_dynamic = 1;    // eskf_ctx_set_option knobs (initialised from the environment)
   int opt_l2_persist = 1;
+  int opt_trace = 0;            // ESKF_TRACE=1: per-kernel CUDA-event timings on stderr (debug aid)
+  std::vector<std::pair<const char*, cudaEvent_t>> trace_marks;
   int opt_knn_buffer = 128;
   int opt_insert_sorted = 0;    // 1: always take the radix-sort insert path
   size_t l2_persist_bytes = 0;  // persisting-L2 carve-out (0 = unavailable)
@@ -259,5 +262,27 @@ struct AlignArgs {
 int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align_info* info);
 
 inline void count_launch(eskf_ctx* ctx, int n = 1) { ctx->launches += n; }
+
+// ESKF_TRACE=1: event marks between kernels; trace_flush synchronises and prints the gaps
+inline void trace_mark(eskf_ctx* ctx, const char* label) {
+  if (!ctx->opt_trace) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, ctx->stream);
+  ctx->trace_marks.emplace_back(label, e);
+}
+inline void trace_flush(eskf_ctx* ctx, const char* what) {
+  if (!ctx->opt_trace || ctx->trace_marks.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  std::fprintf(stderr, "[eskf trace] %s:", what);
+  for (size_t i = 1; i < ctx->trace_marks.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->trace_marks[i - 1].second, ctx->trace_marks[i].second);
+    std::fprintf(stderr, " %s %.1f", ctx->trace_marks[i].first, ms * 1e3f);
+  }
+  std::fprintf(stderr, " (us)\n");
+  for (auto& m : ctx->trace_marks) cudaEventDestroy(m.second);
+  ctx->trace_marks.clear();
+}
 
 }  // namespace eskf

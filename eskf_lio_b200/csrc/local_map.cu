@@ -673,10 +673,14 @@ int eskf_map_insert_cloud(eskf_map* m, eskf_cloud* cloud, const double T[16]) {
       for (int j = 0; j < 3; ++j) L.T[3 * i + j] = T[4 * i + j];
       L.T[9 + i] = T[4 * i + 3];
     }
+    trace_mark(ctx, "start");
     link_points_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(L);
     ESKF_CUDA(cudaGetLastError());
+    trace_mark(ctx, "link");
     fold_lists_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(L);
     ESKF_CUDA(cudaGetLastError());
+    trace_mark(ctx, "fold");
+    trace_flush(ctx, "map_insert");
     count_launch(ctx, 2);
     cloud->has_c32 = false;  // fp32 mirror is stale after the in-place transform
     m->count_upper += cloud->n;

@@ -69,6 +69,8 @@ struct KnnParams {
   size_t nbr_pitch;
   unsigned* knn_next;     // work counter of the search kernel (VoxelHeader::knn_next)
   unsigned buf_limit;     // <= kBuf: survivors beyond this take the serial-insertion path
+  unsigned long long* stats;  // ESKF_TRACE: [0] queries [1] level attempts [2] pass-1 candidates
+                              // [3] pass-2 candidates [4] survivors [5] overflows [6] levels skipped
 };
 
 __device__ __forceinline__ unsigned lower_bound_u64(const uint64_t* a, unsigned lo, unsigned hi,
@@ -537,7 +539,10 @@ __global__ void __launch_bounds__(kSearchThreads) knn_search_kernel(KnnParams P)
       // Too few candidates to finish here.  (K is the hard limit; below ~2K
       // the K-th neighbour almost never lies inside the inscribed ball, and
       // starting one level up is cheaper than a failed attempt.)
-      if (total < static_cast<unsigned>(2 * K) && !all) continue;
+      if (total < static_cast<unsigned>(2 * K) && !all) {
+        if (P.stats && lane == 0) atomicAdd(P.stats + 6, 1ull);
+        continue;
+      }
 
       // ---- pass 1: two smallest distances per lane, own block first
       double mn1 = kInf, mn2 = kInf;
@@ -578,6 +583,17 @@ __global__ void __launch_bounds__(kSearchThreads) knn_search_kernel(KnnParams P)
                            S += __popc(bal);
                          });
       __syncwarp();
+      if (P.stats) {
+        const unsigned n2 = warp_reduce_add((lane == 13 || box2 <= b1) ? len : 0u);
+        const unsigned n1 = own_len + warp_reduce_add(len1b);
+        if (lane == 0) {
+          atomicAdd(P.stats + 1, 1ull);
+          atomicAdd(P.stats + 2, static_cast<unsigned long long>(n1));
+          atomicAdd(P.stats + 3, static_cast<unsigned long long>(n2));
+          atomicAdd(P.stats + 4, static_cast<unsigned long long>(S));
+          if (S > P.buf_limit) atomicAdd(P.stats + 5, 1ull);
+        }
+      }
       double kth = kInf;
       if (S <= P.buf_limit) {
         // rank-count sort: entry e goes to position #{o : (d_o, id_o) < (d_e, id_e)}
@@ -644,7 +660,10 @@ __global__ void __launch_bounds__(kSearchThreads) knn_search_kernel(KnnParams P)
       }
     }
     if (static_cast<int>(lane) < cnt) P.nbr[static_cast<size_t>(lane) * P.nbr_pitch + r] = static_cast<uint32_t>(my_id);
-    if (lane == 0) P.nbr_cnt[r] = static_cast<uint32_t>(cnt);
+    if (lane == 0) {
+      P.nbr_cnt[r] = static_cast<uint32_t>(cnt);
+      if (P.stats) atomicAdd(P.stats, 1ull);
+    }
   }
 }
 
@@ -909,6 +928,12 @@ int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
   P.nbr_pitch = pitch;
   P.knn_next = &v.hdr->knn_next;
   P.buf_limit = static_cast<unsigned>(ctx->opt_knn_buffer);
+  P.stats = nullptr;
+  if (ctx->opt_trace) {
+    ESKF_TRY(ctx->misc.ensure(256));
+    P.stats = ctx->misc.as<unsigned long long>();
+    ESKF_CUDA(cudaMemsetAsync(P.stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  }
   static const int legacy = [] {
     const char* e = getenv("ESKF_KNN_LEGACY");  // A/B knob: the one-kernel shuffle-insertion search
     return e ? atoi(e) : 0;
@@ -930,12 +955,24 @@ int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
                                                 static_cast<unsigned>(ctx->sm_count * per_sm));
     knn_search_kernel<<<sblocks, kSearchThreads, 0, ctx->stream>>>(P);
     ESKF_CUDA(cudaGetLastError());
+    trace_mark(ctx, "knn_search");
     knn_finish_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(P);
     ESKF_CUDA(cudaGetLastError());
+    trace_mark(ctx, "knn_finish");
     count_launch(ctx, 2);
   }
   unsigned n_out = 0;
   ESKF_TRY(check_header(ctx, &n_out));
+  trace_flush(ctx, "preprocess");
+  if (ctx->opt_trace) {
+    unsigned long long h[8];
+    if (cudaMemcpy(h, ctx->misc.p, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess && h[0] > 0)
+      std::fprintf(stderr, "[eskf trace] knn: %llu queries, %.2f attempts/query (+%.2f levels skipped), per attempt: "
+                   "%.0f pass-1 + %.0f pass-2 candidates, %.1f survivors, %llu overflows\n", h[0],
+                   static_cast<double>(h[1]) / h[0], static_cast<double>(h[6]) / h[0],
+                   static_cast<double>(h[2]) / (h[1] ? h[1] : 1), static_cast<double>(h[3]) / (h[1] ? h[1] : 1),
+                   static_cast<double>(h[4]) / (h[1] ? h[1] : 1), h[5]);
+  }
   out->n = n_out;
   out->has_cov = true;
   out->has_c32 = true;

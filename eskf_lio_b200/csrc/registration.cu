@@ -1284,9 +1284,13 @@ int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align
   }
   void* args[] = {&P};
   void* fn = g_variants[variant_index(a)].align;
+  trace_mark(ctx, "start");
   ESKF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(kT), args, 0, ctx->stream));
   count_launch(ctx);
-  return read_back(ctx, a, L, max_it, T_out, info);
+  trace_mark(ctx, "align");
+  const int rc = read_back(ctx, a, L, max_it, T_out, info);
+  trace_flush(ctx, "align");
+  return rc;
 }
 
 int align_max_blocks(int sm_count, int* out) {

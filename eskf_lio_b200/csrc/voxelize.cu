@@ -79,6 +79,9 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* s
     tot += c;
   }
   if (total) *total = tot;
+  // all reads of s_tmp done before any warp runs ahead into code that may write shared memory
+  // again (compute-sanitizer racecheck flagged a WAR against the next phase's stores)
+  __syncthreads();
   return woff + inc - v;
 }
 
@@ -430,14 +433,17 @@ int voxelize(eskf_ctx* ctx, const VoxelizeArgs& a) {
   ESKF_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(v.hdr) + offsetof(VoxelHeader, error), 0,
                             sizeof(VoxelHeader) - offsetof(VoxelHeader, error), ctx->stream));
   void* args[] = {&P};
+  trace_mark(ctx, "start");
   ESKF_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(voxelize_kernel), dim3(G), dim3(kT),
                                         args, 0, ctx->stream));
   count_launch(ctx);
+  trace_mark(ctx, "voxelize");
   if (a.mode == 1) {
     knn_levels_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(v.key[0], v.key[1], v.hdr, v.levels,
                                                                 v.level_stride, n);
     ESKF_CUDA(cudaGetLastError());
     count_launch(ctx);
+    trace_mark(ctx, "knn_levels");
   }
   return ESKF_OK;
 }
