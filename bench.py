@@ -196,8 +196,8 @@ def run_oracle(scans, imu, first_timed, threads=None):
     (src/Odometry.cpp:73-87), summed over the frames from `first_timed` on."""
     import oracle as O
     O.build()
-    if threads:
-        O.set_num_threads(threads)
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1)
+    O.set_num_threads(threads or len(os.sched_getaffinity(0)))
     od = O.Odometry(O.odom_default_config(**odom_overrides()))
     base = [None]
 

@@ -109,7 +109,7 @@ def main():
         if cpu:
             import oracle as O
             O.build()
-            O.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
+            O.set_num_threads(len(os.sched_getaffinity(0)))  # torchrun exports OMP_NUM_THREADS=1
             t_cpu = 0.0
             worst = 0.0
             for i, (mp, mc, sp, sc, guess) in enumerate(cpu):

@@ -84,6 +84,7 @@ def main():
     if not a.no_oracle:
         import oracle as O
         O.build()
+        O.set_num_threads(len(os.sched_getaffinity(0)))
         oo = O.Odometry(O.odom_default_config(**bench.odom_overrides()))
         t1 = time.time()
         _, oposes, _ = bench.replay(oo, scans, imu, lambda i: oo.feed_lidar(scans[i][0], scans[i][1]), 1)
