@@ -103,6 +103,7 @@ def main():
     ncu_rep(tag, "prof_knnf", "knn_finish_kernel on a 64k-point frame")
     ncu_rep(tag, "prof_vox", "voxelize_kernel on a 64k-point frame")
     ncu_rep(tag, "prof_ins", "insert_runs_kernel on one frame")
+    ncu_rep(tag, "prof_fold", "fold_lists_kernel on one frame (sort-free map insert)")
     for n in (f"bench_{tag}.json", f"bench_ref_{tag}.json"):
         s = os.path.join(G, n)
         if os.path.exists(s):
