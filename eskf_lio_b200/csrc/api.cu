@@ -41,6 +41,23 @@ int ctx_pinned(eskf_ctx* ctx, size_t bytes, void** out) {
   return ESKF_OK;
 }
 
+int wait_mail(eskf_ctx* ctx, const volatile unsigned* word, unsigned seq) {
+  for (unsigned spins = 1;; ++spins) {
+    if (*word == seq) return ESKF_OK;
+    if ((spins & 2047u) == 0u) {  // every few microseconds: is the stream still busy?
+      const cudaError_t q = cudaStreamQuery(ctx->stream);
+      if (q == cudaSuccess) return *word == seq ? ESKF_OK : 1;
+      if (q != cudaErrorNotReady) {
+        set_error("stream error while waiting for a kernel result: %s", cudaGetErrorString(q));
+        return ESKF_ERR_CUDA;
+      }
+    }
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+
 namespace {
 
 // AoS (host layout) <-> SoA (device layout)
@@ -220,6 +237,7 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
   if (const char* e = getenv("ESKF_ALIGN_DYNAMIC")) ctx->opt_align_dynamic = atoi(e) != 0;
   if (const char* e = getenv("ESKF_L2_PERSIST")) ctx->opt_l2_persist = atoi(e) != 0;
   if (const char* e = getenv("ESKF_TRACE")) ctx->opt_trace = atoi(e) != 0;
+  if (const char* e = getenv("ESKF_MAPPED_RESULTS")) ctx->opt_mapped_results = atoi(e) != 0;
   if (cuda_stream) {
     ctx->stream = static_cast<cudaStream_t>(cuda_stream);
     ctx->own_stream = false;
@@ -241,6 +259,20 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
   cudaGetLastError();
   int st = voxelize_max_blocks(ctx->sm_count, &ctx->max_blocks_voxelize);
   if (st == ESKF_OK) st = align_max_blocks(ctx->sm_count, &ctx->max_blocks_align);
+  if (st == ESKF_OK) {
+    void* hp = nullptr;
+    void* dp = nullptr;
+    if (cudaHostAlloc(&hp, sizeof(HostMail), cudaHostAllocMapped) == cudaSuccess &&
+        cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
+      std::memset(hp, 0, sizeof(HostMail));
+      ctx->mail_h = static_cast<HostMail*>(hp);
+      ctx->mail_d = static_cast<HostMail*>(dp);
+    } else {
+      if (hp) cudaFreeHost(hp);
+      cudaGetLastError();
+      ctx->opt_mapped_results = 0;  // no zero-copy memory: results come back by copy
+    }
+  }
   if (st == ESKF_OK && cudaEventCreate(&ctx->ev0) != cudaSuccess) st = ESKF_ERR_CUDA;
   if (st == ESKF_OK && cudaEventCreate(&ctx->ev1) != cudaSuccess) st = ESKF_ERR_CUDA;
   if (st != ESKF_OK) {
@@ -264,6 +296,7 @@ int eskf_ctx_destroy(eskf_ctx* ctx) {
                           &ctx->misc, &ctx->knn_levels, &ctx->knn_nbr, &ctx->link};
   for (auto* b : bufs) b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->mail_h) cudaFreeHost(ctx->mail_h);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -296,6 +329,8 @@ int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
     ctx->opt_align_dynamic = value != 0;
   } else if (n == "l2_persist") {
     ctx->opt_l2_persist = value != 0;
+  } else if (n == "mapped_results") {
+    ctx->opt_mapped_results = (value != 0 && ctx->mail_h != nullptr) ? 1 : 0;
   } else if (n == "map_insert_sorted") {
     ctx->opt_insert_sorted = value != 0;
   } else if (n == "knn_buffer") {

@@ -103,6 +103,23 @@ struct VoxelHeader {
   GridBarrier gb;
 };
 
+// Host-mapped (zero-copy) result words: a kernel stores its few result bytes here, fences at
+// system scope and bumps the sequence word; the host polls it instead of paying a D2H copy + a
+// stream synchronisation per call (and, for the preprocessor, returns as soon as the voxelize
+// kernel has published the kept-point count, while the k-NN kernels are still running).
+struct HostMail {
+  unsigned vox_seq;       // = the call's sequence number once the fields below are valid
+  unsigned vox_n_out;
+  unsigned vox_error;     // VoxelHeader::error
+  unsigned vox_gb_error;  // grid barrier timeout
+  unsigned align_seq;
+  unsigned align_error;
+  int align_iter;
+  int align_converged;
+  unsigned long long align_ncorr;
+  double align_T[12];
+};
+
 }  // namespace eskf
 
 struct eskf_ctx {
@@ -134,12 +151,18 @@ struct eskf_ctx {
   int max_blocks_align = 0;
   int opt_align_dynamic = 1;    // eskf_ctx_set_option knobs (initialised from the environment)
   int opt_l2_persist = 1;
+  eskf::HostMail* mail_h = nullptr;  // cudaHostAllocMapped
+  eskf::HostMail* mail_d = nullptr;  // the same memory as the device sees it
+  unsigned vox_seq = 0, align_seq = 0;
+  int opt_mapped_results = 1;   // 0: always cudaMemcpyAsync + cudaStreamSynchronize
   int opt_trace = 0;            // ESKF_TRACE=1: per-kernel CUDA-event timings on stderr (debug aid)
   std::vector<std::pair<const char*, cudaEvent_t>> trace_marks;
   int opt_knn_buffer = 128;
   int opt_insert_sorted = 0;    // 1: always take the radix-sort insert path
   size_t l2_persist_bytes = 0;  // persisting-L2 carve-out (0 = unavailable)
   size_t l2_window_max = 0;     // max access-policy window
+  const void* l2_win_ptr = nullptr;  // window currently set on the stream
+  size_t l2_win_bytes = 0;
 };
 
 struct eskf_cloud {
@@ -215,6 +238,8 @@ struct VoxelizeArgs {
   const DeskewSeg* segs;
   int n_segs;
   int mode;  // 0: runs in sorted order (map insert), 1: kept points in source order (preprocess)
+  HostMail* mail;     // mode 1, nullable: publish n_out / error words here when known
+  unsigned mail_seq;
 };
 // After it returns (asynchronously): ctx->hdr holds the VoxelHeader; the
 // sorted (key, idx) are in sort buffer hdr.sel; mode 0: runs[0..n_out] =
@@ -242,6 +267,10 @@ SortView sort_view(eskf_ctx* ctx, unsigned n);
 int map_reserve(eskf_map* m, uint64_t incoming_points);
 
 // preprocess.cu -----------------------------------------------------------
+// spin on a host-mapped sequence word; ESKF_OK when it reached `seq`, 1 when the stream went idle
+// without it (caller falls back to a copy), ESKF_ERR_CUDA on a stream error
+int wait_mail(eskf_ctx* ctx, const volatile unsigned* word, unsigned seq);
+
 int compute_deskew_segments(const double* point_time, size_t n, const eskf_state* states,
                             size_t n_states, std::vector<DeskewSeg>* out);
 

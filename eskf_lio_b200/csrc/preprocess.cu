@@ -893,6 +893,11 @@ int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
     a.n_segs = static_cast<int>(segs.size());
   }
   a.mode = 1;
+  const bool mapped = ctx->opt_mapped_results && ctx->mail_h != nullptr && !ctx->opt_trace;
+  if (mapped) {
+    a.mail = ctx->mail_d;
+    a.mail_seq = ++ctx->vox_seq;
+  }
   ESKF_TRY(voxelize(ctx, a));
   SortView v = sort_view(ctx, n);
   KnnParams P;
@@ -962,7 +967,25 @@ int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
     count_launch(ctx, 2);
   }
   unsigned n_out = 0;
-  ESKF_TRY(check_header(ctx, &n_out));
+  int waited = 1;
+  if (mapped) {
+    // returns as soon as the voxelize kernel has published the count: the k-NN kernels keep
+    // running behind (everything that follows is ordered on the same stream)
+    waited = wait_mail(ctx, &ctx->mail_h->vox_seq, ctx->vox_seq);
+    if (waited == ESKF_ERR_CUDA) return waited;
+    if (waited == ESKF_OK) {
+      if (ctx->mail_h->vox_gb_error) {
+        set_error("grid barrier timeout in voxelize kernel");
+        return ESKF_ERR_INTERNAL;
+      }
+      if (ctx->mail_h->vox_error & 1u) {
+        set_error("voxel coordinate outside the 21-bit key range");
+        return ESKF_ERR_RANGE;
+      }
+      n_out = ctx->mail_h->vox_n_out;
+    }
+  }
+  if (waited != ESKF_OK) ESKF_TRY(check_header(ctx, &n_out));
   trace_flush(ctx, "preprocess");
   if (ctx->opt_trace) {
     unsigned long long h[8];

@@ -327,7 +327,17 @@ __global__ void __launch_bounds__(kT) voxelize_kernel(VoxParams P) {
       }
       base += tot;
     }
-    if (b == G - 1 && t == 0) P.hdr->n_out = base;
+    if (b == G - 1 && t == 0) {
+      P.hdr->n_out = base;
+      if (P.a.mail != nullptr) {  // the host is polling for the kept-point count
+        volatile HostMail* m = P.a.mail;
+        m->vox_n_out = base;
+        m->vox_error = ld_cg(&P.hdr->error);
+        m->vox_gb_error = ld_cg(&P.hdr->gb.error);
+        __threadfence_system();
+        m->vox_seq = P.a.mail_seq;
+      }
+    }
   }
 }
 

@@ -112,6 +112,8 @@ int eskf_ctx_launch_count(eskf_ctx* ctx, uint64_t* n);
  *   "align_dynamic_tiles"  0 = fully static tile schedule in the registration kernel (bit-
  *                          reproducible summation order), 1 = static + dynamic tail (default)
  *   "l2_persist"           0 = no persisting-L2 window on the map's tag array (default 1)
+ *   "mapped_results"       0 = results always come back by cudaMemcpyAsync + stream sync (default 1:
+ *                          kernels publish them in host-mapped memory and the host polls)
  *   "map_insert_sorted"    1 = every map insert goes through the radix-sort path (default 0:
  *                          batches up to 131072 points take the sort-free list path; both give
  *                          bit-identical maps)
