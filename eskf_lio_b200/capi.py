@@ -51,7 +51,8 @@ SYMBOLS = [
     "eskf_map_create", "eskf_map_destroy", "eskf_map_insert", "eskf_map_insert_cloud",
     "eskf_map_evict", "eskf_map_size", "eskf_map_capacity", "eskf_map_query", "eskf_map_export",
     "eskf_preprocess", "eskf_preprocess_cloud", "eskf_downsample_cov",
-    "eskf_align", "eskf_align_cloud", "eskf_linearize", "eskf_align_cloud_fixed",
+    "eskf_align", "eskf_align_cloud", "eskf_align_cloud_begin", "eskf_align_end", "eskf_linearize",
+    "eskf_align_cloud_fixed",
     "eskf_align_cloud_sharded",
     "eskf_comm_create", "eskf_comm_destroy", "eskf_comm_local_handle", "eskf_comm_connect",
     "eskf_align_cloud_p2p",

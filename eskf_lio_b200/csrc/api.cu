@@ -545,6 +545,21 @@ int eskf_align_cloud(eskf_ctx* ctx, const eskf_map* map, const eskf_cloud* cloud
   return align_device(ctx, a, T_out, info);
 }
 
+int eskf_align_cloud_begin(eskf_ctx* ctx, const eskf_map* map, const eskf_cloud* cloud,
+                           const double guess[16], const eskf_icp_params* params,
+                           const eskf_align_info* info) {
+  ESKF_REQUIRE(ctx, "null argument");
+  AlignArgs a;
+  ESKF_TRY(fill_align_args(map, cloud, guess, params, &a));
+  ESKF_TRY(cloud_build_c32(const_cast<eskf_cloud*>(cloud)));
+  return align_begin(ctx, a, info);
+}
+
+int eskf_align_end(eskf_ctx* ctx, double T_out[16], eskf_align_info* info) {
+  ESKF_REQUIRE(ctx && T_out, "null argument");
+  return align_end(ctx, T_out, info);
+}
+
 int eskf_align(eskf_ctx* ctx, const eskf_map* map, const double* xyz, const double* cov, size_t n,
                const double guess[16], const eskf_icp_params* params, double T_out[16],
                eskf_align_info* info) {

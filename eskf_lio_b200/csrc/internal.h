@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <utility>
 #include <vector>
@@ -155,6 +156,7 @@ struct eskf_ctx {
   eskf::HostMail* mail_d = nullptr;  // the same memory as the device sees it
   unsigned vox_seq = 0, align_seq = 0;
   int opt_mapped_results = 1;   // 0: always cudaMemcpyAsync + cudaStreamSynchronize
+  std::shared_ptr<void> pending_align;  // registration.cu: state between align_begin / align_end
   int opt_trace = 0;            // ESKF_TRACE=1: per-kernel CUDA-event timings on stderr (debug aid)
   std::vector<std::pair<const char*, cudaEvent_t>> trace_marks;
   int opt_knn_buffer = 128;
@@ -289,6 +291,8 @@ struct AlignArgs {
   eskf_comm* comm;       // non-null + world > 1: fused NVLink exchange of the sums
 };
 int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align_info* info);
+int align_begin(eskf_ctx* ctx, const AlignArgs& a, const eskf_align_info* info);
+int align_end(eskf_ctx* ctx, double T_out[16], eskf_align_info* info);
 
 inline void count_launch(eskf_ctx* ctx, int n = 1) { ctx->launches += n; }
 

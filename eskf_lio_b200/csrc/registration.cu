@@ -17,6 +17,7 @@
 // = 136 B.
 #include <cfloat>
 #include <cstdlib>
+#include <memory>
 
 #include "internal.h"
 
@@ -1274,27 +1275,44 @@ int read_back(eskf_ctx* ctx, const AlignArgs& a, const TraceLayout& L, int max_i
   return ESKF_OK;
 }
 
+// A registration in flight between align_begin and align_end (one per context)
+struct PendingAlign {
+  bool active = false;
+  bool trivial = false;  // empty cloud: nothing was launched
+  AlignArgs a;
+  TraceLayout L;
+  int max_it = 0;
+  unsigned mail_seq = 0;
+};
+PendingAlign* pending(eskf_ctx* ctx) {
+  if (!ctx->pending_align) ctx->pending_align = std::shared_ptr<void>(new PendingAlign(), [](void* p) {
+    delete static_cast<PendingAlign*>(p);
+  });
+  return static_cast<PendingAlign*>(ctx->pending_align.get());
+}
+
 }  // namespace
 
-int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align_info* info) {
+// launch the persistent Gauss-Newton kernel and return; align_end collects the result
+int align_begin(eskf_ctx* ctx, const AlignArgs& a, const eskf_align_info* info) {
   ESKF_CUDA(cudaSetDevice(ctx->device));
+  PendingAlign* pd = pending(ctx);
+  ESKF_REQUIRE(!pd->active, "a registration is already in flight on this context (call eskf_align_end)");
   const int max_it = a.fixed_iterations > 0 ? a.fixed_iterations : a.max_iteration;
   const bool p2p = a.comm != nullptr && a.comm->world > 1;
-  if (a.cloud && a.cloud->n == 0 && !p2p) {
-    // zero correspondences: zero step, "converged" after one iteration
-    // (SURVEY.md section 5; Eigen LDLT of a zero matrix solves to zero)
-    for (int i = 0; i < 16; ++i) T_out[i] = a.guess[i];
-    if (info) {
-      info->iterations = 1;
-      info->converged = 1;
-      info->n_corr_last = 0;
-    }
+  pd->a = a;
+  pd->max_it = max_it;
+  pd->mail_seq = 0u;
+  pd->trivial = a.cloud && a.cloud->n == 0 && !p2p;
+  if (pd->trivial) {
+    pd->active = true;
     return ESKF_OK;
   }
   AlignParams P;
   TraceLayout L;
   int G = 1;
   ESKF_TRY(fill_params(ctx, a, max_it, &P, &L, &G));
+  pd->L = L;
   if (p2p) {
     eskf_comm* c = a.comm;
     ESKF_REQUIRE(c->ctx == ctx, "communicator belongs to another context");
@@ -1306,12 +1324,11 @@ int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align
     for (int r = 0; r < c->world; ++r) P.peers[r] = c->peers[r];
   }
   const bool want_trace = info && (info->trace_H || info->trace_b || info->trace_ncorr || info->trace_step);
-  unsigned mail_seq = 0u;
   if (ctx->opt_mapped_results && ctx->mail_h != nullptr && !want_trace && !ctx->opt_trace) {
-    mail_seq = ++ctx->align_seq;
-    if (mail_seq == 0u) mail_seq = ++ctx->align_seq;
+    pd->mail_seq = ++ctx->align_seq;
+    if (pd->mail_seq == 0u) pd->mail_seq = ++ctx->align_seq;
     P.mail = ctx->mail_d;
-    P.mail_seq = mail_seq;
+    P.mail_seq = pd->mail_seq;
   }
   ESKF_CUDA(cudaMemsetAsync(ctx->astate.p, 0, L.o_H, ctx->stream));
   // keep the probed tag array resident in L2 across iterations (the position /
@@ -1339,9 +1356,33 @@ int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align
   ESKF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(kT), args, 0, ctx->stream));
   count_launch(ctx);
   trace_mark(ctx, "align");
-  const int rc = read_back(ctx, a, L, max_it, T_out, info, mail_seq);
+  pd->active = true;
+  return ESKF_OK;
+}
+
+int align_end(eskf_ctx* ctx, double T_out[16], eskf_align_info* info) {
+  PendingAlign* pd = pending(ctx);
+  ESKF_REQUIRE(pd->active, "no registration in flight (call eskf_align_cloud_begin first)");
+  pd->active = false;
+  if (pd->trivial) {
+    // zero correspondences: zero step, "converged" after one iteration
+    // (SURVEY.md section 5; Eigen LDLT of a zero matrix solves to zero)
+    for (int i = 0; i < 16; ++i) T_out[i] = pd->a.guess[i];
+    if (info) {
+      info->iterations = 1;
+      info->converged = 1;
+      info->n_corr_last = 0;
+    }
+    return ESKF_OK;
+  }
+  const int rc = read_back(ctx, pd->a, pd->L, pd->max_it, T_out, info, pd->mail_seq);
   trace_flush(ctx, "align");
   return rc;
+}
+
+int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align_info* info) {
+  ESKF_TRY(align_begin(ctx, a, info));
+  return align_end(ctx, T_out, info);
 }
 
 int align_max_blocks(int sm_count, int* out) {

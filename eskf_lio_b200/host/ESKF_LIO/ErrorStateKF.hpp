@@ -257,7 +257,27 @@ public:
     Isometry3d guess;
     guess.linear() = prevState.attitude.toRotationMatrix();
     guess.translation() = prevState.position;
-    const Isometry3d observation = icp_->align(*lidar.cloud, localMap, guess);
+    // icp_->align (:130) in two halves: the gain below does not depend on the observation, so
+    // it is computed while the Gauss-Newton kernel runs (same operations, same results)
+    icp_->alignBegin(*lidar.cloud, localMap, guess);
+
+    // H (6x18): I at (0,0) and (3,6)  (:55-57)
+    Mat<6, 18> H;
+    for (int i = 0; i < 3; ++i) {
+      H(i, i) = 1.0;
+      H(3 + i, 6 + i) = 1.0;
+    }
+    const Mat18d P = toMat18(prevState.P);
+    const Mat<18, 6> PHt = P * H.transpose();
+    Mat6d S = H * PHt;
+    for (int i = 0; i < 36; ++i) {S.a[i] += V_.a[i];}
+    const Mat<18, 6> K = PHt * inverse6(S);
+    Mat18d I_KH = Mat18d::Identity();
+    const Mat18d KH = K * H;
+    for (int i = 0; i < 18 * 18; ++i) {I_KH.a[i] -= KH.a[i];}
+    Mat18d Pn = I_KH * P;  // :142 (the Joseph form is commented out in the reference)
+
+    const Isometry3d observation = icp_->alignEnd();
 
     Mat<6, 1> residual;
     for (int i = 0; i < 3; ++i) {residual(i, 0) = observation.t(i) - guess.t(i);}
@@ -271,23 +291,7 @@ public:
     const Vector3d rv = Utils::rotationMatrixToVector(Rrel);
     for (int i = 0; i < 3; ++i) {residual(3 + i, 0) = rv(i);}
 
-    // H (6x18): I at (0,0) and (3,6)  (:55-57)
-    Mat<6, 18> H;
-    for (int i = 0; i < 3; ++i) {
-      H(i, i) = 1.0;
-      H(3 + i, 6 + i) = 1.0;
-    }
-    const Mat18d P = toMat18(prevState.P);
-    const Mat<18, 6> PHt = P * H.transpose();
-    Mat6d S = H * PHt;
-    for (int i = 0; i < 36; ++i) {S.a[i] += V_.a[i];}
-    const Mat<18, 6> K = PHt * inverse6(S);
     const Vec18d errorState = K * residual;
-
-    Mat18d I_KH = Mat18d::Identity();
-    const Mat18d KH = K * H;
-    for (int i = 0; i < 18 * 18; ++i) {I_KH.a[i] -= KH.a[i];}
-    Mat18d Pn = I_KH * P;  // :142 (the Joseph form is commented out in the reference)
     injectError(newState, errorState);
     // reset (:174-180)
     Mat18d G = Mat18d::Identity();

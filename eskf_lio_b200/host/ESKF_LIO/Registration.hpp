@@ -48,6 +48,38 @@ public:
     return Isometry3d::fromMatrix(T);
   }
 
+  // ---- not in the reference: align() in two halves, so the caller's host work that does not
+  // depend on the result overlaps the Gauss-Newton kernel (device-resident clouds; a host
+  // cloud is simply registered synchronously in alignBegin)
+  void alignBegin(const PointCloud & cloud, const LocalMap & localMap, const Isometry3d & guess)
+  {
+    if (!cloud.device_) {
+      pendingHost_ = true;
+      hostResult_ = align(cloud, localMap, guess);
+      return;
+    }
+    pendingHost_ = false;
+    eskf_icp_params prm = {maxIteration_, neighborMode_, translationSquaredThreshold_,
+      cosineThreshold_};
+    const auto G = guess.matrix();
+    gpuCheck(
+      eskf_align_cloud_begin(
+        GpuContext::get(), localMap.handle(), cloud.device_.get(), G.data(), &prm, nullptr),
+      "eskf_align_cloud_begin");
+  }
+
+  Isometry3d alignEnd()
+  {
+    if (pendingHost_) {return hostResult_;}
+    eskf_align_info info = {};
+    double T[16];
+    gpuCheck(eskf_align_end(GpuContext::get(), T, &info), "eskf_align_end");
+    lastIterations_ = info.iterations;
+    if (info.converged) {converged_ = true;}
+    if (!converged_) {std::cout << "ICP not converged!\n";}
+    return Isometry3d::fromMatrix(T);
+  }
+
   int lastIterations() const {return lastIterations_;}  // not in the reference
 
 private:
@@ -58,6 +90,8 @@ private:
   int neighborMode_;
   bool converged_ = false;  // sticky, like the reference (Registration.hpp:50)
   int lastIterations_ = 0;
+  bool pendingHost_ = false;
+  Isometry3d hostResult_;
 };
 }  // namespace ESKF_LIO
 

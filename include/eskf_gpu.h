@@ -205,6 +205,14 @@ int eskf_align(eskf_ctx* ctx, const eskf_map* map, const double* xyz, const doub
 int eskf_align_cloud(eskf_ctx* ctx, const eskf_map* map, const eskf_cloud* cloud,
                      const double guess[16], const eskf_icp_params* params, double T_out[16],
                      eskf_align_info* info);
+/* the same in two halves, so that host work which does not depend on the result (the Kalman
+ * gain of src/ErrorStateKF.cpp:136) overlaps the Gauss-Newton kernel: begin launches and
+ * returns, end collects the pose.  One registration in flight per context; `info` at begin
+ * only tells whether traces are wanted (may be NULL). */
+int eskf_align_cloud_begin(eskf_ctx* ctx, const eskf_map* map, const eskf_cloud* cloud,
+                           const double guess[16], const eskf_icp_params* params,
+                           const eskf_align_info* info);
+int eskf_align_end(eskf_ctx* ctx, double T_out[16], eskf_align_info* info);
 /* parity / debug: one linearisation of the cloud posed at T
  * (LocalMap::correspondenceMatching src/LocalMap.cpp:78-112 + the accumulation
  * of ICP::computeTransform src/Registration.cpp:56-76).  hit: n bytes
