@@ -161,6 +161,12 @@ class Context:
     def set_option(self, name: str, value: int):
         check(lib().eskf_ctx_set_option(self._h, name.encode(), C.c_int64(int(value))))
 
+    def align_end(self):
+        info, bufs = _make_info(1, False)
+        T = np.zeros(16)
+        check(lib().eskf_align_end(self._h, _d(T), C.byref(info)))
+        return _info_dict(T, info, bufs)
+
     def timer_start(self):
         check(lib().eskf_ctx_timer_start(self._h))
 
@@ -426,6 +432,12 @@ class Map:
         check(lib().eskf_align_cloud(self.ctx._h, self._h, cloud._h, _d(_f64(guess)), C.byref(prm),
                                      _d(T), C.byref(info)))
         return _info_dict(T, info, bufs)
+
+    def align_cloud_begin(self, cloud: Cloud, guess, max_iteration=100, translation_sq_threshold=1e-6,
+                          cosine_threshold=0.9999, neighbor_mode=1):
+        """Launch the registration and return; collect it with Context.align_end()."""
+        prm = IcpParams(max_iteration, neighbor_mode, translation_sq_threshold, cosine_threshold)
+        check(lib().eskf_align_cloud_begin(self.ctx._h, self._h, cloud._h, _d(_f64(guess)), C.byref(prm), None))
 
     def align_cloud_fixed(self, cloud: Cloud, guess, iterations, neighbor_mode=1, trace=False):
         info, bufs = _make_info(iterations, trace)

@@ -405,6 +405,35 @@ def test_device_resident_pipeline_matches_host_entry_points(ctx, oracle, frames)
     assert r3["iterations"] == 7
 
 
+def test_align_begin_end_and_result_paths(ctx, oracle, frames):
+    """align in two halves equals align; results through host-mapped words equal the copy path;
+    misuse (two registrations in flight, end without begin) is an error, not a hang."""
+    om, gm = frames.build_maps(oracle, capi, ctx, 4)
+    p, c = frames.ds[4]
+    guess = frames.poses[4] @ S.perturbation()
+    cl = capi.Cloud(ctx).upload(p, c)
+    ref = gm.align_cloud(cl, guess)
+    gm.align_cloud_begin(cl, guess)
+    with pytest.raises(capi.EskfError):
+        gm.align_cloud_begin(cl, guess)          # one registration in flight per context
+    r = ctx.align_end()
+    np.testing.assert_array_equal(r["T"], ref["T"])
+    assert r["iterations"] == ref["iterations"] and r["converged"] == ref["converged"]
+    with pytest.raises(capi.EskfError):
+        ctx.align_end()
+    ctx.set_option("mapped_results", 0)
+    try:
+        r0 = gm.align_cloud(cl, guess)
+        xyz, t = frames.raw[3]
+        a = ctx.preprocess(xyz, t, frames.T_il, None, 0.5)
+    finally:
+        ctx.set_option("mapped_results", 1)
+    np.testing.assert_array_equal(r0["T"], ref["T"])
+    b = ctx.preprocess(xyz, t, frames.T_il, None, 0.5)
+    for u, v in zip(a, b):
+        np.testing.assert_array_equal(u, v)
+
+
 def test_sharded_align_single_rank_equals_align(ctx, oracle, frames):
     om, gm = frames.build_maps(oracle, capi, ctx, 4)
     p, c = frames.ds[4]
