@@ -26,8 +26,12 @@ namespace eskf {
 
 namespace {
 
-constexpr int kT = 256;  // threads per CTA
+#ifndef ESKF_VOX_THREADS
+#define ESKF_VOX_THREADS 256
+#endif
+constexpr int kT = ESKF_VOX_THREADS;  // threads per CTA (>= 256: thread t < 256 owns radix digit t)
 constexpr int kW = kT / 32;
+static_assert(kT >= 256 && kT % 32 == 0, "the digit-per-thread steps need at least 256 threads");
 
 struct VoxParams {
   VoxelizeArgs a;
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(kT) voxelize_kernel(VoxParams P) {
     }
     __syncthreads();
     unsigned* histp = P.hist + static_cast<size_t>(p & 1u) * G * 256u;
-    {
+    if (t < 256u) {
       unsigned s = 0;
 #pragma unroll
       for (int i = 0; i < kW; ++i) s += s_whist[i][t];
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(kT) voxelize_kernel(VoxParams P) {
     // (16 independent loads in flight per thread: this scan is one L2 round
     // trip per batch, and it sits on the critical path of every pass)
     unsigned total = 0, pre = 0;
-    for (unsigned b0 = 0; b0 < G; b0 += 16) {
+    for (unsigned b0 = 0; b0 < G && t < 256u; b0 += 16) {
       unsigned v[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) v[k] = b0 + k < G ? ld_cg(&histp[(b0 + k) * 256u + t]) : 0u;
@@ -226,9 +230,9 @@ __global__ void __launch_bounds__(kT) voxelize_kernel(VoxParams P) {
     // a digit shared by every key makes the pass the identity: skip it
     // (decision is identical in every CTA; hist is double-buffered so the
     // next pass may start writing without another barrier)
-    if (__syncthreads_or(total == n)) continue;
+    if (__syncthreads_or(t < 256u && total == n)) continue;
     unsigned base = block_exclusive_scan(total, s_tmp, nullptr);
-    {
+    if (t < 256u) {
       unsigned run = base + pre;
 #pragma unroll
       for (int i = 0; i < kW; ++i) {
@@ -410,7 +414,7 @@ int voxelize(eskf_ctx* ctx, const VoxelizeArgs& a) {
   static const unsigned epb = [] {
     const char* e = getenv("ESKF_VOX_EPB");  // tuning knob
     const int v = e ? atoi(e) : 0;
-    return v >= 256 ? static_cast<unsigned>(v) : 1024u;
+    return v >= 256 ? static_cast<unsigned>(v) : 4u * kT;
   }();
   int G = static_cast<int>((n + epb - 1) / epb);
   if (G > ctx->max_blocks_voxelize) G = ctx->max_blocks_voxelize;
