@@ -160,10 +160,13 @@ def replay(odom, scans, imu, feed, first_timed, on_timed_start=None):
     """Deliver the log the way the two sensor callbacks would (IMU samples in time order, a sweep
     once its last point is measured, one spin per delivery) and time, per frame from `first_timed`
     on, the delivery of the sweep + the spin that consumes it (wall clock)."""
+    import gc
     k = 0
     n_imu = imu.shape[0]
     wall = 0.0
     poses, iters = [], []
+    gc.collect()
+    gc.disable()  # no collector pauses inside the wall-clock legs (re-enabled by the callers' exit)
     for i, (xyz, t) in enumerate(scans):
         if i == first_timed and on_timed_start:
             on_timed_start()
@@ -187,6 +190,7 @@ def replay(odom, scans, imu, feed, first_timed, on_timed_start=None):
             wall += t1 - t0
             iters.append(odom.info().last_iterations)
         poses.append(pose)
+    gc.enable()
     return wall, poses, iters
 
 

@@ -33,9 +33,13 @@ public:
     // stamp is <= the first point time consumes no point (:54-65): only the
     // states from the last such one onwards are handed to the device path, so
     // the per-frame cost does not grow with the (never trimmed) history.
+    const double * pointTime =
+      lidarMeas->pointTimeView ? lidarMeas->pointTimeView : lidarMeas->pointTime.data();
+    const std::size_t nTimes =
+      lidarMeas->pointTimeView ? lidarMeas->pointTimeCount : lidarMeas->pointTime.size();
     std::size_t first = 0;
-    if (!states.empty() && !lidarMeas->pointTime.empty()) {
-      const double t0 = lidarMeas->pointTime.front();
+    if (!states.empty() && nTimes > 0) {
+      const double t0 = pointTime[0];
       std::size_t lo = 0, hi = states.size();  // first state with timestamp > t0
       while (lo < hi) {
         const std::size_t mid = (lo + hi) / 2;
@@ -54,9 +58,11 @@ public:
       o.attitude_xyzw[3] = states[i].attitude.w;
     }
     const auto T = T_il_.matrix();
-    run(*lidarMeas->cloud, lidarMeas->pointTime.data(), T.data(), st.data(), st.size());
+    run(*lidarMeas->cloud, pointTime, T.data(), st.data(), st.size());
     lidarMeas->pointTime.clear();
     lidarMeas->pointTime.shrink_to_fit();
+    lidarMeas->pointTimeView = nullptr;
+    lidarMeas->pointTimeCount = 0;
   }
 
   // CloudPreprocessor::voxelDownsampleAndEstimateCovariances (:76-127)

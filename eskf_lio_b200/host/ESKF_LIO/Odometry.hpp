@@ -133,15 +133,17 @@ public:
     if (deviceResident_) {
       cloud->device_ = rawPool_.acquire(n);
       gpuCheck(eskf_cloud_upload_f32(cloud->device_.get(), xyz, n), "eskf_cloud_upload_f32");
+      measurement->pointTimeView = pointTime;  // the caller keeps both buffers until the frame is consumed
+      measurement->pointTimeCount = n;
     } else {
       cloud->points_.resize(n);
       for (std::size_t i = 0; i < n; ++i) {
         cloud->points_[i] = Vector3d(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
       }
+      measurement->pointTime.assign(pointTime, pointTime + n);
     }
-    measurement->pointTime.assign(pointTime, pointTime + n);
-    measurement->startTime = measurement->pointTime.front();
-    measurement->endTime = measurement->pointTime.back();
+    measurement->startTime = pointTime[0];
+    measurement->endTime = pointTime[n - 1];
     measurement->cloud = std::move(cloud);
     cloudBuffer_->push(std::move(measurement));
   }
@@ -154,9 +156,10 @@ public:
     auto measurement = std::make_shared<LidarMeasurement>();
     auto cloud = std::make_shared<PointCloud>();
     cloud->device_ = std::shared_ptr<eskf_cloud>(raw, [](eskf_cloud *) {});  // borrowed
-    measurement->pointTime.assign(pointTime, pointTime + n);
-    measurement->startTime = measurement->pointTime.front();
-    measurement->endTime = measurement->pointTime.back();
+    measurement->pointTimeView = pointTime;
+    measurement->pointTimeCount = n;
+    measurement->startTime = pointTime[0];
+    measurement->endTime = pointTime[n - 1];
     measurement->cloud = std::move(cloud);
     cloudBuffer_->push(std::move(measurement));
   }

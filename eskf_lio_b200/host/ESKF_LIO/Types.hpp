@@ -172,6 +172,11 @@ struct LidarMeasurement
   std::vector<double> pointTime;
   double startTime;
   double endTime;
+  // Not in the reference (Config::device_resident): per-point times left in the caller's
+  // buffer instead of being copied into pointTime (512 KB per sweep); valid until the
+  // frame has been consumed.  Null => pointTime is used.
+  const double * pointTimeView = nullptr;
+  std::size_t pointTimeCount = 0;
 };
 using LidarMeasurementPtr = std::shared_ptr<LidarMeasurement>;
 

@@ -112,7 +112,7 @@ class Odometry:
         """xyz_f32: float32[N,3] (the PointCloud2 wire format); kept alive until consumed."""
         xyz = np.ascontiguousarray(xyz_f32, dtype=np.float32)
         t = np.ascontiguousarray(point_time, dtype=np.float64)
-        self._keep.append(xyz)
+        self._keep.append((xyz, t))
         _check(lib().eskf_odom_feed_lidar(self._h, xyz.ctypes.data_as(C.POINTER(C.c_float)),
                                           t.ctypes.data_as(_dp), C.c_size_t(t.shape[0])))
 
@@ -124,6 +124,7 @@ class Odometry:
     def feed_lidar_cloud(self, cloud, point_time):
         """cloud: capi.Cloud on self.context() holding the raw sweep (xyz only)."""
         t = np.ascontiguousarray(point_time, dtype=np.float64)
+        self._keep.append((cloud, t))
         _check(lib().eskf_odom_feed_lidar_cloud(self._h, cloud._h, t.ctypes.data_as(_dp),
                                                 C.c_size_t(t.shape[0])))
 

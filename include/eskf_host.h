@@ -67,8 +67,9 @@ int eskf_odom_destroy(eskf_odom* o);
 int eskf_odom_feed_imu(eskf_odom* o, double t, const double gyro[3], const double acc[3]);
 /* LidarSubscriber::cloudCallback (Subscriber.hpp:80-103): float32 x,y,z per
  * point + one double time stamp per point (ascending).  With device_resident
- * the sweep is copied to HBM asynchronously: keep xyz valid (pinned memory,
- * eskf_host_alloc) until the frame has been consumed by eskf_odom_spin_once. */
+ * the sweep is copied to HBM asynchronously and the times are read in place:
+ * keep xyz (pinned memory, eskf_host_alloc) and point_time valid until the frame
+ * has been consumed by eskf_odom_spin_once. */
 int eskf_odom_feed_lidar(eskf_odom* o, const float* xyz, const double* point_time, size_t n);
 /* a sweep already resident in HBM: raw_cloud is an eskf_cloud* (include/eskf_gpu.h,
  * xyz only) created on eskf_odom_context(); it is clobbered when the frame is
