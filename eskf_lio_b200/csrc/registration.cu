@@ -1111,7 +1111,7 @@ enum { V_F32_N1 = 0, V_F32_N7, V_F64_N1, V_F64_N7, V_COUNT };
 
 // measured on B200, dense config (2M pts, 10 iterations per launch):
 //   U=1/3 CTAs 1.267 ms, U=1/4 CTAs 1.246 ms, U=2/3 CTAs 1.303 ms,
-//   U=2/2 CTAs 1.396 ms, U=4/2 CTAs 1.417 ms  (profiles/r1_align_variants.md)
+//   U=2/2 CTAs 1.396 ms, U=4/2 CTAs 1.417 ms  
 #ifndef ESKF_ALIGN_U
 #define ESKF_ALIGN_U 1
 #endif
