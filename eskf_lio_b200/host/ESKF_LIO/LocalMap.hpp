@@ -1,13 +1,17 @@
 // LocalMap.hpp — drop-in for include/ESKF_LIO/LocalMap.hpp + src/LocalMap.cpp
 // of the reference: same public names and argument meaning, the voxel map
 // itself lives in HBM behind the C ABI (include/eskf_gpu.h).
-// Out of scope: visualiser, save(), raw per-voxel points.
+// Out of scope: the Open3D visualiser and the raw per-voxel
+// point list; save() therefore exports the voxel MEANS instead of the raw points.
 #ifndef ESKF_LIO_B200_LOCAL_MAP_HPP_
 #define ESKF_LIO_B200_LOCAL_MAP_HPP_
 
 #include <chrono>
+#include <cstdio>
+#include <fstream>
 #include <functional>
 #include <iostream>
+#include <string>
 #include <limits>
 #include <tuple>
 
@@ -57,6 +61,7 @@ public:
   void updateLocalMap(PointCloudPtr cloud, const Isometry3d & transform, bool initialize = false)
   {
     const auto T = transform.matrix();
+    trajectory_.push_back(transform);  // :16-18 (PinholeCameraTrajectory of the reference)
     lastInserted_ = false;
     if (initialize == false && needsMapUpdate(transform) == false) {
       // :15 — the caller's cloud always ends up in the world frame
@@ -116,6 +121,48 @@ public:
     return correspondence;
   }
 
+  // LocalMap::save (src/LocalMap.cpp:156-167).  The reference writes every raw point it kept
+  // per voxel with Open3D; the HBM table keeps per-voxel statistics only, so the cloud written
+  // here holds one point per voxel (its mean), as an ASCII PCD, and the trajectory is written
+  // in the layout of Open3D's PinholeCameraTrajectory JSON (extrinsic = the pose, column-major).
+  void save(const std::string & cloud_path, const std::string & trajectory_path) const
+  {
+    const std::size_t n = size();
+    std::vector<int32_t> keys(3 * n);
+    std::vector<uint32_t> count(n);
+    std::vector<double> mean(3 * n), cov(9 * n);
+    std::size_t m = 0;
+    gpuCheck(
+      eskf_map_export(map_, n, &m, keys.data(), count.data(), mean.data(), cov.data()),
+      "eskf_map_export");
+    std::ofstream pcd(cloud_path);
+    pcd << "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z\nSIZE 8 8 8\n"
+        << "TYPE F F F\nCOUNT 1 1 1\nWIDTH " << m << "\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS "
+        << m << "\nDATA ascii\n";
+    char line[128];
+    for (std::size_t i = 0; i < m; ++i) {
+      std::snprintf(line, sizeof line, "%.9g %.9g %.9g\n", mean[3 * i], mean[3 * i + 1], mean[3 * i + 2]);
+      pcd << line;
+    }
+    std::ofstream js(trajectory_path);
+    js << "{\n\t\"class_name\" : \"PinholeCameraTrajectory\",\n\t\"parameters\" :\n\t[";
+    for (std::size_t k = 0; k < trajectory_.size(); ++k) {
+      const auto M = trajectory_[k].matrix();  // row-major
+      js << (k ? "," : "") << "\n\t\t{\n\t\t\t\"class_name\" : \"PinholeCameraParameters\",\n\t\t\t\"extrinsic\" : [";
+      for (int c = 0; c < 4; ++c) {
+        for (int r = 0; r < 4; ++r) {
+          std::snprintf(line, sizeof line, "%s%.17g", (c || r) ? ", " : " ", M[4 * r + c]);
+          js << line;
+        }
+      }
+      js << " ],\n\t\t\t\"intrinsic\" : { \"height\" : -1, \"width\" : -1, \"intrinsic_matrix\" : "
+         << "[ 0, 0, 0, 0, 0, 0, 0, 0, 0 ] },\n\t\t\t\"version_major\" : 1,\n\t\t\t\"version_minor\" : 0\n\t\t}";
+    }
+    js << "\n\t],\n\t\"version_major\" : 1,\n\t\"version_minor\" : 0\n}\n";
+  }
+
+  const std::vector<Isometry3d> & trajectory() const {return trajectory_;}
+
   // ---- not in the reference: handles / test seams
   eskf_map * handle() const {return map_;}
   std::size_t size() const
@@ -164,6 +211,7 @@ private:
   std::size_t capacityHint_ = std::size_t(1) << 16;
   double currentRemoveTime_ = std::numeric_limits<double>::lowest();  // LocalMap.hpp:40
   Isometry3d prevTransform_;  // uninitialised in the reference; identity here
+  std::vector<Isometry3d> trajectory_;
   std::function<double()> clock_;
   bool verbose_ = true;
   bool lastInserted_ = false;

@@ -5,7 +5,7 @@
 //
 // Differences, all forced by the environment or by undefined behaviour in the
 // reference (SURVEY.md sections 5 and 7):
-//   - no visualiser / saveMapcloud (Open3D GUI + PCD export: out of scope);
+//   - no visualiser (Open3D GUI); saveMapcloud exports voxel means + the trajectory;
 //   - spinOnce() is one trip of run()'s busy loop, so a test or bench can
 //     drive it deterministically; run() loops on it until setExit();
 //   - the first scan is inserted with initialize = true (the reference tests
@@ -65,6 +65,12 @@ public:
   }
 
   void setExit() {exitFlag_ = true;}
+
+  // include/ESKF_LIO/Odometry.hpp:37-40 (see LocalMap::save for what the cloud holds)
+  void saveMapcloud(const std::string & cloud_path, const std::string & trajectory_path) const
+  {
+    localMap_->save(cloud_path, trajectory_path);
+  }
 
   // One trip of the loop body (src/Odometry.cpp:17-97).  True when a LiDAR
   // frame was consumed (initialisation frame included).

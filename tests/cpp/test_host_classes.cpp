@@ -61,5 +61,9 @@ int main(int argc, char ** argv)
     std::printf("map %zu first_world %.17g %.17g %.17g\n", map.size(), meas->cloud->points_[0].v[0],
       meas->cloud->points_[0].v[1], meas->cloud->points_[0].v[2]);
   }
+  if (argc > 3) {
+    map.save(argv[2], argv[3]);
+    std::printf("saved %zu poses\n", map.trajectory().size());
+  }
   return 0;
 }

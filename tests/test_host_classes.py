@@ -91,7 +91,8 @@ def test_host_classes_match_oracle(tmp_path, oracle):
             f.write(np.ascontiguousarray(xyz).tobytes())
             f.write(np.ascontiguousarray(t).tobytes())
             f.write(np.ascontiguousarray(guess if k == 3 else poses[k]).tobytes())
-    out = subprocess.check_output([exe, path], text=True)
+    pcd_path, traj_path = str(tmp_path / "map_cloud.pcd"), str(tmp_path / "trajectory.json")
+    out = subprocess.check_output([exe, path, pcd_path, traj_path], text=True)
     lines = out.strip().splitlines()
     # oracle replay of the same call sequence
     om = oracle.Map(0.5, 1000)
@@ -121,3 +122,11 @@ def test_host_classes_match_oracle(tmp_path, oracle):
         w = np.array([float(v) for v in [l for l in lines if l.startswith("map")][k].split()[3:6]])
         np.testing.assert_array_equal(w, first[k])  # caller's cloud left in the world frame, bit-exact
     assert "ICP not converged" not in out
+    # LocalMap::save (src/LocalMap.cpp:156-167): one point per voxel + the pose of every frame
+    import json
+    traj = json.load(open(traj_path))
+    assert traj["class_name"] == "PinholeCameraTrajectory" and len(traj["parameters"]) == len(scans)
+    E = np.array(traj["parameters"][0]["extrinsic"]).reshape(4, 4).T   # column-major like Open3D
+    np.testing.assert_allclose(E, poses[0], atol=1e-15)
+    body = open(pcd_path).read().split("DATA ascii\n")[1].strip().splitlines()
+    assert len(body) == got_maps[-1]
