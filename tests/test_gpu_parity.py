@@ -251,6 +251,21 @@ def test_knn_search_corner_paths(ctx, oracle):
     np.testing.assert_allclose(gc, oc, atol=1e-7)
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_knn_ties_on_a_lattice(ctx, oracle, seed):
+    """Exact lattices make whole shells of neighbours equidistant; the 30th neighbour falls inside a
+    shell, so the (distance, index) tie order decides the set — and with it the covariance."""
+    rng = np.random.default_rng(seed)
+    g = np.stack(np.meshgrid(np.arange(14), np.arange(11), np.arange(5), indexing="ij"), -1).reshape(-1, 3)
+    pts = (g * 0.125)[rng.permutation(len(g))] + rng.integers(-3, 4, size=3) * 0.5
+    for voxel in (0.5, 0.3):
+        op, oc, osrc = oracle.downsample_cov(pts, voxel)
+        gp, gc, gsrc = ctx.downsample_cov(pts, voxel)
+        np.testing.assert_array_equal(gsrc, osrc)
+        np.testing.assert_array_equal(gp, op)
+        np.testing.assert_allclose(gc, oc, atol=1e-9)
+
+
 def test_preprocess_with_deskew(ctx, oracle, frames):
     xyz, t = frames.raw[1]
     t0, t1 = t[0], t[-1]

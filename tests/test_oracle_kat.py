@@ -181,6 +181,21 @@ def test_knn_kdtree_matches_bruteforce(oracle):
     assert (i3[:, 5:] == -1).all() and sorted(i3[0, :5].tolist()) == [0, 1, 2, 3, 4]
 
 
+def test_knn_tie_order_on_a_lattice(oracle):
+    """Equidistant neighbours: KD-tree and brute force agree on the (distance, index) order."""
+    g = np.stack(np.meshgrid(np.arange(12), np.arange(12), np.arange(6), indexing="ij"), -1).reshape(-1, 3) * 0.125
+    pts = g[np.random.default_rng(4).permutation(len(g))].astype(np.float64)
+    i1, d1 = oracle.knn(pts, pts[:150], 30)
+    i2, d2 = oracle.knn(pts, pts[:150], 30, bruteforce=True)
+    np.testing.assert_array_equal(i1, i2)
+    np.testing.assert_array_equal(d1, d2)
+    # ties resolved by ascending index
+    for row_i, row_d in zip(i1[:20], d1[:20]):
+        for a in range(29):
+            if row_d[a] == row_d[a + 1]:
+                assert row_i[a] < row_i[a + 1]
+
+
 def test_regularize_cov(oracle):
     # CloudPreprocessor.cpp:120-123 == I - 0.99 n n^T for a PSD input
     rng = np.random.default_rng(4)
