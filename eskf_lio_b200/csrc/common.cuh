@@ -158,13 +158,15 @@ __host__ __device__ __forceinline__ unsigned knn_level_slots(unsigned n, unsigne
   const unsigned b = bits > static_cast<unsigned>(L) ? bits - static_cast<unsigned>(L) : 0u;
   unsigned long long most = n;  // occupied blocks <= min(n, 8^b)
   if (b < 10u && (1ull << (3u * b)) < most) most = 1ull << (3u * b);
-  unsigned s = 8u;
-  while (static_cast<unsigned long long>(s) < 2ull * most) s <<= 1;
-  return s;
+  const unsigned long long want = 2ull * most > 8ull ? 2ull * most : 8ull;  // next power of two >= want
+#ifdef __CUDA_ARCH__
+  return 1u << (64 - __clzll(static_cast<long long>(want - 1ull)));
+#else
+  return 1u << (64 - __builtin_clzll(want - 1ull));
+#endif
 }
 
-__device__ __forceinline__ uint4* knn_level_claim(uint4* tab, unsigned mask, uint64_t bk) {
-  unsigned h = static_cast<unsigned>(hash_key(bk)) & mask;
+__device__ __forceinline__ uint4* knn_level_claim_from(uint4* tab, unsigned mask, uint64_t bk, unsigned h) {
   for (;;) {
     unsigned long long* kp = reinterpret_cast<unsigned long long*>(tab + h);
     const unsigned long long old = atomicCAS(kp, ~0ull, static_cast<unsigned long long>(bk));

@@ -272,38 +272,42 @@ __global__ void __launch_bounds__(128) fold_lists_kernel(ListInsertParams P) {
   if (i >= P.n) return;
   const uint32_t s = P.slot_of[i];
   if (s == kNoSlot || P.next[i] != kListEnd) return;  // only the first arrival of a list folds it
-  const uint32_t first = P.head[s];
+  // everything that only needs the slot index is requested at once (list head, record key +
+  // count, fp64 master statistics): one HBM round trip instead of three dependent ones
+  const uint32_t first = ld_cg(P.head + s);
+  const uint4 rec0 = ld_cg(reinterpret_cast<const uint4*>(P.slots + s));  // key (8) count (4) pad (4)
+  double* M = P.master + static_cast<size_t>(s) * kMasterStride;
+  double mean[3], C[9];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) mean[k] = ld_cg(M + k);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) C[k] = ld_cg(M + 3 + k);
   P.head[s] = kListEnd;  // ready for the next batch
   uint32_t idx[kListLocal];
-  unsigned L = 0;
-  for (uint32_t h = first; h != kListEnd; h = P.next[h]) {
-    if (L < kListLocal) idx[L] = h;
-    ++L;
-  }
-  if (L <= kListLocal) {  // insertion sort, ascending point index (= the reference's input order)
-    for (unsigned a = 1; a < L; ++a) {
-      const uint32_t v = idx[a];
-      unsigned b = a;
-      while (b > 0 && idx[b - 1] > v) {
-        idx[b] = idx[b - 1];
-        --b;
+  unsigned L = 1;
+  idx[0] = i;
+  if (first != i) {  // more than this point in the voxel: collect the list
+    L = 0;
+    for (uint32_t h = first; h != kListEnd; h = P.next[h]) {
+      if (L < kListLocal) idx[L] = h;
+      ++L;
+    }
+    if (L <= kListLocal) {  // insertion sort, ascending point index (= the reference's input order)
+      for (unsigned a = 1; a < L; ++a) {
+        const uint32_t v = idx[a];
+        unsigned b = a;
+        while (b > 0 && idx[b - 1] > v) {
+          idx[b] = idx[b - 1];
+          --b;
+        }
+        idx[b] = v;
       }
-      idx[b] = v;
     }
   }
   int kx, ky, kz;
-  unpack_key(P.slots[s].key, kx, ky, kz);
-  double* M = P.master + static_cast<size_t>(s) * kMasterStride;
-  double mean[3], C[9];
-  uint32_t cnt = P.slots[s].count;
-  if (cnt == 0) {
-    atomicAdd(P.d_count, 1ull);  // a voxel claimed by this batch
-  } else {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) mean[k] = M[k];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) C[k] = M[3 + k];
-  }
+  unpack_key((static_cast<uint64_t>(rec0.y) << 32) | rec0.x, kx, ky, kz);
+  uint32_t cnt = rec0.z;
+  if (cnt == 0) atomicAdd(P.d_count, 1ull);  // a voxel claimed by this batch (mean / C are overwritten below)
   const uint32_t before = cnt;
   uint32_t last = 0;
   for (unsigned j = 0; j < L && cnt < P.cap_pts; ++j) {

@@ -359,13 +359,35 @@ __global__ void __launch_bounds__(256) knn_levels_kernel(const uint64_t* key0, c
   const uint64_t cur = __ldg(sk + j);
   const uint64_t dprev = j == 0 ? ~0ull : (__ldg(sk + j - 1) ^ cur);
   const uint64_t dnext = j + 1 == n ? ~0ull : (__ldg(sk + j + 1) ^ cur);
+  // first claim attempt of every level this element heads / tails, all atomics in flight at once
+  // (one L2 round trip instead of up to six dependent ones); collisions are resolved below
+  bool head[kKnnHashLevels], tail[kKnnHashLevels];
+  unsigned mask[kKnnHashLevels], slot[kKnnHashLevels];
+  unsigned long long old[kKnnHashLevels];
+#pragma unroll
   for (int L = 0; L < kKnnHashLevels; ++L) {
-    const bool head = (dprev >> (3 * L)) != 0, tail = (dnext >> (3 * L)) != 0;
-    if (!head && !tail) break;  // inside a block of level L => inside all coarser ones
-    uint4* e = knn_level_claim(levels + static_cast<size_t>(L) * level_stride,
-                               knn_level_slots(n, bits, L) - 1u, cur >> (3 * L));
-    if (head) e->z = j;
-    if (tail) e->w = j + 1u;
+    head[L] = (dprev >> (3 * L)) != 0;
+    tail[L] = (dnext >> (3 * L)) != 0;
+    mask[L] = knn_level_slots(n, bits, L) - 1u;
+    const uint64_t bk = cur >> (3 * L);
+    slot[L] = static_cast<unsigned>(hash_key(bk)) & mask[L];
+    old[L] = 0ull;
+    if (head[L] || tail[L]) {
+      uint4* tab = levels + static_cast<size_t>(L) * level_stride;
+      old[L] = atomicCAS(reinterpret_cast<unsigned long long*>(tab + slot[L]), ~0ull,
+                         static_cast<unsigned long long>(bk));
+    }
+  }
+#pragma unroll
+  for (int L = 0; L < kKnnHashLevels; ++L) {
+    if (!head[L] && !tail[L]) continue;
+    uint4* tab = levels + static_cast<size_t>(L) * level_stride;
+    const uint64_t bk = cur >> (3 * L);
+    uint4* e = tab + slot[L];
+    if (old[L] != ~0ull && old[L] != bk)  // somebody else's block sits there: keep probing
+      e = knn_level_claim_from(tab, mask[L], bk, (slot[L] + 1u) & mask[L]);
+    if (head[L]) e->z = j;
+    if (tail[L]) e->w = j + 1u;
   }
 }
 
