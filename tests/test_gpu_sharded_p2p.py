@@ -21,6 +21,8 @@ def test_two_ranks_fused_exchange_matches_unsharded():
            os.path.join(ROOT, "scripts", "dense_sharded.py"), "--same-device", "--backend", "gloo",
            "--src", "150001", "--map", "600000", "--voxel", "0.25", "--iters", "4", "--reps", "1"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    if out.returncode != 0 and any(k in out.stderr for k in ("busy or unavailable", "exclusive", "EXCLUSIVE")):
+        pytest.skip("the GPU is in exclusive-process mode: two ranks cannot share it")
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     r = json.loads(line)
