@@ -42,10 +42,13 @@ def make_pair(k, map_points, scan_points):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pairs", type=int, default=512)
-    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--map-points", type=int, default=300_000)
     ap.add_argument("--scan-points", type=int, default=15_000)
     ap.add_argument("--cpu-sample", type=int, default=8)
+    ap.add_argument("--pipelined", type=int, default=1,
+                    help="1: one host thread keeps one registration in flight per context (begin/end); "
+                         "0: one blocking host thread per context")
     ap.add_argument("--repeat", type=int, default=8, help="timed passes over the batch (pairs are independent)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -81,17 +84,42 @@ def main():
                 if rep == 0:
                     results[s].append(r)
 
+    def work_pipelined():
+        """One host thread, one registration in flight per context (eskf_align_cloud_begin / _end):
+        the launches of the other contexts overlap the kernel each end() waits for."""
+        for rep in range(a.repeat):
+            pending = [None] * a.streams
+            for k in range(max(len(j) for j in jobs)):
+                for s in range(a.streams):
+                    if pending[s] is not None:
+                        r = ctxs[s].align_end()
+                        if rep == 0:
+                            results[s].append(r)
+                        pending[s] = None
+                    if k < len(jobs[s]):
+                        gmap, cloud, guess = jobs[s][k]
+                        gmap.align_cloud_begin(cloud, guess)
+                        pending[s] = True
+            for s in range(a.streams):
+                if pending[s] is not None:
+                    r = ctxs[s].align_end()
+                    if rep == 0:
+                        results[s].append(r)
+
     for s in range(a.streams):       # warm-up: first job of every stream
         if jobs[s]:
             jobs[s][0][0].align_cloud(jobs[s][0][1], jobs[s][0][2])
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
-    threads = [threading.Thread(target=work, args=(s,)) for s in range(a.streams)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+    if a.pipelined:
+        work_pipelined()
+    else:
+        threads = [threading.Thread(target=work, args=(s,)) for s in range(a.streams)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
     for c in ctxs:
         c.sync()
     dt = time.perf_counter() - t0
@@ -102,7 +130,7 @@ def main():
         dt = float(tt[0])
     if rank == 0:
         its = [r["iterations"] for rs in results for r in rs]
-        out = {"pairs": a.pairs, "world": world, "streams_per_gpu": a.streams, "map_points": a.map_points,
+        out = {"pairs": a.pairs, "world": world, "streams_per_gpu": a.streams, "pipelined": a.pipelined, "map_points": a.map_points,
                "scan_points": a.scan_points, "passes": a.repeat, "seconds": dt,
                "registrations_per_s": a.pairs * a.repeat / dt,
                "gn_iterations_mean": float(np.mean(its)), "all_converged": all(r["converged"] for rs in results for r in rs)}
