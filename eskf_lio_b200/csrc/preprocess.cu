@@ -382,37 +382,35 @@ __device__ __forceinline__ void for_each_candidate(const KnnParams& P, const uin
   }
 }
 
-// ascending bitonic sort of one non-negative double per lane (bit patterns of
-// non-negative doubles order like unsigned integers)
-__device__ __forceinline__ unsigned long long warp_sort_u64(unsigned long long v, unsigned lane) {
+// ascending bitonic sort of one float per lane
+__device__ __forceinline__ float warp_sort_f32(float v, unsigned lane) {
 #pragma unroll
   for (unsigned k = 2; k <= 32; k <<= 1) {
 #pragma unroll
     for (unsigned j = k >> 1; j > 0; j >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
+      const float o = __shfl_xor_sync(0xffffffffu, v, j);
       const bool up = (lane & k) == 0u || k == 32u;
       const bool lower = (lane & j) == 0u;
-      const unsigned long long mn = v < o ? v : o, mx = v < o ? o : v;
-      v = (lower == up) ? mn : mx;
+      v = (lower == up) ? fminf(v, o) : fmaxf(v, o);
     }
   }
   return v;
 }
 
-// upper bound of the K-th (K <= 32) smallest candidate distance from the two
-// smallest distances every lane has seen: the K-th smallest of the 64 values
-__device__ __forceinline__ double bound_from_minima(double m1, double m2, unsigned lane, int K) {
-  const unsigned long long a = warp_sort_u64(static_cast<unsigned long long>(__double_as_longlong(m1)), lane);
-  const unsigned long long b = warp_sort_u64(static_cast<unsigned long long>(__double_as_longlong(m2)), lane);
-  const unsigned long long br = __shfl_sync(0xffffffffu, b, 31u - lane);
-  unsigned long long c = a < br ? a : br;  // the 32 smallest of the union, a bitonic sequence
+// Upper bound of the K-th (K <= 32) smallest candidate distance from the two smallest
+// distances every lane has seen: the K-th smallest of the 64 values.  The minima are
+// tracked as floats rounded UP from the fp64 distances (an upper bound is all that is
+// needed; the selection itself stays exact), which makes the two sorts a third as long.
+__device__ __forceinline__ float bound_from_minima(float m1, float m2, unsigned lane, int K) {
+  const float a = warp_sort_f32(m1, lane);
+  const float b = warp_sort_f32(m2, lane);
+  float c = fminf(a, __shfl_sync(0xffffffffu, b, 31u - lane));  // the 32 smallest of the union, bitonic
 #pragma unroll
   for (unsigned j = 16; j > 0; j >>= 1) {  // bitonic merge -> ascending
-    const unsigned long long o = __shfl_xor_sync(0xffffffffu, c, j);
-    const unsigned long long mn = c < o ? c : o, mx = c < o ? o : c;
-    c = (lane & j) == 0u ? mn : mx;
+    const float o = __shfl_xor_sync(0xffffffffu, c, j);
+    c = (lane & j) == 0u ? fminf(c, o) : fmaxf(c, o);
   }
-  return __longlong_as_double(static_cast<long long>(__shfl_sync(0xffffffffu, c, K - 1)));
+  return __shfl_sync(0xffffffffu, c, K - 1);
 }
 
 // Overflow path (and the reference behaviour the selection above must equal):
@@ -523,14 +521,6 @@ __global__ void __launch_bounds__(kSearchThreads) knn_search_kernel(KnnParams P)
             start = lower_bound_u64(keys, 0, n, lo);
             end = lower_bound_u64(keys, start, n, lo + (1ull << (3 * L)));
           }
-          const double x0 = (static_cast<double>(m0) + static_cast<double>(nx) * span) * P.voxel;
-          const double y0 = (static_cast<double>(m1) + static_cast<double>(ny) * span) * P.voxel;
-          const double z0 = (static_cast<double>(m2) + static_cast<double>(nz) * span) * P.voxel;
-          const double w = span * P.voxel;
-          const double ex = fmax(fmax(x0 - qx, qx - (x0 + w)) - 1e-9, 0.0);
-          const double ey = fmax(fmax(y0 - qy, qy - (y0 + w)) - 1e-9, 0.0);
-          const double ez = fmax(fmax(z0 - qz, qz - (z0 + w)) - 1e-9, 0.0);
-          box2 = ex * ex + ey * ey + ez * ez;
         }
       }
       const unsigned len = end - start;
@@ -543,16 +533,31 @@ __global__ void __launch_bounds__(kSearchThreads) knn_search_kernel(KnnParams P)
         if (P.stats && lane == 0) atomicAdd(P.stats + 6, 1ull);
         continue;
       }
+      if (len != 0u) {  // squared distance from the query to this lane's block (only for levels that are searched)
+        const int nx = bx + static_cast<int>(dxl) - 1;
+        const int ny = by + static_cast<int>(dyl) - 1;
+        const int nz = bz + static_cast<int>(dzl) - 1;
+        const double x0 = (static_cast<double>(m0) + static_cast<double>(nx) * span) * P.voxel;
+        const double y0 = (static_cast<double>(m1) + static_cast<double>(ny) * span) * P.voxel;
+        const double z0 = (static_cast<double>(m2) + static_cast<double>(nz) * span) * P.voxel;
+        const double w = span * P.voxel;
+        const double ex = fmax(fmax(x0 - qx, qx - (x0 + w)) - 1e-9, 0.0);
+        const double ey = fmax(fmax(y0 - qy, qy - (y0 + w)) - 1e-9, 0.0);
+        const double ez = fmax(fmax(z0 - qz, qz - (z0 + w)) - 1e-9, 0.0);
+        box2 = ex * ex + ey * ey + ez * ez;
+      }
 
       // ---- pass 1: two smallest distances per lane, own block first
-      double mn1 = kInf, mn2 = kInf;
+      const float kInfF = __int_as_float(0x7f800000);
+      float mn1 = kInfF, mn2 = kInfF;  // rounded up: (double)mn >= the exact distance
       auto track = [&](bool valid, double d, int) {
         if (valid) {
-          if (d < mn1) {
+          const float df = __double2float_ru(d);
+          if (df < mn1) {
             mn2 = mn1;
-            mn1 = d;
-          } else if (d < mn2) {
-            mn2 = d;
+            mn1 = df;
+          } else if (df < mn2) {
+            mn2 = df;
           }
         }
       };
@@ -560,14 +565,16 @@ __global__ void __launch_bounds__(kSearchThreads) knn_search_kernel(KnnParams P)
       for_each_candidate(P, sidx, start, lane == 13 ? len : 0u, qx, qy, qz, lane, track);
       double b0 = kInf;  // 32 distinct candidates are <= max(mn1) once every lane has one
       if (own_len >= 32u) {
-        b0 = mn1;
+        float m = mn1;
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) b0 = fmax(b0, __shfl_xor_sync(0xffffffffu, b0, o));
+        for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        b0 = static_cast<double>(m);
       }
       const unsigned len1b = (lane != 13 && box2 <= b0) ? len : 0u;
       for_each_candidate(P, sidx, start, len1b, qx, qy, qz, lane, track);
       // with no more than 2 x 32 candidates everything fits the rank sort below: no bound needed
-      const double b1 = own_len + warp_reduce_add(len1b) > 64u ? bound_from_minima(mn1, mn2, lane, K) : kInf;
+      const double b1 = own_len + warp_reduce_add(len1b) > 64u
+                            ? static_cast<double>(bound_from_minima(mn1, mn2, lane, K)) : kInf;
 
       // ---- pass 2: compact the candidates under the bound
       unsigned S = 0;
