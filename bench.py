@@ -263,9 +263,13 @@ def impl_reference(args, rank, world):
 def gpu_sequence(capi, odometry, device, scans, imu, first_timed, mode):
     """mode 'resident': every raw sweep is uploaded to HBM before the timed region (the frames are
     fed as device clouds); 'e2e': sweeps sit in pinned host memory in the float32 wire format and
-    are copied to the device when they are delivered, the pose is read back every frame."""
+    are copied to the device when they are delivered, the pose is read back every frame; 'host':
+    like 'e2e' but through the plain drop-in classes (Config::device_resident = false): every one
+    of the three calls takes and returns host vectors like the reference's, so the downsampled
+    cloud crosses PCIe three times per frame."""
     import ctypes as C
-    od = odometry.Odometry(odometry.default_config(device_resident=1, **odom_overrides()), device)
+    od = odometry.Odometry(odometry.default_config(device_resident=0 if mode == "host" else 1,
+                                                   **odom_overrides()), device)
     ctx = od.context()
     keep = []
     if mode == "resident":
@@ -429,6 +433,8 @@ def main():
     barrier()
     e2e = gpu_sequence(capi, odometry, local_rank, scans, imu, first_timed, "e2e")
     barrier()
+    host = gpu_sequence(capi, odometry, local_rank, scans, imu, first_timed, "host") if rank == 0 else None
+    barrier()
 
     ms = res["device_ms"]
     ms_e2e = e2e["wall_ms"]
@@ -457,6 +463,10 @@ def main():
                     "d2h_bytes_per_step": e2e["d2h"],
                     "stage_ms": dict(zip(("preprocess", "filter_update", "map_update"), e2e["stage_ms"])),
                     "replay_wall_ms_per_frame_incl_imu_propagation": e2e["replay_wall_ms"] / args.steps},
+            "e2e_host_vector_classes": {
+                "value": host["wall_ms"] / args.steps, "unit": "ms",
+                "note": "the same frames through the drop-in classes with host std::vector clouds at "
+                        "every call (Config::device_resident = false), rank 0"},
             "gpu_launches": res["launches"], "clocks": res["clocks"],
             "frames_per_s": 1e3 / value,
             "stage_ms": dict(zip(("preprocess", "filter_update", "map_update"), res["stage_ms"])),
