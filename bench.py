@@ -483,7 +483,7 @@ def main():
             dctx = capi.Context(local_rank)
             line["roofline"] = dense_roofline(dctx, capi, peak, peak_src)
             dctx.close()
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # (the other ranks would be spinning at the barrier)
             n_cpu = first_timed + args.cpu_frames
             r = run_oracle(scans[:n_cpu], imu, first_timed)
             od, oe = zip(*[pose_delta(a, b) for a, b in zip(r["poses"], res["poses"][:n_cpu])])
