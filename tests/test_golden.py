@@ -74,3 +74,53 @@ def test_gpu_matches_golden(gold):
     E = np.linalg.inv(g["align_T"]) @ r["T"]
     assert np.linalg.norm(E[:3, 3]) < 1e-5
     assert np.arccos(np.clip(0.5 * (np.trace(E[:3, :3]) - 1), -1, 1)) < 1e-5
+
+
+# ------------------------------------------------- ErrorStateKF + Odometry::run
+GOLD_ODOM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "odometry_v1.npz")
+
+
+def _odom_log(g):
+    off = np.concatenate([[0], np.cumsum(g["n"])])
+    scans = [(g["xyz"][off[i]:off[i + 1]].astype(np.float64), g["time"][off[i]:off[i + 1]])
+             for i in range(len(g["n"]))]
+    return scans, g["imu"]
+
+
+def test_oracle_reproduces_golden_odometry(oracle):
+    """tests/golden/odometry_v1.npz (make_golden_odometry.py): filter + call order of Odometry::run."""
+    g = dict(np.load(GOLD_ODOM))
+    scans, imu = _odom_log(g)
+    oracle.set_num_threads(1)
+    od = oracle.Odometry(oracle.odom_default_config(map_voxel_size=0.5, preprocess_voxel_size=0.5))
+    rec = []
+    poses = oracle.run_sequence(od, scans, imu, lambda i, o: rec.append(
+        (o.info().last_iterations, o.info().last_inserted, o.info().map_voxels, o.info().last_kept)))
+    oracle.set_num_threads(oracle.num_threads())
+    np.testing.assert_array_equal(np.array(rec), g["rec"])
+    np.testing.assert_allclose(np.stack(poses), g["poses"], atol=1e-10)
+    st = od.last_state(with_P=True)
+    got = np.concatenate([[st["t"]], st["p"], st["v"], st["q"], st["ba"], st["bg"], st["g"]])
+    np.testing.assert_allclose(got, g["state"], atol=1e-9)
+    assert np.linalg.norm(st["P"] - g["P"]) / np.linalg.norm(g["P"]) < 1e-9
+
+
+@pytest.mark.gpu
+def test_gpu_odometry_matches_golden():
+    """The product's host ESKF + Odometry with the hot path on the B200, against the committed
+    oracle trajectory (no liboracle.so involved)."""
+    from eskf_lio_b200 import odometry
+    from gpu_common import pose_err
+    g = dict(np.load(GOLD_ODOM))
+    scans, imu = _odom_log(g)
+    od = odometry.Odometry(odometry.default_config(map_voxel_size=0.5, preprocess_voxel_size=0.5))
+    rec = []
+    poses = odometry.run_sequence(od, scans, imu, lambda i, o: rec.append(
+        (o.info().last_iterations, o.info().last_inserted, o.info().map_voxels)))
+    assert [r[0] for r in rec] == g["rec"][:, 0].tolist()      # Gauss-Newton iteration counts
+    assert [r[1] for r in rec] == g["rec"][:, 1].tolist()      # keyframe-gate decisions
+    assert all(abs(int(a[2]) - int(b)) <= 3 for a, b in zip(rec, g["rec"][:, 2]))
+    for a, b in zip(poses, g["poses"]):
+        dt, dr = pose_err(b, a)
+        assert dt < 1e-5 and dr < 1e-5
+    od.close()
