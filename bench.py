@@ -54,7 +54,7 @@ DENSE_ITERS = 10
 VOXEL = 0.3
 # untimed lead-in: frame 0 initialises the map, the trajectory starts from rest (the keyframe gate of
 # LocalMap.cpp:132-147 only opens at ~1 m/s), so ~35 frames put >= 20 scans into the local map
-LEAD_IN = 35
+LEAD_IN = int(os.environ.get("ESKF_BENCH_LEAD_IN", "35"))  # (the contract test shortens it)
 CACHE_DIR = os.environ.get("ESKF_BENCH_CACHE", "/tmp/eskf_lio_b200_cache")
 
 
