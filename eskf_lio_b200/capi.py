@@ -49,7 +49,7 @@ SYMBOLS = [
     "eskf_cloud_create", "eskf_cloud_destroy", "eskf_cloud_upload", "eskf_cloud_upload_f32",
     "eskf_cloud_download", "eskf_cloud_size", "eskf_cloud_transform", "eskf_cloud_copy",
     "eskf_map_create", "eskf_map_destroy", "eskf_map_insert", "eskf_map_insert_cloud",
-    "eskf_map_evict", "eskf_map_size", "eskf_map_capacity", "eskf_map_query", "eskf_map_export",
+    "eskf_map_evict", "eskf_map_size", "eskf_map_capacity", "eskf_map_compact", "eskf_map_query", "eskf_map_export",
     "eskf_preprocess", "eskf_preprocess_cloud", "eskf_downsample_cov",
     "eskf_align", "eskf_align_cloud", "eskf_align_cloud_begin", "eskf_align_end", "eskf_linearize",
     "eskf_align_cloud_fixed",
@@ -396,6 +396,10 @@ class Map:
         n = C.c_uint64(0)
         check(lib().eskf_map_capacity(self._h, C.byref(n)))
         return n.value
+
+    def compact(self):
+        """Re-hash into a table of 2 x size() slots (load factor 1/2, smallest tag array)."""
+        check(lib().eskf_map_compact(self._h))
 
     def query(self, xyz):
         xyz = _f64(xyz, (-1, 3))

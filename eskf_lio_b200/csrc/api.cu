@@ -238,6 +238,14 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
   if (const char* e = getenv("ESKF_L2_PERSIST")) ctx->opt_l2_persist = atoi(e) != 0;
   if (const char* e = getenv("ESKF_TRACE")) ctx->opt_trace = atoi(e) != 0;
   if (const char* e = getenv("ESKF_MAPPED_RESULTS")) ctx->opt_mapped_results = atoi(e) != 0;
+  if (const char* e = getenv("ESKF_ALIGN_BLOCK")) {
+    const int v = atoi(e);
+    if (v == 0 || v == 256 || v == 384 || v == 768) ctx->opt_align_block = v;
+  }
+  if (const char* e = getenv("ESKF_ALIGN_CHUNK")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) ctx->opt_align_chunk = v;
+  }
   if (cuda_stream) {
     ctx->stream = static_cast<cudaStream_t>(cuda_stream);
     ctx->own_stream = false;
@@ -333,6 +341,13 @@ int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
     ctx->opt_mapped_results = (value != 0 && ctx->mail_h != nullptr) ? 1 : 0;
   } else if (n == "map_insert_sorted") {
     ctx->opt_insert_sorted = value != 0;
+  } else if (n == "align_block") {
+    ESKF_REQUIRE(value == 0 || value == 256 || value == 384 || value == 768,
+                 "align_block must be 0 (by cloud size), 256, 384 or 768");
+    ctx->opt_align_block = static_cast<int>(value);
+  } else if (n == "align_ticket_chunk") {
+    ESKF_REQUIRE(value == 1 || value == 2 || value == 4, "align_ticket_chunk must be 1, 2 or 4");
+    ctx->opt_align_chunk = static_cast<int>(value);
   } else if (n == "knn_buffer") {
     ESKF_REQUIRE(value >= 1 && value <= 128, "knn_buffer must be in [1, 128]");
     ctx->opt_knn_buffer = static_cast<int>(value);

@@ -798,6 +798,15 @@ int eskf_map_capacity(eskf_map* m, uint64_t* n_slots) {
   return ESKF_OK;
 }
 
+int eskf_map_compact(eskf_map* m) {
+  ESKF_REQUIRE(m, "null map");
+  uint64_t n = 0;
+  ESKF_TRY(eskf_map_size(m, &n));
+  const uint64_t want = table_size_for(n);
+  if (want == m->n_slots) return ESKF_OK;
+  return rebuild(m, want, 0, nullptr, 0.0, nullptr);
+}
+
 int eskf_map_query(eskf_map* m, const double* xyz, size_t n, int32_t* key_xyz, uint8_t* hit,
                    uint32_t* count, double* mean, double* cov) {
   ESKF_REQUIRE(m, "null map");

@@ -25,8 +25,8 @@ namespace eskf {
 
 namespace {
 
-constexpr int kT = 256;
-constexpr int kW = kT / 32;
+constexpr int kT = 256;   // default CTA size (small clouds; the 7-neighbour / fp64 variants)
+constexpr int kMaxT = 768;  // largest CTA size a variant may use (one CTA of 24 warps per SM)
 constexpr int kAcc = 28;  // A(6) B(9) D(6) b(6) + correspondence count
 constexpr int kMaxWorld = ESKF_MAX_WORLD;
 constexpr int kMailStride = 32;  // doubles per (parity, source rank): 28 sums, [28] = flag
@@ -79,6 +79,7 @@ struct AlignParams {
   double cos_thr;
   int fixed_iterations;
   int dynamic_tiles;  // 1: warps pull tiles from a counter (load-balanced, summation order varies)
+  int ticket_chunk;   // tiles per ticket in that dynamic tail (1, 2 or 4)
   AlignState* st;
   double* partials;  // [G][kAcc]
   double* sums;      // [kAcc] (single_pass output / solve input)
@@ -224,13 +225,13 @@ __device__ __forceinline__ const VoxelSlot* resolve_probe(const tag_t* tags,
 // payload) so U independent dependent-load chains are in flight per thread.
 // Per tile the 28 per-lane partial terms (fp32) are folded with a warp
 // reduce-scatter and added to ONE fp64 accumulator per lane (lane l = term l).
-template <typename F, int U, int NN>
+template <typename F, int U, int NN, int NW>
 __device__ __forceinline__ double accumulate_points(const AlignParams& P, const double* sT,
                                                     const F* sR, bool first, bool write_hit) {
   const unsigned lane = threadIdx.x & 31;
   const unsigned tile_pts = 32u * U;
-  const unsigned wglobal = blockIdx.x * kW + (threadIdx.x >> 5);
-  const unsigned wstride = gridDim.x * kW;
+  const unsigned wglobal = blockIdx.x * NW + (threadIdx.x >> 5);
+  const unsigned wstride = gridDim.x * NW;
   const double* sx = first ? P.x0 : P.wx;
   const double* sy = first ? P.y0 : P.wy;
   const double* sz = first ? P.z0 : P.wz;
@@ -401,27 +402,47 @@ __device__ __forceinline__ void prefetch_record(const void* p) {
   asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
 }
 
-// scan 8 tags (w) starting at slot h for `tag`; returns the matching slot,
-// kNoCand on an empty slot, or kMore if the group is exhausted
+// A lookup first sees a WINDOW of 8 tags: slots [b, b+4) and the 4 slots that follow them in
+// probe order, b = home & ~(kTagAlign - 1).  With kTagAlign = 4 (two 8 B loads) the window always
+// holds >= 5 tags from `home` on and ~1e-3 of the lookups need a second, dependent L2 round trip;
+// with one 16 B-aligned group (kTagAlign = 8) 3/8 of the lookups start with < 4 tags left, ~5 % of
+// them run off the group, and a warp of 32 lookups paid the second round trip on most of its trips.
+#ifndef ESKF_TAG_ALIGN
+#define ESKF_TAG_ALIGN 4
+#endif
+constexpr uint32_t kTagAlign = ESKF_TAG_ALIGN;
+static_assert(kTagAlign == 4 || kTagAlign == 8, "tag window alignment");
+
+// scan the window's tags from position k0 on: position of the first tag equal to `tag`,
+// kNoCand on an empty slot, kMore if the window is exhausted
 constexpr uint32_t kMore = 0xfffffffeu;
-__device__ __forceinline__ uint32_t scan_tag_group(uint4 w, uint32_t h, uint32_t tag) {
+__device__ __forceinline__ uint32_t scan_tag_window(uint4 w, uint32_t k0, uint32_t tag) {
   const uint64_t lo = (static_cast<uint64_t>(w.y) << 32) | w.x;
   const uint64_t hi = (static_cast<uint64_t>(w.w) << 32) | w.z;
-  for (uint32_t k = h & 7u; k < 8u; ++k) {
+  for (uint32_t k = k0; k < 8u; ++k) {
     const uint32_t t = static_cast<uint32_t>((k < 4u ? lo >> (16u * k) : hi >> (16u * (k - 4u))) & 0xffffu);
     if (t == 0u) return kNoCand;
-    if (t == tag) return (h & ~7u) + k;
+    if (t == tag) return k;
   }
   return kMore;
 }
 
-template <typename F>
+// the window that starts at slot b (a multiple of 4; n_slots is a multiple of 64, so neither half
+// straddles the end of the table); b2 = first slot of its second half
+__device__ __forceinline__ uint4 load_tag_window(const tag_t* tags, uint32_t b, uint32_t b2) {
+  if (kTagAlign == 8) return __ldg(reinterpret_cast<const uint4*>(tags + b));
+  const uint2 lo = __ldg(reinterpret_cast<const uint2*>(tags + b));
+  const uint2 hi = __ldg(reinterpret_cast<const uint2*>(tags + b2));
+  return make_uint4(lo.x, lo.y, hi.x, hi.y);
+}
+
+template <typename F, int NW>
 __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams& P,
                                                               const double* sT, const F* sR,
                                                               bool first, bool write_hit) {
   const unsigned lane = threadIdx.x & 31;
-  const unsigned wglobal = blockIdx.x * kW + (threadIdx.x >> 5);
-  const unsigned wstride = gridDim.x * kW;
+  const unsigned wglobal = blockIdx.x * NW + (threadIdx.x >> 5);
+  const unsigned wstride = gridDim.x * NW;
   const double* sx = first ? P.x0 : P.wx;
   const double* sy = first ? P.y0 : P.wy;
   const double* sz = first ? P.z0 : P.wz;
@@ -459,20 +480,28 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
       rz = first ? __ldcs(sz + i) : __ldcg(sz + i);
     }
   };
-  // finish the tag scan of s given its first group w (rarely needs more groups)
+  auto wrap4 = [&](uint32_t b) -> uint32_t { return b + 4u == P.n_slots ? 0u : b + 4u; };
+  // first tag window of a transformed point (zeros = "empty" when it has no lookup)
+  auto first_window = [&](const PtState& s) -> uint4 {
+    if (s.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t b = s.home & ~(kTagAlign - 1u);
+    return load_tag_window(P.tags, b, wrap4(b));
+  };
+  // finish the tag scan of s given its first window w (rarely needs more windows)
   auto finish_scan = [&](PtState& s, uint4 w) {
     if (s.tag == 0u) return;
-    uint32_t h = s.home;
-    uint32_t r = scan_tag_group(w, h, s.tag);
-    uint32_t scanned = 8u - (h & 7u);
+    uint32_t b = s.home & ~(kTagAlign - 1u), b2 = wrap4(b);
+    uint32_t r = scan_tag_window(w, s.home & (kTagAlign - 1u), s.tag);
+    uint32_t scanned = 8u - (s.home & (kTagAlign - 1u));
     while (r == kMore && scanned < P.n_slots) {
-      h = (h & ~7u) + 8u == P.n_slots ? 0u : (h & ~7u) + 8u;
-      r = scan_tag_group(__ldg(reinterpret_cast<const uint4*>(P.tags + h)), h, s.tag);
+      b = wrap4(b2);
+      b2 = wrap4(b);
+      r = scan_tag_window(load_tag_window(P.tags, b, b2), 0u, s.tag);
       scanned += 8u;
     }
-    if (r != kNoCand && r != kMore) {
-      s.cand = r;
-      prefetch_record(P.slots + r);
+    if (r < 8u) {
+      s.cand = r < 4u ? b + r : b2 + (r - 4u);
+      prefetch_record(P.slots + s.cand);
     }
   };
 
@@ -480,34 +509,37 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
   // Tiles: a fixed stride per warp for the first 13/16 of every pass, the rest
   // pulled from a global counter.  The spread of per-warp progress (HBM channel
   // luck) otherwise leaves most warps waiting ~20 % of the pass at the
-  // iteration barrier for the slowest one.  A ticket is requested one trip
-  // before it is used (lane 0 keeps the raw value, the broadcast happens at the
-  // use), so the atomic's latency never stalls the pipeline.
+  // iteration barrier for the slowest one.  A ticket is requested at least one
+  // trip before it is used (lane 0 keeps the raw value, the broadcast happens
+  // at the use), so the atomic's latency stays off the pipeline.
   // Measured: 189 -> 160 us per iteration at 0.5 m voxels (every point hits).
   // Clouds with fewer than 8 tiles per warp, or dynamic_tiles == 0
   // (ESKF_ALIGN_DYNAMIC=0), run fully static: bit-reproducible summation order.
   const bool dynamic = P.dynamic_tiles != 0 && n_tiles >= 8u * wstride;  // small clouds: nothing to balance
   const unsigned k_static = dynamic ? (n_tiles - n_tiles * 3u / 16u) / wstride : 0xffffffffu;
   const unsigned dyn_base = dynamic ? k_static * wstride : 0u;
+  // A ticket is worth `chunk` consecutive tiles (fewer same-address atomics, and chunk trips of
+  // lead time): lane 0 keeps the chunk in use and the one requested ahead.
+  const unsigned chunk = static_cast<unsigned>(P.ticket_chunk);
   unsigned k_next = 0;
-  unsigned ticket_raw = 0;  // lane 0: result of the atomic issued one call earlier
-  auto request = [&]() {
-    if (k_next >= k_static && lane == 0) ticket_raw = atomicAdd(&P.st->tile_counter, 1u);
-  };
+  unsigned tk_cur = 0, tk_next = 0;
   auto next_tile = [&]() -> unsigned {
     unsigned t;
     if (k_next < k_static) {
       t = wglobal + k_next * wstride;
-      if (t > n_tiles) t = n_tiles;  // (static mode: past the end)
     } else {
-      t = dyn_base + __shfl_sync(0xffffffffu, ticket_raw, 0);
-      if (t > n_tiles) t = n_tiles;
+      const unsigned sub = (k_next - k_static) & (chunk - 1u);
+      if (sub == 0u) {
+        tk_cur = tk_next;  // (waits for the atomic issued >= one call ago)
+        if (lane == 0) tk_next = atomicAdd(&P.st->tile_counter, chunk);
+      }
+      t = dyn_base + __shfl_sync(0xffffffffu, tk_cur, 0) + sub;
     }
+    if (t > n_tiles) t = n_tiles;  // past the end (static mode, or the last tickets of a pass)
     ++k_next;
-    request();  // for the NEXT call
+    if (k_next == k_static && lane == 0) tk_next = atomicAdd(&P.st->tile_counter, chunk);  // first chunk
     return t;
   };
-  request();
   // ---- prologue: cur = first tile (scanned), nxt = second tile (transformed)
   PtState cur, nxt;
   unsigned tile = next_tile(), tile_n = next_tile();
@@ -520,9 +552,7 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
     load_pos(tile, rx, ry, rz);
     load_pos(tile_n, qx, qy, qz);
     xform(tile, rx, ry, rz, cur);
-    uint4 w = make_uint4(0u, 0u, 0u, 0u);
-    if (cur.tag != 0u) w = __ldg(reinterpret_cast<const uint4*>(P.tags + (cur.home & ~7u)));
-    finish_scan(cur, w);
+    finish_scan(cur, first_window(cur));
     xform(tile_n, qx, qy, qz, nxt);
   }
   while (tile < n_tiles) {
@@ -531,8 +561,7 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
     // ---- issue: three independent groups of loads
     double rx, ry, rz;
     load_pos(tile_r, rx, ry, rz);
-    uint4 tagw = make_uint4(0u, 0u, 0u, 0u);
-    if (nxt.tag != 0u) tagw = __ldg(reinterpret_cast<const uint4*>(P.tags + (nxt.home & ~7u)));
+    const uint4 tagw = first_window(nxt);
     uint4 r0 = make_uint4(0u, 0u, 0u, 0u);
     float4 pa, pc, pd, s4;
     float2 s2;
@@ -596,6 +625,7 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
 }
 
 // deterministic CTA reduction: lane l of every warp holds term l
+template <int NW>
 __device__ __forceinline__ void block_reduce_store(double acc, double (*s_part)[32], double* out) {
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   s_part[w][lane] = acc;
@@ -603,13 +633,14 @@ __device__ __forceinline__ void block_reduce_store(double acc, double (*s_part)[
   if (threadIdx.x < kAcc) {
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < kW; ++i) s += s_part[i][threadIdx.x];
+    for (int i = 0; i < NW; ++i) s += s_part[i][threadIdx.x];
     out[threadIdx.x] = s;
   }
   __syncthreads();
 }
 
 // sum partials[0..G) in a fixed order -> s_sum[kAcc]  (whole CTA cooperates)
+template <int NW>
 __device__ __forceinline__ void final_reduce(const double* partials, unsigned G,
                                              double (*s_part)[32], double* s_sum) {
   const unsigned term = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -617,11 +648,11 @@ __device__ __forceinline__ void final_reduce(const double* partials, unsigned G,
   if (term < kAcc) {
     // 16 independent loads in flight per thread (a dependent chain of ~G/8 L2
     // round trips used to cost ~20 us per iteration): one round trip up to 128 CTAs
-    for (unsigned bb = grp; bb < G; bb += kW * 16) {
+    for (unsigned bb = grp; bb < G; bb += NW * 16) {
       double v[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const unsigned b2 = bb + kW * k;
+        const unsigned b2 = bb + NW * k;
         v[k] = b2 < G ? ld_cg(partials + static_cast<size_t>(b2) * kAcc + term) : 0.0;
       }
 #pragma unroll
@@ -633,7 +664,7 @@ __device__ __forceinline__ void final_reduce(const double* partials, unsigned G,
   if (threadIdx.x < kAcc) {
     double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < kW; ++i) t += s_part[i][threadIdx.x];
+    for (int i = 0; i < NW; ++i) t += s_part[i][threadIdx.x];
     s_sum[threadIdx.x] = t;
   }
   __syncthreads();
@@ -961,7 +992,7 @@ __device__ __forceinline__ bool exchange_sums(const AlignParams& P, int it, doub
   const int W = P.world;
   const size_t slot = (static_cast<size_t>(it & 1) * W + P.rank) * kMailStride;
   const double flag = static_cast<double>(P.seq) * 65536.0 + static_cast<double>(it + 1);
-  for (unsigned k = t; k < static_cast<unsigned>(kAcc * W); k += kT)
+  for (unsigned k = t; k < static_cast<unsigned>(kAcc * W); k += blockDim.x)
     P.peers[k / kAcc][slot + k % kAcc] = s_sum[k % kAcc];
   __syncthreads();
   // (st.release.sys orders the CTA's data stores, made visible to this thread by
@@ -998,11 +1029,12 @@ __device__ __forceinline__ bool exchange_sums(const AlignParams& P, int it, doub
   return *s_flag != 0;
 }
 
-template <typename F, int U, int NN, int MINB>
-__global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
+template <typename F, int U, int NN, int MINB, int T = kT>
+__global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
+  constexpr int NW = T / 32;
   __shared__ double s_T[12];
   __shared__ F s_R[9];
-  __shared__ double s_part[kW][32];
+  __shared__ double s_part[NW][32];
   __shared__ double s_sum[kAcc];
   __shared__ double s_solve[96];
   __shared__ int s_last, s_done, s_xchg;
@@ -1017,9 +1049,9 @@ __global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
   for (int it = 0; it < max_it; ++it) {
 
     const double acc = (NN == 1 && U == 1 && ESKF_PIPELINED)
-                           ? accumulate_points_pipelined<F>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0)
-                           : accumulate_points<F, U, NN>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0);
-    block_reduce_store(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
+                           ? accumulate_points_pipelined<F, NW>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0)
+                           : accumulate_points<F, U, NN, NW>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0);
+    block_reduce_store<NW>(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
 
     // last CTA to arrive reduces the partials and solves
     if (t == 0) {
@@ -1028,7 +1060,7 @@ __global__ void __launch_bounds__(kT, MINB) align_kernel(AlignParams P) {
     }
     __syncthreads();
     if (s_last) {
-      final_reduce(P.partials, G, s_part, s_sum);
+      final_reduce<NW>(P.partials, G, s_part, s_sum);
       bool ok = true;
       if (P.world > 1) ok = exchange_sums(P, it, s_sum, &s_xchg);
       if (t < 32) {
@@ -1072,11 +1104,12 @@ __global__ void solve_kernel(AlignParams P, int it) {
 
 // sharded mode: ONE linearisation of this rank's point range; the 28 sums go
 // to P.sums for the caller's all-reduce, solve_kernel follows
-template <typename F, int U, int NN, int MINB>
-__global__ void __launch_bounds__(kT, MINB) linearize_pass_kernel(AlignParams P, int it) {
+template <typename F, int U, int NN, int MINB, int T = kT>
+__global__ void __launch_bounds__(T, MINB) linearize_pass_kernel(AlignParams P, int it) {
+  constexpr int NW = T / 32;
   __shared__ double s_T[12];
   __shared__ F s_R[9];
-  __shared__ double s_part[kW][32];
+  __shared__ double s_part[NW][32];
   __shared__ double s_sum[kAcc];
   __shared__ int s_flag;
   const unsigned G = gridDim.x, t = threadIdx.x;
@@ -1085,16 +1118,16 @@ __global__ void __launch_bounds__(kT, MINB) linearize_pass_kernel(AlignParams P,
   if (t < 9) s_R[t] = (it == 0) ? F(P.guess[t]) : F(ld_cg(&st->Rf[t]));
   __syncthreads();
   const double acc = (NN == 1 && U == 1 && ESKF_PIPELINED)
-                         ? accumulate_points_pipelined<F>(P, s_T, s_R, it == 0, false)
-                         : accumulate_points<F, U, NN>(P, s_T, s_R, it == 0, false);
-  block_reduce_store(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
+                         ? accumulate_points_pipelined<F, NW>(P, s_T, s_R, it == 0, false)
+                         : accumulate_points<F, U, NN, NW>(P, s_T, s_R, it == 0, false);
+  block_reduce_store<NW>(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
   if (t == 0) {
     const unsigned ticket = atom_add_acq_rel(&st->block_counter, 1u);
     s_flag = (ticket == G * static_cast<unsigned>(it + 1) - 1u) ? 1 : 0;
   }
   __syncthreads();
   if (s_flag) {
-    final_reduce(P.partials, G, s_part, s_sum);
+    final_reduce<NW>(P.partials, G, s_part, s_sum);
     if (t < kAcc) P.sums[t] = s_sum[t];
   }
 }
@@ -1103,11 +1136,16 @@ __global__ void __launch_bounds__(kT, MINB) linearize_pass_kernel(AlignParams P,
 struct Variant {
   void* align;
   void* pass;
+  int threads;  // CTA size
   int pts_per_block;
   int per_sm;  // filled by align_max_blocks()
 };
 
-enum { V_F32_N1 = 0, V_F32_N7, V_F64_N1, V_F64_N7, V_COUNT };
+// The 1-neighbour fp32 kernel exists at three CTA shapes with the same 24 warps per SM:
+// 3 x 256, 2 x 384 and 1 x 768 threads.  Fewer, fatter CTAs shorten the per-iteration
+// hand-off of a large cloud (148 instead of 444 partial sums to reduce, tickets to take and
+// epoch pollers); small clouds keep 256-thread CTAs so that they spread over more SMs.
+enum { V_F32_N1 = 0, V_F32_N7, V_F64_N1, V_F64_N7, V_F32_N1_T384, V_F32_N1_T768, V_COUNT };
 
 // measured on B200, dense config (2M pts, 10 iterations per launch):
 //   U=1/3 CTAs 1.267 ms, U=1/4 CTAs 1.246 ms, U=2/3 CTAs 1.303 ms,
@@ -1118,21 +1156,37 @@ enum { V_F32_N1 = 0, V_F32_N7, V_F64_N1, V_F64_N7, V_COUNT };
 #ifndef ESKF_ALIGN_MINB
 #define ESKF_ALIGN_MINB 3
 #endif
+#ifndef ESKF_ALIGN_FAT_T
+// measured on B200, dense config, us per GN iteration at 0.1 m / 0.5 m voxels with 2-tile tickets:
+// 3 x 256 threads 86.9 / 163.9, 2 x 384 85.6 / 161.7, 1 x 768 85.1 / 158.2
+#define ESKF_ALIGN_FAT_T 768  // CTA size for clouds >= kFatCtaPoints (256 | 384 | 768)
+#endif
 
 Variant g_variants[V_COUNT] = {
     {reinterpret_cast<void*>(align_kernel<float, ESKF_ALIGN_U, 1, ESKF_ALIGN_MINB>),
      reinterpret_cast<void*>(linearize_pass_kernel<float, ESKF_ALIGN_U, 1, ESKF_ALIGN_MINB>),
-     kT * ESKF_ALIGN_U, 1},
+     kT, kT * ESKF_ALIGN_U, 1},
     {reinterpret_cast<void*>(align_kernel<float, 1, 7, 2>),
-     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 7, 2>), kT, 1},
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 7, 2>), kT, kT, 1},
     {reinterpret_cast<void*>(align_kernel<double, 1, 1, 1>),
-     reinterpret_cast<void*>(linearize_pass_kernel<double, 1, 1, 1>), kT, 1},
+     reinterpret_cast<void*>(linearize_pass_kernel<double, 1, 1, 1>), kT, kT, 1},
     {reinterpret_cast<void*>(align_kernel<double, 1, 7, 1>),
-     reinterpret_cast<void*>(linearize_pass_kernel<double, 1, 7, 1>), kT, 1},
+     reinterpret_cast<void*>(linearize_pass_kernel<double, 1, 7, 1>), kT, kT, 1},
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 2, 384>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 2, 384>), 384, 384, 1},
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, kMaxT>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, kMaxT>), kMaxT, kMaxT, 1},
 };
 
-int variant_index(const AlignArgs& a) {
-  return (a.fp64_math ? 2 : 0) + (a.neighbor_mode == 7 ? 1 : 0);
+// clouds whose 256-thread grid would be capped at 3 CTAs per SM anyway
+constexpr size_t kFatCtaPoints = static_cast<size_t>(1) << 18;
+
+int variant_index(const eskf_ctx* ctx, const AlignArgs& a) {
+  const int base = (a.fp64_math ? 2 : 0) + (a.neighbor_mode == 7 ? 1 : 0);
+  if (base != V_F32_N1) return base;
+  int threads = ctx->opt_align_block;  // 0 = choose by cloud size
+  if (threads == 0) threads = (a.cloud && a.cloud->n >= kFatCtaPoints) ? ESKF_ALIGN_FAT_T : kT;
+  return threads == 768 ? V_F32_N1_T768 : threads == 384 ? V_F32_N1_T384 : V_F32_N1;
 }
 
 struct TraceLayout {
@@ -1164,7 +1218,7 @@ int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, T
   const unsigned n = static_cast<unsigned>(c->n);
   const size_t pitch = (static_cast<size_t>(n) + 63) / 64 * 64 + 64;
   ESKF_TRY(ctx->work.ensure(pitch * 3 * sizeof(double)));
-  const Variant& var = g_variants[variant_index(a)];
+  const Variant& var = g_variants[variant_index(ctx, a)];
   int g = static_cast<int>((n + var.pts_per_block - 1) / var.pts_per_block);
   const int g_max = var.per_sm * ctx->sm_count;
   if (g > g_max) g = g_max;
@@ -1198,6 +1252,7 @@ int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, T
   P->cos_thr = a.cos_thr;
   P->fixed_iterations = a.fixed_iterations;
   P->dynamic_tiles = ctx->opt_align_dynamic;
+  P->ticket_chunk = ctx->opt_align_chunk;
   P->st = reinterpret_cast<AlignState*>(base + L->o_state);
   P->partials = ctx->partials.as<double>();
   P->sums = reinterpret_cast<double*>(base + L->o_sums);
@@ -1351,9 +1406,9 @@ int align_begin(eskf_ctx* ctx, const AlignArgs& a, const eskf_align_info* info) 
     }
   }
   void* args[] = {&P};
-  void* fn = g_variants[variant_index(a)].align;
+  const Variant& var = g_variants[variant_index(ctx, a)];
   trace_mark(ctx, "start");
-  ESKF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(kT), args, 0, ctx->stream));
+  ESKF_CUDA(cudaLaunchCooperativeKernel(var.align, dim3(G), dim3(var.threads), args, 0, ctx->stream));
   count_launch(ctx);
   trace_mark(ctx, "align");
   pd->active = true;
@@ -1389,7 +1444,8 @@ int align_max_blocks(int sm_count, int* out) {
   int best = 1;
   for (int v = 0; v < V_COUNT; ++v) {
     int per_sm = 0;
-    ESKF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g_variants[v].align, kT, 0));
+    ESKF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g_variants[v].align,
+                                                            g_variants[v].threads, 0));
     if (per_sm < 1) per_sm = 1;
     g_variants[v].per_sm = per_sm;
     if (per_sm > best) best = per_sm;
@@ -1416,8 +1472,8 @@ int align_sharded(eskf_ctx* ctx, const AlignArgs& a, eskf_allreduce_fn allreduce
   for (int it = 0; it < max_it; ++it) {
     if (P.n > 0) {
       void* pargs[] = {&P, &it};
-      ESKF_CUDA(cudaLaunchKernel(g_variants[variant_index(a)].pass, dim3(G), dim3(kT), pargs, 0,
-                                 ctx->stream));
+      const Variant& var = g_variants[variant_index(ctx, a)];
+      ESKF_CUDA(cudaLaunchKernel(var.pass, dim3(G), dim3(var.threads), pargs, 0, ctx->stream));
       count_launch(ctx);
     } else {
       ESKF_CUDA(cudaMemsetAsync(P.sums, 0, kAcc * sizeof(double), ctx->stream));

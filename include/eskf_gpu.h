@@ -118,7 +118,11 @@ int eskf_ctx_launch_count(eskf_ctx* ctx, uint64_t* n);
  *                          batches up to 131072 points take the sort-free list path; both give
  *                          bit-identical maps)
  *   "knn_buffer"           candidates the 30-NN selection keeps in shared memory before it falls
- *                          back to serial insertion (1..128, default 128; tests force the fallback) */
+ *                          back to serial insertion (1..128, default 128; tests force the fallback)
+ *   "align_block"          CTA size of the 1-neighbour fp32 registration kernel: 0 = chosen by cloud
+ *                          size (default), 256, 384 or 768 threads (always 24 warps per SM)
+ *   "align_ticket_chunk"   warp tiles taken per ticket in the load-balanced tail of a pass over a
+ *                          large cloud (1, 2 or 4; default 2) */
 int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value);
 /* CUDA-event timing on the context's own stream (bench.py's roofline leg) */
 int eskf_ctx_timer_start(eskf_ctx* ctx);
@@ -165,6 +169,10 @@ int eskf_map_insert_cloud(eskf_map* m, eskf_cloud* cloud, const double T[16]);
 int eskf_map_evict(eskf_map* m, const double pos[3], double dist_thresh, uint64_t* removed);
 int eskf_map_size(eskf_map* m, uint64_t* n_voxels);
 int eskf_map_capacity(eskf_map* m, uint64_t* n_slots);
+/* Re-hash the map into a table of exactly 2 x (occupied voxels) slots.  Bulk inserts grow the
+ * table for the worst case (every incoming point a new voxel); after a map build this brings the
+ * load factor back to 1/2, i.e. the smallest (most L2-resident) tag array.  Contents unchanged. */
+int eskf_map_compact(eskf_map* m);
 /* parity / debug: per-point lookup (getVoxelIndex + find, src/LocalMap.cpp:93-100,
  * 114-118).  Any output may be NULL. */
 int eskf_map_query(eskf_map* m, const double* xyz, size_t n, int32_t* key_xyz, uint8_t* hit,

@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""A/B of the registration kernel's run-time knobs on the dense config (BASELINE.json
+configs[2]): CTA shape (align_block) x tiles per ticket (align_ticket_chunk), one map build per
+voxel size.  Every cell is checked against the fully static 256-thread run: per-iteration
+correspondence counts must be identical, the final pose equal to rounding.
+
+    python scripts/ab_align_opts.py [--voxels 0.1,0.5] [--blocks 256,384,768] [--chunks 1,2,4]
+"""
+import argparse
+import itertools
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from eskf_lio_b200 import capi, synth as S  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--src", type=int, default=2_000_000)
+    ap.add_argument("--map", type=int, default=10_000_000)
+    ap.add_argument("--voxels", default="0.1,0.5")
+    ap.add_argument("--blocks", default="256,384,768")
+    ap.add_argument("--chunks", default="1,2,4")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--compact", default="0,1", help="also time the map after eskf_map_compact")
+    a = ap.parse_args()
+    ctx = capi.Context(0)
+    try:  # what the persisting-L2 window of the tag array has to work with
+        from cuda import cudart
+        for name in ("cudaDevAttrMaxPersistingL2CacheSize", "cudaDevAttrMaxAccessPolicyWindowSize",
+                     "cudaDevAttrL2CacheSize"):
+            print(name, cudart.cudaDeviceGetAttribute(getattr(cudart.cudaDeviceAttr, name), 0)[1], flush=True)
+    except Exception as e:  # noqa: BLE001
+        print("cudart attributes unavailable:", e)
+    rows = []
+    for voxel in [float(v) for v in a.voxels.split(",")]:
+        rng = np.random.default_rng(44)
+        scene = S.block_scene()
+        gmap = capi.Map(ctx, voxel, 1000, 9_000_000)
+        left = a.map
+        while left > 0:
+            n = min(2_500_000, left)
+            p, c = S.dense_cloud(scene, n, rng)
+            gmap.insert(p, c, np.eye(4))
+            left -= n
+        p, c = S.dense_cloud(scene, a.src, rng)
+        src = capi.Cloud(ctx, a.src).upload(p, c)
+        guess = S.perturbation(dt=(0.03, -0.015, 0.01), angle_deg=0.3)
+        ctx.set_option("align_block", 256)
+        ctx.set_option("align_dynamic_tiles", 0)
+        ref = gmap.align_cloud_fixed(src, guess, a.iters, trace=True)
+        ctx.set_option("align_dynamic_tiles", 1)
+        blocks = [int(b) for b in a.blocks.split(",")]
+        chunks = [int(c) for c in a.chunks.split(",")]
+        for compact in [int(c) for c in a.compact.split(",")]:
+            if compact:
+                gmap.compact()
+            for block, chunk in itertools.product(blocks, chunks):
+                ctx.set_option("align_block", block)
+                ctx.set_option("align_ticket_chunk", chunk)
+                for _ in range(2):
+                    gmap.align_cloud_fixed(src, guess, a.iters)
+                times = []
+                for _ in range(a.reps):
+                    ctx.sync()
+                    ctx.timer_start()
+                    r = gmap.align_cloud_fixed(src, guess, a.iters, trace=True)
+                    times.append(ctx.timer_stop())
+                us = float(np.median(times)) * 1e3 / a.iters
+                same = bool(np.array_equal(r["ncorr"], ref["ncorr"]))
+                dT = float(np.abs(r["T"] - ref["T"]).max())
+                rows.append({"voxel": voxel, "slots": gmap.capacity(), "voxels": gmap.size(), "block": block,
+                             "chunk": chunk, "us_per_iter": round(us, 2),
+                             "ncorr_equal": same, "max_abs_dT": dT})
+                print(json.dumps(rows[-1]), flush=True)
+        del src, gmap
+    bad = [r for r in rows if not r["ncorr_equal"] or r["max_abs_dT"] > 1e-9]
+    print("PARITY", "FAIL" if bad else "OK")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

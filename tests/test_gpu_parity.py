@@ -459,3 +459,77 @@ def test_sharded_align_single_rank_equals_align(ctx, oracle, frames):
     assert r1["iterations"] == r2["iterations"]
     dt, dr = pose_err(r1["T"], r2["T"])
     assert dt < 1e-9 and dr < 1e-9
+
+
+def test_map_compact_keeps_contents(ctx, oracle, frames):
+    """eskf_map_compact re-hashes into 2 x size() slots: same voxels, same statistics, and a
+    registration against the compacted table gives the bit-identical pose."""
+    om = oracle.Map(0.5, 1000)
+    gm = capi.Map(ctx, 0.5, 1000, 1 << 18)        # far too large a table for ~1e4 voxels
+    for (p, c), T in zip(frames.ds[:4], frames.poses[:4]):
+        om.update(p, c, T, initialize=True)
+        gm.insert(p, c, T)
+    p, c = frames.ds[4]
+    guess = frames.poses[4] @ S.perturbation()
+    before = gm.export()
+    r0 = ctx.align(gm, p, c, guess)
+    cap0 = gm.capacity()
+    gm.compact()
+    assert gm.capacity() < cap0
+    assert gm.capacity() == max(1024, gm.size()) * 2 + (-(max(1024, gm.size()) * 2)) % 64
+    assert gm.size() == om.size()
+    for u, v in zip(before, gm.export()):
+        np.testing.assert_array_equal(u, v)
+    r1 = ctx.align(gm, p, c, guess)
+    np.testing.assert_array_equal(r1["T"], r0["T"])
+    np.testing.assert_array_equal(r1["ncorr"], r0["ncorr"])
+    gm.compact()                                   # already compact: a no-op
+    assert gm.capacity() == max(1024, gm.size()) * 2 + (-(max(1024, gm.size()) * 2)) % 64
+    # the compacted table keeps accepting inserts (it grows again)
+    gm.insert(p, c, frames.poses[4])
+    om.update(p, c, frames.poses[4], initialize=True)
+    assert gm.size() == om.size()
+    np.testing.assert_array_equal(gm.export()[0], om.export()[0])
+
+
+def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
+    """A cloud large enough for the load-balanced (ticketed) tail of a pass, at every CTA shape
+    and ticket size: per-iteration correspondence counts identical to the oracle's, H/b and the
+    pose within the bars, whichever warps end up summing which tiles."""
+    c2 = capi.Context(0)
+    rng = np.random.default_rng(5)
+    scene = S.block_scene()
+    mp, mc = S.dense_cloud(scene, 2_000_000, rng)
+    p, c = S.dense_cloud(scene, 1_000_000, rng)
+    om = oracle.Map(0.5, 1000)
+    om.update(mp, mc, np.eye(4), initialize=True)
+    gm = capi.Map(c2, 0.5, 1000, 1 << 20)
+    gm.insert(mp, mc, np.eye(4))
+    gm.compact()
+    assert gm.size() == om.size()
+    guess = S.perturbation(dt=(0.03, -0.015, 0.01), angle_deg=0.3)
+    ro = om.align(p, c, guess)
+    cl = capi.Cloud(c2, len(p)).upload(p, c)
+    try:
+        for block, chunk, dyn in [(256, 1, 1), (256, 2, 1), (384, 4, 1), (768, 1, 1), (768, 2, 1),
+                                  (768, 4, 1), (0, 2, 1), (768, 2, 0)]:
+            c2.set_option("align_block", block)
+            c2.set_option("align_ticket_chunk", chunk)
+            c2.set_option("align_dynamic_tiles", dyn)
+            rg = gm.align_cloud(cl, guess, trace=True)
+            tag = (block, chunk, dyn)
+            assert rg["converged"] and rg["iterations"] == ro["iterations"], tag
+            np.testing.assert_array_equal(rg["ncorr"], ro["ncorr"], err_msg=str(tag))
+            for k in range(ro["iterations"]):
+                assert rel_err(rg["H"][k], ro["H"][k]) < H_TOL, (tag, k)
+                assert b_rel(rg["b"][k], ro["b"][k], ro["H"][k]) < H_TOL, (tag, k)
+            dt, dr = pose_err(ro["T"], rg["T"])
+            assert dt < POSE_T_TOL and dr < POSE_R_TOL, (tag, dt, dr)
+        with pytest.raises(capi.EskfError):
+            c2.set_option("align_block", 512)
+        with pytest.raises(capi.EskfError):
+            c2.set_option("align_ticket_chunk", 3)
+    finally:
+        c2.set_option("align_block", 0)
+        c2.set_option("align_ticket_chunk", 2)
+        c2.set_option("align_dynamic_tiles", 1)
