@@ -56,6 +56,7 @@ VOXEL = 0.3
 # LocalMap.cpp:132-147 only opens at ~1 m/s), so ~35 frames put >= 20 scans into the local map
 LEAD_IN = int(os.environ.get("ESKF_BENCH_LEAD_IN", "35"))  # (the contract test shortens it)
 CACHE_DIR = os.environ.get("ESKF_BENCH_CACHE", "/tmp/eskf_lio_b200_cache")
+MAP_HINT = int(os.environ.get("ESKF_BENCH_MAP_HINT", "0"))  # 0: Config::local_map.capacity_hint's default
 
 
 def make_log(n_frames, seed):
@@ -268,8 +269,9 @@ def gpu_sequence(capi, odometry, device, scans, imu, first_timed, mode):
     of the three calls takes and returns host vectors like the reference's, so the downsampled
     cloud crosses PCIe three times per frame."""
     import ctypes as C
+    extra = {"map_capacity_hint": MAP_HINT} if MAP_HINT else {}
     od = odometry.Odometry(odometry.default_config(device_resident=0 if mode == "host" else 1,
-                                                   **odom_overrides()), device)
+                                                   **odom_overrides(), **extra), device)
     ctx = od.context()
     keep = []
     if mode == "resident":
@@ -362,8 +364,8 @@ def dense_roofline(ctx, capi, peak_gbs, peak_src):
                     f"{DENSE_VOXEL} m voxels ({n_vox} voxels), {DENSE_ITERS} GN iterations per launch",
         "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
         "peak_source": peak_src, "frac_of_8TBs_spec": achieved / 8000.0,
-        "traffic": DENSE_TRAFFIC_BYTES,
-        "traffic_source": DENSE_TRAFFIC_SOURCE,
+        "traffic": dense_traffic()[0],
+        "traffic_source": dense_traffic()[1],
         "algorithmic_bytes_per_launch": bytes_launch,
         "hit_weighted": {"note": "only the points that find a voxel need the 64 B record and the 24 B "
                                  "source covariance; bytes = 48 N + 88 hits per iteration",
@@ -377,10 +379,27 @@ def dense_roofline(ctx, capi, peak_gbs, peak_src):
     }
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE align_kernel launch of this very workload from the
-# committed `ncu --set full` capture (profiles/); None until a capture of the current kernel exists
-DENSE_TRAFFIC_BYTES = 2_212_161_000 + 536_666_000
-DENSE_TRAFFIC_SOURCE = "profiles/r1_prof_align_ncu.md (ncu --set full, one launch)"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE align_kernel launch of this very workload, read from
+# the committed summary of the `ncu --set full` capture (profiles/); None when there is no capture
+DENSE_TRAFFIC_FILE = "profiles/r1_prof_align_ncu.md"
+
+
+def dense_traffic():
+    path = os.path.join(ROOT, DENSE_TRAFFIC_FILE)
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total, seen = 0.0, 0
+    try:
+        with open(path) as f:
+            for line in f:
+                cells = [c.strip() for c in line.strip().strip("|").split("|")]
+                if len(cells) == 3 and cells[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    total += float(cells[2].replace(",", "")) * scale[cells[1]]
+                    seen += 1
+    except (OSError, KeyError, ValueError):
+        return None, None
+    if seen != 2:
+        return None, None
+    return int(total), DENSE_TRAFFIC_FILE + " (ncu --set full, one launch)"
 
 
 def pose_delta(A, B):

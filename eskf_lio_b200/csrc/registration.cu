@@ -37,9 +37,16 @@ constexpr int kMailStride = 32;  // doubles per (parity, source rank): 28 sums, 
 #define ESKF_ALIGN_FOLD 1
 #endif
 constexpr int kFold = ESKF_ALIGN_FOLD;  // warp tiles (x 32 points) summed per lane in fp32 between reduce-scatters
+#ifndef ESKF_TERMS_ASSIGN
+#define ESKF_TERMS_ASSIGN 1
+#endif
+constexpr bool kAssign = kFold == 1 && ESKF_TERMS_ASSIGN != 0;
 
 #ifndef ESKF_PIPELINED
 #define ESKF_PIPELINED 1
+#endif
+#ifndef ESKF_COV_PREFETCH
+#define ESKF_COV_PREFETCH 0
 #endif
 
 struct AlignState {
@@ -115,8 +122,8 @@ __device__ __forceinline__ void publish_result(const AlignParams& P, const doubl
 
 // ------------------------------------------------------------ per point math
 // adds the 27 unique terms of J^T W J / J^T W r (+ a correspondence count) of
-// one correspondence into v[0..27]
-template <typename F>
+// one correspondence into v[0..27]  (SET: stores them instead: v starts undefined)
+template <typename F, bool SET = false>
 __device__ __forceinline__ void point_terms(F px, F py, F pz, F rx, F ry, F rz, F m00, F m01,
                                             F m02, F m11, F m12, F m22, F* v) {
   // W = M^-1 by cofactors (Eigen Matrix3d::inverse(), Registration.cpp:95)
@@ -141,13 +148,10 @@ __device__ __forceinline__ void point_terms(F px, F py, F pz, F rx, F ry, F rz, 
   const F g1 = w01 * rx + w11 * ry + w12 * rz;
   const F g2 = w02 * rx + w12 * ry + w22 * rz;
   const F g3 = py * g2 - pz * g1, g4 = pz * g0 - px * g2, g5 = px * g1 - py * g0;
-  v[0] += w00; v[1] += w01; v[2] += w02; v[3] += w11; v[4] += w12; v[5] += w22;
-  v[6] += b00; v[7] += b01; v[8] += b02;
-  v[9] += b10; v[10] += b11; v[11] += b12;
-  v[12] += b20; v[13] += b21; v[14] += b22;
-  v[15] += d00; v[16] += d01; v[17] += d02; v[18] += d11; v[19] += d12; v[20] += d22;
-  v[21] += g0; v[22] += g1; v[23] += g2; v[24] += g3; v[25] += g4; v[26] += g5;
-  v[27] += F(1);
+  const F t[28] = {w00, w01, w02, w11, w12, w22, b00, b01, b02, b10, b11, b12, b20, b21,
+                   b22, d00, d01, d02, d11, d12, d22, g0,  g1,  g2,  g3,  g4,  g5,  F(1)};
+#pragma unroll
+  for (int k = 0; k < 28; ++k) v[k] = SET ? t[k] : v[k] + t[k];
 }
 
 // C' = R S R^T for symmetric S, 6 unique outputs
@@ -540,9 +544,23 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
     if (k_next == k_static && lane == 0) tk_next = atomicAdd(&P.st->tile_counter, chunk);  // first chunk
     return t;
   };
+  // the fp32 source covariances of a tile (512 + 256 B, consumed two trips after the tile id is
+  // known) are pulled into L2 ahead of time, 64 B per lane of lanes 0..11
+  auto prefetch_cov = [&](unsigned t) {
+#if ESKF_COV_PREFETCH
+    if (t < n_tiles && lane < 12u) {
+      const char* a = lane < 8u ? reinterpret_cast<const char*>(P.c4 + static_cast<size_t>(t) * 32u) + 64u * lane
+                                : reinterpret_cast<const char*>(P.c2 + static_cast<size_t>(t) * 32u) + 64u * (lane - 8u);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    }
+#else
+    (void)t;
+#endif
+  };
   // ---- prologue: cur = first tile (scanned), nxt = second tile (transformed)
   PtState cur, nxt;
   unsigned tile = next_tile(), tile_n = next_tile();
+  prefetch_cov(tile_n);
   F v[32];
 #pragma unroll
   for (int k = 0; k < 32; ++k) v[k] = F(0);
@@ -558,6 +576,7 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
   while (tile < n_tiles) {
     const unsigned i = tile * 32u + lane;
     const unsigned tile_r = next_tile();
+    prefetch_cov(tile_r);
     // ---- issue: three independent groups of loads
     double rx, ry, rz;
     load_pos(tile_r, rx, ry, rz);
@@ -604,15 +623,22 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
       const double cy = __dmul_rn(static_cast<double>(cur.ky) + 0.5, P.voxel);
       const double cz = __dmul_rn(static_cast<double>(cur.kz) + 0.5, P.voxel);
       const F ex = F(cur.x - cx) - F(pa.x), ey = F(cur.y - cy) - F(pa.y), ez = F(cur.z - cz) - F(pa.z);
-      point_terms<F>(F(cur.x), F(cur.y), F(cur.z), ex, ey, ez, cr[0] + F(pc.x), cr[1] + F(pc.y),
-                     cr[2] + F(pc.z), cr[3] + F(pc.w), cr[4] + F(pd.x), cr[5] + F(pd.y), v);
+      // kFold == 1: v is dead between trips, so a hit lane stores its terms and a miss lane
+      // zeros instead of "zero all, then add" (28 FADDs and the zeroing of hit lanes less per trip)
+      point_terms<F, kAssign>(F(cur.x), F(cur.y), F(cur.z), ex, ey, ez, cr[0] + F(pc.x), cr[1] + F(pc.y),
+                              cr[2] + F(pc.z), cr[3] + F(pc.w), cr[4] + F(pd.x), cr[5] + F(pd.y), v);
+    } else if (kAssign) {
+#pragma unroll
+      for (int k = 0; k < 28; ++k) v[k] = F(0);
     }
     // the 31-shuffle reduce-scatter runs once per kFold tiles (the shuffles
     // were ~17 % of the issue slots): lanes keep fp32 partial sums in between
     if (++folded == kFold) {
       acc += static_cast<double>(warp_reduce_scatter32<F>(v, lane));
+      if (!kAssign) {
 #pragma unroll
-      for (int k = 0; k < 32; ++k) v[k] = F(0);
+        for (int k = 0; k < 32; ++k) v[k] = F(0);
+      }
       folded = 0;
     }
     cur = nxt;

@@ -71,6 +71,7 @@ Config toConfig(const eskf_odom_config & c)
   k.registration.translation_sq_threshold = c.icp_translation_sq_threshold;
   k.registration.cosine_threshold = c.icp_cosine_threshold;
   k.device_resident = c.device_resident != 0;
+  if (c.map_capacity_hint != 0) {k.local_map.capacity_hint = static_cast<std::size_t>(c.map_capacity_hint);}
   return k;
 }
 }  // namespace
@@ -109,6 +110,7 @@ void eskf_odom_default_config(eskf_odom_config * c)
   c->icp_translation_sq_threshold = k.registration.translation_sq_threshold;
   c->icp_cosine_threshold = k.registration.cosine_threshold;
   c->device_resident = 1;
+  c->map_capacity_hint = k.local_map.capacity_hint;
 }
 
 int eskf_odom_create(const eskf_odom_config * cfg, int device, eskf_odom ** out)

@@ -28,7 +28,8 @@ class OdomConfig(C.Structure):
                 ("remove_distance_threshold", C.c_double), ("remove_period", C.c_double),
                 ("preprocess_voxel_size", C.c_double), ("max_iteration", C.c_int32),
                 ("neighbor_mode", C.c_int32), ("icp_translation_sq_threshold", C.c_double),
-                ("icp_cosine_threshold", C.c_double), ("device_resident", C.c_int32)]
+                ("icp_cosine_threshold", C.c_double), ("device_resident", C.c_int32),
+                ("map_capacity_hint", C.c_uint64)]
 
 
 class OdomInfo(C.Structure):

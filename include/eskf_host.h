@@ -42,6 +42,8 @@ typedef struct {
   int32_t max_iteration, neighbor_mode;   /* registration.* (neighbor_mode 7 = DIRECT7 extension) */
   double icp_translation_sq_threshold, icp_cosine_threshold;
   int32_t device_resident;                /* 1: frames stay in HBM between the three calls */
+  uint64_t map_capacity_hint;             /* not in the reference: voxels the HBM table is sized for up
+                                           * front (it doubles by itself when it fills up) */
 } eskf_odom_config;
 
 typedef struct {
