@@ -161,8 +161,9 @@ struct eskf_ctx {
   std::vector<std::pair<const char*, cudaEvent_t>> trace_marks;
   int opt_knn_buffer = 128;
   int opt_insert_sorted = 0;    // 1: always take the radix-sort insert path
-  int opt_align_block = 0;      // CTA size of the 1-neighbour fp32 align kernel: 0 = by cloud size, 256 | 384 | 768
+  int opt_align_block = 0;      // CTA size of the 1-neighbour fp32 align kernel: 0 = by cloud size, 256 | 384 | 512 | 640 | 768
   int opt_align_chunk = 2;      // tiles taken per ticket in the dynamic tail of an align pass (1 | 2 | 4)
+  int opt_align_depth = 0;      // load rotation of the 768-thread align kernel: 0 = build default, 3 | 4
   size_t l2_persist_bytes = 0;  // persisting-L2 carve-out (0 = unavailable)
   size_t l2_window_max = 0;     // max access-policy window
   const void* l2_win_ptr = nullptr;  // window currently set on the stream

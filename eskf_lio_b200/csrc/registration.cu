@@ -48,6 +48,9 @@ constexpr bool kAssign = kFold == 1 && ESKF_TERMS_ASSIGN != 0;
 #ifndef ESKF_COV_PREFETCH
 #define ESKF_COV_PREFETCH 0
 #endif
+#ifndef ESKF_FAT_DEPTH
+#define ESKF_FAT_DEPTH 3  // pipeline depth of the fat-CTA variants: 3 = issue and consume in the same trip; 4 = consume one trip later
+#endif
 
 struct AlignState {
   double T_total[12];  // R row-major (9) + t (3)
@@ -440,7 +443,7 @@ __device__ __forceinline__ uint4 load_tag_window(const tag_t* tags, uint32_t b, 
   return make_uint4(lo.x, lo.y, hi.x, hi.y);
 }
 
-template <typename F, int NW>
+template <typename F, int NW, int DEPTH>
 __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams& P,
                                                               const double* sT, const F* sR,
                                                               bool first, bool write_hit) {
@@ -557,14 +560,177 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
     (void)t;
 #endif
   };
-  // ---- prologue: cur = first tile (scanned), nxt = second tile (transformed)
-  PtState cur, nxt;
-  unsigned tile = next_tile(), tile_n = next_tile();
-  prefetch_cov(tile_n);
   F v[32];
 #pragma unroll
   for (int k = 0; k < 32; ++k) v[k] = F(0);
   int folded = 0;
+  PtState cur, nxt;
+  if constexpr (DEPTH == 4) {
+  // ---- 4-deep rotation: every load is consumed ONE TRIP AFTER it was issued.  Across the loop's
+  // back edge a warp has in flight: the 64 B record + source covariance of `cur` (tile t), the tag
+  // window of `nxt` (tile t+1) and the raw positions of tile t+2; a trip consumes them in that
+  // order and, right after each consumption, issues the same loads one tile further on into the
+  // registers it just freed.  (The 3-stage loop below issues and consumes in the same trip: one
+  // exposed memory round trip per trip, 50 % of the warp-stall samples on the dense config.)
+  // A point waiting for its lookup keeps only what the algebra needs: the position and its
+  // offset from the voxel centre already rounded to F, and the packed key.
+  struct Slim {
+    F px, py, pz;     // transformed position
+    F dx, dy, dz;     // position - voxel centre (formed in fp64)
+    uint32_t klo, khi;  // packed voxel key
+    uint32_t home;
+    uint32_t tag;     // 0 = no lookup (invalid lane / out of key range)
+    uint32_t cand;    // candidate slot after the tag scan, kNoCand if none
+  };
+  struct RecRegs {
+    uint2 key;
+    float4 pa, pc;
+    float2 pd;
+    float4 s4;
+    float2 s2;
+  };
+  auto xform4 = [&](unsigned tile, double x, double y, double z, Slim& q) {
+    const unsigned i = tile * 32u + lane;
+    q.px = q.py = q.pz = q.dx = q.dy = q.dz = F(0);
+    q.klo = q.khi = 0u;
+    q.home = 0u;
+    q.tag = 0u;
+    q.cand = kNoCand;
+    if (tile >= n_tiles || i >= P.n) return;
+    transform_point_rn(sT, x, y, z);
+    P.wx[i] = x;
+    P.wy[i] = y;
+    P.wz[i] = z;
+    const int kx = voxel_coord(x, P.voxel, inv_voxel);
+    const int ky = voxel_coord(y, P.voxel, inv_voxel);
+    const int kz = voxel_coord(z, P.voxel, inv_voxel);
+    if (coord_in_range(kx) && coord_in_range(ky) && coord_in_range(kz)) {
+      const uint64_t key = pack_key(kx, ky, kz);
+      const SlotAddr ad = slot_addr(key, P.n_slots);
+      q.klo = static_cast<uint32_t>(key);
+      q.khi = static_cast<uint32_t>(key >> 32);
+      q.home = ad.home;
+      q.tag = ad.tag;
+      // residual against the voxel mean is formed relative to the voxel centre
+      q.px = F(x); q.py = F(y); q.pz = F(z);
+      q.dx = F(x - __dmul_rn(static_cast<double>(kx) + 0.5, P.voxel));
+      q.dy = F(y - __dmul_rn(static_cast<double>(ky) + 0.5, P.voxel));
+      q.dz = F(z - __dmul_rn(static_cast<double>(kz) + 0.5, P.voxel));
+    }
+  };
+  auto window4 = [&](const Slim& q) -> uint4 {
+    if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t b0 = q.home & ~(kTagAlign - 1u);
+    return load_tag_window(P.tags, b0, wrap4(b0));
+  };
+  auto scan4 = [&](Slim& q, uint4 w) {
+    if (q.tag == 0u) return;
+    uint32_t b0 = q.home & ~(kTagAlign - 1u), b2 = wrap4(b0);
+    uint32_t r = scan_tag_window(w, q.home & (kTagAlign - 1u), q.tag);
+    uint32_t scanned = 8u - (q.home & (kTagAlign - 1u));
+    while (r == kMore && scanned < P.n_slots) {
+      b0 = wrap4(b2);
+      b2 = wrap4(b0);
+      r = scan_tag_window(load_tag_window(P.tags, b0, b2), 0u, q.tag);
+      scanned += 8u;
+    }
+    if (r < 8u) q.cand = r < 4u ? b0 + r : b2 + (r - 4u);
+  };
+  auto issue_record = [&](const Slim& q, unsigned tile_of_q, RecRegs& r) {
+    r.key = make_uint2(0u, 0u);
+    if (q.cand != kNoCand) {
+      const float4* rec = reinterpret_cast<const float4*>(P.slots + q.cand);
+      const unsigned i = tile_of_q * 32u + lane;
+      prefetch_record(rec);  // (evict_last: the voxels a registration keeps touching stay in L2)
+      r.key = __ldg(reinterpret_cast<const uint2*>(rec));     // key
+      r.pa = __ldg(rec + 1);                                   // mx my mz -
+      r.pc = __ldg(rec + 2);                                   // c00 c01 c02 c11
+      r.pd = __ldg(reinterpret_cast<const float2*>(rec + 3));  // c12 c22
+      r.s4 = __ldcs(P.c4 + i);
+      r.s2 = __ldcs(P.c2 + i);
+    }
+  };
+  Slim c4s, n4s;
+  unsigned tile = next_tile(), tile_n = next_tile(), tile_r = next_tile();
+  RecRegs rec;
+  uint4 tagw;
+  double rx, ry, rz;
+  {
+    double ax, ay, az, bx, by, bz;
+    load_pos(tile, ax, ay, az);
+    load_pos(tile_n, bx, by, bz);
+    load_pos(tile_r, rx, ry, rz);
+    xform4(tile, ax, ay, az, c4s);
+    scan4(c4s, window4(c4s));
+    issue_record(c4s, tile, rec);
+    xform4(tile_n, bx, by, bz, n4s);
+    tagw = window4(n4s);
+  }
+  while (tile < n_tiles) {
+    const unsigned i = tile * 32u + lane;
+    // ---- 1. the record + covariance of the current tile
+    float4 pa = rec.pa, pc = rec.pc;
+    float2 pd = rec.pd;
+    bool hit = false;
+    if (c4s.cand != kNoCand) {
+      hit = rec.key.x == c4s.klo && rec.key.y == c4s.khi;
+      if (!hit) {
+        // 16-bit tag collision (1/65536 per occupied probe): walk on, slowly
+        const uint64_t key = (static_cast<uint64_t>(c4s.khi) << 32) | c4s.klo;
+        SlotAddr rest;
+        rest.home = next_slot(c4s.cand, P.n_slots);
+        rest.tag = static_cast<tag_t>(c4s.tag);
+        const VoxelSlot* far = resolve_probe(P.tags, P.slots, P.n_slots, key, rest, __ldg(P.tags + rest.home));
+        if (far != nullptr) {
+          hit = true;
+          pa = __ldg(reinterpret_cast<const float4*>(far) + 1);
+          pc = __ldg(reinterpret_cast<const float4*>(far) + 2);
+          pd = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float4*>(far) + 3));
+        }
+      }
+    }
+    if (write_hit && i < P.n) P.hit[i] = hit ? 1 : 0;
+    if (hit) {
+      F cr[6];
+      rotate_sym<F>(sR, F(rec.s4.x), F(rec.s4.y), F(rec.s4.z), F(rec.s4.w), F(rec.s2.x), F(rec.s2.y), cr);
+      point_terms<F, kAssign>(c4s.px, c4s.py, c4s.pz, c4s.dx - F(pa.x), c4s.dy - F(pa.y), c4s.dz - F(pa.z),
+                              cr[0] + F(pc.x), cr[1] + F(pc.y), cr[2] + F(pc.z), cr[3] + F(pc.w),
+                              cr[4] + F(pd.x), cr[5] + F(pd.y), v);
+    } else if (kAssign) {
+#pragma unroll
+      for (int k = 0; k < 28; ++k) v[k] = F(0);
+    }
+    if (++folded == kFold) {
+      acc += static_cast<double>(warp_reduce_scatter32<F>(v, lane));
+      if (!kAssign) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = F(0);
+      }
+      folded = 0;
+    }
+    // ---- 2. the tag window of the next tile; its record + covariance loads go out
+    scan4(n4s, tagw);
+    issue_record(n4s, tile_n, rec);
+    c4s = n4s;
+    // ---- 3. the positions of tile t+2; its tag window load goes out
+    xform4(tile_r, rx, ry, rz, n4s);
+    tagw = window4(n4s);
+    tile = tile_n;
+    tile_n = tile_r;
+    // ---- 4. positions of the tile after that
+    tile_r = next_tile();
+    load_pos(tile_r, rx, ry, rz);
+  }
+  (void)cur;
+  (void)nxt;
+  (void)finish_scan;
+  (void)first_window;
+  (void)xform;
+  (void)prefetch_cov;
+  } else {
+  // ---- prologue: cur = first tile (scanned), nxt = second tile (transformed)
+  unsigned tile = next_tile(), tile_n = next_tile();
+  prefetch_cov(tile_n);
   {
     double rx, ry, rz, qx, qy, qz;
     load_pos(tile, rx, ry, rz);
@@ -645,6 +811,7 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
     xform(tile_r, rx, ry, rz, nxt);
     tile = tile_n;
     tile_n = tile_r;
+  }
   }
   if (folded != 0) acc += static_cast<double>(warp_reduce_scatter32<F>(v, lane));
   return acc;
@@ -1055,7 +1222,7 @@ __device__ __forceinline__ bool exchange_sums(const AlignParams& P, int it, doub
   return *s_flag != 0;
 }
 
-template <typename F, int U, int NN, int MINB, int T = kT>
+template <typename F, int U, int NN, int MINB, int T = kT, int DEPTH = 3>
 __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
   constexpr int NW = T / 32;
   __shared__ double s_T[12];
@@ -1075,7 +1242,7 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
   for (int it = 0; it < max_it; ++it) {
 
     const double acc = (NN == 1 && U == 1 && ESKF_PIPELINED)
-                           ? accumulate_points_pipelined<F, NW>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0)
+                           ? accumulate_points_pipelined<F, NW, DEPTH>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0)
                            : accumulate_points<F, U, NN, NW>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0);
     block_reduce_store<NW>(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
 
@@ -1130,7 +1297,7 @@ __global__ void solve_kernel(AlignParams P, int it) {
 
 // sharded mode: ONE linearisation of this rank's point range; the 28 sums go
 // to P.sums for the caller's all-reduce, solve_kernel follows
-template <typename F, int U, int NN, int MINB, int T = kT>
+template <typename F, int U, int NN, int MINB, int T = kT, int DEPTH = 3>
 __global__ void __launch_bounds__(T, MINB) linearize_pass_kernel(AlignParams P, int it) {
   constexpr int NW = T / 32;
   __shared__ double s_T[12];
@@ -1144,7 +1311,7 @@ __global__ void __launch_bounds__(T, MINB) linearize_pass_kernel(AlignParams P, 
   if (t < 9) s_R[t] = (it == 0) ? F(P.guess[t]) : F(ld_cg(&st->Rf[t]));
   __syncthreads();
   const double acc = (NN == 1 && U == 1 && ESKF_PIPELINED)
-                         ? accumulate_points_pipelined<F, NW>(P, s_T, s_R, it == 0, false)
+                         ? accumulate_points_pipelined<F, NW, DEPTH>(P, s_T, s_R, it == 0, false)
                          : accumulate_points<F, U, NN, NW>(P, s_T, s_R, it == 0, false);
   block_reduce_store<NW>(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
   if (t == 0) {
@@ -1171,7 +1338,11 @@ struct Variant {
 // 3 x 256, 2 x 384 and 1 x 768 threads.  Fewer, fatter CTAs shorten the per-iteration
 // hand-off of a large cloud (148 instead of 444 partial sums to reduce, tickets to take and
 // epoch pollers); small clouds keep 256-thread CTAs so that they spread over more SMs.
-enum { V_F32_N1 = 0, V_F32_N7, V_F64_N1, V_F64_N7, V_F32_N1_T384, V_F32_N1_T768, V_COUNT };
+// The fat shapes also exist with the 4-deep load rotation (accumulate_points_pipelined): at 768
+// threads it has to live in 80 registers; 640 threads (20 warps) get 96 and 512 (16 warps) 128
+// (ptxas budgets registers for the CTA size rounded up to a multiple of 128 threads).
+enum { V_F32_N1 = 0, V_F32_N7, V_F64_N1, V_F64_N7, V_F32_N1_T384, V_F32_N1_T768, V_F32_N1_T768D4,
+       V_F32_N1_T640D4, V_F32_N1_T512D4, V_COUNT };
 
 // measured on B200, dense config (2M pts, 10 iterations per launch):
 //   U=1/3 CTAs 1.267 ms, U=1/4 CTAs 1.246 ms, U=2/3 CTAs 1.303 ms,
@@ -1202,6 +1373,12 @@ Variant g_variants[V_COUNT] = {
      reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 2, 384>), 384, 384, 1},
     {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, kMaxT>),
      reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, kMaxT>), kMaxT, kMaxT, 1},
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, kMaxT, 4>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, kMaxT, 4>), kMaxT, kMaxT, 1},
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 640, 4>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 640, 4>), 640, 640, 1},
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 512, 4>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 512, 4>), 512, 512, 1},
 };
 
 // clouds whose 256-thread grid would be capped at 3 CTAs per SM anyway
@@ -1212,7 +1389,14 @@ int variant_index(const eskf_ctx* ctx, const AlignArgs& a) {
   if (base != V_F32_N1) return base;
   int threads = ctx->opt_align_block;  // 0 = choose by cloud size
   if (threads == 0) threads = (a.cloud && a.cloud->n >= kFatCtaPoints) ? ESKF_ALIGN_FAT_T : kT;
-  return threads == 768 ? V_F32_N1_T768 : threads == 384 ? V_F32_N1_T384 : V_F32_N1;
+  const int depth = ctx->opt_align_depth != 0 ? ctx->opt_align_depth : ESKF_FAT_DEPTH;
+  switch (threads) {
+    case 768: return depth == 4 ? V_F32_N1_T768D4 : V_F32_N1_T768;
+    case 640: return V_F32_N1_T640D4;
+    case 512: return V_F32_N1_T512D4;
+    case 384: return V_F32_N1_T384;
+    default: return V_F32_N1;
+  }
 }
 
 struct TraceLayout {

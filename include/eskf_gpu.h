@@ -120,7 +120,10 @@ int eskf_ctx_launch_count(eskf_ctx* ctx, uint64_t* n);
  *   "knn_buffer"           candidates the 30-NN selection keeps in shared memory before it falls
  *                          back to serial insertion (1..128, default 128; tests force the fallback)
  *   "align_block"          CTA size of the 1-neighbour fp32 registration kernel: 0 = chosen by cloud
- *                          size (default), 256, 384 or 768 threads (always 24 warps per SM)
+ *                          size (default); 256, 384 or 768 threads (24 warps per SM), 640 or 512
+ *                          (20 / 16 warps with 96 / 128 registers, 4-deep load rotation)
+ *   "align_depth"          load rotation of the 768-thread kernel: 3 = loads issued and consumed in
+ *                          the same trip, 4 = consumed one trip later; 0 = the build's default
  *   "align_ticket_chunk"   warp tiles taken per ticket in the load-balanced tail of a pass over a
  *                          large cloud (1, 2 or 4; default 2) */
 int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value);

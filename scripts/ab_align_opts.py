@@ -1,13 +1,12 @@
 #!/usr/bin/env python
 """A/B of the registration kernel's run-time knobs on the dense config (BASELINE.json
-configs[2]): CTA shape (align_block) x tiles per ticket (align_ticket_chunk), one map build per
-voxel size.  Every cell is checked against the fully static 256-thread run: per-iteration
+configs[2]): CTA shape (align_block) x load rotation (align_depth) x tiles per ticket
+(align_ticket_chunk), one map build per voxel size, as grown and after eskf_map_compact.  Every cell is checked against the fully static 256-thread run: per-iteration
 correspondence counts must be identical, the final pose equal to rounding.
 
-    python scripts/ab_align_opts.py [--voxels 0.1,0.5] [--blocks 256,384,768] [--chunks 1,2,4]
+    python scripts/ab_align_opts.py [--voxels 0.1,0.5] [--variants 256:3:2,768:4:2,...] [--compact 0,1]
 """
 import argparse
-import itertools
 import json
 import os
 import sys
@@ -23,8 +22,8 @@ def main():
     ap.add_argument("--src", type=int, default=2_000_000)
     ap.add_argument("--map", type=int, default=10_000_000)
     ap.add_argument("--voxels", default="0.1,0.5")
-    ap.add_argument("--blocks", default="256,384,768")
-    ap.add_argument("--chunks", default="1,2,4")
+    ap.add_argument("--variants", default="256:3:2,768:3:1,768:3:2,768:4:2,640:4:2,512:4:2",
+                    help="comma list of block:depth:chunk (align_block, align_depth, align_ticket_chunk)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--compact", default="0,1", help="also time the map after eskf_map_compact")
@@ -55,13 +54,13 @@ def main():
         ctx.set_option("align_dynamic_tiles", 0)
         ref = gmap.align_cloud_fixed(src, guess, a.iters, trace=True)
         ctx.set_option("align_dynamic_tiles", 1)
-        blocks = [int(b) for b in a.blocks.split(",")]
-        chunks = [int(c) for c in a.chunks.split(",")]
+        variants = [tuple(int(x) for x in v.split(":")) for v in a.variants.split(",")]
         for compact in [int(c) for c in a.compact.split(",")]:
             if compact:
                 gmap.compact()
-            for block, chunk in itertools.product(blocks, chunks):
+            for block, depth, chunk in variants:
                 ctx.set_option("align_block", block)
+                ctx.set_option("align_depth", depth)
                 ctx.set_option("align_ticket_chunk", chunk)
                 for _ in range(2):
                     gmap.align_cloud_fixed(src, guess, a.iters)
@@ -75,7 +74,7 @@ def main():
                 same = bool(np.array_equal(r["ncorr"], ref["ncorr"]))
                 dT = float(np.abs(r["T"] - ref["T"]).max())
                 rows.append({"voxel": voxel, "slots": gmap.capacity(), "voxels": gmap.size(), "block": block,
-                             "chunk": chunk, "us_per_iter": round(us, 2),
+                             "depth": depth, "chunk": chunk, "us_per_iter": round(us, 2),
                              "ncorr_equal": same, "max_abs_dT": dT})
                 print(json.dumps(rows[-1]), flush=True)
         del src, gmap

@@ -493,8 +493,8 @@ def test_map_compact_keeps_contents(ctx, oracle, frames):
 
 
 def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
-    """A cloud large enough for the load-balanced (ticketed) tail of a pass, at every CTA shape
-    and ticket size: per-iteration correspondence counts identical to the oracle's, H/b and the
+    """A cloud large enough for the load-balanced (ticketed) tail of a pass, at every CTA shape,
+    load rotation depth and ticket size: per-iteration correspondence counts identical to the oracle's, H/b and the
     pose within the bars, whichever warps end up summing which tiles."""
     c2 = capi.Context(0)
     rng = np.random.default_rng(5)
@@ -511,13 +511,16 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
     ro = om.align(p, c, guess)
     cl = capi.Cloud(c2, len(p)).upload(p, c)
     try:
-        for block, chunk, dyn in [(256, 1, 1), (256, 2, 1), (384, 4, 1), (768, 1, 1), (768, 2, 1),
-                                  (768, 4, 1), (0, 2, 1), (768, 2, 0)]:
+        for block, depth, chunk, dyn in [(256, 0, 1, 1), (256, 0, 2, 1), (384, 0, 4, 1), (768, 3, 1, 1),
+                                         (768, 3, 2, 1), (768, 3, 4, 1), (0, 0, 2, 1), (768, 3, 2, 0),
+                                         (768, 4, 2, 1), (768, 4, 1, 0), (640, 0, 2, 1), (640, 0, 4, 0),
+                                         (512, 0, 2, 1), (512, 0, 1, 1)]:
             c2.set_option("align_block", block)
+            c2.set_option("align_depth", depth)
             c2.set_option("align_ticket_chunk", chunk)
             c2.set_option("align_dynamic_tiles", dyn)
             rg = gm.align_cloud(cl, guess, trace=True)
-            tag = (block, chunk, dyn)
+            tag = (block, depth, chunk, dyn)
             assert rg["converged"] and rg["iterations"] == ro["iterations"], tag
             np.testing.assert_array_equal(rg["ncorr"], ro["ncorr"], err_msg=str(tag))
             for k in range(ro["iterations"]):
@@ -526,10 +529,13 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
             dt, dr = pose_err(ro["T"], rg["T"])
             assert dt < POSE_T_TOL and dr < POSE_R_TOL, (tag, dt, dr)
         with pytest.raises(capi.EskfError):
-            c2.set_option("align_block", 512)
+            c2.set_option("align_block", 500)
+        with pytest.raises(capi.EskfError):
+            c2.set_option("align_depth", 5)
         with pytest.raises(capi.EskfError):
             c2.set_option("align_ticket_chunk", 3)
     finally:
         c2.set_option("align_block", 0)
+        c2.set_option("align_depth", 0)
         c2.set_option("align_ticket_chunk", 2)
         c2.set_option("align_dynamic_tiles", 1)
