@@ -1354,9 +1354,12 @@ enum { V_F32_N1 = 0, V_F32_N7, V_F64_N1, V_F64_N7, V_F32_N1_T384, V_F32_N1_T768,
 #define ESKF_ALIGN_MINB 3
 #endif
 #ifndef ESKF_ALIGN_FAT_T
-// measured on B200, dense config, us per GN iteration at 0.1 m / 0.5 m voxels with 2-tile tickets:
-// 3 x 256 threads 86.9 / 163.9, 2 x 384 85.6 / 161.7, 1 x 768 85.1 / 158.2
-#define ESKF_ALIGN_FAT_T 768  // CTA size for clouds >= kFatCtaPoints (256 | 384 | 768)
+// measured on B200, dense config, us per GN iteration at 0.1 m / 0.5 m voxels (tables as grown by the
+// bulk inserts), 2-tile tickets; first box: 3 x 256 threads 86.9 / 163.9, 2 x 384 85.6 / 161.7,
+// 1 x 768 85.1 / 158.2; a slower box: 3 x 256 105.5 / 162.8, 1 x 768 101.3 / 158.8, 1 x 640 with the
+// 4-deep rotation 93.6 / 148.7, 1 x 512 4-deep 102.3 / 147.8, 1 x 768 4-deep (spills at 80 registers)
+// 177.7 / 241.1  (profiles/r1_align_ab.md)
+#define ESKF_ALIGN_FAT_T 640  // CTA size for clouds >= kFatCtaPoints (256 | 384 | 512 | 640 | 768)
 #endif
 
 Variant g_variants[V_COUNT] = {
