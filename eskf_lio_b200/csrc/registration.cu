@@ -48,6 +48,9 @@ constexpr bool kAssign = kFold == 1 && ESKF_TERMS_ASSIGN != 0;
 #ifndef ESKF_COV_PREFETCH
 #define ESKF_COV_PREFETCH 0
 #endif
+#ifndef ESKF_POS_PREFETCH
+#define ESKF_POS_PREFETCH 0  // 4-deep rotation: L2-prefetch the positions of the tile this many trips ahead (0 = off)
+#endif
 #ifndef ESKF_FAT_DEPTH
 #define ESKF_FAT_DEPTH 3  // pipeline depth of the fat-CTA variants: 3 = issue and consume in the same trip; 4 = consume one trip later
 #endif
@@ -720,6 +723,18 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
     // ---- 4. positions of the tile after that
     tile_r = next_tile();
     load_pos(tile_r, rx, ry, rz);
+#if ESKF_POS_PREFETCH
+    // statically dealt tiles are known ahead: pull the positions of the tile ESKF_POS_PREFETCH
+    // trips further on into L2 (3 x 256 B, 64 B per lane of lanes 0..11)
+    {
+      const unsigned kp = k_next - 1u + ESKF_POS_PREFETCH;
+      const unsigned tp = wglobal + kp * wstride;
+      if (kp < k_static && tp < n_tiles && lane < 12u) {
+        const double* base = lane < 4u ? sx : lane < 8u ? sy : sz;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + static_cast<size_t>(tp) * 32u + 8u * (lane & 3u)));
+      }
+    }
+#endif
   }
   (void)cur;
   (void)nxt;
