@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY — may be imported by tests/, __graft_entry__.smoke()
 and bench.py's cpu_baseline / ``--impl reference`` legs, never by the product
-package ``eskf_lio_b200``.  PARITY UNPINNED by the reference (it has no tests);
-see eskf_oracle.h for how the oracle is pinned instead.
+package ``eskf_lio_b200``.  The reference has no tests and cannot be built as shipped;
+see eskf_oracle.h for how the oracle is pinned instead (incl. oracle/ref.py: the reference's
+own sources compiled against API shims).
 """
 from __future__ import annotations
 

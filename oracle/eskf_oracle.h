@@ -6,10 +6,20 @@
  * bench.py's cpu_baseline / --impl reference legs use it, as the checker or as
  * the CPU baseline — never as the thing shipped.
  *
- * PARITY UNPINNED: the reference (LimHaeryong/ESKF_LIO) ships no tests, golden
- * vectors or fixtures, and cannot be compiled in this environment (Eigen,
+ * PARITY: the reference (LimHaeryong/ESKF_LIO) ships no tests, golden vectors
+ * or fixtures, and cannot be built as shipped in this environment (Eigen,
  * Open3D, yaml-cpp and rclcpp are all absent, no network).  This file is a
  * dependency-free restatement of the reference algorithm; it is pinned by
+ *   (0) the reference's OWN hot-path sources (Registration, LocalMap,
+ *       CloudPreprocessor, Utils, ErrorStateKF .cpp), compiled where they lie
+ *       against from-scratch shims of the Eigen / Open3D / yaml-cpp API subset
+ *       they use (oracle/refshim, `make ref`): bit-identical voxel keys, kept
+ *       sets, map statistics, correspondence sets and per-point J^T W J terms,
+ *       poses / filter states to 1e-12 (tests/test_reference_shim.py).  That
+ *       pins the CONTROL FLOW AND FORMULAS to the reference's text; the
+ *       third-party arithmetic underneath (Eigen's LDLT / inverse / SVD /
+ *       quaternions, Open3D's Transform / k-NN / ComputeCovariance) is restated
+ *       in the shims as it is here, so in that respect parity stays UNPINNED;
  *   (1) an independent NumPy/SciPy second oracle (oracle/np_oracle.py),
  *   (2) analytic known-answer tests (tests/test_oracle_kat.py),
  *   (3) committed fixtures generated from it (tests/golden/).

@@ -1,0 +1,321 @@
+"""The ORACLE against the REFERENCE'S OWN SOURCES.
+
+/root/reference/src/{Registration,LocalMap,CloudPreprocessor,Utils,ErrorStateKF}.cpp are compiled
+where they lie (oracle/Makefile `ref`) against from-scratch shims of the Eigen / Open3D / yaml-cpp
+API subset they use (oracle/refshim/include; the real libraries do not exist here) and driven
+through oracle/refshim/ref_capi.cpp.  This pins the oracle's restatement of the reference's
+control flow and formulas — loop structure, thresholds, gates, the deskew quirk, first-point-per-
+voxel, addPoint order and cap, J^T W J / J^T W r, the LDLT step, convergence, the filter's
+predict / update / reset — to the reference's text; the third-party arithmetic underneath is
+the shims' (restated from the libraries' published algorithms, like the oracle's).
+
+Two builds of the same sources: `seq` sums short inner products left to right (the oracle's
+documented convention) => results must be BIT-IDENTICAL wherever no parallel summation order is
+involved; `tree` pairs them as Eigen's unrolled reductions do (a0 + (a1 + a2)) => results agree to
+a few ulp and every discrete outcome (voxel keys, kept sets, correspondence sets, gates,
+convergence, iteration counts) is unchanged.
+
+Skipped where neither /root/reference nor the prebuilt oracle/_ref libraries exist."""
+import numpy as np
+import pytest
+from scipy.spatial.transform import Rotation as Rot
+
+import oracle as O
+from oracle import ref as R
+from eskf_lio_b200 import synth as S
+from gpu_common import Frames, pose_err
+
+pytestmark = pytest.mark.skipif(not R.available(), reason="reference sources / prebuilt oracle/_ref not present")
+
+KINDS = ["seq", "tree"]
+
+
+@pytest.fixture(scope="module", params=KINDS)
+def ref(request):
+    return R.Ref(request.param)
+
+
+@pytest.fixture(scope="module")
+def frames():
+    return Frames(O, n_scans=5, seed=11, decim=4, voxel=0.5)
+
+
+def exact(ref):
+    return ref.kind == "seq"
+
+
+def close(a, b, ref, ulps=64):
+    """bit-identical in the `seq` build, within `ulps` units of the largest magnitude in `tree`"""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if exact(ref):
+        np.testing.assert_array_equal(a, b)
+    else:
+        scale = max(float(np.abs(b).max()), 1e-300)
+        assert float(np.abs(a - b).max()) <= ulps * np.finfo(np.float64).eps * scale
+
+
+# ------------------------------------------------------------------ Utils.cpp
+def test_utils_match(ref):
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        v = rng.normal(size=3)
+        np.testing.assert_array_equal(ref.skew(v), O.skew(v))
+        rv = rng.normal(size=3) * rng.choice([0.0, 1e-9, 1e-7, 1e-3, 0.5, 3.0])
+        close(ref.rotvec_to_matrix(rv), O.rotvec_to_matrix(rv), ref)
+        se3 = rng.normal(size=6) * rng.choice([0.0, 1e-9, 1e-7, 1e-3, 0.5])   # both branches of computeJ
+        close(ref.se3_to_SE3(se3), O.se3_to_SE3(se3), ref)
+        Rm = S.rotvec_matrix(rng.normal(size=3) * rng.choice([1e-9, 1e-6, 0.1, 3.0, 3.14159]))
+        a, b = ref.rotation_matrix_to_vector(Rm), O.rotation_matrix_to_vector(Rm)
+        if exact(ref):
+            np.testing.assert_array_equal(a, b)
+        else:
+            assert np.abs(a - b).max() < 1e-12
+
+
+def test_interpolate_se3_matches(ref):
+    rng = np.random.default_rng(4)
+    for _ in range(100):
+        t1 = rng.uniform(0, 10)
+        t2 = t1 + rng.uniform(1e-4, 0.1)
+        p1, p2 = rng.normal(size=3), rng.normal(size=3)
+        q1 = Rot.from_rotvec(rng.normal(size=3)).as_quat()
+        q2 = (Rot.from_quat(q1) * Rot.from_rotvec(rng.normal(size=3) * rng.choice([1e-9, 0.01, 1.0]))).as_quat()
+        if rng.random() < 0.3:
+            q2 = -q2                                     # slerp's d < 0 branch
+        t = rng.uniform(t1, t2)
+        close(ref.interpolate_SE3((t1, p1, q1), (t2, p2, q2), t),
+              O.interpolate_SE3((t1, p1, q1), (t2, p2, q2), t), ref)
+
+
+# ---------------------------------------- Open3D Transform, getVoxelIndex
+def test_transform_and_voxel_index_match(ref):
+    rng = np.random.default_rng(5)
+    xyz = rng.normal(size=(2000, 3)) * 30.0
+    A = rng.normal(size=(2000, 3, 3))
+    cov = A @ A.transpose(0, 2, 1)
+    T = np.eye(4)
+    T[:3, :3] = S.rotvec_matrix([0.1, -0.2, 0.3])
+    T[:3, 3] = [1.0, -2.0, 3.0]
+    rp, rc = ref.transform_cloud(xyz, cov, T)
+    op, oc = O.transform_cloud(xyz, cov, T)
+    np.testing.assert_array_equal(rp, op)                 # (4x4 homogeneous product: same order in both builds)
+    close(rc, oc, ref)
+    edge = np.array([[-0.1, -0.5, -0.0], [0.5, 0.4999999999999999, 0.3], [0.6, 0.9, -0.3], [1e-300, -1e-300, 0.0]])
+    for v in (0.1, 0.3, 0.5, 1.0):
+        np.testing.assert_array_equal(ref.voxel_index(xyz, v), O.voxel_index(xyz, v))
+        np.testing.assert_array_equal(ref.voxel_index(edge, v), O.voxel_index(edge, v))
+
+
+# ------------------------------------------------------------ LocalMap.cpp
+def build_maps(ref, frames, n, cap=1000, **over):
+    om = O.Map(0.5, cap)
+    om.set_update_params(remove_enabled=False)
+    rm = ref.Map(voxel_map=0.5, max_points_per_voxel=cap, remove_enabled=0, **over)
+    for (p, c), T in zip(frames.ds[:n], frames.poses[:n]):
+        _, _, ox, oc = om.update(p, c, T, initialize=True)
+        rx, rc = rm.update(p, c, T, initialize=True)
+        np.testing.assert_array_equal(rx, ox)             # the caller's cloud ends up in the world frame
+        close(rc, oc, ref)
+    return om, rm
+
+
+@pytest.mark.parametrize("cap", [1000, 3])
+def test_map_update_matches(ref, frames, cap):
+    om, rm = build_maps(ref, frames, 4, cap)
+    assert rm.size() == om.size()
+    ok, oc, omean, ocov = om.export()
+    rk, rc, rmean, rcov = rm.export()
+    np.testing.assert_array_equal(rk, ok)
+    np.testing.assert_array_equal(rc, oc)                  # numPoints, incl. the hard cap
+    np.testing.assert_array_equal(rmean, omean)
+    close(rcov, ocov, ref)
+    assert int(oc.max()) == (cap if cap == 3 else int(oc.max()))
+
+
+def test_keyframe_gate_matches(ref, frames):
+    om, rm = build_maps(ref, frames, 1)
+    rng = np.random.default_rng(6)
+    prev = frames.poses[0]
+    for _ in range(200):
+        # around both thresholds (cos 0.985 <-> 9.94 deg, |t|^2 = 1e-2)
+        d = S.perturbation(dt=tuple(rng.normal(size=3) * 0.06), angle_deg=float(rng.uniform(0, 20)))
+        cur = prev @ d
+        assert rm.needs_map_update(prev, cur) == O.needs_map_update(prev, cur, 1e-2, 0.985)
+    # gated-out frames must leave the map untouched but still move prevTransform_ (LocalMap.cpp:39-42)
+    p, c = frames.ds[1]
+    small = prev @ S.perturbation(dt=(0.01, 0.0, 0.0), angle_deg=0.1)
+    n0 = rm.size()
+    ins, _, _, _ = om.update(p, c, small, initialize=False)
+    rm.update(p, c, small, initialize=False)
+    assert not ins and rm.size() == n0 == om.size()
+
+
+def test_eviction_matches(ref, frames):
+    om = O.Map(0.5, 1000)
+    om.set_update_params(remove_enabled=False)
+    # removing_period 0: the reference sweeps on every inserting call (its clock is omp_get_wtime())
+    rm = ref.Map(voxel_map=0.5, remove_enabled=1, remove_distance=12.0, remove_period=0.0)
+    for (p, c), T in zip(frames.ds[:3], frames.poses[:3]):
+        om.update(p, c, T, initialize=True)
+        om.evict(T[:3, 3], 12.0)
+        rm.update(p, c, T, initialize=True)
+        assert rm.size() == om.size()
+    np.testing.assert_array_equal(rm.export()[0], om.export()[0])
+
+
+def test_correspondences_match(ref, frames):
+    om, rm = build_maps(ref, frames, 4)
+    p, c = frames.ds[4]
+    wp, wc = O.transform_cloud(p, c, frames.poses[4] @ S.perturbation())
+    _, hit, _, mean, cov = om.query(wp)
+    sp, sc, mp, mc = rm.correspondences(wp, wc)
+    assert len(sp) == int(hit.sum()) > 500
+    np.testing.assert_array_equal(sp, wp[hit])             # the correspondence SET, point for point
+    np.testing.assert_array_equal(sc, wc[hit])
+    np.testing.assert_array_equal(mp, mean[hit])
+    close(mc, cov[hit], ref)
+
+
+# -------------------------------------------------------- Registration.cpp
+def test_jtj_jtr_matches(ref, frames):
+    om, rm = build_maps(ref, frames, 4)
+    p, c = frames.ds[4]
+    wp, wc = O.transform_cloud(p, c, frames.poses[4] @ S.perturbation())
+    _, hit, _, mean, cov = om.query(wp)
+    for i in np.nonzero(hit)[0][:300]:
+        Ho, bo = O.jtj_jtr(wp[i], mean[i], wc[i] + cov[i])
+        Hr, br = rm.jtj_jtr(wp[i], mean[i], wc[i] + cov[i])
+        close(Hr, Ho, ref, ulps=256)
+        close(br, bo, ref, ulps=4096)                      # (b is a difference of nearly equal terms)
+
+
+def test_gauss_newton_step_and_align_match(ref, frames):
+    om, rm = build_maps(ref, frames, 4)
+    p, c = frames.ds[4]
+    guess = frames.poses[4] @ S.perturbation()
+    ro = om.align(p, c, guess)
+    assert ro["converged"] and 2 <= ro["iterations"] <= 20
+    # every iteration: the reference's correspondenceMatching + computeTransform on the oracle's
+    # working cloud gives the oracle's step (sums differ only in OpenMP chunking: 1e-16 relative)
+    wp, wc = O.transform_cloud(p, c, guess)
+    for k in range(ro["iterations"]):
+        Ts, nc = rm.gn_step(wp, wc)
+        assert nc == int(ro["ncorr"][k])
+        assert np.abs(Ts - ro["step"][k]).max() < 1e-12
+        assert rm.convergence_check(Ts) == (k == ro["iterations"] - 1)
+        wp, wc = O.transform_cloud(wp, wc, ro["step"][k])
+    Tr, conv = rm.align(p, c, guess)
+    assert conv
+    dt, dr = pose_err(ro["T"], Tr)
+    assert dt < 1e-12 and dr < 1e-12
+    # no correspondences at all: LDLT of a zero matrix solves to zero => identity step, "converged"
+    far = p + np.array([1e4, 0.0, 0.0])
+    To, Tr = om.align(far, c, np.eye(4)), rm.align(far, c, np.eye(4))
+    np.testing.assert_array_equal(Tr[0], To["T"])
+    assert Tr[1] and To["converged"] and To["iterations"] == 1
+    # max_iteration exhausted: last estimate, not converged
+    o1 = om.align(p, c, guess, max_iteration=2)
+    r1 = ref.Map(cfg=R.default_config(voxel_map=0.5, remove_enabled=0, max_iteration=2))
+    for (pp, cc), T in zip(frames.ds[:4], frames.poses[:4]):
+        r1.update(pp, cc, T, initialize=True)
+    T1, c1 = r1.align(p, c, guess)
+    assert not c1 and not o1["converged"] and o1["iterations"] == 2
+    assert max(pose_err(o1["T"], T1)) < 1e-12
+
+
+# ---------------------------------------------------- CloudPreprocessor.cpp
+def sweep_and_states(seed, late_states):
+    rng = np.random.default_rng(seed)
+    scene, poses = S.hall_scene(), S.arc_trajectory(3)
+    xyz, t = S.make_scan(scene, poses[1], rng)
+    xyz, t = xyz[::4].copy(), t[::4].copy()
+    # 400 Hz filter states, `late_states` of them after the sweep's last point (the reference needs
+    # at least one: CloudPreprocessor.cpp:45).  For the first state after the sweep the scan for "the
+    # first point not older than the state" runs off the end, so the tail of the sweep stays
+    # untransformed (CloudPreprocessor.cpp:54-65): the quirk the oracle has to reproduce
+    n = int(np.ceil((t[-1] - t[0] + 0.01) / 0.0025)) + late_states
+    ts = t[0] - 0.01 + np.arange(n) * 0.0025
+    pos = np.stack([0.5 * (ts - ts[0]), 0.1 * np.sin(3 * ts), 0.02 * ts], 1)
+    quat = Rot.from_rotvec(np.stack([0.02 * np.sin(2 * ts), 0.01 * ts, 0.3 * (ts - ts[0])], 1)).as_quat()
+    return xyz, t, (ts, pos, quat)
+
+
+def rows_sorted(p, c):
+    o = np.lexsort((p[:, 2], p[:, 1], p[:, 0]))
+    return p[o], c[o]
+
+
+@pytest.mark.parametrize("case", ["no_states", "three_states_after_sweep", "one_state_after_sweep"])
+@pytest.mark.parametrize("voxel", [0.5, 0.3])
+def test_preprocess_matches(ref, case, voxel):
+    xyz, t, states = sweep_and_states(7, late_states=3 if case == "three_states_after_sweep" else 1)
+    if case == "no_states":
+        states = None
+    T_il = S.default_T_il()
+    op, oc, _ = O.preprocess(xyz, t, T_il, states, voxel)
+    rp, rc = ref.preprocess(xyz, t, T_il, states, voxel)
+    assert len(rp) == len(op) > 1000                        # the kept SET (first point per voxel)
+    (op, oc), (rp, rc) = rows_sorted(op, oc), rows_sorted(rp, rc)
+    if exact(ref) or states is None:
+        np.testing.assert_array_equal(rp, op)
+    else:
+        assert np.abs(rp - op).max() < 1e-12                 # Isometry * point: inner order of three
+    # 30-NN covariance + U diag(1,1,0.01) V^T (two different Jacobi solvers: ~1e-9 where two
+    # singular values nearly coincide, 1e-15 typically)
+    assert np.abs(rc - oc).max() < 5e-8
+    # (in the `tree` build the deskewed points themselves differ by ~1e-14, which the regularisation amplifies)
+    med = 1e-13 if (exact(ref) or states is None) else 1e-11
+    assert np.median(np.abs(rc - oc).reshape(len(rc), -1).max(axis=1)) < med
+
+
+# ----------------------------------------------------------- ErrorStateKF.cpp
+def test_filter_predict_update_match(ref, frames):
+    om, rm = build_maps(ref, frames, 4)
+    rng = np.random.default_rng(8)
+    # IMU at 400 Hz for 0.1 s, consistent with standing still at the pose of frame 4 ... roughly:
+    # the point is identical inputs, not realism
+    g = np.array(R.default_config().gravity)
+    ts = 0.0025 * np.arange(1, 45)
+    gyro = 0.05 * rng.normal(size=(len(ts), 3)) + np.array(R.default_config().bias_g)
+    acc = -g + 0.2 * rng.normal(size=(len(ts), 3)) + np.array(R.default_config().bias_a)
+    lidar_end = float(ts[39]) + 1e-4                          # 4 samples lie beyond it: rolled back
+
+    kf = ref.Eskf()
+    kf.initialize(0.0)
+    od, twin = O.Odometry(), O.Odometry()
+    kf.process(-1.0, gyro[0], acc[0])                         # dt < 0: ignored (ErrorStateKF.cpp:77-79)
+    od.kf_process(-1.0, gyro[0], acc[0])
+    for i, t in enumerate(ts):
+        kf.process(float(t), gyro[i], acc[i])
+        od.kf_process(float(t), gyro[i], acc[i])
+        if t <= lidar_end:
+            twin.kf_process(float(t), gyro[i], acc[i])
+    assert kf.num_states() == len(ts) + 1 == od.info().n_states
+
+    def same_state(tol_P):
+        a, b = kf.state(-1, with_P=True), od.last_state(with_P=True)
+        assert a["timestamp"] == b["t"]
+        for x, y in (("position", "p"), ("velocity", "v"), ("attitude_xyzw", "q"), ("bias_a", "ba"),
+                     ("bias_g", "bg"), ("gravity", "g")):
+            assert np.abs(a[x] - b[y]).max() < 1e-12, x
+        assert np.abs(a["P"] - b["P"]).max() <= tol_P * np.abs(b["P"]).max()
+
+    same_state(1e-12)                                         # 44 predict steps: F P F^T + F_i Q F_i^T
+
+    # update(): rollback, ICP from the predicted pose, Kalman update, injection, reset
+    p, c = frames.ds[4]
+    s = twin.last_state()
+    guess = np.eye(4)
+    guess[:3, :3] = O.quat_to_matrix(s["q"])
+    guess[:3, 3] = s["p"]
+    # (the filter starts at the origin while the map was built along the arc: register the cloud of
+    #  frame 4 moved into the filter's frame so that ICP has something to converge to)
+    p4, c4 = O.transform_cloud(p, c, np.linalg.inv(guess) @ frames.poses[4] @ S.perturbation())
+    obs = om.align(p4, c4, guess)
+    assert obs["converged"]
+    T_ref = kf.update(rm, p4, c4, lidar_end)
+    g_or, T_or = od.kf_update_with_observation(lidar_end, obs["T"])
+    np.testing.assert_allclose(g_or, guess, rtol=0, atol=0)
+    assert kf.num_states() == 41 + 1 == od.info().n_states     # 4 states rolled back, 1 appended
+    assert max(pose_err(T_or, T_ref)) < 1e-11
+    same_state(1e-9)
