@@ -319,3 +319,37 @@ def test_filter_predict_update_match(ref, frames):
     assert kf.num_states() == 41 + 1 == od.info().n_states     # 4 states rolled back, 1 appended
     assert max(pose_err(T_or, T_ref)) < 1e-11
     same_state(1e-9)
+
+
+# ------------------------------------ the committed golden fixture (what the GPU test is held to)
+def test_reference_sources_reproduce_golden_fixture(ref):
+    """tests/golden/hotpath_v1.npz was generated from the oracle; the reference's own sources (on the
+    shims) reproduce it: kept sets, covariances, map, correspondence set at the guess, final pose."""
+    import os
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hotpath_v1.npz")))
+    v = float(g["voxel"])
+    rm = ref.Map(voxel_map=v, remove_enabled=0)
+    for k in range(3):
+        xyz, t = g[f"raw{k}"].astype(np.float64), g[f"time{k}"]
+        rp, rc = ref.preprocess(xyz, t, g["T_il"], None, v)
+        # golden rows are in ascending source index: the kept points are the T_il-transformed raw ones
+        gp = O.transform_cloud(xyz, None, g["T_il"])[0][g[f"kept{k}"]]
+        assert len(rp) == len(gp)
+        (rp, rc), (gp_s, gc_s) = rows_sorted(rp, rc), rows_sorted(gp, g[f"cov{k}"])
+        np.testing.assert_array_equal(rp, gp_s)                       # kept set, bit for bit
+        assert np.abs(rc - gc_s).max() < 1e-7
+        if k < 2:
+            rm.update(gp, g[f"cov{k}"], g["poses"][k], initialize=True)   # golden covariances: exact map
+    keys, count, mean, cov = rm.export()
+    np.testing.assert_array_equal(keys, g["map_keys"])
+    np.testing.assert_array_equal(count, g["map_count"])
+    np.testing.assert_array_equal(mean, g["map_mean"])
+    close(cov, g["map_cov"], ref)
+    pg, cg = O.transform_cloud(gp, g["cov2"], g["guess"])
+    np.testing.assert_array_equal(ref.voxel_index(pg, v), g["keys_at_guess"])
+    sp, _, _, _ = rm.correspondences(pg, cg)
+    np.testing.assert_array_equal(sp, pg[g["lin_hit"].astype(bool)])  # correspondence set
+    T, conv = rm.align(gp, g["cov2"], g["guess"])
+    # (this sparse fixture exhausts max_iteration = 100: "ICP not converged!", last estimate returned)
+    assert int(g["align_iterations"]) == 100 and not conv
+    assert max(pose_err(g["align_T"], T)) < 1e-10
