@@ -184,6 +184,30 @@ class Ref:
                                   C.c_size_t(ns), _d(oxyz), _d(ocov))
         return oxyz[:m].copy(), ocov[:m].reshape(m, 3, 3).copy()
 
+    def run_odometry(self, scans, imu, state_time, cfg: Config | None = None, **overrides):
+        """ESKF_LIO::Odometry::run over a whole log (scans: [(xyz, point_time)], imu: n x 7).
+        Returns (poses of every updateLocalMap call, filter state at/before state_time with P,
+        map voxel count, number of filter states)."""
+        cfg = cfg if cfg is not None else default_config(**overrides)
+        xyz = _f64(np.concatenate([x for x, _ in scans]), (-1, 3))
+        t = _f64(np.concatenate([tt for _, tt in scans]))
+        n_per = np.array([len(tt) for _, tt in scans], dtype=np.uint64)
+        imu = _f64(imu, (-1, 7))
+        poses = np.zeros((len(scans), 16))
+        st = State()
+        P = np.zeros((18, 18))
+        vox = C.c_uint64(0)
+        self.L.ref_odom_run.restype = C.c_longlong
+        ns = self.L.ref_odom_run(C.byref(cfg), _d(imu), C.c_size_t(len(imu)), _d(xyz), _d(t),
+                                 n_per.ctypes.data_as(_u64p), C.c_size_t(len(scans)), _d(poses),
+                                 C.c_double(state_time), C.byref(st), _d(P), C.byref(vox))
+        if ns < 0:
+            raise RuntimeError("reference Odometry::run did not finish")
+        state = {"timestamp": st.timestamp, "position": np.array(st.position), "velocity": np.array(st.velocity),
+                 "attitude_xyzw": np.array(st.attitude_xyzw), "bias_a": np.array(st.bias_a),
+                 "bias_g": np.array(st.bias_g), "gravity": np.array(st.gravity), "P": P}
+        return poses.reshape(-1, 4, 4), state, int(vox.value), int(ns)
+
     def Map(self, cfg: Config | None = None, **overrides):
         return RefMap(self, cfg if cfg is not None else default_config(**overrides))
 

@@ -8,7 +8,9 @@
 #include <cstdint>
 #include <cstring>
 #include <deque>
+#include <chrono>
 #include <memory>
+#include <thread>
 #include <vector>
 
 #include <omp.h>
@@ -19,6 +21,7 @@
 #include "ESKF_LIO/CloudPreprocessor.hpp"
 #include "ESKF_LIO/ErrorStateKF.hpp"
 #include "ESKF_LIO/LocalMap.hpp"
+#include "ESKF_LIO/Odometry.hpp"
 #include "ESKF_LIO/Registration.hpp"
 #include "ESKF_LIO/Utils.hpp"
 #undef private
@@ -368,6 +371,66 @@ void ref_eskf_state(const ref_eskf * e, long long index, RefState * out, double 
   const auto & st = e->kf->getStates();
   const size_t i = index < 0 ? st.size() + index : static_cast<size_t>(index);
   from_state(st[i], out, P);
+}
+
+// ---------------------------------------------------------------- Odometry
+// Odometry::run (src/Odometry.cpp:9-98) over a whole log.  Both queues are filled before run()
+// starts, so the loop's outcome does not depend on thread timing: the first trip queues every IMU
+// sample and initialises on sweep 0 (which processes the whole IMU log), every later trip finds
+// the filter ahead of the sweep, rolls back to its end time and replays the rest — the states at
+// and before each sweep's end are those of the online interleaving.  run() is stopped with
+// setExit() once the last sweep has reached updateLocalMap (the trip in flight completes).
+// Outputs: the pose of every updateLocalMap call (LocalMap::trajectory_, one per sweep), the
+// filter's last state at or before `state_time`, the map's voxel count.
+long long ref_odom_run(
+  const RefConfig * cfg, const double * imu /* n_imu x (t, gyro xyz, acc xyz) */, size_t n_imu, const double * xyz,
+  const double * point_time, const uint64_t * n_per_scan, size_t n_scans, double * poses /* n_scans x 16 */,
+  double state_time, RefState * state, double * P, uint64_t * map_voxels)
+{
+  auto imuBuf = std::make_shared<SynchronizedQueue<ImuMeasurementPtr>>();
+  auto cloudBuf = std::make_shared<SynchronizedQueue<LidarMeasurementPtr>>();
+  for (size_t i = 0; i < n_imu; ++i) {
+    auto m = std::make_shared<ImuMeasurement>();
+    m->timestamp = imu[7 * i];
+    m->angularVelocity = Eigen::Vector3d(imu[7 * i + 1], imu[7 * i + 2], imu[7 * i + 3]);
+    m->acceleration = Eigen::Vector3d(imu[7 * i + 4], imu[7 * i + 5], imu[7 * i + 6]);
+    imuBuf->push(m);
+  }
+  size_t off = 0;
+  for (size_t k = 0; k < n_scans; ++k) {
+    const size_t n = n_per_scan[k];
+    auto meas = std::make_shared<LidarMeasurement>();
+    meas->cloud = make_cloud(xyz + 3 * off, nullptr, n);
+    meas->pointTime.assign(point_time + off, point_time + off + n);
+    meas->startTime = point_time[off];
+    meas->endTime = point_time[off + n - 1];
+    cloudBuf->push(meas);
+    off += n;
+  }
+  Odometry odom(to_yaml(*cfg), imuBuf, cloudBuf, open3d::camera::PinholeCameraParameters(), false);
+  std::thread th([&odom]() {odom.run();});
+  const auto t0 = std::chrono::steady_clock::now();
+  bool timed_out = false;
+  for (;;) {
+    const volatile size_t * done = nullptr;
+    (void)done;
+    if (odom.localMap_->trajectory_.parameters_.size() >= n_scans) {break;}
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(600)) {timed_out = true; break;}
+    std::this_thread::sleep_for(std::chrono::milliseconds(2));
+  }
+  odom.setExit();
+  th.join();
+  if (timed_out) {return -1;}
+  const auto & traj = odom.localMap_->trajectory_.parameters_;
+  for (size_t k = 0; k < n_scans; ++k) {
+    for (int i = 0; i < 4; ++i) {for (int j = 0; j < 4; ++j) {poses[16 * k + 4 * i + j] = traj[k].extrinsic_(i, j);}}
+  }
+  const auto & st = odom.kalmanFilter_->getStates();
+  size_t pick = 0;
+  for (size_t i = 0; i < st.size(); ++i) {if (st[i].timestamp <= state_time) {pick = i;}}
+  from_state(st[pick], state, P);
+  *map_voxels = odom.localMap_->voxelGrid_.size();
+  return static_cast<long long>(st.size());
 }
 
 }  // extern "C"

@@ -353,3 +353,26 @@ def test_reference_sources_reproduce_golden_fixture(ref):
     # (this sparse fixture exhausts max_iteration = 100: "ICP not converged!", last estimate returned)
     assert int(g["align_iterations"]) == 100 and not conv
     assert max(pose_err(g["align_T"], T)) < 1e-10
+
+
+# ----------------------------------------------------------------- Odometry.cpp
+def test_reference_odometry_run_reproduces_golden_trajectory(ref):
+    """ESKF_LIO::Odometry::run itself (src/Odometry.cpp, with the reference's ErrorStateKF,
+    CloudPreprocessor, ICP and LocalMap) over the committed 20-frame log: the trajectory, the final
+    filter state and covariance and the map occupancy of tests/golden/odometry_v1.npz — which the
+    oracle generated and the GPU path is held to — come out of the reference's own loop."""
+    import os
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "odometry_v1.npz")))
+    off = np.concatenate([[0], np.cumsum(g["n"])])
+    scans = [(g["xyz"][off[i]:off[i + 1]].astype(np.float64), g["time"][off[i]:off[i + 1]])
+             for i in range(len(g["n"]))]
+    poses, state, voxels, n_states = ref.run_odometry(scans, g["imu"], float(g["state"][0]),
+                                                      voxel_map=0.5, voxel_pre=0.5)
+    assert len(poses) == len(g["poses"]) == 20
+    for a, b in zip(g["poses"], poses):
+        assert max(pose_err(a, b)) < 1e-9
+    assert voxels == int(g["rec"][-1, 2])                              # map occupancy after the last frame
+    got = np.concatenate([[state["timestamp"]], state["position"], state["velocity"], state["attitude_xyzw"],
+                          state["bias_a"], state["bias_g"], state["gravity"]])
+    np.testing.assert_allclose(got, g["state"], atol=1e-9)
+    assert np.linalg.norm(state["P"] - g["P"]) / np.linalg.norm(g["P"]) < 1e-9
