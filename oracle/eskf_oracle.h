@@ -10,12 +10,13 @@
  * or fixtures, and cannot be built as shipped in this environment (Eigen,
  * Open3D, yaml-cpp and rclcpp are all absent, no network).  This file is a
  * dependency-free restatement of the reference algorithm; it is pinned by
- *   (0) the reference's OWN hot-path sources (Registration, LocalMap,
- *       CloudPreprocessor, Utils, ErrorStateKF .cpp), compiled where they lie
+ *   (0) the reference's OWN sources (Registration, LocalMap, CloudPreprocessor,
+ *       Utils, ErrorStateKF, Odometry .cpp), compiled where they lie
  *       against from-scratch shims of the Eigen / Open3D / yaml-cpp API subset
  *       they use (oracle/refshim, `make ref`): bit-identical voxel keys, kept
  *       sets, map statistics, correspondence sets and per-point J^T W J terms,
- *       poses / filter states to 1e-12 (tests/test_reference_shim.py).  That
+ *       poses / filter states to 1e-12, the reference's Odometry::run loop
+ *       reproducing the golden trajectory (tests/test_reference_shim.py).  That
  *       pins the CONTROL FLOW AND FORMULAS to the reference's text; the
  *       third-party arithmetic underneath (Eigen's LDLT / inverse / SVD /
  *       quaternions, Open3D's Transform / k-NN / ComputeCovariance) is restated

@@ -1,5 +1,5 @@
 """ctypes binding of oracle/_ref/libref_shim*.so: the REFERENCE'S OWN sources
-(/root/reference/src/{Registration,LocalMap,CloudPreprocessor,Utils,ErrorStateKF}.cpp), compiled
+(/root/reference/src/{Registration,LocalMap,CloudPreprocessor,Utils,ErrorStateKF,Odometry}.cpp), compiled
 where they lie against the API shims in oracle/refshim/include (Eigen, Open3D and yaml-cpp do
 not exist in this environment), behind the small C ABI of oracle/refshim/ref_capi.cpp.
 

@@ -1,6 +1,6 @@
 """The ORACLE against the REFERENCE'S OWN SOURCES.
 
-/root/reference/src/{Registration,LocalMap,CloudPreprocessor,Utils,ErrorStateKF}.cpp are compiled
+/root/reference/src/{Registration,LocalMap,CloudPreprocessor,Utils,ErrorStateKF,Odometry}.cpp are compiled
 where they lie (oracle/Makefile `ref`) against from-scratch shims of the Eigen / Open3D / yaml-cpp
 API subset they use (oracle/refshim/include; the real libraries do not exist here) and driven
 through oracle/refshim/ref_capi.cpp.  This pins the oracle's restatement of the reference's
