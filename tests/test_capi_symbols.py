@@ -62,3 +62,32 @@ def test_host_driver_symbols_all_exported(built):
         with pytest.raises(RuntimeError) as e:
             odometry.Odometry(cfg)
         assert "no CPU fallback" in str(e.value)
+
+
+def test_ctypes_structs_match_the_c_headers(tmp_path):
+    """The ctypes mirrors of the structs that cross the C ABI have the size and field offsets the
+    C compiler gives the headers' definitions."""
+    import subprocess
+    from eskf_lio_b200 import odometry
+    pairs = [("eskf_odom_config", odometry.OdomConfig, "eskf_host.h"),
+             ("eskf_odom_info", odometry.OdomInfo, "eskf_host.h"),
+             ("eskf_state", capi.State, "eskf_gpu.h"),
+             ("eskf_icp_params", capi.IcpParams, "eskf_gpu.h"),
+             ("eskf_align_info", capi.AlignInfo, "eskf_gpu.h")]
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "eskf_gpu.h"', '#include "eskf_host.h"',
+             'int main(void) {']
+    for cname, cls, _ in pairs:
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, *_ in cls._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)], text=True).strip().splitlines()
+    for (cname, cls, _), line in zip(pairs, out):
+        nums = [int(x) for x in line.split()[1:]]
+        assert nums[0] == ctypes.sizeof(cls), cname
+        assert nums[1:] == [getattr(cls, f[0]).offset for f in cls._fields_], cname

@@ -539,3 +539,16 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
         c2.set_option("align_depth", 0)
         c2.set_option("align_ticket_chunk", 2)
         c2.set_option("align_dynamic_tiles", 1)
+
+
+def test_cuda_path_against_the_reference_sources(ctx, oracle, frames):
+    """The CUDA path held DIRECTLY against the reference's own sources (compiled on the API shims,
+    oracle/ref.py): kept sets with deskew, map statistics, correspondence set bit for bit, final
+    pose within the bar.  The prebuilt oracle/_ref libraries travel with the snapshot."""
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref libraries not present on this box")
+    from ref_check import GpuImpl, check_against_reference
+    from test_reference_shim import sweep_and_states
+    check_against_reference(R.Ref("seq"), GpuImpl(capi, ctx), frames, sweep_and_states(7, 2),
+                            cov_tol=1e-6, pose_tol=POSE_T_TOL)

@@ -376,3 +376,11 @@ def test_reference_odometry_run_reproduces_golden_trajectory(ref):
                           state["bias_a"], state["bias_g"], state["gravity"]])
     np.testing.assert_allclose(got, g["state"], atol=1e-9)
     assert np.linalg.norm(state["P"] - g["P"]) / np.linalg.norm(g["P"]) < 1e-9
+
+
+# ------------------------------------------- the checker the GPU suite runs, on the oracle
+def test_pipeline_checker_on_the_oracle(frames):
+    """tests/ref_check.py holds an implementation directly against the reference's sources; the
+    GPU suite runs it on the CUDA path (test_gpu_parity.py), here it runs on the oracle."""
+    from ref_check import OracleImpl, check_against_reference
+    check_against_reference(R.Ref("seq"), OracleImpl(O), frames, sweep_and_states(7, 2), cov_tol=1e-9, pose_tol=1e-12)
