@@ -384,3 +384,25 @@ def test_pipeline_checker_on_the_oracle(frames):
     GPU suite runs it on the CUDA path (test_gpu_parity.py), here it runs on the oracle."""
     from ref_check import OracleImpl, check_against_reference
     check_against_reference(R.Ref("seq"), OracleImpl(O), frames, sweep_and_states(7, 2), cov_tol=1e-9, pose_tol=1e-12)
+
+
+def test_full_size_sweep_matches(ref):
+    """BASELINE.json's frame: a full 32 x 2000 sweep, deskewed against 400 Hz states, 0.3 m voxels."""
+    rng = np.random.default_rng(21)
+    xyz, t = S.make_scan(S.hall_scene(), S.arc_trajectory(3)[1], rng)
+    assert len(xyz) == 64000
+    n = int(np.ceil((t[-1] - t[0] + 0.01) / 0.0025)) + 2
+    ts = t[0] - 0.01 + np.arange(n) * 0.0025
+    pos = np.stack([0.5 * (ts - ts[0]), 0.1 * np.sin(3 * ts), 0.02 * ts], 1)
+    quat = Rot.from_rotvec(np.stack([0.02 * np.sin(2 * ts), 0.01 * ts, 0.3 * (ts - ts[0])], 1)).as_quat()
+    T_il = S.default_T_il()
+    op, oc, _ = O.preprocess(xyz, t, T_il, (ts, pos, quat), 0.3)
+    rp, rc = ref.preprocess(xyz, t, T_il, (ts, pos, quat), 0.3)
+    assert len(op) == len(rp) > 10000
+    (op, oc), (rp, rc) = rows_sorted(op, oc), rows_sorted(rp, rc)
+    if exact(ref):
+        np.testing.assert_array_equal(rp, op)
+        assert np.abs(rc - oc).max() < 1e-12
+    else:
+        assert np.abs(rp - op).max() < 1e-12
+        assert np.abs(rc - oc).max() < 5e-8
