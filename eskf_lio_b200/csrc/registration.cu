@@ -51,6 +51,9 @@ constexpr bool kAssign = kFold == 1 && ESKF_TERMS_ASSIGN != 0;
 #ifndef ESKF_POS_PREFETCH
 #define ESKF_POS_PREFETCH 0  // 4-deep rotation: L2-prefetch the positions of the tile this many trips ahead (0 = off)
 #endif
+#ifndef ESKF_POS_AHEAD
+#define ESKF_POS_AHEAD 0  // 4-deep rotation: 1 = keep two tiles of raw positions in flight instead of one
+#endif
 #ifndef ESKF_FAT_DEPTH
 #define ESKF_FAT_DEPTH 3  // pipeline depth of the fat-CTA variants: 3 = issue and consume in the same trip; 4 = consume one trip later
 #endif
@@ -658,11 +661,21 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
   RecRegs rec;
   uint4 tagw;
   double rx, ry, rz;
+#if ESKF_POS_AHEAD
+  // experiment (default off): a second tile of raw positions in flight (t+3), i.e. the HBM stream is
+  // requested two trips before it is consumed; +6 registers
+  unsigned tile_q = 0;
+  double qx = 0.0, qy = 0.0, qz = 0.0;
+#endif
   {
     double ax, ay, az, bx, by, bz;
     load_pos(tile, ax, ay, az);
     load_pos(tile_n, bx, by, bz);
     load_pos(tile_r, rx, ry, rz);
+#if ESKF_POS_AHEAD
+    tile_q = next_tile();
+    load_pos(tile_q, qx, qy, qz);
+#endif
     xform4(tile, ax, ay, az, c4s);
     scan4(c4s, window4(c4s));
     issue_record(c4s, tile, rec);
@@ -721,8 +734,15 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
     tile = tile_n;
     tile_n = tile_r;
     // ---- 4. positions of the tile after that
+#if ESKF_POS_AHEAD
+    tile_r = tile_q;
+    rx = qx; ry = qy; rz = qz;
+    tile_q = next_tile();
+    load_pos(tile_q, qx, qy, qz);
+#else
     tile_r = next_tile();
     load_pos(tile_r, rx, ry, rz);
+#endif
 #if ESKF_POS_PREFETCH
     // statically dealt tiles are known ahead: pull the positions of the tile ESKF_POS_PREFETCH
     // trips further on into L2 (3 x 256 B, 64 B per lane of lanes 0..11)
