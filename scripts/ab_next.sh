@@ -19,8 +19,8 @@ for s in 0 1; do
 done
 # where do the tag probes of the compact 0.1 m table hit?  (L2 hit rate / DRAM bytes of one launch)
 M=dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct,lts__t_sectors_srcunit_tex_op_read.sum
-for hint in 9000000 4300000; do
-  ncu --metrics $M --clock-control none -k regex:align_kernel -s 2 -c 1 --csv --log-file gpurun_out/next_ncu_hint$hint.csv \
-      python scripts/dense_align.py --reps 1 --warmup 2 --hint $hint > /dev/null 2>&1
-  grep -h "align_kernel" gpurun_out/next_ncu_hint$hint.csv | cut -d, -f13- | tr '\n' ' '; echo " (hint $hint)"
+for c in 0 1; do
+  ncu --metrics $M --clock-control none -k regex:align_kernel -s 2 -c 1 --csv --log-file gpurun_out/next_ncu_compact$c.csv \
+      python scripts/dense_align.py --reps 1 --warmup 2 --compact $c > /dev/null 2>&1
+  grep -h "align_kernel" gpurun_out/next_ncu_compact$c.csv | cut -d, -f13- | tr '\n' ' '; echo " (compact $c)"
 done

@@ -2,7 +2,7 @@
 """Profiling harness: the dense registration leg of bench.py on its own
 (BASELINE.json configs[2]/[3]), small enough to sit under ncu.
 
-    python scripts/dense_align.py [--src N] [--map N] [--voxel V] [--iters I] [--mode 1|7] [--reps R]
+    python scripts/dense_align.py [--src N] [--map N] [--voxel V] [--iters I] [--mode 1|7] [--reps R] [--sort 0|1] [--compact 0|1]
 """
 import argparse
 import json
@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--sort", type=int, default=0, help="1: sort the source by voxel brick on the host")
     ap.add_argument("--hint", type=int, default=9_000_000, help="voxel capacity hint of the map")
+    ap.add_argument("--compact", type=int, default=0, help="1: eskf_map_compact after the map build")
     a = ap.parse_args()
     ctx = capi.Context(0)
     rng = np.random.default_rng(44)
@@ -38,6 +39,8 @@ def main():
         p, c = S.dense_cloud(scene, n, rng)
         gmap.insert(p, c, np.eye(4))
         left -= n
+    if a.compact:
+        gmap.compact()
     p, c = S.dense_cloud(scene, a.src, rng)
     if a.sort:
         k = np.floor(p / a.voxel).astype(np.int64)
