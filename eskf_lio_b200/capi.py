@@ -51,7 +51,8 @@ SYMBOLS = [
     "eskf_map_create", "eskf_map_destroy", "eskf_map_insert", "eskf_map_insert_cloud",
     "eskf_map_evict", "eskf_map_size", "eskf_map_capacity", "eskf_map_compact", "eskf_map_query", "eskf_map_export",
     "eskf_preprocess", "eskf_preprocess_cloud", "eskf_downsample_cov",
-    "eskf_align", "eskf_align_cloud", "eskf_align_cloud_begin", "eskf_align_end", "eskf_linearize",
+    "eskf_align", "eskf_align_cloud", "eskf_align_cloud_begin", "eskf_align_end", "eskf_align_batch",
+    "eskf_linearize",
     "eskf_align_cloud_fixed",
     "eskf_align_cloud_sharded",
     "eskf_comm_create", "eskf_comm_destroy", "eskf_comm_local_handle", "eskf_comm_connect",
@@ -491,3 +492,23 @@ class Map:
             raise err[0]
         check(st)
         return _info_dict(T, info, bufs)
+
+
+def align_batch(ctxs, maps, clouds, guesses, max_iteration=100, translation_sq_threshold=1e-6,
+                cosine_threshold=0.9999, neighbor_mode=1):
+    """eskf_align_batch: job i = (maps[i], clouds[i], guesses[i]) runs on ctxs[i % len(ctxs)], to
+    which its map and cloud must belong; one registration stays in flight per context.
+    Returns one result dict per job."""
+    n = len(maps)
+    if not (len(clouds) == n and len(guesses) == n):
+        raise ValueError("maps, clouds and guesses must have the same length")
+    prm = IcpParams(max_iteration, neighbor_mode, translation_sq_threshold, cosine_threshold)
+    carr = (C.c_void_p * len(ctxs))(*[c._h.value for c in ctxs])
+    marr = (C.c_void_p * max(n, 1))(*[m._h.value for m in maps])
+    karr = (C.c_void_p * max(n, 1))(*[c._h.value for c in clouds])
+    G = np.ascontiguousarray(np.stack([_f64(g).reshape(16) for g in guesses]) if n else np.zeros((0, 16)))
+    T = np.zeros((n, 16))
+    infos = (AlignInfo * max(n, 1))()
+    check(lib().eskf_align_batch(carr, C.c_int(len(ctxs)), marr, karr, _d(G), C.c_size_t(n), C.byref(prm),
+                                 _d(T), infos))
+    return [_info_dict(T[i], infos[i], None) for i in range(n)]

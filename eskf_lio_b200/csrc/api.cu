@@ -582,6 +582,47 @@ int eskf_align_end(eskf_ctx* ctx, double T_out[16], eskf_align_info* info) {
   return align_end(ctx, T_out, info);
 }
 
+int eskf_align_batch(eskf_ctx* const* ctxs, int n_ctx, const eskf_map* const* maps,
+                     const eskf_cloud* const* clouds, const double* guesses, size_t n,
+                     const eskf_icp_params* params, double* T_out, eskf_align_info* infos) {
+  ESKF_REQUIRE(ctxs && n_ctx > 0 && n_ctx <= 256, "eskf_align_batch needs 1..256 contexts");
+  for (int s = 0; s < n_ctx; ++s) {
+    ESKF_REQUIRE(ctxs[s], "null context in the batch");
+    for (int r = 0; r < s; ++r) ESKF_REQUIRE(ctxs[r] != ctxs[s], "the contexts of a batch must be distinct");
+  }
+  ESKF_REQUIRE(params, "null params");
+  if (n == 0) return ESKF_OK;
+  ESKF_REQUIRE(maps && clouds && guesses && T_out, "null argument");
+  std::vector<long long> pending(static_cast<size_t>(n_ctx), -1);  // job in flight on each context
+  auto collect = [&](int s) -> int {
+    const long long j = pending[static_cast<size_t>(s)];
+    pending[static_cast<size_t>(s)] = -1;
+    return eskf_align_end(ctxs[s], T_out + 16 * j, infos ? &infos[j] : nullptr);
+  };
+  int rc = ESKF_OK;
+  std::string first_error;
+  for (size_t i = 0; i < n && rc == ESKF_OK; ++i) {
+    const int s = static_cast<int>(i % static_cast<size_t>(n_ctx));
+    if (pending[static_cast<size_t>(s)] >= 0) rc = collect(s);
+    if (rc == ESKF_OK) {
+      rc = eskf_align_cloud_begin(ctxs[s], maps[i], clouds[i], guesses + 16 * i, params,
+                                  infos ? &infos[i] : nullptr);
+      if (rc == ESKF_OK) pending[static_cast<size_t>(s)] = static_cast<long long>(i);
+    }
+  }
+  if (rc != ESKF_OK) first_error = eskf_last_error();
+  for (int s = 0; s < n_ctx; ++s) {
+    if (pending[static_cast<size_t>(s)] < 0) continue;
+    const int r2 = collect(s);
+    if (rc == ESKF_OK && r2 != ESKF_OK) {
+      rc = r2;
+      first_error = eskf_last_error();
+    }
+  }
+  if (rc != ESKF_OK) set_error("%s", first_error.c_str());
+  return rc;
+}
+
 int eskf_align(eskf_ctx* ctx, const eskf_map* map, const double* xyz, const double* cov, size_t n,
                const double guess[16], const eskf_icp_params* params, double T_out[16],
                eskf_align_info* info) {

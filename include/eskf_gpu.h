@@ -224,6 +224,16 @@ int eskf_align_cloud_begin(eskf_ctx* ctx, const eskf_map* map, const eskf_cloud*
                            const double guess[16], const eskf_icp_params* params,
                            const eskf_align_info* info);
 int eskf_align_end(eskf_ctx* ctx, double T_out[16], eskf_align_info* info);
+/* n independent registrations (BASELINE.json configs[4]; SURVEY.md 8b eskf_align_batch): job i runs on
+ * ctxs[i % n_ctx], to which maps[i] and clouds[i] must belong; the n_ctx contexts must be distinct.
+ * One host thread keeps one registration in flight per context with the begin / end pair above, so
+ * the launches of the other contexts overlap the kernel each end waits for (a 15k-point
+ * registration occupies well under half of the SMs).  guesses, T_out: n x 16; infos: n entries or
+ * NULL.  On an error no further job is started, the ones in flight are still collected (the
+ * contexts stay usable) and the first error is returned. */
+int eskf_align_batch(eskf_ctx* const* ctxs, int n_ctx, const eskf_map* const* maps,
+                     const eskf_cloud* const* clouds, const double* guesses, size_t n,
+                     const eskf_icp_params* params, double* T_out, eskf_align_info* infos);
 /* parity / debug: one linearisation of the cloud posed at T
  * (LocalMap::correspondenceMatching src/LocalMap.cpp:78-112 + the accumulation
  * of ICP::computeTransform src/Registration.cpp:56-76).  hit: n bytes

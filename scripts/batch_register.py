@@ -48,7 +48,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--pipelined", type=int, default=1,
                     help="1: one host thread keeps one registration in flight per context (begin/end); "
-                         "0: one blocking host thread per context")
+                         "0: one blocking host thread per context; "
+                         "2: the same pipelining inside the library, one eskf_align_batch call per pass")
     ap.add_argument("--repeat", type=int, default=8, help="timed passes over the batch (pairs are independent)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -112,7 +113,14 @@ def main():
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
-    if a.pipelined:
+    if a.pipelined == 2:
+        flat = [jobs[n % a.streams][n // a.streams] for n in range(len(mine))]
+        for rep in range(a.repeat):
+            rs = capi.align_batch(ctxs, [j[0] for j in flat], [j[1] for j in flat], [j[2] for j in flat])
+            if rep == 0:
+                for n, r in enumerate(rs):
+                    results[n % a.streams].append(r)
+    elif a.pipelined:
         work_pipelined()
     else:
         threads = [threading.Thread(target=work, args=(s,)) for s in range(a.streams)]

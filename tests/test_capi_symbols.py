@@ -91,3 +91,17 @@ def test_ctypes_structs_match_the_c_headers(tmp_path):
         nums = [int(x) for x in line.split()[1:]]
         assert nums[0] == ctypes.sizeof(cls), cname
         assert nums[1:] == [getattr(cls, f[0]).offset for f in cls._fields_], cname
+
+
+def test_align_batch_argument_checks_without_gpu(built):
+    """eskf_align_batch validates its context list and returns for an empty batch before it touches
+    any context (the array marshalling of the ctypes binding is exercised here, the compute in -m gpu)."""
+    class Fake:
+        def __init__(self, v):
+            self._h = ctypes.c_void_p(v)
+    assert capi.align_batch([Fake(0x1000), Fake(0x2000)], [], [], []) == []
+    with pytest.raises(capi.EskfError) as e:
+        capi.align_batch([Fake(0x1000), Fake(0x1000)], [], [], [])
+    assert "distinct" in str(e.value)
+    with pytest.raises(ValueError):
+        capi.align_batch([Fake(0x1000)], [Fake(1)], [], [])

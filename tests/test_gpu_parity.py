@@ -552,3 +552,40 @@ def test_cuda_path_against_the_reference_sources(ctx, oracle, frames):
     from test_reference_shim import sweep_and_states
     check_against_reference(R.Ref("seq"), GpuImpl(capi, ctx), frames, sweep_and_states(7, 2),
                             cov_tol=1e-6, pose_tol=POSE_T_TOL)
+
+
+def test_align_batch_equals_individual_registrations(oracle, frames):
+    """eskf_align_batch (configs[4]): 7 jobs over 3 contexts, one in flight per context, give the
+    bit-identical poses and iteration counts of 7 separate eskf_align_cloud calls (and the oracle's
+    pose within the bar); a job on the wrong context is an error that leaves the contexts usable."""
+    ctxs = [capi.Context(0) for _ in range(3)]
+    jobs, want = [], []
+    for i in range(7):
+        c = ctxs[i % 3]
+        om = oracle.Map(0.5, 1000)
+        gm = capi.Map(c, 0.5, 1000, 1 << 14)
+        for (p, cv), T in zip(frames.ds[:3 + i % 2], frames.poses[:3 + i % 2]):
+            om.update(p, cv, T, initialize=True)
+            gm.insert(p, cv, T)
+        p, cv = frames.ds[4]
+        f = 0.4 + 0.1 * i                                   # scaled config-1 perturbations: all converge
+        guess = frames.poses[4] @ S.perturbation(dt=(0.10 * f, -0.05 * f, 0.03 * f), angle_deg=f)
+        cl = capi.Cloud(c, len(p)).upload(p, cv)
+        jobs.append((gm, cl, guess))
+        want.append((gm.align_cloud(cl, guess), om.align(p, cv, guess)))
+    res = capi.align_batch(ctxs, [j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
+    assert len(res) == 7
+    for r, (single, ro) in zip(res, want):
+        np.testing.assert_array_equal(r["T"], single["T"])
+        assert r["iterations"] == single["iterations"] == ro["iterations"]
+        assert r["converged"] == single["converged"] == bool(ro["converged"])
+        dt, dr = pose_err(ro["T"], r["T"])
+        assert dt < POSE_T_TOL and dr < POSE_R_TOL
+    assert capi.align_batch(ctxs, [], [], []) == []
+    # job 1 handed a cloud of context 0: refused; job 0 (in flight then) is still collected
+    bad_clouds = [jobs[0][1], jobs[0][1], jobs[2][1]]
+    with pytest.raises(capi.EskfError):
+        capi.align_batch(ctxs, [j[0] for j in jobs[:3]], bad_clouds, [j[2] for j in jobs[:3]])
+    again = capi.align_batch(ctxs, [j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs])
+    for r, (single, _) in zip(again, want):
+        np.testing.assert_array_equal(r["T"], single["T"])
