@@ -528,6 +528,15 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
                 assert b_rel(rg["b"][k], ro["b"][k], ro["H"][k]) < H_TOL, (tag, k)
             dt, dr = pose_err(ro["T"], rg["T"])
             assert dt < POSE_T_TOL and dr < POSE_R_TOL, (tag, dt, dr)
+        # the per-point correspondence flags of a cloud this size (written by the 4-deep loop)
+        for block in (0, 256):
+            c2.set_option("align_block", block)
+            c2.set_option("align_depth", 0)
+            Ho, bo, hito, nco = om.linearize(*oracle.transform_cloud(p, c, guess))
+            Hg, bg, hitg, ncg = c2.linearize(gm, p, c, T=guess)
+            np.testing.assert_array_equal(hitg, hito)
+            assert ncg == nco == int(ro["ncorr"][0])
+            assert rel_err(Hg, Ho) < H_TOL and b_rel(bg, bo, Ho) < H_TOL
         with pytest.raises(capi.EskfError):
             c2.set_option("align_block", 500)
         with pytest.raises(capi.EskfError):
