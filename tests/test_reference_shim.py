@@ -406,3 +406,38 @@ def test_full_size_sweep_matches(ref):
     else:
         assert np.abs(rp - op).max() < 1e-12
         assert np.abs(rc - oc).max() < 5e-8
+
+
+def test_gpu_adapter_of_the_checker_on_a_stand_in(frames):
+    """The GPU suite's adapter (ref_check.GpuImpl) driven by a stand-in with capi's call shapes and
+    dtypes built on the oracle: keeps the adapter's plumbing tested where there is no GPU."""
+    from ref_check import GpuImpl, check_against_reference
+
+    class FakeMap:
+        def __init__(self, ctx, voxel, cap, hint):
+            self.m = O.Map(voxel, cap)
+            self.m.set_update_params(remove_enabled=False)
+
+        def insert(self, p, c, T):
+            self.m.update(p, c, T, initialize=True)
+
+        def export(self):
+            k, n, mean, cov = self.m.export()
+            return k, n.astype(np.uint32), mean, cov
+
+        def query(self, xyz):
+            k, hit, n, mean, cov = self.m.query(xyz)
+            return k, hit, n.astype(np.uint32), mean, cov
+
+    class FakeCtx:
+        def preprocess(self, xyz, t, T_il, states, voxel):
+            return O.preprocess(xyz, t, T_il, states, voxel)
+
+        def align(self, m, p, c, guess):
+            return m.m.align(p, c, guess)
+
+    class FakeCapi:
+        Map = FakeMap
+
+    check_against_reference(R.Ref("seq"), GpuImpl(FakeCapi, FakeCtx()), frames, sweep_and_states(7, 2),
+                            cov_tol=1e-6, pose_tol=1e-5)
