@@ -441,3 +441,50 @@ def test_gpu_adapter_of_the_checker_on_a_stand_in(frames):
 
     check_against_reference(R.Ref("seq"), GpuImpl(FakeCapi, FakeCtx()), frames, sweep_and_states(7, 2),
                             cov_tol=1e-6, pose_tol=1e-5)
+
+
+def test_default_configs_equal_the_references_yaml():
+    """config/hilti_config.yaml, read where it lies: the drop-in's defaults (host Config via
+    eskf_odom_default_config), the oracle's and the shim wrapper's are the reference's."""
+    import os
+    import yaml
+    path = os.path.join(R.REFERENCE_ROOT, "config", "hilti_config.yaml")
+    if not os.path.exists(path):
+        pytest.skip("/root/reference is not present on this box")
+    y = yaml.safe_load(open(path))
+    imu = y["sensors"]["imu"]["intrinsics"]["parameters"]
+    lid = y["sensors"]["lidar"]["extrinsics"]
+    lm, reg = y["local_map"], y["registration"]
+    want = {
+        "imu_update_rate": y["sensors"]["imu"]["update_rate"], "bias_a": imu["bias_a"], "bias_g": imu["bias_g"],
+        "gravity": imu["gravity"], "accel_noise_density": imu["accel_noise_density"],
+        "accel_zero_g_offset": imu["accel_zero_g_offset"], "gyro_noise_density": imu["gyro_noise_density"],
+        "gyro_zero_rate_offset": imu["gyro_zero_rate_offset"],
+        "translation_noise": y["kalman_filter"]["update"]["translation_noise"],
+        "rotation_noise": y["kalman_filter"]["update"]["rotation_noise"],
+        "lidar_quaternion_xyzw": lid["quaternion"], "lidar_translation": lid["translation"],
+        "map_voxel_size": lm["voxel_size"], "max_points_per_voxel": lm["max_num_points_per_voxel"],
+        "update_translation_sq_threshold": lm["update"]["translation_sq_threshold"],
+        "update_cosine_threshold": lm["update"]["cosine_threshold"],
+        "remove_enabled": int(lm["remove_distant_points"]["enabled"]),
+        "remove_distance_threshold": lm["remove_distant_points"]["distance_threshold"],
+        "remove_period": lm["remove_distant_points"]["removing_period"],
+        "preprocess_voxel_size": y["cloud_preprocessor"]["voxel_size"], "max_iteration": reg["max_iteration"],
+        "icp_translation_sq_threshold": reg["translation_sq_threshold"], "icp_cosine_threshold": reg["cosine_threshold"],
+    }
+
+    def same(cfg, names):
+        for k, v in want.items():
+            got = getattr(cfg, names.get(k, k))
+            got = list(got) if hasattr(got, "__len__") else got
+            assert got == (list(map(float, v)) if isinstance(v, list) else v), k
+
+    from eskf_lio_b200 import odometry
+    same(odometry.default_config(), {})                                   # the product's host classes
+    same(O.odom_default_config(), {})                                     # the oracle
+    same(R.default_config(), {                                            # the wrapper over the reference's classes
+        "imu_update_rate": "imu_rate", "lidar_quaternion_xyzw": "lidar_quat_xyzw", "lidar_translation": "lidar_trans",
+        "map_voxel_size": "voxel_map", "update_translation_sq_threshold": "update_tsq",
+        "update_cosine_threshold": "update_cos", "remove_distance_threshold": "remove_distance",
+        "preprocess_voxel_size": "voxel_pre", "icp_translation_sq_threshold": "icp_tsq",
+        "icp_cosine_threshold": "icp_cos"})
