@@ -412,8 +412,8 @@ long long ref_odom_run(
   const auto t0 = std::chrono::steady_clock::now();
   bool timed_out = false;
   for (;;) {
-    const volatile size_t * done = nullptr;
-    (void)done;
+    // (a racy read of a vector's size from the polling thread: benign here — it only decides when
+    //  to raise the exit flag; everything read after join() is synchronised by it)
     if (odom.localMap_->trajectory_.parameters_.size() >= n_scans) {break;}
     if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(600)) {timed_out = true; break;}
     std::this_thread::sleep_for(std::chrono::milliseconds(2));
