@@ -244,8 +244,11 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
   }
   if (const char* e = getenv("ESKF_ALIGN_DEPTH")) {
     const int v = atoi(e);
-    if (v == 0 || v == 3 || v == 4) ctx->opt_align_depth = v;
+    if (v == 0 || v == 3 || v == 4 || v == 5) ctx->opt_align_depth = v;
   }
+  if (const char* e = getenv("ESKF_ALIGN_RESIDENT")) ctx->opt_align_resident = atoi(e);
+  if (const char* e = getenv("ESKF_ALIGN_FAT_POINTS")) ctx->opt_align_fat_points = atoll(e);
+  if (const char* e = getenv("ESKF_ALIGN_LL")) ctx->opt_align_ll = atoi(e) != 0;
   if (const char* e = getenv("ESKF_ALIGN_CHUNK")) {
     const int v = atoi(e);
     if (v == 1 || v == 2 || v == 4) ctx->opt_align_chunk = v;
@@ -350,8 +353,16 @@ int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
                  "align_block must be 0 (by cloud size), 256, 384, 512, 640 or 768");
     ctx->opt_align_block = static_cast<int>(value);
   } else if (n == "align_depth") {
-    ESKF_REQUIRE(value == 0 || value == 3 || value == 4, "align_depth must be 0 (default), 3 or 4");
+    ESKF_REQUIRE(value == 0 || value == 3 || value == 4 || value == 5, "align_depth must be 0 (default), 3, 4 or 5");
     ctx->opt_align_depth = static_cast<int>(value);
+  } else if (n == "align_resident") {
+    ESKF_REQUIRE(value >= -1 && value <= 1024, "align_resident must be -1 (auto) or a tile count");
+    ctx->opt_align_resident = static_cast<int>(value);
+  } else if (n == "align_fat_points") {
+    ESKF_REQUIRE(value >= 0, "align_fat_points must be non-negative");
+    ctx->opt_align_fat_points = value;
+  } else if (n == "align_ll") {
+    ctx->opt_align_ll = value != 0;
   } else if (n == "align_ticket_chunk") {
     ESKF_REQUIRE(value == 1 || value == 2 || value == 4, "align_ticket_chunk must be 1, 2 or 4");
     ctx->opt_align_chunk = static_cast<int>(value);

@@ -163,7 +163,10 @@ struct eskf_ctx {
   int opt_insert_sorted = 0;    // 1: always take the radix-sort insert path
   int opt_align_block = 0;      // CTA size of the 1-neighbour fp32 align kernel: 0 = by cloud size, 256 | 384 | 512 | 640 | 768
   int opt_align_chunk = 2;      // tiles taken per ticket in the dynamic tail of an align pass (1 | 2 | 4)
-  int opt_align_depth = 0;      // load rotation of the 768-thread align kernel: 0 = build default, 3 | 4
+  int opt_align_depth = 0;      // large-cloud align kernel: 0 = default (5), 3 | 4 = round-1 register pipelines, 5 = SM-resident positions + probe filter + bulk-copy ring
+  int opt_align_resident = -1;  // depth 5: resident warp tiles per warp (-1 = as many as shared memory holds)
+  int64_t opt_align_fat_points = 1 << 17;  // clouds with at least this many points take the large-cloud kernel
+  int opt_align_ll = 1;         // depth 5: flagged-word (LL) pose broadcast instead of epoch word + second round trip
   size_t l2_persist_bytes = 0;  // persisting-L2 carve-out (0 = unavailable)
   size_t l2_window_max = 0;     // max access-policy window
   const void* l2_win_ptr = nullptr;  // window currently set on the stream
@@ -203,6 +206,12 @@ struct eskf_map {
   eskf::VoxelSlot* spare_slots = nullptr;
   double* spare_master = nullptr;
   uint64_t spare_n = 0;
+  // 8-bit probe filter of the table (local_map.cu, map_probe_filter): derived from `tags` on demand
+  // by the dense registration, valid while filt_version == version
+  uint64_t version = 1;                // bumped by every call that changes the table
+  mutable uint8_t* filt = nullptr;     // [filt_slots + kFilterPad]
+  mutable uint64_t filt_slots = 0;
+  mutable uint64_t filt_version = 0;
 };
 
 #define ESKF_MAX_WORLD 16
@@ -270,6 +279,17 @@ SortView sort_view(eskf_ctx* ctx, unsigned n);
 
 // local_map.cu ------------------------------------------------------------
 int map_reserve(eskf_map* m, uint64_t incoming_points);
+// The 8-bit probe filter of the map's table: filt[i] = 0 for an empty slot, else filter_tag(tags[i])
+// in 1..255; the first kFilterPad entries are repeated after the end so that a 16-entry window never
+// wraps.  1 B/slot: the filter of the 36 M-slot dense map is 36 MB and stays L2-resident next to the
+// position / covariance streams, where the 72 MB tag array did not (78 % of the tag probes went to HBM,
+// profiles/r1_prof_align_ncu.md).  (Re)built only when the table changed since the last build.
+constexpr uint32_t kFilterPad = 16;
+__host__ __device__ __forceinline__ uint32_t filter_tag(uint32_t tag16) {
+  const uint32_t t = tag16 >> 8;
+  return t != 0u ? t : 1u;
+}
+int map_probe_filter(const eskf_map* m, const uint8_t** filt);
 
 // preprocess.cu -----------------------------------------------------------
 // spin on a host-mapped sequence word; ESKF_OK when it reached `seq`, 1 when the stream went idle

@@ -94,6 +94,32 @@ __global__ void clear_slots_kernel(VoxelSlot* slots, tag_t* tags, uint64_t n) {
   p[3] = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// 16 slots per thread: 32 B of tags in, 16 B of filter out (+ the wrap-around pad)
+__global__ void __launch_bounds__(256) build_filter_kernel(const tag_t* __restrict__ tags, uint64_t n_slots,
+                                                           uint8_t* __restrict__ filt) {
+  const uint64_t groups = n_slots / 16;  // n_slots is a multiple of 64
+  for (uint64_t g = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; g < groups;
+       g += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint4 a = __ldcs(reinterpret_cast<const uint4*>(tags) + 2 * g);
+    const uint4 b = __ldcs(reinterpret_cast<const uint4*>(tags) + 2 * g + 1);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const uint32_t t = (w[2 * k + (h >> 1)] >> (16 * (h & 1))) & 0xffffu;
+        v |= (t != 0u ? filter_tag(t) : 0u) << (8 * h);
+      }
+      o[k] = v;
+    }
+    const uint4 out = make_uint4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<uint4*>(filt)[g] = out;
+    if (g == 0) reinterpret_cast<uint4*>(filt + n_slots)[0] = out;  // kFilterPad = 16 entries
+  }
+}
+
 // K5: one thread per key run.  The points of a run are folded in input-index
 // order with the exact expression of Voxel::addPoint (LocalMap.hpp:79-87):
 //   mean = (n * mean + p) / (n + 1) ; cov likewise ; hard cap on n.
@@ -554,6 +580,7 @@ int rebuild(eskf_map* m, uint64_t new_slots, int evict, const double* pos, doubl
   m->slots = ns;
   m->master = nm;
   m->n_slots = new_slots;
+  ++m->version;
   m->count_upper = h[0];
   if (removed) *removed = h[2];
   if (h[1] != 0) {
@@ -564,6 +591,32 @@ int rebuild(eskf_map* m, uint64_t new_slots, int evict, const double* pos, doubl
 }
 
 }  // namespace
+
+int map_probe_filter(const eskf_map* m, const uint8_t** filt) {
+  eskf_ctx* ctx = m->ctx;
+  static_assert(kFilterPad == 16, "build_filter_kernel writes one 16-entry pad group");
+  if (m->filt_slots != m->n_slots) {
+    if (m->filt) {
+      ESKF_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaFree(m->filt);
+    }
+    m->filt = nullptr;
+    m->filt_slots = 0;
+    m->filt_version = 0;
+    ESKF_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->filt), m->n_slots + kFilterPad));
+    m->filt_slots = m->n_slots;
+  }
+  if (m->filt_version != m->version) {
+    const uint64_t groups = m->n_slots / 16;
+    const unsigned blocks = static_cast<unsigned>(std::min<uint64_t>((groups + 255) / 256, 148ull * 8));
+    build_filter_kernel<<<blocks, 256, 0, ctx->stream>>>(m->tags, m->n_slots, m->filt);
+    ESKF_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    m->filt_version = m->version;
+  }
+  *filt = m->filt;
+  return ESKF_OK;
+}
 
 // make room for up to `incoming` new voxels at load factor <= 1/2
 int map_reserve(eskf_map* m, uint64_t incoming) {
@@ -631,6 +684,7 @@ int eskf_map_destroy(eskf_map* m) {
   }
   cudaFree(m->d_count);
   if (m->head) cudaFree(m->head);
+  if (m->filt) cudaFree(m->filt);
   delete m;
   return ESKF_OK;
 }
@@ -644,6 +698,7 @@ int eskf_map_insert_cloud(eskf_map* m, eskf_cloud* cloud, const double T[16]) {
   if (cloud->n == 0) return ESKF_OK;
   ESKF_REQUIRE(cloud->n < (1ull << 31), "cloud too large");
   ESKF_TRY(map_reserve(m, cloud->n));
+  ++m->version;  // (the probe filter of the dense registration is stale from here on)
   if (!ctx->opt_insert_sorted && cloud->n <= kListInsertMax) {
     // sort-free path: link every point to its voxel's pending list, fold the lists
     if (m->head_n != m->n_slots) {

@@ -113,6 +113,11 @@ struct AlignParams {
   double* peers[kMaxWorld]; // mailbox base of every rank (peers[rank] = the local one)
   HostMail* mail;           // nullable: host-mapped result words (internal.h)
   unsigned mail_seq;
+  // depth-5 kernel (accumulate_points_resident)
+  const uint8_t* filt;      // 8-bit probe filter of the table (internal.h, map_probe_filter)
+  int k_res;                // warp tiles per warp whose working positions live in shared memory
+  int ll;                   // 1: the next pose reaches the CTAs as flagged words (LL), no epoch round trip
+  unsigned long long* llbox;  // [2][kLLWords] flagged words
 };
 
 // final pose + bookkeeping straight into host-mapped memory (the host polls align_seq)
@@ -852,6 +857,386 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
   return acc;
 }
 
+
+// ------------------------------------------------------------------------
+// Large clouds (depth 5): SM-resident working positions + 8-bit probe filter
+// + a bulk-copy ring.
+//
+// The reference transforms its working copy of the cloud in place, once per
+// Gauss-Newton iteration (Registration.cpp:13,27): 24 B read + 24 B written per
+// point and iteration, the largest stream of the round-1 kernel.  Here the
+// kernel is persistent over the whole loop, so a warp keeps the transformed
+// positions of its first k_res (statically dealt) tiles in its own slice of
+// shared memory from one iteration to the next — lane l only ever touches
+// entry l of a tile, so no synchronisation at all — and only the tiles beyond
+// that (and every tile of the first iteration, which reads the caller's cloud)
+// stream through HBM.  Those arrive through a per-warp ring of kRing tiles
+// filled by cp.async.bulk (3 x 256 B per tile, completion on an mbarrier,
+// L2 evict-first), requested kRing trips before they are consumed and without
+// occupying a register; their transformed positions go back with plain
+// stores.  With 20 warps x (11 resident + 3 ring) tiles x 768 B = 210 KB of
+// shared memory a 2 M-point cloud keeps 52 % of its positions on the SMs.
+//
+// Lookups probe the map's 8-bit FILTER (1 B per slot, L2-resident) instead
+// of the 16-bit tag array: one 16-entry window = two 8 B loads from the same
+// or adjacent sectors, scanned with byte-parallel arithmetic.
+constexpr int kRing = 3;
+constexpr unsigned kTileBytes = 3u * 32u * sizeof(double);  // x[32] y[32] z[32]
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0u;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// global -> shared bulk copy (async proxy; SASS: UBLKCP), completion counted on `bar`
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, unsigned bytes, uint64_t* bar,
+                                          uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+// generic-proxy writes (other SMs' position stores of the previous iteration, acquired through the
+// iteration hand-off) -> this thread's async-proxy reads
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// scan the 16 filter bytes of a window from position k0 (< 8) on: position of the first byte equal to
+// t8, kNoCand when an empty slot (0) comes first, kMore when the window is exhausted.  Byte-parallel:
+// (v - 0x01..) & ~v & 0x80.. flags the zero bytes of v, exactly so at the lowest flagged position.
+__device__ __forceinline__ uint32_t scan_filter_window(uint4 w, uint32_t k0, uint32_t t8) {
+  const uint64_t ones = 0x0101010101010101ull, highs = 0x8080808080808080ull;
+  const uint64_t pat = ones * t8;
+  const uint64_t lo = (static_cast<uint64_t>(w.y) << 32) | w.x;
+  const uint64_t hi = (static_cast<uint64_t>(w.w) << 32) | w.z;
+  const uint64_t skip = (1ull << (8u * k0)) - 1ull;  // bytes before k0 never terminate the scan
+  {
+    const uint64_t e = lo | skip, m = (lo ^ pat) | skip;
+    const uint64_t ze = (e - ones) & ~e & highs, zm = (m - ones) & ~m & highs;
+    const uint64_t any = ze | zm;
+    if (any != 0ull) {
+      const int bit = __ffsll(static_cast<long long>(any)) - 1;
+      return ((zm >> bit) & 1ull) ? static_cast<uint32_t>(bit >> 3) : kNoCand;
+    }
+  }
+  {
+    const uint64_t e = hi, m = hi ^ pat;
+    const uint64_t ze = (e - ones) & ~e & highs, zm = (m - ones) & ~m & highs;
+    const uint64_t any = ze | zm;
+    if (any != 0ull) {
+      const int bit = __ffsll(static_cast<long long>(any)) - 1;
+      return ((zm >> bit) & 1ull) ? 8u + static_cast<uint32_t>(bit >> 3) : kNoCand;
+    }
+  }
+  return kMore;
+}
+
+// slow path after a filter match whose record holds another key (1/255 per occupied probe)
+__device__ __noinline__ const VoxelSlot* resolve_probe_filter(const uint8_t* filt, const VoxelSlot* slots,
+                                                              uint32_t n_slots, uint64_t key, uint32_t h,
+                                                              uint32_t t8) {
+  for (uint32_t probe = 0; probe < n_slots; ++probe) {
+    const uint32_t t = __ldg(filt + h);
+    if (t == 0u) return nullptr;
+    if (t == t8 && load_key(slots + h) == key) return slots + h;
+    h = next_slot(h, n_slots);
+  }
+  return nullptr;
+}
+
+struct RingState {   // per warp, lives across the passes of one launch
+  unsigned issued;   // bulk loads issued so far   (slot = n % kRing, parity = (n / kRing) & 1)
+  unsigned consumed;
+};
+
+template <typename F, int NW>
+__device__ __forceinline__ double accumulate_points_resident(const AlignParams& P, const double* sT,
+                                                             const F* sR, bool first, bool write_hit,
+                                                             double* wsm, uint64_t* wbar, RingState& ring) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned wglobal = blockIdx.x * NW + (threadIdx.x >> 5);
+  const unsigned wstride = gridDim.x * NW;
+  const double* sx = first ? P.x0 : P.wx;
+  const double* sy = first ? P.y0 : P.wy;
+  const double* sz = first ? P.z0 : P.wz;
+  const unsigned n_tiles = (P.n + 31u) / 32u;
+  const double inv_voxel = 1.0 / P.voxel;
+  const unsigned K = static_cast<unsigned>(P.k_res);
+  double* const ring_sm = wsm + static_cast<size_t>(K) * 96u;  // after the resident tiles
+  const uint64_t policy = l2_policy_evict_first();
+
+  // tiles: a fixed stride per warp for the first 13/16 of every pass (at least the resident ones),
+  // the rest pulled from a global counter (see accumulate_points_pipelined)
+  const bool dynamic = P.dynamic_tiles != 0 && n_tiles >= 8u * wstride;
+  unsigned k_static = 0xffffffffu;
+  if (dynamic) {
+    k_static = (n_tiles - n_tiles * 3u / 16u) / wstride;
+    if (k_static < K) k_static = K;
+  }
+  const unsigned dyn_base = dynamic ? k_static * wstride : 0u;
+  const unsigned chunk = static_cast<unsigned>(P.ticket_chunk);
+  unsigned k_next = first ? 0u : K;  // the generator only deals the tiles that come through the ring
+  unsigned tk_cur = 0, tk_next = 0;
+  if (dynamic && k_next == k_static && lane == 0) tk_next = atomicAdd(&P.st->tile_counter, chunk);
+  auto gen = [&]() -> unsigned {
+    unsigned t;
+    if (k_next < k_static) {
+      t = k_next < 0x7fffffffu / wstride ? wglobal + k_next * wstride : n_tiles;
+    } else {
+      const unsigned sub = (k_next - k_static) & (chunk - 1u);
+      if (sub == 0u) {
+        tk_cur = tk_next;  // (waits for the atomic issued >= one call ago)
+        if (lane == 0) tk_next = atomicAdd(&P.st->tile_counter, chunk);
+      }
+      t = dyn_base + __shfl_sync(0xffffffffu, tk_cur, 0) + sub;
+    }
+    if (t > n_tiles) t = n_tiles;
+    ++k_next;
+    if (k_next == k_static && lane == 0) tk_next = atomicAdd(&P.st->tile_counter, chunk);  // first chunk
+    return t;
+  };
+  // ring: request the positions of tile `t` (no-op past the end)
+  auto issue = [&](unsigned t) {
+    if (t >= n_tiles) return;
+    if (lane == 0) {
+      const unsigned slot = ring.issued % kRing;
+      double* dst = ring_sm + slot * 96u;
+      uint64_t* bar = wbar + slot;
+      mbar_arrive_expect_tx(bar, kTileBytes);
+      bulk_load(dst, sx + static_cast<size_t>(t) * 32u, 256u, bar, policy);
+      bulk_load(dst + 32, sy + static_cast<size_t>(t) * 32u, 256u, bar, policy);
+      bulk_load(dst + 64, sz + static_cast<size_t>(t) * 32u, 256u, bar, policy);
+    }
+    ++ring.issued;
+  };
+  // ring: wait for the oldest outstanding tile and read this lane's point
+  auto consume = [&](double& x, double& y, double& z) {
+    const unsigned slot = ring.consumed % kRing;
+    const unsigned parity = (ring.consumed / kRing) & 1u;
+    uint64_t* bar = wbar + slot;
+    if (!mbar_try_wait(bar, parity)) {
+      unsigned spins = 0;
+      while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(20);
+        if (++spins > kSpinLimit) {
+          atomicExch(&P.st->error, 3u);
+          break;
+        }
+      }
+    }
+    const double* src = ring_sm + slot * 96u;
+    x = src[lane];
+    y = src[32 + lane];
+    z = src[64 + lane];
+    ++ring.consumed;
+  };
+
+  struct Slim {
+    F px, py, pz;       // transformed position
+    F dx, dy, dz;       // position - voxel centre (formed in fp64)
+    uint32_t klo, khi;  // packed voxel key
+    uint32_t home;
+    uint32_t tag;       // 8-bit filter tag; 0 = no lookup (invalid lane / out of key range)
+    uint32_t cand;      // candidate slot after the filter scan, kNoCand if none
+  };
+  struct RecRegs {
+    uint2 key;
+    float4 pa, pc;
+    float2 pd;
+    float4 s4;
+    float2 s2;
+  };
+  // fp64 transform, write-back (shared memory for a resident tile, HBM otherwise), key, table address
+  auto xform = [&](unsigned tile, unsigned j, double x, double y, double z, Slim& q) {
+    const unsigned i = tile * 32u + lane;
+    q.px = q.py = q.pz = q.dx = q.dy = q.dz = F(0);
+    q.klo = q.khi = 0u;
+    q.home = 0u;
+    q.tag = 0u;
+    q.cand = kNoCand;
+    if (tile >= n_tiles || i >= P.n) return;
+    transform_point_rn(sT, x, y, z);
+    if (j < K) {
+      double* dst = wsm + j * 96u;
+      dst[lane] = x;
+      dst[32 + lane] = y;
+      dst[64 + lane] = z;
+    } else {
+      P.wx[i] = x;
+      P.wy[i] = y;
+      P.wz[i] = z;
+    }
+    const int kx = voxel_coord(x, P.voxel, inv_voxel);
+    const int ky = voxel_coord(y, P.voxel, inv_voxel);
+    const int kz = voxel_coord(z, P.voxel, inv_voxel);
+    if (coord_in_range(kx) && coord_in_range(ky) && coord_in_range(kz)) {
+      const uint64_t key = pack_key(kx, ky, kz);
+      const SlotAddr ad = slot_addr(key, P.n_slots);
+      q.klo = static_cast<uint32_t>(key);
+      q.khi = static_cast<uint32_t>(key >> 32);
+      q.home = ad.home;
+      q.tag = filter_tag(ad.tag);
+      // residual against the voxel mean is formed relative to the voxel centre
+      q.px = F(x); q.py = F(y); q.pz = F(z);
+      q.dx = F(x - __dmul_rn(static_cast<double>(kx) + 0.5, P.voxel));
+      q.dy = F(y - __dmul_rn(static_cast<double>(ky) + 0.5, P.voxel));
+      q.dz = F(z - __dmul_rn(static_cast<double>(kz) + 0.5, P.voxel));
+    }
+  };
+  auto window = [&](const Slim& q) -> uint4 {
+    if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
+    const uint8_t* b = P.filt + (q.home & ~7u);
+    const uint2 lo = __ldg(reinterpret_cast<const uint2*>(b));
+    const uint2 hi = __ldg(reinterpret_cast<const uint2*>(b + 8));  // (the filter is padded: no wrap)
+    return make_uint4(lo.x, lo.y, hi.x, hi.y);
+  };
+  auto scan = [&](Slim& q, uint4 w) {
+    if (q.tag == 0u) return;
+    uint32_t b0 = q.home & ~7u;
+    uint32_t r = scan_filter_window(w, q.home & 7u, q.tag);
+    uint32_t scanned = 16u - (q.home & 7u);
+    while (r == kMore && scanned < P.n_slots) {  // (about 1e-6 of the lookups at load factor 1/4)
+      b0 += 16u;
+      if (b0 >= P.n_slots) b0 -= P.n_slots;
+      const uint2 lo = __ldg(reinterpret_cast<const uint2*>(P.filt + b0));
+      const uint2 hi = __ldg(reinterpret_cast<const uint2*>(P.filt + b0 + 8));
+      r = scan_filter_window(make_uint4(lo.x, lo.y, hi.x, hi.y), 0u, q.tag);
+      scanned += 16u;
+    }
+    if (r < 16u) {
+      uint32_t c = b0 + r;
+      if (c >= P.n_slots) c -= P.n_slots;
+      q.cand = c;
+    }
+  };
+  auto issue_record = [&](const Slim& q, unsigned tile_of_q, RecRegs& r) {
+    r.key = make_uint2(0u, 0u);
+    if (q.cand != kNoCand) {
+      const float4* rec = reinterpret_cast<const float4*>(P.slots + q.cand);
+      const unsigned i = tile_of_q * 32u + lane;
+      prefetch_record(rec);  // (evict_last: the voxels a registration keeps touching stay in L2)
+      r.key = __ldg(reinterpret_cast<const uint2*>(rec));     // key
+      r.pa = __ldg(rec + 1);                                   // mx my mz -
+      r.pc = __ldg(rec + 2);                                   // c00 c01 c02 c11
+      r.pd = __ldg(reinterpret_cast<const float2*>(rec + 3));  // c12 c22
+      r.s4 = __ldcs(P.c4 + i);
+      r.s2 = __ldcs(P.c2 + i);
+    }
+  };
+  // raw positions of the j-th tile of this warp's pass: the resident copy, or the head of the ring
+  // (whose slot is then refilled with the tile kRing places further on)
+  unsigned q0, q1, q2;  // tiles in the ring, oldest first
+  static_assert(kRing == 3, "the ring's tile queue is three registers");
+  auto stage_in = [&](unsigned j, unsigned& tile, Slim& q) {
+    double x = 0.0, y = 0.0, z = 0.0;
+    const bool resident = !first && j < K;
+    if (resident) {
+      tile = j < 0x7fffffffu / wstride ? wglobal + j * wstride : n_tiles;
+      if (tile < n_tiles) {
+        const double* src = wsm + j * 96u;
+        x = src[lane];
+        y = src[32 + lane];
+        z = src[64 + lane];
+      }
+    } else {
+      tile = q0;
+      if (tile < n_tiles) consume(x, y, z);
+    }
+    xform(tile, j, x, y, z, q);
+    if (!resident) {
+      q0 = q1;
+      q1 = q2;
+      q2 = gen();
+      __syncwarp();  // every lane has read (and used) its entry of the slot that is refilled now
+      issue(q2);
+    }
+  };
+
+  double acc = 0.0;
+  F v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = F(0);
+  // cross-proxy: the positions this pass bulk-loads were stored through the generic proxy
+  // (by any SM) before the hand-off this thread has just acquired
+  if (!first && lane == 0) fence_proxy_async();
+  q0 = gen(); issue(q0);
+  q1 = gen(); issue(q1);
+  q2 = gen(); issue(q2);
+  Slim cur, nxt;
+  RecRegs rec;
+  uint4 tagw;
+  unsigned tile = 0, tile_n = 0, j = 0;
+  stage_in(j++, tile, cur);
+  scan(cur, window(cur));
+  issue_record(cur, tile, rec);
+  stage_in(j++, tile_n, nxt);
+  tagw = window(nxt);
+  while (tile < n_tiles) {
+    const unsigned i = tile * 32u + lane;
+    // ---- 1. the record + covariance of the current tile
+    float4 pa = rec.pa, pc = rec.pc;
+    float2 pd = rec.pd;
+    bool hit = false;
+    if (cur.cand != kNoCand) {
+      hit = rec.key.x == cur.klo && rec.key.y == cur.khi;
+      if (!hit) {
+        const uint64_t key = (static_cast<uint64_t>(cur.khi) << 32) | cur.klo;
+        const VoxelSlot* far = resolve_probe_filter(P.filt, P.slots, P.n_slots, key,
+                                                    next_slot(cur.cand, P.n_slots), cur.tag);
+        if (far != nullptr) {
+          hit = true;
+          pa = __ldg(reinterpret_cast<const float4*>(far) + 1);
+          pc = __ldg(reinterpret_cast<const float4*>(far) + 2);
+          pd = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float4*>(far) + 3));
+        }
+      }
+    }
+    if (write_hit && i < P.n) P.hit[i] = hit ? 1 : 0;
+    if (hit) {
+      F cr[6];
+      rotate_sym<F>(sR, F(rec.s4.x), F(rec.s4.y), F(rec.s4.z), F(rec.s4.w), F(rec.s2.x), F(rec.s2.y), cr);
+      point_terms<F, true>(cur.px, cur.py, cur.pz, cur.dx - F(pa.x), cur.dy - F(pa.y), cur.dz - F(pa.z),
+                           cr[0] + F(pc.x), cr[1] + F(pc.y), cr[2] + F(pc.z), cr[3] + F(pc.w),
+                           cr[4] + F(pd.x), cr[5] + F(pd.y), v);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 28; ++k) v[k] = F(0);
+    }
+    acc += static_cast<double>(warp_reduce_scatter32<F>(v, lane));
+    // ---- 2. the filter window of the next tile; its record + covariance loads go out
+    scan(nxt, tagw);
+    issue_record(nxt, tile_n, rec);
+    cur = nxt;
+    tile = tile_n;
+    // ---- 3. the tile after that: positions (shared memory), transform, key; its window load goes out
+    stage_in(j++, tile_n, nxt);
+    tagw = window(nxt);
+  }
+  return acc;
+}
+
 // deterministic CTA reduction: lane l of every warp holds term l
 template <int NW>
 __device__ __forceinline__ void block_reduce_store(double acc, double (*s_part)[32], double* out) {
@@ -1134,7 +1519,14 @@ __device__ __noinline__ void solve_and_update_warp(const AlignParams& P, const d
   }
   ok = __all_sync(0xffffffffu, ok);
   if (!ok) {  // singular / indefinite system: the Eigen-style pivoted path decides
-    if (lane == 0) solve_and_update(P, S, it);
+    if (lane == 0) {
+      solve_and_update(P, S, it);
+      for (int i = 0; i < 12; ++i) {  // (what the flagged-word broadcast reads)
+        stp[i] = st->T_step[i];
+        tot[i] = st->T_total[i];
+      }
+      sm[84] = static_cast<double>(st->done);
+    }
     __syncwarp();
     return;
   }
@@ -1191,9 +1583,72 @@ __device__ __noinline__ void solve_and_update_warp(const AlignParams& P, const d
     const int done = P.fixed_iterations > 0 ? (it + 1 >= P.fixed_iterations)
                                             : (conv || it + 1 >= P.max_iteration);
     st->done = done;
+    sm[84] = static_cast<double>(done);
     if (done && P.mail != nullptr) publish_result(P, tot, it + 1, conv, static_cast<unsigned long long>(S[27]));
   }
   __syncwarp();
+}
+
+// ---- flagged-word ("LL") broadcast of the next pose ------------------------
+// The solver warp publishes T_step (12 fp64 = 24 words), the fp32 rotation of
+// T_total (9 words) and the done flag as 34 eight-byte words {payload, it + 1};
+// a 64-bit store is single-copy atomic, so a poller that sees the flag has the
+// payload: one L2 round trip per CTA instead of "poll the epoch word, then
+// fetch the pose".  The box is zeroed with the rest of the state before every
+// launch; the solver of iteration it + 1 cannot run before every CTA has read
+// iteration it's words (it needs their tickets), so one buffer suffices.
+constexpr int kLLWords = 34;
+__device__ __forceinline__ void ll_publish(const AlignParams& P, const double* sm, int it) {
+  const unsigned lane = threadIdx.x & 31;
+  const double* stp = sm + 36;
+  const double* tot = sm + 60;
+  __threadfence();  // this warp's state stores (tile counter reset ...) and, cumulatively, every
+                    // CTA's position stores acquired with the tickets, before the words below
+  volatile unsigned long long* box = P.llbox;
+  const unsigned long long flag = static_cast<unsigned long long>(it + 1) << 32;
+  for (int w = lane; w < kLLWords; w += 32) {
+    unsigned payload;
+    if (w < 24) {
+      const double d = stp[w >> 1];
+      payload = (w & 1) ? static_cast<unsigned>(__double2hiint(d)) : static_cast<unsigned>(__double2loint(d));
+    } else if (w < 33) {
+      payload = __float_as_uint(static_cast<float>(tot[w - 24]));
+    } else {
+      payload = static_cast<unsigned>(sm[84] != 0.0);
+    }
+    box[w] = flag | payload;
+  }
+}
+
+// warp 0 of every CTA: wait for iteration `it`'s words, rebuild the pose in shared memory
+template <typename F>
+__device__ __forceinline__ int ll_receive(const AlignParams& P, int it, double* s_T, F* s_R, int* s_done) {
+  const unsigned lane = threadIdx.x & 31;
+  const volatile unsigned long long* box = P.llbox;
+  const unsigned want = static_cast<unsigned>(it + 1);
+  unsigned long long a = box[lane], b = lane < kLLWords - 32 ? box[32 + lane] : (static_cast<unsigned long long>(want) << 32);
+  unsigned spins = 0;
+  int ok = 1;
+  while (static_cast<unsigned>(a >> 32) != want || static_cast<unsigned>(b >> 32) != want) {
+    __nanosleep(20);
+    if (static_cast<unsigned>(a >> 32) != want) a = box[lane];
+    if (static_cast<unsigned>(b >> 32) != want) b = box[32 + lane];
+    if (++spins > kSpinLimit || ((spins & 63u) == 0u && ld_acquire_u32(&P.st->error) != 0)) {
+      atomicCAS(&P.st->error, 0u, 1u);
+      ok = 0;
+      break;
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  __threadfence();  // acquire side: the other CTAs' position stores before this CTA's next pass
+  const unsigned pa = static_cast<unsigned>(a);
+  const unsigned src = (2u * lane) & 31u;
+  const unsigned lo = __shfl_sync(0xffffffffu, pa, src), hi = __shfl_sync(0xffffffffu, pa, src + 1u);
+  if (lane < 12) s_T[lane] = __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
+  if (lane >= 24) s_R[lane - 24] = F(__uint_as_float(pa));
+  if (lane == 0) s_R[8] = F(__uint_as_float(static_cast<unsigned>(b)));
+  if (lane == 1) *s_done = (ok && static_cast<unsigned>(b) == 0u) ? 0 : 1;
+  return ok;
 }
 
 // ---- fused H/b exchange over NVLink / NVSwitch peer memory ---------------
@@ -1266,19 +1721,37 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
   __shared__ double s_sum[kAcc];
   __shared__ double s_solve[96];
   __shared__ int s_last, s_done, s_xchg;
+  extern __shared__ __align__(128) unsigned char s_dyn[];  // depth 5: [NW][k_res + kRing] tiles, then the ring's mbarriers
   const unsigned G = gridDim.x, t = threadIdx.x;
   AlignState* st = P.st;
   const int max_it = P.fixed_iterations > 0 ? P.fixed_iterations : P.max_iteration;
 
+  RingState ring = {0u, 0u};
+  double* wsm = nullptr;
+  uint64_t* wbar = nullptr;
+  if constexpr (DEPTH == 5) {
+    const unsigned per_warp = static_cast<unsigned>(P.k_res + kRing) * 96u;  // doubles
+    double* base = reinterpret_cast<double*>(s_dyn);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + static_cast<size_t>(NW) * per_warp);
+    wsm = base + static_cast<size_t>(t >> 5) * per_warp;
+    wbar = bars + (t >> 5) * kRing;
+    if (t < NW * kRing) mbar_init(bars + t, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
   // pose of the first iteration: the guess (later ones arrive with the hand-off below)
   if (t < 12) s_T[t] = P.guess[t];
   if (t < 9) s_R[t] = F(P.guess[t]);
   __syncthreads();
   for (int it = 0; it < max_it; ++it) {
-
-    const double acc = (NN == 1 && U == 1 && ESKF_PIPELINED)
-                           ? accumulate_points_pipelined<F, NW, DEPTH>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0)
-                           : accumulate_points<F, U, NN, NW>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0);
+    double acc;
+    if constexpr (DEPTH == 5) {
+      acc = accumulate_points_resident<F, NW>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0, wsm, wbar, ring);
+    } else {
+      acc = (NN == 1 && U == 1 && ESKF_PIPELINED)
+                ? accumulate_points_pipelined<F, NW, DEPTH>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0)
+                : accumulate_points<F, U, NN, NW>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0);
+    }
     block_reduce_store<NW>(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
 
     // last CTA to arrive reduces the partials and solves
@@ -1287,6 +1760,7 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
       s_last = (ticket == G * static_cast<unsigned>(it + 1) - 1u) ? 1 : 0;
     }
     __syncthreads();
+    const bool ll = DEPTH == 5 && P.ll != 0;
     if (s_last) {
       final_reduce<NW>(P.partials, G, s_part, s_sum);
       bool ok = true;
@@ -1295,26 +1769,35 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
         if (ok) solve_and_update_warp(P, s_sum, it, s_solve);
         __syncwarp();
         // (on an exchange timeout st->error is set: the waiters below bail out)
-        if (t == 0) st_release_u32(&st->epoch, static_cast<unsigned>(it + 1));
-      }
-    }
-    // everyone waits for the solver (bounded spin): warp 0 polls the epoch word,
-    // then its lanes fetch the next pose and the done flag in ONE round trip
-    if (t < 32) {
-      unsigned spins = 0;
-      int ok = 1;
-      while (ld_acquire_u32(&st->epoch) < static_cast<unsigned>(it + 1)) {
-        __nanosleep(20);
-        if (++spins > kSpinLimit || ld_acquire_u32(&st->error) != 0) {
-          atomicExch(&st->error, 1u);
-          ok = 0;
-          break;
+        if (ll) {
+          if (ok) ll_publish(P, s_solve, it);
+        } else if (t == 0) {
+          st_release_u32(&st->epoch, static_cast<unsigned>(it + 1));
         }
       }
-      ok = __all_sync(0xffffffffu, ok);
-      if (t < 12) s_T[t] = ld_cg(&st->T_step[t]);
-      else if (t < 21) s_R[t - 12] = sizeof(F) == 8 ? F(ld_cg(&st->T_total[t - 12])) : F(ld_cg(&st->Rf[t - 12]));
-      else if (t == 21) s_done = (ok && ld_acquire_u32(&st->error) == 0) ? ld_cg(&st->done) : 1;
+    }
+    // everyone waits for the solver (bounded spin).  LL: the lanes of warp 0 poll the flagged words
+    // that carry the next pose.  Otherwise warp 0 polls the epoch word, then its lanes fetch the next
+    // pose and the done flag in one more round trip.
+    if (t < 32) {
+      if (ll) {
+        ll_receive<F>(P, it, s_T, s_R, &s_done);
+      } else {
+        unsigned spins = 0;
+        int ok = 1;
+        while (ld_acquire_u32(&st->epoch) < static_cast<unsigned>(it + 1)) {
+          __nanosleep(20);
+          if (++spins > kSpinLimit || ld_acquire_u32(&st->error) != 0) {
+            atomicCAS(&st->error, 0u, 1u);
+            ok = 0;
+            break;
+          }
+        }
+        ok = __all_sync(0xffffffffu, ok);
+        if (t < 12) s_T[t] = ld_cg(&st->T_step[t]);
+        else if (t < 21) s_R[t - 12] = sizeof(F) == 8 ? F(ld_cg(&st->T_total[t - 12])) : F(ld_cg(&st->Rf[t - 12]));
+        else if (t == 21) s_done = (ok && ld_acquire_u32(&st->error) == 0) ? ld_cg(&st->done) : 1;
+      }
     }
     __syncthreads();
     if (s_done) return;
@@ -1367,6 +1850,8 @@ struct Variant {
   int threads;  // CTA size
   int pts_per_block;
   int per_sm;  // filled by align_max_blocks()
+  int depth5;  // 1: accumulate_points_resident (dynamic shared memory, probe filter)
+  size_t max_dyn_smem;  // depth 5: opt-in dynamic shared memory available to the kernel (align_max_blocks)
 };
 
 // The 1-neighbour fp32 kernel exists at three CTA shapes with the same 24 warps per SM:
@@ -1377,7 +1862,7 @@ struct Variant {
 // threads it has to live in 80 registers; 640 threads (20 warps) get 96 and 512 (16 warps) 128
 // (ptxas budgets registers for the CTA size rounded up to a multiple of 128 threads).
 enum { V_F32_N1 = 0, V_F32_N7, V_F64_N1, V_F64_N7, V_F32_N1_T384, V_F32_N1_T768, V_F32_N1_T768D4,
-       V_F32_N1_T640D4, V_F32_N1_T512D4, V_COUNT };
+       V_F32_N1_T640D4, V_F32_N1_T512D4, V_F32_N1_T640R, V_F32_N1_T512R, V_COUNT };
 
 // measured on B200, dense config (2M pts, 10 iterations per launch):
 //   U=1/3 CTAs 1.267 ms, U=1/4 CTAs 1.246 ms, U=2/3 CTAs 1.303 ms,
@@ -1417,35 +1902,43 @@ Variant g_variants[V_COUNT] = {
      reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 640, 4>), 640, 640, 1},
     {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 512, 4>),
      reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 512, 4>), 512, 512, 1},
+    // depth 5 (SM-resident positions, probe filter, bulk-copy ring); the one-pass-per-launch kernels
+    // of the NCCL-baseline mode cannot keep shared memory between launches and stay on depth 4
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 640, 5>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 640, 4>), 640, 640, 1, 1},
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 512, 5>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 512, 4>), 512, 512, 1, 1},
 };
 
-// clouds whose 256-thread grid would be capped at 3 CTAs per SM anyway
-constexpr size_t kFatCtaPoints = static_cast<size_t>(1) << 18;
-
+// Large clouds (>= ctx->opt_align_fat_points, default 2^17) take one fat CTA per SM: fewer partial
+// sums, tickets and pollers at the per-iteration hand-off, and with depth 5 the working positions
+// stay in shared memory.  Frames (tens of thousands of points) keep 256-thread CTAs.
 int variant_index(const eskf_ctx* ctx, const AlignArgs& a) {
   const int base = (a.fp64_math ? 2 : 0) + (a.neighbor_mode == 7 ? 1 : 0);
   if (base != V_F32_N1) return base;
   int threads = ctx->opt_align_block;  // 0 = choose by cloud size
-  if (threads == 0) threads = (a.cloud && a.cloud->n >= kFatCtaPoints) ? ESKF_ALIGN_FAT_T : kT;
-  const int depth = ctx->opt_align_depth != 0 ? ctx->opt_align_depth : ESKF_FAT_DEPTH;
+  const bool fat = a.cloud && static_cast<int64_t>(a.cloud->n) >= ctx->opt_align_fat_points;
+  if (threads == 0) threads = fat ? ESKF_ALIGN_FAT_T : kT;
+  const int depth = ctx->opt_align_depth != 0 ? ctx->opt_align_depth : 5;
   switch (threads) {
     case 768: return depth == 4 ? V_F32_N1_T768D4 : V_F32_N1_T768;
-    case 640: return V_F32_N1_T640D4;
-    case 512: return V_F32_N1_T512D4;
+    case 640: return depth == 5 ? V_F32_N1_T640R : V_F32_N1_T640D4;
+    case 512: return depth == 5 ? V_F32_N1_T512R : V_F32_N1_T512D4;
     case 384: return V_F32_N1_T384;
     default: return V_F32_N1;
   }
 }
 
 struct TraceLayout {
-  size_t o_state, o_sums, o_H, o_b, o_nc, o_step, total;
+  size_t o_state, o_sums, o_ll, o_H, o_b, o_nc, o_step, total;
 };
 
 TraceLayout trace_layout(int max_it) {
   TraceLayout L;
   L.o_state = 0;
   L.o_sums = 512;
-  L.o_H = L.o_sums + 32 * 8;
+  L.o_ll = L.o_sums + 32 * 8;  // flagged words of the pose broadcast (zeroed with the state)
+  L.o_H = L.o_ll + 40 * 8;
   L.o_b = L.o_H + static_cast<size_t>(max_it) * 36 * 8;
   L.o_nc = L.o_b + static_cast<size_t>(max_it) * 6 * 8;
   L.o_step = L.o_nc + static_cast<size_t>(max_it) * 8;
@@ -1454,7 +1947,8 @@ TraceLayout trace_layout(int max_it) {
 }
 static_assert(sizeof(AlignState) <= 512, "AlignState grew past its slot");
 
-int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, TraceLayout* L, int* G) {
+int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, TraceLayout* L, int* G,
+                size_t* dyn_smem = nullptr) {
   const eskf_map* m = a.map;
   const eskf_cloud* c = a.cloud;
   ESKF_REQUIRE(m && c, "null map/cloud");
@@ -1512,6 +2006,25 @@ int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, T
   P->world = 1;
   P->rank = 0;
   P->mail = nullptr;
+  P->llbox = reinterpret_cast<unsigned long long*>(base + L->o_ll);
+  P->ll = ctx->opt_align_ll;
+  if (dyn_smem) *dyn_smem = 0;
+  if (var.depth5 && dyn_smem) {
+    // resident tiles per warp: all of a warp's statically dealt tiles if shared memory holds them
+    const unsigned nw = static_cast<unsigned>(var.threads / 32);
+    const unsigned n_tiles = (n + 31u) / 32u;
+    const unsigned warps = static_cast<unsigned>(g) * nw;
+    unsigned per_warp = (n_tiles + warps - 1u) / warps;
+    const size_t fixed = static_cast<size_t>(nw) * kRing * (kTileBytes + sizeof(uint64_t));
+    const size_t room = var.max_dyn_smem > fixed ? var.max_dyn_smem - fixed : 0;
+    const unsigned k_max = static_cast<unsigned>(room / (static_cast<size_t>(nw) * kTileBytes));
+    unsigned k = per_warp < k_max ? per_warp : k_max;
+    if (ctx->opt_align_resident >= 0 && static_cast<unsigned>(ctx->opt_align_resident) < k)
+      k = static_cast<unsigned>(ctx->opt_align_resident);
+    P->k_res = static_cast<int>(k);
+    *dyn_smem = static_cast<size_t>(nw) * (k + kRing) * kTileBytes + static_cast<size_t>(nw) * kRing * sizeof(uint64_t);
+    ESKF_TRY(map_probe_filter(m, &P->filt));
+  }
   return ESKF_OK;
 }
 
@@ -1614,7 +2127,8 @@ int align_begin(eskf_ctx* ctx, const AlignArgs& a, const eskf_align_info* info) 
   AlignParams P;
   TraceLayout L;
   int G = 1;
-  ESKF_TRY(fill_params(ctx, a, max_it, &P, &L, &G));
+  size_t dyn_smem = 0;
+  ESKF_TRY(fill_params(ctx, a, max_it, &P, &L, &G, &dyn_smem));
   pd->L = L;
   if (p2p) {
     eskf_comm* c = a.comm;
@@ -1639,24 +2153,26 @@ int align_begin(eskf_ctx* ctx, const AlignArgs& a, const eskf_align_info* info) 
   if (ctx->opt_l2_persist && ctx->l2_persist_bytes > 0) {
     cudaStreamAttrValue attr;
     std::memset(&attr, 0, sizeof attr);
-    size_t bytes = static_cast<size_t>(a.map->n_slots) * sizeof(tag_t);
+    // (depth 5 probes the 1 B/slot filter instead of the tags)
+    const void* probed = P.filt ? static_cast<const void*>(P.filt) : static_cast<const void*>(a.map->tags);
+    size_t bytes = static_cast<size_t>(a.map->n_slots) * (P.filt ? 1 : sizeof(tag_t));
     if (bytes > ctx->l2_window_max) bytes = ctx->l2_window_max;
-    attr.accessPolicyWindow.base_ptr = a.map->tags;
+    attr.accessPolicyWindow.base_ptr = const_cast<void*>(probed);
     attr.accessPolicyWindow.num_bytes = bytes;
     const double ratio = static_cast<double>(ctx->l2_persist_bytes) / static_cast<double>(bytes);
     attr.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : static_cast<float>(ratio);
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    if (ctx->l2_win_ptr != a.map->tags || ctx->l2_win_bytes != bytes) {  // the attribute sticks to the stream
+    if (ctx->l2_win_ptr != probed || ctx->l2_win_bytes != bytes) {  // the attribute sticks to the stream
       ESKF_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-      ctx->l2_win_ptr = a.map->tags;
+      ctx->l2_win_ptr = probed;
       ctx->l2_win_bytes = bytes;
     }
   }
   void* args[] = {&P};
   const Variant& var = g_variants[variant_index(ctx, a)];
   trace_mark(ctx, "start");
-  ESKF_CUDA(cudaLaunchCooperativeKernel(var.align, dim3(G), dim3(var.threads), args, 0, ctx->stream));
+  ESKF_CUDA(cudaLaunchCooperativeKernel(var.align, dim3(G), dim3(var.threads), args, dyn_smem, ctx->stream));
   count_launch(ctx);
   trace_mark(ctx, "align");
   pd->active = true;
@@ -1690,8 +2206,21 @@ int align_device(eskf_ctx* ctx, const AlignArgs& a, double T_out[16], eskf_align
 
 int align_max_blocks(int sm_count, int* out) {
   int best = 1;
+  int dev = 0, optin = 0;
+  ESKF_CUDA(cudaGetDevice(&dev));
+  ESKF_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   for (int v = 0; v < V_COUNT; ++v) {
     int per_sm = 0;
+    if (g_variants[v].depth5) {
+      // one CTA per SM with all the opt-in shared memory its static allocations leave
+      cudaFuncAttributes fa;
+      ESKF_CUDA(cudaFuncGetAttributes(&fa, g_variants[v].align));
+      const size_t room = static_cast<size_t>(optin) > fa.sharedSizeBytes + 1024 ? static_cast<size_t>(optin) - fa.sharedSizeBytes - 1024 : 0;
+      ESKF_CUDA(cudaFuncSetAttribute(g_variants[v].align, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(room)));
+      g_variants[v].max_dyn_smem = room;
+      g_variants[v].per_sm = 1;
+      continue;
+    }
     ESKF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, g_variants[v].align,
                                                             g_variants[v].threads, 0));
     if (per_sm < 1) per_sm = 1;

@@ -511,16 +511,26 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
     ro = om.align(p, c, guess)
     cl = capi.Cloud(c2, len(p)).upload(p, c)
     try:
-        for block, depth, chunk, dyn in [(256, 0, 1, 1), (256, 0, 2, 1), (384, 0, 4, 1), (768, 3, 1, 1),
-                                         (768, 3, 2, 1), (768, 3, 4, 1), (0, 0, 2, 1), (768, 3, 2, 0),
-                                         (768, 4, 2, 1), (768, 4, 1, 0), (640, 0, 2, 1), (640, 0, 4, 0),
-                                         (512, 0, 2, 1), (512, 0, 1, 1)]:
+        # (block, depth, chunk, dynamic tiles, resident tiles per warp, flagged-word pose broadcast)
+        for block, depth, chunk, dyn, res, ll in [
+                (256, 3, 1, 1, -1, 1), (256, 3, 2, 1, -1, 1), (384, 3, 4, 1, -1, 1), (768, 3, 1, 1, -1, 1),
+                (768, 3, 2, 1, -1, 1), (768, 3, 4, 1, -1, 1), (768, 3, 2, 0, -1, 1),
+                (768, 4, 2, 1, -1, 1), (768, 4, 1, 0, -1, 1), (640, 4, 2, 1, -1, 1), (640, 4, 4, 0, -1, 1),
+                (512, 4, 2, 1, -1, 1), (512, 4, 1, 1, -1, 1),
+                # depth 5: SM-resident positions + probe filter + bulk-copy ring (the default for a cloud
+                # this size): everything resident, nothing resident (all tiles through the ring, ticketed
+                # tail), a few tiles resident, both CTA shapes, both pose broadcasts
+                (0, 0, 2, 1, -1, 1), (640, 5, 2, 1, -1, 0), (640, 5, 2, 1, 0, 1), (640, 5, 1, 1, 0, 0),
+                (640, 5, 4, 1, 3, 1), (640, 5, 2, 0, 3, 1), (640, 5, 2, 0, 0, 1), (512, 5, 2, 1, -1, 1),
+                (512, 5, 2, 1, 2, 0)]:
             c2.set_option("align_block", block)
             c2.set_option("align_depth", depth)
             c2.set_option("align_ticket_chunk", chunk)
             c2.set_option("align_dynamic_tiles", dyn)
+            c2.set_option("align_resident", res)
+            c2.set_option("align_ll", ll)
             rg = gm.align_cloud(cl, guess, trace=True)
-            tag = (block, depth, chunk, dyn)
+            tag = (block, depth, chunk, dyn, res, ll)
             assert rg["converged"] and rg["iterations"] == ro["iterations"], tag
             np.testing.assert_array_equal(rg["ncorr"], ro["ncorr"], err_msg=str(tag))
             for k in range(ro["iterations"]):
@@ -528,19 +538,43 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
                 assert b_rel(rg["b"][k], ro["b"][k], ro["H"][k]) < H_TOL, (tag, k)
             dt, dr = pose_err(ro["T"], rg["T"])
             assert dt < POSE_T_TOL and dr < POSE_R_TOL, (tag, dt, dr)
-        # the per-point correspondence flags of a cloud this size (written by the 4-deep loop)
-        for block in (0, 256):
+            # the result that comes back through the host-mapped words (no trace requested)
+            rq = gm.align_cloud(cl, guess)
+            assert rq["iterations"] == ro["iterations"], tag
+            dt, dr = pose_err(ro["T"], rq["T"])
+            assert dt < POSE_T_TOL and dr < POSE_R_TOL, (tag, dt, dr)
+        # the per-point correspondence flags of a cloud this size (depth 5, the 4-deep loop, 256-thread CTAs)
+        for block, depth, res in ((0, 0, -1), (640, 5, 0), (640, 4, -1), (256, 3, -1)):
             c2.set_option("align_block", block)
-            c2.set_option("align_depth", 0)
+            c2.set_option("align_depth", depth)
+            c2.set_option("align_resident", res)
             Ho, bo, hito, nco = om.linearize(*oracle.transform_cloud(p, c, guess))
             Hg, bg, hitg, ncg = c2.linearize(gm, p, c, T=guess)
             np.testing.assert_array_equal(hitg, hito)
             assert ncg == nco == int(ro["ncorr"][0])
             assert rel_err(Hg, Ho) < H_TOL and b_rel(bg, bo, Ho) < H_TOL
+        # the probe filter follows the table: insert more points, evict, compact -> still the oracle's result
+        c2.set_option("align_block", 0)
+        c2.set_option("align_depth", 0)
+        c2.set_option("align_resident", -1)
+        mp2, mc2 = S.dense_cloud(scene, 300_000, rng)
+        gm.insert(mp2, mc2, np.eye(4))
+        om.update(mp2, mc2, np.eye(4), initialize=True)
+        for step in ("insert", "evict", "compact"):
+            if step == "evict":
+                assert gm.evict(np.zeros(3), 60.0) == om.evict(np.zeros(3), 60.0)
+            if step == "compact":
+                gm.compact()
+            ro2 = om.align(p, c, guess)
+            rg2 = gm.align_cloud(cl, guess, trace=True)
+            assert rg2["iterations"] == ro2["iterations"], step
+            np.testing.assert_array_equal(rg2["ncorr"], ro2["ncorr"], err_msg=step)
+            dt, dr = pose_err(ro2["T"], rg2["T"])
+            assert dt < POSE_T_TOL and dr < POSE_R_TOL, (step, dt, dr)
         with pytest.raises(capi.EskfError):
             c2.set_option("align_block", 500)
         with pytest.raises(capi.EskfError):
-            c2.set_option("align_depth", 5)
+            c2.set_option("align_depth", 6)
         with pytest.raises(capi.EskfError):
             c2.set_option("align_ticket_chunk", 3)
     finally:
@@ -548,6 +582,8 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
         c2.set_option("align_depth", 0)
         c2.set_option("align_ticket_chunk", 2)
         c2.set_option("align_dynamic_tiles", 1)
+        c2.set_option("align_resident", -1)
+        c2.set_option("align_ll", 1)
 
 
 def test_cuda_path_against_the_reference_sources(ctx, oracle, frames):
