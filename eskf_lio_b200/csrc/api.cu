@@ -244,11 +244,15 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
   }
   if (const char* e = getenv("ESKF_ALIGN_DEPTH")) {
     const int v = atoi(e);
-    if (v == 0 || v == 3 || v == 4 || v == 5) ctx->opt_align_depth = v;
+    if (v == 0 || (v >= 3 && v <= 7)) ctx->opt_align_depth = v;
   }
   if (const char* e = getenv("ESKF_ALIGN_RESIDENT")) ctx->opt_align_resident = atoi(e);
   if (const char* e = getenv("ESKF_ALIGN_FAT_POINTS")) ctx->opt_align_fat_points = atoll(e);
   if (const char* e = getenv("ESKF_ALIGN_LL")) ctx->opt_align_ll = atoi(e) != 0;
+  if (const char* e = getenv("ESKF_ALIGN_FLAGS")) ctx->opt_align_flags = atoi(e);
+  if (const char* e = getenv("ESKF_ALIGN_FILTER")) ctx->opt_align_filter = atoi(e) != 0;
+  if (const char* e = getenv("ESKF_ALIGN_STAMPS")) ctx->opt_align_stamps = atoi(e) != 0;
+  if (const char* e = getenv("ESKF_L2_CARVEOUT")) ctx->opt_l2_carveout = atoi(e) != 0;
   if (const char* e = getenv("ESKF_ALIGN_CHUNK")) {
     const int v = atoi(e);
     if (v == 1 || v == 2 || v == 4) ctx->opt_align_chunk = v;
@@ -266,7 +270,9 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
     ctx->own_stream = true;
   }
   // persisting-L2 carve-out for the map's tag array (registration.cu)
-  if (prop.persistingL2CacheMaxSize > 0 &&
+  if (!ctx->opt_l2_carveout) {
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+  } else if (prop.persistingL2CacheMaxSize > 0 &&
       cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, prop.persistingL2CacheMaxSize) == cudaSuccess) {
     ctx->l2_persist_bytes = static_cast<size_t>(prop.persistingL2CacheMaxSize);
     ctx->l2_window_max = static_cast<size_t>(prop.accessPolicyMaxWindowSize);
@@ -307,7 +313,7 @@ int eskf_ctx_destroy(eskf_ctx* ctx) {
     c = nullptr;
   }
   eskf::DevBuf* bufs[] = {&ctx->stage, &ctx->sortbuf, &ctx->hist, &ctx->hdr, &ctx->runs,
-                          &ctx->sorted_xyz, &ctx->segs, &ctx->work, &ctx->partials, &ctx->astate,
+                          &ctx->sorted_xyz, &ctx->segs, &ctx->work, &ctx->spill, &ctx->partials, &ctx->astate,
                           &ctx->misc, &ctx->knn_levels, &ctx->knn_nbr, &ctx->link};
   for (auto* b : bufs) b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -353,7 +359,7 @@ int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
                  "align_block must be 0 (by cloud size), 256, 384, 512, 640 or 768");
     ctx->opt_align_block = static_cast<int>(value);
   } else if (n == "align_depth") {
-    ESKF_REQUIRE(value == 0 || value == 3 || value == 4 || value == 5, "align_depth must be 0 (default), 3, 4 or 5");
+    ESKF_REQUIRE(value == 0 || (value >= 3 && value <= 7), "align_depth must be 0 (default) or 3 .. 7");
     ctx->opt_align_depth = static_cast<int>(value);
   } else if (n == "align_resident") {
     ESKF_REQUIRE(value >= -1 && value <= 1024, "align_resident must be -1 (auto) or a tile count");
@@ -361,6 +367,14 @@ int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
   } else if (n == "align_fat_points") {
     ESKF_REQUIRE(value >= 0, "align_fat_points must be non-negative");
     ctx->opt_align_fat_points = value;
+  } else if (n == "align_filter") {
+    ctx->opt_align_filter = value != 0;
+  } else if (n == "align_cons") {
+    ESKF_REQUIRE(value >= 0 && value <= 20, "align_cons must be 0 (adaptive) or a warp count");
+    ctx->opt_align_cons = static_cast<int>(value);
+  } else if (n == "align_flags") {
+    ESKF_REQUIRE(value >= 0 && value < 256, "align_flags is a bit mask below 256");
+    ctx->opt_align_flags = static_cast<int>(value);
   } else if (n == "align_ll") {
     ctx->opt_align_ll = value != 0;
   } else if (n == "align_ticket_chunk") {
@@ -724,7 +738,7 @@ int eskf_comm_create(eskf_ctx* ctx, int rank, int world, eskf_comm** out) {
   c->ctx = ctx;
   c->rank = rank;
   c->world = world;
-  const size_t bytes = static_cast<size_t>(2) * world * 32 * sizeof(double);
+  const size_t bytes = static_cast<size_t>(4) * world * 32 * sizeof(double);  // [call parity][iteration parity][rank][32]
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->local), bytes);
   if (e == cudaSuccess) e = cudaMemset(c->local, 0, bytes);
   if (e != cudaSuccess) {

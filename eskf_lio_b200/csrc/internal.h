@@ -142,6 +142,7 @@ struct eskf_ctx {
   eskf::DevBuf link;       // next[] / slot_of[] of the sort-free map insert
   eskf::DevBuf segs;       // deskew segments
   eskf::DevBuf work;       // align working positions (SoA)
+  eskf::DevBuf spill;      // align depth 7: hit-list entries beyond shared memory
   eskf::DevBuf partials;   // align per-block partial sums
   eskf::DevBuf astate;     // align state + traces
   eskf::DevBuf misc;       // small outputs (query / export counters)
@@ -163,9 +164,14 @@ struct eskf_ctx {
   int opt_insert_sorted = 0;    // 1: always take the radix-sort insert path
   int opt_align_block = 0;      // CTA size of the 1-neighbour fp32 align kernel: 0 = by cloud size, 256 | 384 | 512 | 640 | 768
   int opt_align_chunk = 2;      // tiles taken per ticket in the dynamic tail of an align pass (1 | 2 | 4)
-  int opt_align_depth = 0;      // large-cloud align kernel: 0 = default (5), 3 | 4 = round-1 register pipelines, 5 = SM-resident positions + probe filter + bulk-copy ring
+  int opt_align_depth = 0;      // large-cloud align kernel: 0 = default (6), 3 | 4 = round-1 register pipelines, 5 = SM-resident positions + probe filter + bulk-copy ring, 6 = producer / consumer warps around a shared-memory hit queue
   int opt_align_resident = -1;  // depth 5: resident warp tiles per warp (-1 = as many as shared memory holds)
   int64_t opt_align_fat_points = 1 << 17;  // clouds with at least this many points take the large-cloud kernel
+  int opt_align_stamps = 0;     // ESKF_ALIGN_STAMPS=1: globaltimer stamps of the iteration hand-off on stderr (traced calls)
+  int opt_align_filter = 1;     // depth 4 (fat CTAs): probe the 8-bit L2-resident filter instead of the 16-bit tags
+  int opt_align_cons = 0;       // depth 6: consumer warps per CTA (0 = follow the hit rate)
+  int opt_align_flags = 0;      // depth 5: L2 policy experiments (registration.cu, kFlag*)
+  int opt_l2_carveout = 1;      // 0: no persisting-L2 set-aside (ESKF_L2_CARVEOUT=0; decided at context creation)
   int opt_align_ll = 1;         // depth 5: flagged-word (LL) pose broadcast instead of epoch word + second round trip
   size_t l2_persist_bytes = 0;  // persisting-L2 carve-out (0 = unavailable)
   size_t l2_window_max = 0;     // max access-policy window
@@ -220,7 +226,7 @@ struct eskf_map {
 struct eskf_comm {
   eskf_ctx* ctx = nullptr;
   int rank = 0, world = 1;
-  double* local = nullptr;                  // [2 parities][world][32] doubles, cudaMalloc'ed
+  double* local = nullptr;                  // [2 call parities][2 iteration parities][world][32] doubles, cudaMalloc'ed
   double* peers[ESKF_MAX_WORLD] = {};       // peers[rank] == local
   bool opened[ESKF_MAX_WORLD] = {};         // mapped with cudaIpcOpenMemHandle
   bool connected = false;

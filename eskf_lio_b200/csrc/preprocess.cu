@@ -815,6 +815,16 @@ int compute_deskew_segments(const double* point_time, size_t n, const eskf_state
   }
   const long after = before + 1 < static_cast<long>(n_states) ? before + 1 : before;
   const HIso end_inv = iso_inv(interpolate(states[before], states[after], end_time));
+  // The reference finds a segment's end with a forward linear scan: the FIRST point at or after
+  // `start` whose stamp is not below the state's (:54-61).  With non-decreasing stamps (the
+  // reference's own precondition, :33) that is a binary search; ring-major or merged sweeps whose
+  // stamps are not sorted take the reference's scan itself, so the segments stay identical.
+  bool sorted = true;
+  for (size_t i = 1; i < n; ++i)
+    if (point_time[i] < point_time[i - 1]) {
+      sorted = false;
+      break;
+    }
   size_t start = 0, end = 0;
   for (long s = 0; s <= after; ++s) {
     start = end;
@@ -823,6 +833,10 @@ int compute_deskew_segments(const double* point_time, size_t n, const eskf_state
     size_t lo = start, hi = n;
     if (start < n && !(point_time[start] < ts)) {
       hi = start;  // common case for old states: nothing to consume
+    } else if (!sorted) {
+      hi = start;
+      while (hi < n && point_time[hi] < ts) ++hi;
+      if (hi >= n) continue;  // ran off the end: `end` is not advanced, the next state rescans (:54-65)
     } else {
       while (lo < hi) {
         const size_t mid = (lo + hi) / 2;
@@ -830,7 +844,7 @@ int compute_deskew_segments(const double* point_time, size_t n, const eskf_state
       }
       hi = lo;
     }
-    if (hi >= n) break;  // ran off the end: `end` never advances again
+    if (hi >= n) continue;  // ran off the end: `end` is not advanced (with time-ordered states no later one finds a point either)
     end = hi;
     if (start == end) continue;
     HIso st;

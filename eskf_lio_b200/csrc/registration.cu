@@ -117,6 +117,11 @@ struct AlignParams {
   const uint8_t* filt;      // 8-bit probe filter of the table (internal.h, map_probe_filter)
   int k_res;                // warp tiles per warp whose working positions live in shared memory
   int ll;                   // 1: the next pose reaches the CTAs as flagged words (LL), no epoch round trip
+  unsigned flags;           // depth 5 cache-policy experiments (eskf_ctx option "align_flags", see kFlag*)
+  int n_cons;               // depth 6: consumer warps per CTA (0 = follow the hit rate)
+  unsigned long long* stamps;  // nullable: [max_it][8] globaltimer stamps of the iteration hand-off (ESKF_ALIGN_STAMPS=1)
+  uint32_t* spill;          // depth 7: [G][10][spill_cap] words, hit-list entries beyond shared memory
+  unsigned spill_cap;
   unsigned long long* llbox;  // [2][kLLWords] flagged words
 };
 
@@ -454,6 +459,134 @@ __device__ __forceinline__ uint4 load_tag_window(const tag_t* tags, uint32_t b, 
   return make_uint4(lo.x, lo.y, hi.x, hi.y);
 }
 
+// ---- async-proxy, cache-policy and probe-filter helpers (used by depths 4 .. 7)
+constexpr int kRing = 3;
+constexpr unsigned kTileBytes = 3u * 32u * sizeof(double);  // x[32] y[32] z[32]
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0u;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// global -> shared bulk copy (async proxy; SASS: UBLKCP), completion counted on `bar`
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, unsigned bytes, uint64_t* bar,
+                                          uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy(unsigned sel) {  // 0 normal, 1 evict_first, 2 evict_last
+  return sel == 1u ? l2_policy_evict_first() : sel == 2u ? l2_policy_evict_last() : l2_policy_evict_normal();
+}
+// read-only loads / stores that carry an L2 eviction policy
+__device__ __forceinline__ uint2 ldg_u2_hint(const void* p, uint64_t pol) {
+  uint2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float2 ldg_f2_hint(const void* p, uint64_t pol) {
+  float2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const void* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_f64_hint(double* p, double v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+// eskf_ctx option "align_flags" (experiments on what the L2 keeps between Gauss-Newton iterations)
+constexpr unsigned kFlagRecPolicyMask = 3u;    // voxel records: 0 evict_normal, 1 evict_first, 2 evict_last
+constexpr unsigned kFlagNoRecPrefetch = 4u;    // no prefetch.global.L2::evict_last of the record
+constexpr unsigned kFlagFiltPolicyShift = 3u;  // bits 3-4: filter windows: 0 evict_normal, 1 evict_first, 2 evict_last
+constexpr unsigned kFlagStoreFirst = 32u;      // position write-back marked evict_first
+constexpr unsigned kFlagCovAllLanes = 64u;     // every lane loads its source covariance (a coalesced stream)
+
+// generic-proxy writes (other SMs' position stores of the previous iteration, acquired through the
+// iteration hand-off) -> this thread's async-proxy reads
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// scan the 16 filter bytes of a window from position k0 (< 8) on: position of the first byte equal to
+// t8, kNoCand when an empty slot (0) comes first, kMore when the window is exhausted.  Byte-parallel:
+// (v - 0x01..) & ~v & 0x80.. flags the zero bytes of v, exactly so at the lowest flagged position.
+__device__ __forceinline__ uint32_t scan_filter_window(uint4 w, uint32_t k0, uint32_t t8) {
+  const uint64_t ones = 0x0101010101010101ull, highs = 0x8080808080808080ull;
+  const uint64_t pat = ones * t8;
+  const uint64_t lo = (static_cast<uint64_t>(w.y) << 32) | w.x;
+  const uint64_t hi = (static_cast<uint64_t>(w.w) << 32) | w.z;
+  const uint64_t skip = (1ull << (8u * k0)) - 1ull;  // bytes before k0 never terminate the scan
+  {
+    const uint64_t e = lo | skip, m = (lo ^ pat) | skip;
+    const uint64_t ze = (e - ones) & ~e & highs, zm = (m - ones) & ~m & highs;
+    const uint64_t any = ze | zm;
+    if (any != 0ull) {
+      const int bit = __ffsll(static_cast<long long>(any)) - 1;
+      return ((zm >> bit) & 1ull) ? static_cast<uint32_t>(bit >> 3) : kNoCand;
+    }
+  }
+  {
+    const uint64_t e = hi, m = hi ^ pat;
+    const uint64_t ze = (e - ones) & ~e & highs, zm = (m - ones) & ~m & highs;
+    const uint64_t any = ze | zm;
+    if (any != 0ull) {
+      const int bit = __ffsll(static_cast<long long>(any)) - 1;
+      return ((zm >> bit) & 1ull) ? 8u + static_cast<uint32_t>(bit >> 3) : kNoCand;
+    }
+  }
+  return kMore;
+}
+
+// slow path after a filter match whose record holds another key (1/255 per occupied probe)
+__device__ __noinline__ const VoxelSlot* resolve_probe_filter(const uint8_t* filt, const VoxelSlot* slots,
+                                                              uint32_t n_slots, uint64_t key, uint32_t h,
+                                                              uint32_t t8) {
+  for (uint32_t probe = 0; probe < n_slots; ++probe) {
+    const uint32_t t = __ldg(filt + h);
+    if (t == 0u) return nullptr;
+    if (t == t8 && load_key(slots + h) == key) return slots + h;
+    h = next_slot(h, n_slots);
+  }
+  return nullptr;
+}
+
 template <typename F, int NW, int DEPTH>
 __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams& P,
                                                               const double* sT, const F* sR,
@@ -629,13 +762,40 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
       q.dz = F(z - __dmul_rn(static_cast<double>(kz) + 0.5, P.voxel));
     }
   };
+  const bool use_filter = P.filt != nullptr;  // (eskf_ctx option align_filter: the 8-bit L2-resident probe filter)
+  const uint64_t pol_filt = l2_policy((P.flags >> kFlagFiltPolicyShift) & 3u);
   auto window4 = [&](const Slim& q) -> uint4 {
     if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
+    if (use_filter) {
+      const uint8_t* w = P.filt + (q.home & ~7u);
+      const uint2 lo = ldg_u2_hint(w, pol_filt);
+      const uint2 hi = ldg_u2_hint(w + 8, pol_filt);  // (the filter is padded: no wrap)
+      return make_uint4(lo.x, lo.y, hi.x, hi.y);
+    }
     const uint32_t b0 = q.home & ~(kTagAlign - 1u);
     return load_tag_window(P.tags, b0, wrap4(b0));
   };
   auto scan4 = [&](Slim& q, uint4 w) {
     if (q.tag == 0u) return;
+    if (use_filter) {
+      uint32_t b0 = q.home & ~7u;
+      uint32_t r = scan_filter_window(w, q.home & 7u, filter_tag(q.tag));
+      uint32_t scanned = 16u - (q.home & 7u);
+      while (r == kMore && scanned < P.n_slots) {
+        b0 += 16u;
+        if (b0 >= P.n_slots) b0 -= P.n_slots;
+        const uint2 lo = __ldg(reinterpret_cast<const uint2*>(P.filt + b0));
+        const uint2 hi = __ldg(reinterpret_cast<const uint2*>(P.filt + b0 + 8));
+        r = scan_filter_window(make_uint4(lo.x, lo.y, hi.x, hi.y), 0u, filter_tag(q.tag));
+        scanned += 16u;
+      }
+      if (r < 16u) {
+        uint32_t c = b0 + r;
+        if (c >= P.n_slots) c -= P.n_slots;
+        q.cand = c;
+      }
+      return;
+    }
     uint32_t b0 = q.home & ~(kTagAlign - 1u), b2 = wrap4(b0);
     uint32_t r = scan_tag_window(w, q.home & (kTagAlign - 1u), q.tag);
     uint32_t scanned = 8u - (q.home & (kTagAlign - 1u));
@@ -880,92 +1040,6 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
 // Lookups probe the map's 8-bit FILTER (1 B per slot, L2-resident) instead
 // of the 16-bit tag array: one 16-entry window = two 8 B loads from the same
 // or adjacent sectors, scanned with byte-parallel arithmetic.
-constexpr int kRing = 3;
-constexpr unsigned kTileBytes = 3u * 32u * sizeof(double);  // x[32] y[32] z[32]
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0u;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-// global -> shared bulk copy (async proxy; SASS: UBLKCP), completion counted on `bar`
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, unsigned bytes, uint64_t* bar,
-                                          uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-      ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
-// generic-proxy writes (other SMs' position stores of the previous iteration, acquired through the
-// iteration hand-off) -> this thread's async-proxy reads
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-// scan the 16 filter bytes of a window from position k0 (< 8) on: position of the first byte equal to
-// t8, kNoCand when an empty slot (0) comes first, kMore when the window is exhausted.  Byte-parallel:
-// (v - 0x01..) & ~v & 0x80.. flags the zero bytes of v, exactly so at the lowest flagged position.
-__device__ __forceinline__ uint32_t scan_filter_window(uint4 w, uint32_t k0, uint32_t t8) {
-  const uint64_t ones = 0x0101010101010101ull, highs = 0x8080808080808080ull;
-  const uint64_t pat = ones * t8;
-  const uint64_t lo = (static_cast<uint64_t>(w.y) << 32) | w.x;
-  const uint64_t hi = (static_cast<uint64_t>(w.w) << 32) | w.z;
-  const uint64_t skip = (1ull << (8u * k0)) - 1ull;  // bytes before k0 never terminate the scan
-  {
-    const uint64_t e = lo | skip, m = (lo ^ pat) | skip;
-    const uint64_t ze = (e - ones) & ~e & highs, zm = (m - ones) & ~m & highs;
-    const uint64_t any = ze | zm;
-    if (any != 0ull) {
-      const int bit = __ffsll(static_cast<long long>(any)) - 1;
-      return ((zm >> bit) & 1ull) ? static_cast<uint32_t>(bit >> 3) : kNoCand;
-    }
-  }
-  {
-    const uint64_t e = hi, m = hi ^ pat;
-    const uint64_t ze = (e - ones) & ~e & highs, zm = (m - ones) & ~m & highs;
-    const uint64_t any = ze | zm;
-    if (any != 0ull) {
-      const int bit = __ffsll(static_cast<long long>(any)) - 1;
-      return ((zm >> bit) & 1ull) ? 8u + static_cast<uint32_t>(bit >> 3) : kNoCand;
-    }
-  }
-  return kMore;
-}
-
-// slow path after a filter match whose record holds another key (1/255 per occupied probe)
-__device__ __noinline__ const VoxelSlot* resolve_probe_filter(const uint8_t* filt, const VoxelSlot* slots,
-                                                              uint32_t n_slots, uint64_t key, uint32_t h,
-                                                              uint32_t t8) {
-  for (uint32_t probe = 0; probe < n_slots; ++probe) {
-    const uint32_t t = __ldg(filt + h);
-    if (t == 0u) return nullptr;
-    if (t == t8 && load_key(slots + h) == key) return slots + h;
-    h = next_slot(h, n_slots);
-  }
-  return nullptr;
-}
-
 struct RingState {   // per warp, lives across the passes of one launch
   unsigned issued;   // bulk loads issued so far   (slot = n % kRing, parity = (n / kRing) & 1)
   unsigned consumed;
@@ -986,6 +1060,11 @@ __device__ __forceinline__ double accumulate_points_resident(const AlignParams& 
   const unsigned K = static_cast<unsigned>(P.k_res);
   double* const ring_sm = wsm + static_cast<size_t>(K) * 96u;  // after the resident tiles
   const uint64_t policy = l2_policy_evict_first();
+  const uint64_t pol_rec = l2_policy(P.flags & kFlagRecPolicyMask);
+  const uint64_t pol_filt = l2_policy((P.flags >> kFlagFiltPolicyShift) & 3u);
+  const uint64_t pol_store = l2_policy((P.flags & kFlagStoreFirst) ? 1u : 0u);
+  const bool rec_prefetch = (P.flags & kFlagNoRecPrefetch) == 0u;
+  const bool cov_all = (P.flags & kFlagCovAllLanes) != 0u;
 
   // tiles: a fixed stride per warp for the first 13/16 of every pass (at least the resident ones),
   // the rest pulled from a global counter (see accumulate_points_pipelined)
@@ -1084,9 +1163,9 @@ __device__ __forceinline__ double accumulate_points_resident(const AlignParams& 
       dst[32 + lane] = y;
       dst[64 + lane] = z;
     } else {
-      P.wx[i] = x;
-      P.wy[i] = y;
-      P.wz[i] = z;
+      st_f64_hint(P.wx + i, x, pol_store);
+      st_f64_hint(P.wy + i, y, pol_store);
+      st_f64_hint(P.wz + i, z, pol_store);
     }
     const int kx = voxel_coord(x, P.voxel, inv_voxel);
     const int ky = voxel_coord(y, P.voxel, inv_voxel);
@@ -1108,8 +1187,8 @@ __device__ __forceinline__ double accumulate_points_resident(const AlignParams& 
   auto window = [&](const Slim& q) -> uint4 {
     if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
     const uint8_t* b = P.filt + (q.home & ~7u);
-    const uint2 lo = __ldg(reinterpret_cast<const uint2*>(b));
-    const uint2 hi = __ldg(reinterpret_cast<const uint2*>(b + 8));  // (the filter is padded: no wrap)
+    const uint2 lo = ldg_u2_hint(b, pol_filt);
+    const uint2 hi = ldg_u2_hint(b + 8, pol_filt);  // (the filter is padded: no wrap)
     return make_uint4(lo.x, lo.y, hi.x, hi.y);
   };
   auto scan = [&](Slim& q, uint4 w) {
@@ -1133,14 +1212,16 @@ __device__ __forceinline__ double accumulate_points_resident(const AlignParams& 
   };
   auto issue_record = [&](const Slim& q, unsigned tile_of_q, RecRegs& r) {
     r.key = make_uint2(0u, 0u);
+    const unsigned i = tile_of_q * 32u + lane;
     if (q.cand != kNoCand) {
       const float4* rec = reinterpret_cast<const float4*>(P.slots + q.cand);
-      const unsigned i = tile_of_q * 32u + lane;
-      prefetch_record(rec);  // (evict_last: the voxels a registration keeps touching stay in L2)
-      r.key = __ldg(reinterpret_cast<const uint2*>(rec));     // key
-      r.pa = __ldg(rec + 1);                                   // mx my mz -
-      r.pc = __ldg(rec + 2);                                   // c00 c01 c02 c11
-      r.pd = __ldg(reinterpret_cast<const float2*>(rec + 3));  // c12 c22
+      if (rec_prefetch) prefetch_record(rec);  // (evict_last: the voxels a registration keeps touching stay in L2)
+      r.key = ldg_u2_hint(rec, pol_rec);      // key
+      r.pa = ldg_f4_hint(rec + 1, pol_rec);   // mx my mz -
+      r.pc = ldg_f4_hint(rec + 2, pol_rec);   // c00 c01 c02 c11
+      r.pd = ldg_f2_hint(rec + 3, pol_rec);   // c12 c22
+    }
+    if (q.cand != kNoCand || (cov_all && tile_of_q < n_tiles && i < P.n)) {
       r.s4 = __ldcs(P.c4 + i);
       r.s2 = __ldcs(P.c2 + i);
     }
@@ -1233,6 +1314,662 @@ __device__ __forceinline__ double accumulate_points_resident(const AlignParams& 
     // ---- 3. the tile after that: positions (shared memory), transform, key; its window load goes out
     stage_in(j++, tile_n, nxt);
     tagw = window(nxt);
+  }
+  return acc;
+}
+
+
+// ------------------------------------------------------------------------
+// Large clouds (depth 6): role-specialised warps around a shared-memory hit
+// queue.
+//
+// With one thread per point and 27 % of the points finding a voxel (the dense
+// 0.1 m config), a warp that does "look up, then linearise" runs the ~450
+// instructions of the per-point algebra + reduce-scatter for 32 lanes of which
+// 9 have a correspondence; profiles/r2_prof_align_d5.md: 820 warp instructions
+// per 32-point tile, issue slots 41 % busy, DRAM 20 % of peak — the kernel is
+// bound by instruction issue and dependent-load latency, not by HBM.
+// Here the warps of a CTA split into
+//   producers  transform a tile (fp64, exact order), form keys, probe the 8-bit
+//              filter, and push every candidate correspondence — position,
+//              offset from the voxel centre, key, slot, point index: 40 B —
+//              into a ring in shared memory (one warp-aggregated reservation);
+//   consumers  pop DENSE batches of 32 candidates, gather the 64 B records and
+//              the source covariances (next batch's loads in flight while the
+//              current one is linearised), verify keys, accumulate J^T W J / J^T W r.
+// The ring is 32 batch slots x 32 entries (SoA, conflict free); a slot carries a
+// `ready` count (entries written) and a generation (times consumed), so
+// producers and consumers only ever spin on shared memory, with CTA-scope
+// fences.  Producers that run out of tiles turn into consumers; the share of
+// consumer warps follows the hit rate the CTA saw in the previous iteration.
+// Working positions of the CTA's first k_res tiles stay in shared memory across
+// iterations (as in depth 5, but owned by the CTA: any producer warp takes the
+// next tile from a shared counter).
+constexpr unsigned kQ = 1024;   // ring entries
+constexpr unsigned kNB = kQ / 32;  // batch slots
+
+struct HitQueue {
+  float px[kQ], py[kQ], pz[kQ], dx[kQ], dy[kQ], dz[kQ];
+  uint32_t klo[kQ], khi[kQ], cand[kQ], idx[kQ];
+  unsigned ready[kNB];  // entries written into the batch that occupies the slot
+  unsigned gen[kNB];    // times the slot has been consumed in this pass
+  unsigned tail;        // entries reserved
+  unsigned head;        // batches claimed
+  unsigned prod_done;   // producer warps that have finished the pass
+  unsigned next_m;      // next of the CTA's tiles to hand out
+  unsigned n_cons;      // consumer warps of the current pass
+  unsigned pad[3];
+};
+static_assert(sizeof(HitQueue) % 16 == 0, "HitQueue is followed by 16 B aligned data");
+
+__device__ __forceinline__ unsigned ld_volatile_shared(const unsigned* p) {
+  return *reinterpret_cast<const volatile unsigned*>(p);
+}
+
+template <typename F, int NW>
+__device__ __forceinline__ double accumulate_points_roles(const AlignParams& P, const double* sT, const F* sR,
+                                                          bool first, bool write_hit, double* res_sm,
+                                                          HitQueue* Q) {
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned G = gridDim.x, b = blockIdx.x;
+  const unsigned n_tiles = (P.n + 31u) / 32u;
+  const unsigned M = b < n_tiles ? (n_tiles - b + G - 1u) / G : 0u;  // this CTA's tiles: b, b + G, ...
+  const unsigned R = static_cast<unsigned>(P.k_res);                 // of which the first R are resident
+  const double inv_voxel = 1.0 / P.voxel;
+  const unsigned n_cons = ld_volatile_shared(&Q->n_cons);
+  const unsigned n_prod = NW - n_cons;
+  const double* sx = first ? P.x0 : P.wx;
+  const double* sy = first ? P.y0 : P.wy;
+  const double* sz = first ? P.z0 : P.wz;
+  const uint64_t pol_rec = l2_policy(P.flags & kFlagRecPolicyMask);
+  const uint64_t pol_filt = l2_policy((P.flags >> kFlagFiltPolicyShift) & 3u);
+  const bool rec_prefetch = (P.flags & kFlagNoRecPrefetch) == 0u;
+  double acc = 0.0;
+
+  if (warp >= n_cons) {
+    // ======================================================== producer
+    struct Slim {
+      F px, py, pz, dx, dy, dz;
+      uint32_t klo, khi, home, tag;
+      unsigned i;  // point index
+    };
+    auto claim = [&]() -> unsigned {  // index m of the next tile of this CTA (>= M: none left)
+      unsigned m = 0;
+      if (lane == 0) m = atomicAdd(&Q->next_m, 1u);
+      return __shfl_sync(0xffffffffu, m, 0);
+    };
+    auto load_pos = [&](unsigned m, double& x, double& y, double& z) {
+      x = y = z = 0.0;
+      if (m >= M) return;
+      const unsigned i = (b + G * m) * 32u + lane;
+      if (!first && m < R) {
+        const double* src = res_sm + static_cast<size_t>(m) * 96u;
+        x = src[lane];
+        y = src[32 + lane];
+        z = src[64 + lane];
+      } else if (i < P.n) {
+        x = first ? __ldcs(sx + i) : __ldcg(sx + i);
+        y = first ? __ldcs(sy + i) : __ldcg(sy + i);
+        z = first ? __ldcs(sz + i) : __ldcg(sz + i);
+      }
+    };
+    auto xform = [&](unsigned m, double x, double y, double z, Slim& q) {
+      q.tag = 0u;
+      q.home = 0u;
+      if (m >= M) return;
+      const unsigned i = (b + G * m) * 32u + lane;
+      q.i = i;
+      if (i >= P.n) return;
+      transform_point_rn(sT, x, y, z);
+      if (m < R) {
+        double* dst = res_sm + static_cast<size_t>(m) * 96u;
+        dst[lane] = x;
+        dst[32 + lane] = y;
+        dst[64 + lane] = z;
+      } else {
+        P.wx[i] = x;
+        P.wy[i] = y;
+        P.wz[i] = z;
+      }
+      const int kx = voxel_coord(x, P.voxel, inv_voxel);
+      const int ky = voxel_coord(y, P.voxel, inv_voxel);
+      const int kz = voxel_coord(z, P.voxel, inv_voxel);
+      if (coord_in_range(kx) && coord_in_range(ky) && coord_in_range(kz)) {
+        const uint64_t key = pack_key(kx, ky, kz);
+        const SlotAddr ad = slot_addr(key, P.n_slots);
+        q.klo = static_cast<uint32_t>(key);
+        q.khi = static_cast<uint32_t>(key >> 32);
+        q.home = ad.home;
+        q.tag = filter_tag(ad.tag);
+        q.px = F(x); q.py = F(y); q.pz = F(z);
+        // the residual against the voxel mean is formed relative to the voxel centre
+        q.dx = F(x - __dmul_rn(static_cast<double>(kx) + 0.5, P.voxel));
+        q.dy = F(y - __dmul_rn(static_cast<double>(ky) + 0.5, P.voxel));
+        q.dz = F(z - __dmul_rn(static_cast<double>(kz) + 0.5, P.voxel));
+      }
+    };
+    auto window = [&](const Slim& q) -> uint4 {
+      if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
+      const uint8_t* w = P.filt + (q.home & ~7u);
+      const uint2 lo = ldg_u2_hint(w, pol_filt);
+      const uint2 hi = ldg_u2_hint(w + 8, pol_filt);  // (the filter is padded: no wrap)
+      return make_uint4(lo.x, lo.y, hi.x, hi.y);
+    };
+    // candidate slot of q given its first window (kNoCand: the voxel is not in the map)
+    auto scan = [&](const Slim& q, uint4 w) -> uint32_t {
+      if (q.tag == 0u) return kNoCand;
+      uint32_t b0 = q.home & ~7u;
+      uint32_t r = scan_filter_window(w, q.home & 7u, q.tag);
+      uint32_t scanned = 16u - (q.home & 7u);
+      while (r == kMore && scanned < P.n_slots) {
+        b0 += 16u;
+        if (b0 >= P.n_slots) b0 -= P.n_slots;
+        const uint2 lo = __ldg(reinterpret_cast<const uint2*>(P.filt + b0));
+        const uint2 hi = __ldg(reinterpret_cast<const uint2*>(P.filt + b0 + 8));
+        r = scan_filter_window(make_uint4(lo.x, lo.y, hi.x, hi.y), 0u, q.tag);
+        scanned += 16u;
+      }
+      if (r >= 16u) return kNoCand;
+      uint32_t c = b0 + r;
+      if (c >= P.n_slots) c -= P.n_slots;
+      return c;
+    };
+    // push the candidates of a tile: one reservation per warp, entries of a batch become visible
+    // to the consumers through the batch slot's `ready` count
+    auto push = [&](const Slim& q, uint32_t cand) {
+      const bool has = cand != kNoCand;
+      const unsigned mask = __ballot_sync(0xffffffffu, has);
+      if (write_hit && !has && q.i < P.n) P.hit[q.i] = 0;
+      if (mask == 0u) return;
+      const unsigned count = __popc(mask);
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(&Q->tail, count);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const unsigned e = base + __popc(mask & ((1u << lane) - 1u));  // this lane's entry
+      const unsigned batch = e >> 5, slot = batch & (kNB - 1u), g = batch / kNB;
+      if (has) {
+        unsigned spins = 0;
+        while (ld_volatile_shared(&Q->gen[slot]) != g) {  // the slot still holds an unconsumed older batch
+          __nanosleep(20);
+          if (++spins > kSpinLimit) {
+            atomicExch(&P.st->error, 4u);
+            break;
+          }
+        }
+        __threadfence_block();
+        const unsigned pos = e & (kQ - 1u);
+        Q->px[pos] = static_cast<float>(q.px);
+        Q->py[pos] = static_cast<float>(q.py);
+        Q->pz[pos] = static_cast<float>(q.pz);
+        Q->dx[pos] = static_cast<float>(q.dx);
+        Q->dy[pos] = static_cast<float>(q.dy);
+        Q->dz[pos] = static_cast<float>(q.dz);
+        Q->klo[pos] = q.klo;
+        Q->khi[pos] = q.khi;
+        Q->cand[pos] = cand;
+        Q->idx[pos] = q.i;
+        __threadfence_block();  // entries before the count below
+      }
+      __syncwarp();
+      // the reservation touches at most two batches
+      const unsigned b_first = base >> 5, b_last = (base + count - 1u) >> 5;
+      if (lane == 0) {
+        const unsigned n_first = b_first == b_last ? count : 32u - (base & 31u);
+        atomicAdd(&Q->ready[b_first & (kNB - 1u)], n_first);
+        if (b_last != b_first) atomicAdd(&Q->ready[b_last & (kNB - 1u)], count - n_first);
+      }
+    };
+
+    // three tiles in flight per warp: positions requested (c), filter window requested (w), scanned now
+    unsigned m_c = claim();
+    double rx, ry, rz;
+    load_pos(m_c, rx, ry, rz);
+    Slim qw;
+    qw.tag = 0u; qw.home = 0u; qw.i = 0xffffffffu;
+    qw.px = qw.py = qw.pz = qw.dx = qw.dy = qw.dz = F(0);
+    qw.klo = qw.khi = 0u;
+    uint4 tagw = make_uint4(0u, 0u, 0u, 0u);
+    bool have_w = false;
+    for (;;) {
+      const unsigned m_x = m_c;  // tile whose positions have arrived
+      double x = rx, y = ry, z = rz;
+      const bool have_x = m_x < M;
+      if (have_x) {
+        m_c = claim();
+        load_pos(m_c, rx, ry, rz);
+      }
+      // finish the tile whose window was requested a trip ago
+      if (have_w) push(qw, scan(qw, tagw));
+      if (!have_x) break;
+      xform(m_x, x, y, z, qw);
+      tagw = window(qw);
+      have_w = true;
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicAdd(&Q->prod_done, 1u);
+  }
+
+  // ========================================================== consumer
+  // (every warp ends up here: the consumer warps from the start, the producers once the CTA's
+  // tiles are handed out)
+  {
+    struct Entry {
+      F px, py, pz, dx, dy, dz;
+      uint32_t klo, khi, cand, idx;
+      bool valid;
+    };
+    struct RecRegs {
+      uint2 key;
+      float4 pa, pc;
+      float2 pd;
+      float4 s4;
+      float2 s2;
+    };
+    auto claim_batch = [&]() -> unsigned {
+      unsigned c = 0;
+      if (lane == 0) c = atomicAdd(&Q->head, 1u);
+      return __shfl_sync(0xffffffffu, c, 0);
+    };
+    // entries of batch c: > 0 when they can be read, 0 when the pass has no such batch, -1 when
+    // not yet (only returned if !block)
+    auto poll = [&](unsigned c, bool block) -> int {
+      const unsigned slot = c & (kNB - 1u), g = c / kNB;
+      unsigned spins = 0;
+      for (;;) {
+        int res = -1;
+        if (lane == 0) {
+          if (ld_volatile_shared(&Q->gen[slot]) == g) {
+            const unsigned r = ld_volatile_shared(&Q->ready[slot]);
+            if (r == 32u) {
+              res = 32;
+            } else if (ld_volatile_shared(&Q->prod_done) == n_prod) {
+              __threadfence_block();
+              const unsigned t = ld_volatile_shared(&Q->tail);
+              if (c * 32u >= t) res = 0;
+              else {
+                const unsigned need = t - c * 32u < 32u ? t - c * 32u : 32u;
+                if (ld_volatile_shared(&Q->ready[slot]) == need) res = static_cast<int>(need);
+              }
+            }
+          } else if (ld_volatile_shared(&Q->prod_done) == n_prod) {
+            __threadfence_block();
+            if (c * 32u >= ld_volatile_shared(&Q->tail)) res = 0;
+          }
+        }
+        res = __shfl_sync(0xffffffffu, res, 0);
+        if (res >= 0 || !block) {
+          if (res > 0) __threadfence_block();
+          return res;
+        }
+        __nanosleep(40);
+        if (++spins > kSpinLimit) {
+          atomicExch(&P.st->error, 5u);
+          return 0;
+        }
+      }
+    };
+    auto read_entries = [&](unsigned c, int need, Entry& e) {
+      const unsigned pos = (c * 32u + lane) & (kQ - 1u);
+      e.valid = static_cast<int>(lane) < need;
+      e.px = F(Q->px[pos]); e.py = F(Q->py[pos]); e.pz = F(Q->pz[pos]);
+      e.dx = F(Q->dx[pos]); e.dy = F(Q->dy[pos]); e.dz = F(Q->dz[pos]);
+      e.klo = Q->klo[pos]; e.khi = Q->khi[pos];
+      e.cand = e.valid ? Q->cand[pos] : kNoCand;
+      e.idx = Q->idx[pos];
+      __syncwarp();
+      if (lane == 0) {  // hand the slot back to the producers
+        const unsigned slot = c & (kNB - 1u);
+        Q->ready[slot] = 0u;
+        __threadfence_block();
+        *reinterpret_cast<volatile unsigned*>(&Q->gen[slot]) = c / kNB + 1u;
+      }
+    };
+    auto issue = [&](const Entry& e, RecRegs& r) {
+      r.key = make_uint2(0u, 0u);
+      if (e.cand != kNoCand) {
+        const float4* rec = reinterpret_cast<const float4*>(P.slots + e.cand);
+        if (rec_prefetch) prefetch_record(rec);
+        r.key = ldg_u2_hint(rec, pol_rec);
+        r.pa = ldg_f4_hint(rec + 1, pol_rec);
+        r.pc = ldg_f4_hint(rec + 2, pol_rec);
+        r.pd = ldg_f2_hint(rec + 3, pol_rec);
+        r.s4 = __ldcs(P.c4 + e.idx);
+        r.s2 = __ldcs(P.c2 + e.idx);
+      }
+    };
+    F v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = F(0);
+    auto compute = [&](const Entry& e, const RecRegs& r) {
+      float4 pa = r.pa, pc = r.pc;
+      float2 pd = r.pd;
+      bool hit = false;
+      if (e.cand != kNoCand) {
+        hit = r.key.x == e.klo && r.key.y == e.khi;
+        if (!hit) {  // 8-bit filter collision: walk on, slowly
+          const uint64_t key = (static_cast<uint64_t>(e.khi) << 32) | e.klo;
+          const SlotAddr ad = slot_addr(key, P.n_slots);
+          const VoxelSlot* far = resolve_probe_filter(P.filt, P.slots, P.n_slots, key,
+                                                      next_slot(e.cand, P.n_slots), filter_tag(ad.tag));
+          if (far != nullptr) {
+            hit = true;
+            pa = __ldg(reinterpret_cast<const float4*>(far) + 1);
+            pc = __ldg(reinterpret_cast<const float4*>(far) + 2);
+            pd = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float4*>(far) + 3));
+          }
+        }
+        if (write_hit) P.hit[e.idx] = hit ? 1 : 0;
+      }
+      if (hit) {
+        F cr[6];
+        rotate_sym<F>(sR, F(r.s4.x), F(r.s4.y), F(r.s4.z), F(r.s4.w), F(r.s2.x), F(r.s2.y), cr);
+        point_terms<F, true>(e.px, e.py, e.pz, e.dx - F(pa.x), e.dy - F(pa.y), e.dz - F(pa.z),
+                             cr[0] + F(pc.x), cr[1] + F(pc.y), cr[2] + F(pc.z), cr[3] + F(pc.w),
+                             cr[4] + F(pd.x), cr[5] + F(pd.y), v);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 28; ++k) v[k] = F(0);
+      }
+      acc += static_cast<double>(warp_reduce_scatter32<F>(v, lane));
+    };
+
+    Entry cur, nxt;
+    RecRegs rec, nrec;
+    bool have_cur = false;
+    unsigned c = claim_batch();
+    for (;;) {
+      const int need = poll(c, !have_cur);
+      if (need > 0) {
+        read_entries(c, need, nxt);
+        issue(nxt, nrec);
+      }
+      if (have_cur) compute(cur, rec);
+      if (need > 0) {
+        cur = nxt;
+        rec = nrec;
+        have_cur = true;
+        c = claim_batch();
+      } else if (need == 0) {
+        break;
+      } else {
+        have_cur = false;
+      }
+    }
+  }
+  return acc;
+}
+
+
+// ------------------------------------------------------------------------
+// Large clouds (depth 7): phase-split passes around a per-CTA hit list.
+//
+// Depth 6 showed that the producer / consumer split is right (dense algebra,
+// landing registers only for points that found a voxel) and that its cost was
+// the synchronisation: shared-memory atomics, fences and polling in every trip.
+// Here a pass has two phases separated by ONE __syncthreads:
+//   produce   every warp walks its share of the CTA's tiles, U tiles per trip
+//             (the loads of a trip are issued one trip ahead: positions, then
+//             filter windows), and appends every candidate correspondence —
+//             40 B — to the CTA's hit list with one shared-memory atomic per trip;
+//   consume   every warp takes dense batches of 32 entries (static deal), the
+//             next batch's record + covariance loads in flight while the current
+//             one is linearised.
+// The list lives in shared memory (5.6 k entries: a hit rate of up to ~40 % of a
+// 2 M-point cloud's 13.5 k points per CTA); what does not fit spills to a
+// CTA-private region of HBM (the all-hit regime), read back through L2.
+struct HitList {  // SoA words: field k of entry e at base[k * pitch + e]; fields: px py pz dx dy dz klo khi cand idx
+  uint32_t* sm;      // shared memory, `cap` entries per field
+  uint32_t* gm;      // the CTA's spill region, `gcap` entries per field
+  unsigned cap, gcap;
+};
+
+template <typename F, int NW, int U>
+__device__ __forceinline__ double accumulate_points_split(const AlignParams& P, const double* sT, const F* sR,
+                                                          bool first, bool write_hit, const HitList& L,
+                                                          unsigned* s_tail) {
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned G = gridDim.x, b = blockIdx.x;
+  const unsigned n_tiles = (P.n + 31u) / 32u;
+  const unsigned M = b < n_tiles ? (n_tiles - b + G - 1u) / G : 0u;  // this CTA's tiles: b, b + G, ...
+  const double inv_voxel = 1.0 / P.voxel;
+  const double* sx = first ? P.x0 : P.wx;
+  const double* sy = first ? P.y0 : P.wy;
+  const double* sz = first ? P.z0 : P.wz;
+  const uint64_t pol_rec = l2_policy(P.flags & kFlagRecPolicyMask);
+  const uint64_t pol_filt = l2_policy((P.flags >> kFlagFiltPolicyShift) & 3u);
+  const bool rec_prefetch = (P.flags & kFlagNoRecPrefetch) == 0u;
+
+  // =========================================================== produce
+  {
+    struct Slim {
+      F px, py, pz, dx, dy, dz;
+      uint32_t klo, khi, home, tag;
+      unsigned i;  // point index (0xffffffff: no such point)
+    };
+    // trip k of this warp covers the CTA's tiles m = (k * NW + warp) * U + u
+    auto tile_of = [&](unsigned k, int u) -> unsigned {
+      const unsigned m = (k * NW + warp) * U + static_cast<unsigned>(u);
+      return m < M ? b + G * m : 0xffffffffu;
+    };
+    auto load_pos = [&](unsigned tile, double& x, double& y, double& z) {
+      x = y = z = 0.0;
+      const unsigned i = tile * 32u + lane;
+      if (tile != 0xffffffffu && i < P.n) {
+        x = first ? __ldcs(sx + i) : __ldcg(sx + i);
+        y = first ? __ldcs(sy + i) : __ldcg(sy + i);
+        z = first ? __ldcs(sz + i) : __ldcg(sz + i);
+      }
+    };
+    auto xform = [&](unsigned tile, double x, double y, double z, Slim& q) {
+      q.tag = 0u;
+      q.home = 0u;
+      q.i = 0xffffffffu;
+      const unsigned i = tile * 32u + lane;
+      if (tile == 0xffffffffu || i >= P.n) return;
+      q.i = i;
+      transform_point_rn(sT, x, y, z);
+      P.wx[i] = x;
+      P.wy[i] = y;
+      P.wz[i] = z;
+      const int kx = voxel_coord(x, P.voxel, inv_voxel);
+      const int ky = voxel_coord(y, P.voxel, inv_voxel);
+      const int kz = voxel_coord(z, P.voxel, inv_voxel);
+      if (coord_in_range(kx) && coord_in_range(ky) && coord_in_range(kz)) {
+        const uint64_t key = pack_key(kx, ky, kz);
+        const SlotAddr ad = slot_addr(key, P.n_slots);
+        q.klo = static_cast<uint32_t>(key);
+        q.khi = static_cast<uint32_t>(key >> 32);
+        q.home = ad.home;
+        q.tag = filter_tag(ad.tag);
+        q.px = F(x); q.py = F(y); q.pz = F(z);
+        // the residual against the voxel mean is formed relative to the voxel centre
+        q.dx = F(x - __dmul_rn(static_cast<double>(kx) + 0.5, P.voxel));
+        q.dy = F(y - __dmul_rn(static_cast<double>(ky) + 0.5, P.voxel));
+        q.dz = F(z - __dmul_rn(static_cast<double>(kz) + 0.5, P.voxel));
+      }
+    };
+    auto window = [&](const Slim& q) -> uint4 {
+      if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
+      const uint8_t* w = P.filt + (q.home & ~7u);
+      const uint2 lo = ldg_u2_hint(w, pol_filt);
+      const uint2 hi = ldg_u2_hint(w + 8, pol_filt);  // (the filter is padded: no wrap)
+      return make_uint4(lo.x, lo.y, hi.x, hi.y);
+    };
+    auto scan = [&](const Slim& q, uint4 w) -> uint32_t {
+      if (q.tag == 0u) return kNoCand;
+      uint32_t b0 = q.home & ~7u;
+      uint32_t r = scan_filter_window(w, q.home & 7u, q.tag);
+      uint32_t scanned = 16u - (q.home & 7u);
+      while (r == kMore && scanned < P.n_slots) {
+        b0 += 16u;
+        if (b0 >= P.n_slots) b0 -= P.n_slots;
+        const uint2 lo = __ldg(reinterpret_cast<const uint2*>(P.filt + b0));
+        const uint2 hi = __ldg(reinterpret_cast<const uint2*>(P.filt + b0 + 8));
+        r = scan_filter_window(make_uint4(lo.x, lo.y, hi.x, hi.y), 0u, q.tag);
+        scanned += 16u;
+      }
+      if (r >= 16u) return kNoCand;
+      uint32_t c = b0 + r;
+      if (c >= P.n_slots) c -= P.n_slots;
+      return c;
+    };
+    auto store_entry = [&](unsigned e, const Slim& q, uint32_t cand) {
+      uint32_t* w = L.sm + e;
+      unsigned pitch = L.cap;
+      if (e >= L.cap) {
+        w = L.gm + (e - L.cap);
+        pitch = L.gcap;
+      }
+      w[0] = __float_as_uint(static_cast<float>(q.px));
+      w[pitch] = __float_as_uint(static_cast<float>(q.py));
+      w[2 * pitch] = __float_as_uint(static_cast<float>(q.pz));
+      w[3 * pitch] = __float_as_uint(static_cast<float>(q.dx));
+      w[4 * pitch] = __float_as_uint(static_cast<float>(q.dy));
+      w[5 * pitch] = __float_as_uint(static_cast<float>(q.dz));
+      w[6 * pitch] = q.klo;
+      w[7 * pitch] = q.khi;
+      w[8 * pitch] = cand;
+      w[9 * pitch] = q.i;
+    };
+
+    const unsigned trips = (M + NW * U - 1u) / (NW * U);
+    double rx[U], ry[U], rz[U];
+    Slim q[U];
+    uint4 tw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      load_pos(tile_of(0, u), rx[u], ry[u], rz[u]);
+      q[u].tag = 0u; q[u].home = 0u; q[u].i = 0xffffffffu;
+      q[u].px = q[u].py = q[u].pz = q[u].dx = q[u].dy = q[u].dz = F(0);
+      q[u].klo = q[u].khi = 0u;
+      tw[u] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // trip k: scan + push the tiles of trip k - 1 (windows requested a trip ago), transform the tiles
+    // of trip k (positions requested a trip ago) and request their windows, request trip k + 1's positions
+    for (unsigned k = 0; k <= trips; ++k) {
+      uint32_t cand[U];
+      unsigned mask[U], count = 0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        cand[u] = scan(q[u], tw[u]);
+        mask[u] = __ballot_sync(0xffffffffu, cand[u] != kNoCand);
+        count += __popc(mask[u]);
+        if (write_hit && cand[u] == kNoCand && q[u].i < P.n) P.hit[q[u].i] = 0;
+      }
+      if (count != 0u) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(s_tail, count);
+        base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (cand[u] != kNoCand) store_entry(base + __popc(mask[u] & ((1u << lane) - 1u)), q[u], cand[u]);
+          base += __popc(mask[u]);
+        }
+      }
+      if (k == trips) break;
+      double x[U], y[U], z[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        x[u] = rx[u]; y[u] = ry[u]; z[u] = rz[u];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) load_pos(k + 1 < trips ? tile_of(k + 1, u) : 0xffffffffu, rx[u], ry[u], rz[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        xform(tile_of(k, u), x[u], y[u], z[u], q[u]);
+        tw[u] = window(q[u]);
+      }
+    }
+  }
+  __syncthreads();
+
+  // =========================================================== consume
+  double acc = 0.0;
+  {
+    struct Entry {
+      F px, py, pz, dx, dy, dz;
+      uint32_t klo, khi, cand, idx;
+    };
+    struct RecRegs {
+      uint2 key;
+      float4 pa, pc;
+      float2 pd;
+      float4 s4;
+      float2 s2;
+    };
+    const unsigned total = *reinterpret_cast<volatile unsigned*>(s_tail);
+    const unsigned n_batches = (total + 31u) / 32u;
+    auto fetch = [&](unsigned j, Entry& e, RecRegs& r) {  // entries of batch j + their record / covariance loads
+      unsigned idx = j * 32u + lane;
+      e.cand = kNoCand;
+      r.key = make_uint2(0u, 0u);
+      if (j >= n_batches || idx >= total) return;
+      const uint32_t* w = L.sm + idx;
+      unsigned pitch = L.cap;
+      if (idx >= L.cap) {
+        w = L.gm + (idx - L.cap);
+        pitch = L.gcap;
+      }
+      e.px = F(__uint_as_float(w[0])); e.py = F(__uint_as_float(w[pitch])); e.pz = F(__uint_as_float(w[2 * pitch]));
+      e.dx = F(__uint_as_float(w[3 * pitch])); e.dy = F(__uint_as_float(w[4 * pitch]));
+      e.dz = F(__uint_as_float(w[5 * pitch]));
+      e.klo = w[6 * pitch]; e.khi = w[7 * pitch]; e.cand = w[8 * pitch]; e.idx = w[9 * pitch];
+      const float4* rec = reinterpret_cast<const float4*>(P.slots + e.cand);
+      if (rec_prefetch) prefetch_record(rec);
+      r.key = ldg_u2_hint(rec, pol_rec);
+      r.pa = ldg_f4_hint(rec + 1, pol_rec);
+      r.pc = ldg_f4_hint(rec + 2, pol_rec);
+      r.pd = ldg_f2_hint(rec + 3, pol_rec);
+      r.s4 = __ldcs(P.c4 + e.idx);
+      r.s2 = __ldcs(P.c2 + e.idx);
+    };
+    F v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = F(0);
+    auto compute = [&](const Entry& e, const RecRegs& r) {
+      float4 pa = r.pa, pc = r.pc;
+      float2 pd = r.pd;
+      bool hit = false;
+      if (e.cand != kNoCand) {
+        hit = r.key.x == e.klo && r.key.y == e.khi;
+        if (!hit) {  // 8-bit filter collision: walk on, slowly
+          const uint64_t key = (static_cast<uint64_t>(e.khi) << 32) | e.klo;
+          const SlotAddr ad = slot_addr(key, P.n_slots);
+          const VoxelSlot* far = resolve_probe_filter(P.filt, P.slots, P.n_slots, key,
+                                                      next_slot(e.cand, P.n_slots), filter_tag(ad.tag));
+          if (far != nullptr) {
+            hit = true;
+            pa = __ldg(reinterpret_cast<const float4*>(far) + 1);
+            pc = __ldg(reinterpret_cast<const float4*>(far) + 2);
+            pd = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float4*>(far) + 3));
+          }
+        }
+        if (write_hit) P.hit[e.idx] = hit ? 1 : 0;
+      }
+      if (hit) {
+        F cr[6];
+        rotate_sym<F>(sR, F(r.s4.x), F(r.s4.y), F(r.s4.z), F(r.s4.w), F(r.s2.x), F(r.s2.y), cr);
+        point_terms<F, true>(e.px, e.py, e.pz, e.dx - F(pa.x), e.dy - F(pa.y), e.dz - F(pa.z),
+                             cr[0] + F(pc.x), cr[1] + F(pc.y), cr[2] + F(pc.z), cr[3] + F(pc.w),
+                             cr[4] + F(pd.x), cr[5] + F(pd.y), v);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 28; ++k) v[k] = F(0);
+      }
+      acc += static_cast<double>(warp_reduce_scatter32<F>(v, lane));
+    };
+    Entry cur, nxt;
+    RecRegs rec, nrec;
+    unsigned j = warp;
+    fetch(j, cur, rec);
+    while (j < n_batches) {
+      fetch(j + NW, nxt, nrec);
+      compute(cur, rec);
+      cur = nxt;
+      rec = nrec;
+      j += NW;
+    }
   }
   return acc;
 }
@@ -1334,7 +2071,7 @@ __device__ __forceinline__ bool ldlt_solve6_nopivot(const double* H, const doubl
 }
 
 // Eigen LDLT<Matrix6d>::solve restated: diagonal pivoting, zero pivots -> 0
-__device__ void ldlt_solve6(const double* Hin, const double* bin, double* x) {
+__device__ __noinline__ void ldlt_solve6(const double* Hin, const double* bin, double* x) {
   double A[6][6], L[6][6], D[6], y[6];
   int perm[6];
   for (int i = 0; i < 6; ++i) {
@@ -1415,177 +2152,85 @@ __device__ void se3_to_SE3(const double* se3, double* T /* R(9) t(3) */) {
   T[0] = cx * ax + c; T[4] = cy * ay + c; T[8] = cz * az + c;
 }
 
-// thread 0 of the solving CTA: H/b -> step -> total, convergence, bookkeeping
-__device__ __noinline__ void solve_and_update(const AlignParams& P, const double* S, int it) {
-  AlignState* st = P.st;
-  double H[36], b[6], nb[6], se3[6], step[12], tot[12], old[12];
-  // unpack: A(6) B(9) D(6)
-  H[0] = S[0]; H[1] = S[1]; H[2] = S[2]; H[7] = S[3]; H[8] = S[4]; H[14] = S[5];
-  H[6] = S[1]; H[12] = S[2]; H[13] = S[4];
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) {
-      H[6 * i + 3 + j] = S[6 + 3 * i + j];
-      H[6 * (3 + j) + i] = S[6 + 3 * i + j];
-    }
-  H[21] = S[15]; H[22] = S[16]; H[23] = S[17]; H[28] = S[18]; H[29] = S[19]; H[35] = S[20];
-  H[27] = S[16]; H[33] = S[17]; H[34] = S[19];
-  for (int i = 0; i < 6; ++i) {
-    b[i] = S[21 + i];
-    nb[i] = -b[i];
-  }
-  // JTJ.ldlt().solve(-JTr), Registration.cpp:78
-  if (!ldlt_solve6_nopivot(H, nb, se3)) ldlt_solve6(H, nb, se3);
-  se3_to_SE3(se3, step);
-  for (int i = 0; i < 12; ++i) old[i] = (it == 0) ? P.guess[i] : st->T_total[i];
-  // totalTransform = transformIter * totalTransform (Registration.cpp:20)
-  for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j)
-      tot[3 * i + j] = step[3 * i] * old[j] + step[3 * i + 1] * old[3 + j] + step[3 * i + 2] * old[6 + j];
-    tot[9 + i] = (step[3 * i] * old[9] + step[3 * i + 1] * old[10] + step[3 * i + 2] * old[11]) + step[9 + i];
-  }
-  // convergenceCheck (Registration.cpp:37-50)
-  const double cosine = 0.5 * (((step[0] + step[4]) + step[8]) - 1.0);
-  const double tsq = step[9] * step[9] + step[10] * step[10] + step[11] * step[11];
-  const int conv = (cosine >= P.cos_thr && tsq <= P.trans_sq_thr) ? 1 : 0;
-  if (P.trace_H)
-    for (int i = 0; i < 36; ++i) P.trace_H[36 * it + i] = H[i];
-  if (P.trace_b)
-    for (int i = 0; i < 6; ++i) P.trace_b[6 * it + i] = b[i];
-  if (P.trace_ncorr) P.trace_ncorr[it] = static_cast<unsigned long long>(S[27]);
-  if (P.trace_step)
-    for (int i = 0; i < 12; ++i) P.trace_step[12 * it + i] = step[i];
-  for (int i = 0; i < 12; ++i) {
-    st->T_total[i] = tot[i];
-    st->T_step[i] = step[i];
-  }
-  for (int i = 0; i < 9; ++i) st->Rf[i] = static_cast<float>(tot[i]);
-  st->n_corr = static_cast<unsigned long long>(S[27]);
-  st->iter = it + 1;
-  st->converged = conv;
-  st->tile_counter = 0u;
-  const int done = P.fixed_iterations > 0 ? (it + 1 >= P.fixed_iterations)
-                                          : (conv || it + 1 >= P.max_iteration);
-  st->done = done;
-  if (done && P.mail != nullptr) publish_result(P, tot, it + 1, conv, static_cast<unsigned long long>(S[27]));
-}
-
-// Warp-cooperative version of the per-iteration solve (called by the 32 lanes
-// of ONE warp; `sm` is >= 96 doubles of shared scratch).  Same mathematics as
-// solve_and_update below; the 6x6 LDL^T runs in shared memory with the rank-1
-// updates spread over lanes, the triangular solves use shuffles.  Falls back
-// to the serial pivoted path (lane 0) when a pivot is not safely positive.
-__device__ __noinline__ void solve_and_update(const AlignParams& P, const double* S, int it);
-
 // H(6x6, row-major) entry -> index of its unique term in the 27 sums
 __constant__ unsigned char c_hmap[36] = {0, 1, 2,  6,  7,  8,  1, 3,  4,  9,  10, 11,
                                          2, 4, 5,  12, 13, 14, 6, 9,  12, 15, 16, 17,
                                          7, 10, 13, 16, 18, 19, 8, 11, 14, 17, 19, 20};
 
-__device__ __noinline__ void solve_and_update_warp(const AlignParams& P, const double* S, int it,
-                                                   double* sm) {
+// element e (0..8 rotation, 9..11 translation) of step * old: explicit round-to-nearest operations, so
+// that the solver and every CTA's local copy of the total pose agree bit for bit
+__device__ __forceinline__ double compose_elem(const double* step, const double* old, int e) {
+  if (e < 9) {
+    const int i = e / 3, j = e % 3;
+    return dot3_rn(step[3 * i], old[j], step[3 * i + 1], old[3 + j], step[3 * i + 2], old[6 + j]);
+  }
+  const int i = e - 9;
+  return __dadd_rn(dot3_rn(step[3 * i], old[9], step[3 * i + 1], old[10], step[3 * i + 2], old[11]), step[9 + i]);
+}
+
+// ---- the per-iteration solve, fast path -----------------------------------
+// Round 1 ran a warp-cooperative LDL^T over shared memory (a __syncwarp and a
+// shared-memory round trip per elimination step, an IEEE division per lane and
+// step): ESKF_ALIGN_STAMPS measured 12-13 us per Gauss-Newton iteration between
+// "sums reduced" and "pose published" — most of the per-iteration hand-off, and
+// more than an 8-way shard of the dense config computes in.  The system is 6x6:
+// one thread factorises it in registers (fully unrolled, one reciprocal per
+// pivot; ~1.5 k dependent-issue cycles), builds the step and the new total pose
+// and leaves them in shared memory; the lanes of its warp then write the state
+// and trace words in parallel.  `Told` is the total pose before this step
+// (every CTA tracks it in shared memory, see align_kernel: no global load).
+// Falls back to the pivoted restatement of Eigen's LDLT when a pivot is not
+// safely positive.
+__device__ __noinline__ void solve_and_update_fast(const AlignParams& P, const double* S, const double* Told,
+                                                   int it, double* sm) {
   const unsigned lane = threadIdx.x & 31;
-  double* A = sm;          // 36: H, overwritten by L (below diagonal)
-  double* stp = sm + 36;   // 12: step
-  double* old = sm + 48;   // 12: previous total
-  double* tot = sm + 60;   // 12: new total
-  double* Dg = sm + 72;    // 6
+  double* stp = sm + 36;  // 12: step
+  double* tot = sm + 60;  // 12: new total
   AlignState* st = P.st;
-  // unpack S -> full symmetric H (lanes cover the 36 entries)
-  for (int e = lane; e < 36; e += 32) {
-    const double v = S[c_hmap[e]];
-    A[e] = v;
-    if (P.trace_H) P.trace_H[36 * it + e] = v;
-  }
-  if (lane < 12) old[lane] = (it == 0) ? P.guess[lane] : st->T_total[lane];
-  if (lane < 6 && P.trace_b) P.trace_b[6 * it + lane] = S[21 + lane];
-  __syncwarp();
-  double maxd = 0.0;
-#pragma unroll
-  for (int i = 0; i < 6; ++i) maxd = fmax(maxd, fabs(A[7 * i]));
-  const double tol = maxd * 1e-12;
-  bool ok = maxd > 0.0;
-  for (int k = 0; k < 6; ++k) {
-    const double d = A[7 * k];
-    ok = ok && (d > tol);
-    const int m = 5 - k;
-    if (static_cast<int>(lane) < m * m) {
-      const int i = k + 1 + static_cast<int>(lane) / m, j = k + 1 + static_cast<int>(lane) % m;
-      A[6 * i + j] -= A[6 * i + k] * A[6 * j + k] / d;
-    }
-    __syncwarp();
-    if (static_cast<int>(lane) > k && lane < 6) A[6 * lane + k] /= d;
-    if (lane == 0) Dg[k] = d;
-    __syncwarp();
-  }
-  ok = __all_sync(0xffffffffu, ok);
-  if (!ok) {  // singular / indefinite system: the Eigen-style pivoted path decides
-    if (lane == 0) {
-      solve_and_update(P, S, it);
-      for (int i = 0; i < 12; ++i) {  // (what the flagged-word broadcast reads)
-        stp[i] = st->T_step[i];
-        tot[i] = st->T_total[i];
-      }
-      sm[84] = static_cast<double>(st->done);
-    }
-    __syncwarp();
-    return;
-  }
-  // L y = -b ; D z = y ; L^T x = z   (lane i < 6 owns component i)
-  double y = lane < 6 ? -S[21 + lane] : 0.0;
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const double yj = __shfl_sync(0xffffffffu, y, j);
-    if (static_cast<int>(lane) > j && lane < 6) y -= A[6 * lane + j] * yj;
-  }
-  if (lane < 6) y /= Dg[lane];
-#pragma unroll
-  for (int j = 5; j >= 0; --j) {
-    const double xj = __shfl_sync(0xffffffffu, y, j);
-    if (static_cast<int>(lane) < j) y -= A[6 * j + lane] * xj;
-  }
-  if (lane < 6) Dg[lane] = y;  // se3
-  __syncwarp();
   if (lane == 0) {
-    double se3[6];
+    double H[36], nb[6], se3[6], step[12];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) se3[i] = Dg[i];
-    double s12[12];
-    se3_to_SE3(se3, s12);
+    for (int e = 0; e < 36; ++e) H[e] = S[c_hmap[e]];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) stp[i] = s12[i];
+    for (int i = 0; i < 6; ++i) nb[i] = -S[21 + i];
+    // JTJ.ldlt().solve(-JTr), Registration.cpp:78
+    if (!ldlt_solve6_nopivot(H, nb, se3)) ldlt_solve6(H, nb, se3);
+    se3_to_SE3(se3, step);
+    // totalTransform = transformIter * totalTransform (Registration.cpp:20)
+#pragma unroll
+    for (int e = 0; e < 12; ++e) tot[e] = compose_elem(step, Told, e);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) stp[i] = step[i];
+    // convergenceCheck (Registration.cpp:37-50)
+    const double cosine = 0.5 * (((step[0] + step[4]) + step[8]) - 1.0);
+    const double tsq = step[9] * step[9] + step[10] * step[10] + step[11] * step[11];
+    const int conv = (cosine >= P.cos_thr && tsq <= P.trans_sq_thr) ? 1 : 0;
+    const int done = P.fixed_iterations > 0 ? (it + 1 >= P.fixed_iterations) : (conv || it + 1 >= P.max_iteration);
+    sm[84] = static_cast<double>(done);
+    sm[85] = static_cast<double>(conv);
   }
   __syncwarp();
-  // totalTransform = transformIter * totalTransform (Registration.cpp:20)
-  if (lane < 9) {
-    const int i = lane / 3, j = lane % 3;
-    tot[lane] = stp[3 * i] * old[j] + stp[3 * i + 1] * old[3 + j] + stp[3 * i + 2] * old[6 + j];
-  } else if (lane < 12) {
-    const int i = lane - 9;
-    tot[lane] = (stp[3 * i] * old[9] + stp[3 * i + 1] * old[10] + stp[3 * i + 2] * old[11]) + stp[9 + i];
-  }
-  __syncwarp();
+  // state + traces, one word per lane
+  for (int e = lane; e < 36; e += 32)
+    if (P.trace_H) P.trace_H[36 * it + e] = S[c_hmap[e]];
+  if (lane < 6 && P.trace_b) P.trace_b[6 * it + lane] = S[21 + lane];
   if (lane < 12) {
     st->T_total[lane] = tot[lane];
     st->T_step[lane] = stp[lane];
     if (P.trace_step) P.trace_step[12 * it + lane] = stp[lane];
   }
   if (lane < 9) st->Rf[lane] = static_cast<float>(tot[lane]);
-  if (lane == 0) {
-    // convergenceCheck (Registration.cpp:37-50)
-    const double cosine = 0.5 * (((stp[0] + stp[4]) + stp[8]) - 1.0);
-    const double tsq = stp[9] * stp[9] + stp[10] * stp[10] + stp[11] * stp[11];
-    const int conv = (cosine >= P.cos_thr && tsq <= P.trans_sq_thr) ? 1 : 0;
-    if (P.trace_ncorr) P.trace_ncorr[it] = static_cast<unsigned long long>(S[27]);
-    st->n_corr = static_cast<unsigned long long>(S[27]);
+  if (lane == 12) {
+    const unsigned long long nc = static_cast<unsigned long long>(S[27]);
+    if (P.trace_ncorr) P.trace_ncorr[it] = nc;
+    st->n_corr = nc;
     st->iter = it + 1;
-    st->converged = conv;
+    st->converged = static_cast<int>(sm[85]);
     st->tile_counter = 0u;
-    const int done = P.fixed_iterations > 0 ? (it + 1 >= P.fixed_iterations)
-                                            : (conv || it + 1 >= P.max_iteration);
-    st->done = done;
-    sm[84] = static_cast<double>(done);
-    if (done && P.mail != nullptr) publish_result(P, tot, it + 1, conv, static_cast<unsigned long long>(S[27]));
+    st->done = static_cast<int>(sm[84]);
   }
+  if (lane == 0 && sm[84] != 0.0 && P.mail != nullptr)
+    publish_result(P, tot, it + 1, static_cast<int>(sm[85]), static_cast<unsigned long long>(S[27]));
   __syncwarp();
 }
 
@@ -1597,42 +2242,38 @@ __device__ __noinline__ void solve_and_update_warp(const AlignParams& P, const d
 // fetch the pose".  The box is zeroed with the rest of the state before every
 // launch; the solver of iteration it + 1 cannot run before every CTA has read
 // iteration it's words (it needs their tickets), so one buffer suffices.
-constexpr int kLLWords = 34;
+constexpr int kLLWords = 25;
 __device__ __forceinline__ void ll_publish(const AlignParams& P, const double* sm, int it) {
   const unsigned lane = threadIdx.x & 31;
   const double* stp = sm + 36;
-  const double* tot = sm + 60;
   __threadfence();  // this warp's state stores (tile counter reset ...) and, cumulatively, every
                     // CTA's position stores acquired with the tickets, before the words below
   volatile unsigned long long* box = P.llbox;
   const unsigned long long flag = static_cast<unsigned long long>(it + 1) << 32;
-  for (int w = lane; w < kLLWords; w += 32) {
+  if (lane < kLLWords) {
     unsigned payload;
-    if (w < 24) {
-      const double d = stp[w >> 1];
-      payload = (w & 1) ? static_cast<unsigned>(__double2hiint(d)) : static_cast<unsigned>(__double2loint(d));
-    } else if (w < 33) {
-      payload = __float_as_uint(static_cast<float>(tot[w - 24]));
+    if (lane < 24) {
+      const double d = stp[lane >> 1];
+      payload = (lane & 1) ? static_cast<unsigned>(__double2hiint(d)) : static_cast<unsigned>(__double2loint(d));
     } else {
       payload = static_cast<unsigned>(sm[84] != 0.0);
     }
-    box[w] = flag | payload;
+    box[lane] = flag | payload;
   }
 }
 
-// warp 0 of every CTA: wait for iteration `it`'s words, rebuild the pose in shared memory
+// warp 0 of every CTA: wait for iteration `it`'s words; the step lands in s_T, the done flag in *s_done
 template <typename F>
-__device__ __forceinline__ int ll_receive(const AlignParams& P, int it, double* s_T, F* s_R, int* s_done) {
+__device__ __forceinline__ int ll_receive(const AlignParams& P, int it, double* s_T, int* s_done) {
   const unsigned lane = threadIdx.x & 31;
   const volatile unsigned long long* box = P.llbox;
   const unsigned want = static_cast<unsigned>(it + 1);
-  unsigned long long a = box[lane], b = lane < kLLWords - 32 ? box[32 + lane] : (static_cast<unsigned long long>(want) << 32);
+  unsigned long long a = lane < kLLWords ? box[lane] : (static_cast<unsigned long long>(want) << 32);
   unsigned spins = 0;
   int ok = 1;
-  while (static_cast<unsigned>(a >> 32) != want || static_cast<unsigned>(b >> 32) != want) {
+  while (static_cast<unsigned>(a >> 32) != want) {
     __nanosleep(20);
-    if (static_cast<unsigned>(a >> 32) != want) a = box[lane];
-    if (static_cast<unsigned>(b >> 32) != want) b = box[32 + lane];
+    a = box[lane];
     if (++spins > kSpinLimit || ((spins & 63u) == 0u && ld_acquire_u32(&P.st->error) != 0)) {
       atomicCAS(&P.st->error, 0u, 1u);
       ok = 0;
@@ -1644,10 +2285,9 @@ __device__ __forceinline__ int ll_receive(const AlignParams& P, int it, double* 
   const unsigned pa = static_cast<unsigned>(a);
   const unsigned src = (2u * lane) & 31u;
   const unsigned lo = __shfl_sync(0xffffffffu, pa, src), hi = __shfl_sync(0xffffffffu, pa, src + 1u);
+  const unsigned dn = __shfl_sync(0xffffffffu, pa, 24);
   if (lane < 12) s_T[lane] = __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
-  if (lane >= 24) s_R[lane - 24] = F(__uint_as_float(pa));
-  if (lane == 0) s_R[8] = F(__uint_as_float(static_cast<unsigned>(b)));
-  if (lane == 1) *s_done = (ok && static_cast<unsigned>(b) == 0u) ? 0 : 1;
+  if (lane == 0) *s_done = (ok && dn == 0u) ? 0 : 1;
   return ok;
 }
 
@@ -1673,7 +2313,11 @@ __device__ __forceinline__ void st_release_sys_f64(double* p, double v) {
 __device__ __forceinline__ bool exchange_sums(const AlignParams& P, int it, double* s_sum, int* s_flag) {
   const unsigned t = threadIdx.x;
   const int W = P.world;
-  const size_t slot = (static_cast<size_t>(it & 1) * W + P.rank) * kMailStride;
+  // 4-slot ring: (call parity, iteration parity).  With the iteration parity alone, a rank that has
+  // started the NEXT call could overwrite slot 0 of a peer that was descheduled between seeing the flags
+  // of this call's last (even) iteration and reading the data words.
+  const size_t ring = ((static_cast<size_t>(P.seq) & 1u) << 1) | static_cast<size_t>(it & 1);
+  const size_t slot = (ring * W + P.rank) * kMailStride;
   const double flag = static_cast<double>(P.seq) * 65536.0 + static_cast<double>(it + 1);
   for (unsigned k = t; k < static_cast<unsigned>(kAcc * W); k += blockDim.x)
     P.peers[k / kAcc][slot + k % kAcc] = s_sum[k % kAcc];
@@ -1684,7 +2328,7 @@ __device__ __forceinline__ bool exchange_sums(const AlignParams& P, int it, doub
   if (t == 0) *s_flag = 1;
   __syncthreads();
   if (t < static_cast<unsigned>(W)) {
-    const double* f = P.peers[P.rank] + (static_cast<size_t>(it & 1) * W + t) * kMailStride + kAcc;
+    const double* f = P.peers[P.rank] + (ring * W + t) * kMailStride + kAcc;
     unsigned spins = 0;
     while (ld_acquire_sys_f64(f) != flag) {
       __nanosleep(20);
@@ -1699,7 +2343,7 @@ __device__ __forceinline__ bool exchange_sums(const AlignParams& P, int it, doub
   if (t < kAcc) {
     // the flags were acquired at system scope above (+ bar.sync): the data can be
     // read with plain L1-bypassing loads, all of them in flight at once
-    const volatile double* box = P.peers[P.rank] + static_cast<size_t>(it & 1) * W * kMailStride + t;
+    const volatile double* box = P.peers[P.rank] + ring * W * kMailStride + t;
     double v[kMaxWorld];
 #pragma unroll
     for (int r = 0; r < kMaxWorld; ++r) v[r] = r < W ? box[static_cast<size_t>(r) * kMailStride] : 0.0;
@@ -1712,10 +2356,19 @@ __device__ __forceinline__ bool exchange_sums(const AlignParams& P, int it, doub
   return *s_flag != 0;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define ESKF_STAMP(cond, slot) \
+  do { if (P.stamps != nullptr && (cond)) P.stamps[8 * it + (slot)] = globaltimer_ns(); } while (0)
+
 template <typename F, int U, int NN, int MINB, int T = kT, int DEPTH = 3>
 __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
   constexpr int NW = T / 32;
   __shared__ double s_T[12];
+  __shared__ double s_Ttot[12];  // the total pose so far (every CTA composes the steps itself)
   __shared__ F s_R[9];
   __shared__ double s_part[NW][32];
   __shared__ double s_sum[kAcc];
@@ -1729,6 +2382,22 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
   RingState ring = {0u, 0u};
   double* wsm = nullptr;
   uint64_t* wbar = nullptr;
+  HitQueue* hq = nullptr;
+  HitList hl;
+  __shared__ unsigned s_tail;
+  if constexpr (DEPTH == 7) {
+    // [10 fields][cap] words of shared memory + the CTA's spill region of P.spill_cap entries per field
+    hl.sm = reinterpret_cast<uint32_t*>(s_dyn);
+    hl.gm = P.spill + static_cast<size_t>(blockIdx.x) * 10u * P.spill_cap;
+    hl.cap = static_cast<unsigned>(P.k_res);
+    hl.gcap = P.spill_cap;
+    if (t == 0) s_tail = 0u;
+  }
+  if constexpr (DEPTH == 6) {
+    wsm = reinterpret_cast<double*>(s_dyn);  // the CTA's resident tiles
+    hq = reinterpret_cast<HitQueue*>(s_dyn + static_cast<size_t>(P.k_res) * kTileBytes);
+    if (t == 0) hq->tail = 0u;
+  }
   if constexpr (DEPTH == 5) {
     const unsigned per_warp = static_cast<unsigned>(P.k_res + kRing) * 96u;  // doubles
     double* base = reinterpret_cast<double*>(s_dyn);
@@ -1740,40 +2409,78 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
     fence_proxy_async();
   }
   // pose of the first iteration: the guess (later ones arrive with the hand-off below)
-  if (t < 12) s_T[t] = P.guess[t];
+  if (t < 12) {
+    s_T[t] = P.guess[t];
+    s_Ttot[t] = P.guess[t];
+  }
   if (t < 9) s_R[t] = F(P.guess[t]);
   __syncthreads();
   for (int it = 0; it < max_it; ++it) {
+    ESKF_STAMP(blockIdx.x == 0 && t == 0, 0);
     double acc;
-    if constexpr (DEPTH == 5) {
+    if constexpr (DEPTH == 7) {
+      acc = accumulate_points_split<F, NW, 2>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0, hl, &s_tail);
+    } else if constexpr (DEPTH == 6) {
+      // pass set-up: empty queue; the share of consumer warps follows the hit rate of the last pass
+      if (t < kNB) {
+        hq->ready[t] = 0u;
+        hq->gen[t] = 0u;
+      }
+      if (t == 0) {
+        const unsigned n_tiles = (P.n + 31u) / 32u;
+        const unsigned M = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + G - 1u) / G : 0u;
+        unsigned nc = static_cast<unsigned>(P.n_cons);
+        if (nc == 0u) {
+          // producer trip ~ 1, consumer batch ~ 1.6 (instruction counts): consumers get h * 1.6 / (1 + h * 1.6)
+          const float h = (it == 0 || M == 0u) ? 0.33f : static_cast<float>(hq->tail) / static_cast<float>(M * 32u);
+          nc = static_cast<unsigned>(static_cast<float>(NW) * (1.6f * h) / (1.0f + 1.6f * h) + 0.5f);
+        }
+        if (nc < 2u) nc = 2u;
+        if (nc > static_cast<unsigned>(NW) - 4u) nc = static_cast<unsigned>(NW) - 4u;
+        hq->n_cons = nc;
+        hq->tail = 0u;
+        hq->head = 0u;
+        hq->prod_done = 0u;
+        hq->next_m = 0u;
+      }
+      __syncthreads();
+      acc = accumulate_points_roles<F, NW>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0, wsm, hq);
+    } else if constexpr (DEPTH == 5) {
       acc = accumulate_points_resident<F, NW>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0, wsm, wbar, ring);
     } else {
       acc = (NN == 1 && U == 1 && ESKF_PIPELINED)
                 ? accumulate_points_pipelined<F, NW, DEPTH>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0)
                 : accumulate_points<F, U, NN, NW>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0);
     }
+    ESKF_STAMP(blockIdx.x == 0 && t == 0, 1);
     block_reduce_store<NW>(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
 
     // last CTA to arrive reduces the partials and solves
     if (t == 0) {
+      if constexpr (DEPTH == 7) s_tail = 0u;  // (every warp has read the pass's entry count before the block reduce)
       const unsigned ticket = atom_add_acq_rel(&st->block_counter, 1u);
       s_last = (ticket == G * static_cast<unsigned>(it + 1) - 1u) ? 1 : 0;
     }
     __syncthreads();
-    const bool ll = DEPTH == 5 && P.ll != 0;
+    const bool ll = DEPTH >= 5 && P.ll != 0;
     if (s_last) {
+      ESKF_STAMP(t == 0, 2);
       final_reduce<NW>(P.partials, G, s_part, s_sum);
+      ESKF_STAMP(t == 0, 3);
       bool ok = true;
       if (P.world > 1) ok = exchange_sums(P, it, s_sum, &s_xchg);
+      ESKF_STAMP(t == 0, 4);
       if (t < 32) {
-        if (ok) solve_and_update_warp(P, s_sum, it, s_solve);
+        if (ok) solve_and_update_fast(P, s_sum, s_Ttot, it, s_solve);
         __syncwarp();
+        ESKF_STAMP(t == 0, 5);
         // (on an exchange timeout st->error is set: the waiters below bail out)
         if (ll) {
           if (ok) ll_publish(P, s_solve, it);
         } else if (t == 0) {
           st_release_u32(&st->epoch, static_cast<unsigned>(it + 1));
         }
+        ESKF_STAMP(t == 0, 6);
       }
     }
     // everyone waits for the solver (bounded spin).  LL: the lanes of warp 0 poll the flagged words
@@ -1781,7 +2488,7 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
     // pose and the done flag in one more round trip.
     if (t < 32) {
       if (ll) {
-        ll_receive<F>(P, it, s_T, s_R, &s_done);
+        ll_receive<F>(P, it, s_T, &s_done);
       } else {
         unsigned spins = 0;
         int ok = 1;
@@ -1795,11 +2502,19 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
         }
         ok = __all_sync(0xffffffffu, ok);
         if (t < 12) s_T[t] = ld_cg(&st->T_step[t]);
-        else if (t < 21) s_R[t - 12] = sizeof(F) == 8 ? F(ld_cg(&st->T_total[t - 12])) : F(ld_cg(&st->Rf[t - 12]));
         else if (t == 21) s_done = (ok && ld_acquire_u32(&st->error) == 0) ? ld_cg(&st->done) : 1;
       }
+      // total pose <- step * total pose (the same expression as the solver's), and its rotation for the
+      // per-point algebra
+      __syncwarp();
+      double nt = 0.0;
+      if (t < 12) nt = compose_elem(s_T, s_Ttot, static_cast<int>(t));
+      __syncwarp();
+      if (t < 12) s_Ttot[t] = nt;
+      if (t < 9) s_R[t] = F(nt);
     }
     __syncthreads();
+    ESKF_STAMP(blockIdx.x == 0 && t == 0, 7);
     if (s_done) return;
   }
 }
@@ -1810,7 +2525,10 @@ __global__ void solve_kernel(AlignParams P, int it) {
   __shared__ double s_in[kAcc];
   if (threadIdx.x < kAcc) s_in[threadIdx.x] = P.sums[threadIdx.x];
   __syncthreads();
-  if (threadIdx.x < 32) solve_and_update_warp(P, s_in, it, s_solve);
+  __shared__ double s_old[12];
+  if (threadIdx.x < 12) s_old[threadIdx.x] = (it == 0) ? P.guess[threadIdx.x] : P.st->T_total[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x < 32) solve_and_update_fast(P, s_in, s_old, it, s_solve);
 }
 
 // sharded mode: ONE linearisation of this rank's point range; the 28 sums go
@@ -1850,7 +2568,7 @@ struct Variant {
   int threads;  // CTA size
   int pts_per_block;
   int per_sm;  // filled by align_max_blocks()
-  int depth5;  // 1: accumulate_points_resident (dynamic shared memory, probe filter)
+  int depth5;  // 1: accumulate_points_resident, 2: accumulate_points_roles (dynamic shared memory, probe filter)
   size_t max_dyn_smem;  // depth 5: opt-in dynamic shared memory available to the kernel (align_max_blocks)
 };
 
@@ -1862,7 +2580,8 @@ struct Variant {
 // threads it has to live in 80 registers; 640 threads (20 warps) get 96 and 512 (16 warps) 128
 // (ptxas budgets registers for the CTA size rounded up to a multiple of 128 threads).
 enum { V_F32_N1 = 0, V_F32_N7, V_F64_N1, V_F64_N7, V_F32_N1_T384, V_F32_N1_T768, V_F32_N1_T768D4,
-       V_F32_N1_T640D4, V_F32_N1_T512D4, V_F32_N1_T640R, V_F32_N1_T512R, V_COUNT };
+       V_F32_N1_T640D4, V_F32_N1_T512D4, V_F32_N1_T640R, V_F32_N1_T512R, V_F32_N1_T640Q, V_F32_N1_T512Q,
+       V_F32_N1_T640S, V_F32_N1_T512S, V_COUNT };
 
 // measured on B200, dense config (2M pts, 10 iterations per launch):
 //   U=1/3 CTAs 1.267 ms, U=1/4 CTAs 1.246 ms, U=2/3 CTAs 1.303 ms,
@@ -1908,6 +2627,16 @@ Variant g_variants[V_COUNT] = {
      reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 640, 4>), 640, 640, 1, 1},
     {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 512, 5>),
      reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 512, 4>), 512, 512, 1, 1},
+    // depth 6 (producer / consumer warps around a shared-memory hit queue)
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 640, 6>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 640, 4>), 640, 640, 1, 2},
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 512, 6>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 512, 4>), 512, 512, 1, 2},
+    // depth 7 (phase-split passes around a per-CTA hit list)
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 640, 7>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 640, 4>), 640, 640, 1, 3},
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 512, 7>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 512, 4>), 512, 512, 1, 3},
 };
 
 // Large clouds (>= ctx->opt_align_fat_points, default 2^17) take one fat CTA per SM: fewer partial
@@ -1919,18 +2648,18 @@ int variant_index(const eskf_ctx* ctx, const AlignArgs& a) {
   int threads = ctx->opt_align_block;  // 0 = choose by cloud size
   const bool fat = a.cloud && static_cast<int64_t>(a.cloud->n) >= ctx->opt_align_fat_points;
   if (threads == 0) threads = fat ? ESKF_ALIGN_FAT_T : kT;
-  const int depth = ctx->opt_align_depth != 0 ? ctx->opt_align_depth : 5;
+  const int depth = ctx->opt_align_depth != 0 ? ctx->opt_align_depth : 4;
   switch (threads) {
     case 768: return depth == 4 ? V_F32_N1_T768D4 : V_F32_N1_T768;
-    case 640: return depth == 5 ? V_F32_N1_T640R : V_F32_N1_T640D4;
-    case 512: return depth == 5 ? V_F32_N1_T512R : V_F32_N1_T512D4;
+    case 640: return depth == 7 ? V_F32_N1_T640S : depth == 6 ? V_F32_N1_T640Q : depth == 5 ? V_F32_N1_T640R : V_F32_N1_T640D4;
+    case 512: return depth == 7 ? V_F32_N1_T512S : depth == 6 ? V_F32_N1_T512Q : depth == 5 ? V_F32_N1_T512R : V_F32_N1_T512D4;
     case 384: return V_F32_N1_T384;
     default: return V_F32_N1;
   }
 }
 
 struct TraceLayout {
-  size_t o_state, o_sums, o_ll, o_H, o_b, o_nc, o_step, total;
+  size_t o_state, o_sums, o_ll, o_H, o_b, o_nc, o_step, o_stamps, total;
 };
 
 TraceLayout trace_layout(int max_it) {
@@ -1942,7 +2671,8 @@ TraceLayout trace_layout(int max_it) {
   L.o_b = L.o_H + static_cast<size_t>(max_it) * 36 * 8;
   L.o_nc = L.o_b + static_cast<size_t>(max_it) * 6 * 8;
   L.o_step = L.o_nc + static_cast<size_t>(max_it) * 8;
-  L.total = L.o_step + static_cast<size_t>(max_it) * 12 * 8;
+  L.o_stamps = L.o_step + static_cast<size_t>(max_it) * 12 * 8;
+  L.total = L.o_stamps + static_cast<size_t>(max_it) * 8 * 8;
   return L;
 }
 static_assert(sizeof(AlignState) <= 512, "AlignState grew past its slot");
@@ -2007,9 +2737,48 @@ int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, T
   P->rank = 0;
   P->mail = nullptr;
   P->llbox = reinterpret_cast<unsigned long long*>(base + L->o_ll);
+  P->stamps = ctx->opt_align_stamps ? reinterpret_cast<unsigned long long*>(base + L->o_stamps) : nullptr;
   P->ll = ctx->opt_align_ll;
+  P->flags = static_cast<unsigned>(ctx->opt_align_flags);
   if (dyn_smem) *dyn_smem = 0;
-  if (var.depth5 && dyn_smem) {
+  P->n_cons = ctx->opt_align_cons;
+  {
+    const int vi = variant_index(ctx, a);
+    if ((vi == V_F32_N1_T768D4 || vi == V_F32_N1_T640D4 || vi == V_F32_N1_T512D4) && ctx->opt_align_filter && dyn_smem)
+      ESKF_TRY(map_probe_filter(m, &P->filt));  // depth 4 on the 8-bit filter
+  }
+  if (var.depth5 == 3 && dyn_smem) {
+    // hit list: as many 40 B entries as shared memory holds (a multiple of 32), the rest of a CTA's
+    // worst case (every point of its tiles finds a voxel) in its spill region
+    const unsigned n_tiles = (n + 31u) / 32u;
+    const unsigned per_cta = (n_tiles + static_cast<unsigned>(g) - 1u) / static_cast<unsigned>(g) * 32u;  // points
+    unsigned cap = static_cast<unsigned>(var.max_dyn_smem / 40u) / 32u * 32u;
+    if (ctx->opt_align_resident >= 0 && static_cast<unsigned>(ctx->opt_align_resident) * 32u < cap)
+      cap = static_cast<unsigned>(ctx->opt_align_resident) * 32u;  // (tests: force the spill path)
+    if (cap > per_cta) cap = per_cta;
+    if (cap < 32u) cap = 32u;
+    const unsigned spill_cap = per_cta > cap ? per_cta - cap : 32u;
+    ESKF_TRY(ctx->spill.ensure(static_cast<size_t>(g) * 10u * spill_cap * sizeof(uint32_t)));
+    P->spill = ctx->spill.as<uint32_t>();
+    P->spill_cap = spill_cap;
+    P->k_res = static_cast<int>(cap);
+    *dyn_smem = static_cast<size_t>(cap) * 40u;
+    ESKF_TRY(map_probe_filter(m, &P->filt));
+  }
+  if (var.depth5 == 2 && dyn_smem) {
+    // resident tiles per CTA: all of the CTA's tiles (b, b + G, ...) if shared memory holds them
+    const unsigned n_tiles = (n + 31u) / 32u;
+    const unsigned per_cta = (n_tiles + static_cast<unsigned>(g) - 1u) / static_cast<unsigned>(g);
+    const size_t room = var.max_dyn_smem > sizeof(HitQueue) ? var.max_dyn_smem - sizeof(HitQueue) : 0;
+    const unsigned k_max = static_cast<unsigned>(room / kTileBytes);
+    unsigned k = per_cta < k_max ? per_cta : k_max;
+    if (ctx->opt_align_resident >= 0 && static_cast<unsigned>(ctx->opt_align_resident) < k)
+      k = static_cast<unsigned>(ctx->opt_align_resident);
+    P->k_res = static_cast<int>(k);
+    *dyn_smem = static_cast<size_t>(k) * kTileBytes + sizeof(HitQueue);
+    ESKF_TRY(map_probe_filter(m, &P->filt));
+  }
+  if (var.depth5 == 1 && dyn_smem) {
     // resident tiles per warp: all of a warp's statically dealt tiles if shared memory holds them
     const unsigned nw = static_cast<unsigned>(var.threads / 32);
     const unsigned n_tiles = (n + 31u) / 32u;
@@ -2057,6 +2826,19 @@ int read_back(eskf_ctx* ctx, const AlignArgs& a, const TraceLayout& L, int max_i
   ESKF_CUDA(cudaMemcpyAsync(h, ctx->astate.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   ESKF_CUDA(cudaStreamSynchronize(ctx->stream));
   const AlignState* st = reinterpret_cast<const AlignState*>(h + L.o_state);
+  if (ctx->opt_align_stamps && want_trace) {
+    // ESKF_ALIGN_STAMPS=1 (debug aid): where an iteration's time goes, in us relative to the start of the pass on
+    // CTA 0: its own pass end | last CTA's arrival | partials reduced | sums exchanged | solved | pose published |
+    // next pose received by CTA 0
+    const unsigned long long* s8 = reinterpret_cast<const unsigned long long*>(h + L.o_stamps);
+    const int nit = st->iter < max_it ? st->iter : max_it;
+    for (int k = 0; k < nit; ++k) {
+      std::fprintf(stderr, "[eskf stamps] it %d:", k);
+      for (int j = 1; j < 8; ++j)
+        std::fprintf(stderr, " %.1f", (static_cast<double>(s8[8 * k + j]) - static_cast<double>(s8[8 * k])) * 1e-3);
+      std::fprintf(stderr, "\n");
+    }
+  }
   if (st->error) {
     set_error(st->error == 2u ? "align kernel: a peer rank's H/b contribution did not arrive (NVLink mailbox timeout)"
                               : "align kernel: iteration hand-off timed out");
@@ -2168,6 +2950,14 @@ int align_begin(eskf_ctx* ctx, const AlignArgs& a, const eskf_align_info* info) 
       ctx->l2_win_ptr = probed;
       ctx->l2_win_bytes = bytes;
     }
+  } else if (ctx->l2_win_ptr != nullptr) {  // the option was switched off: drop the window the stream still carries
+    cudaStreamAttrValue attr;
+    std::memset(&attr, 0, sizeof attr);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    ESKF_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    ctx->l2_win_ptr = nullptr;
+    ctx->l2_win_bytes = 0;
   }
   void* args[] = {&P};
   const Variant& var = g_variants[variant_index(ctx, a)];

@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from eskf_lio_b200 import capi, synth as S  # noqa: E402
 
 DEFAULTS = {"align_block": 0, "align_depth": 0, "align_ticket_chunk": 2, "align_dynamic_tiles": 1,
-            "align_resident": -1, "align_ll": 1, "l2_persist": 1, "align_fat_points": 1 << 17}
+            "align_resident": -1, "align_ll": 1, "align_flags": 0, "align_cons": 0, "align_filter": 1, "l2_persist": 1, "align_fat_points": 1 << 17}
 
 
 def apply(ctx, cell):
@@ -34,8 +34,8 @@ def apply(ctx, cell):
         ctx.set_option(k, int(v))
 
 
-def timed(ctx, gmap, src, guess, iters, reps):
-    for _ in range(2):
+def timed(ctx, gmap, src, guess, iters, reps, warm=2):
+    for _ in range(warm):
         gmap.align_cloud_fixed(src, guess, iters)
     times = []
     r = None
@@ -58,6 +58,7 @@ def main():
     ap.add_argument("--compact", default="0")
     ap.add_argument("--shards", default="", help="comma list of K: also time the first 1/K of the source")
     ap.add_argument("--out", default="")
+    ap.add_argument("--warm", type=int, default=2)
     a = ap.parse_args()
     ctx = capi.Context(0)
     rows = []
@@ -87,7 +88,7 @@ def main():
                 gmap.compact()
             for cell in cells:
                 apply(ctx, cell)
-                us, r = timed(ctx, gmap, src, guess, a.iters, a.reps)
+                us, r = timed(ctx, gmap, src, guess, a.iters, a.reps, a.warm)
                 row = {"voxel": voxel, "compact": compact, "slots": gmap.capacity(), "voxels": gmap.size(),
                        "cell": cell, "us_per_iter": round(us, 2),
                        "alg_GBps": round(a.src * 136 / us * 1e-3, 1),

@@ -522,7 +522,15 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
                 # tail), a few tiles resident, both CTA shapes, both pose broadcasts
                 (0, 0, 2, 1, -1, 1), (640, 5, 2, 1, -1, 0), (640, 5, 2, 1, 0, 1), (640, 5, 1, 1, 0, 0),
                 (640, 5, 4, 1, 3, 1), (640, 5, 2, 0, 3, 1), (640, 5, 2, 0, 0, 1), (512, 5, 2, 1, -1, 1),
-                (512, 5, 2, 1, 2, 0)]:
+                (512, 5, 2, 1, 2, 0),
+                # depth 6: producer / consumer warps around a shared-memory hit queue (the default for a
+                # cloud this size): everything resident / nothing / a few tiles, both CTA shapes
+                (640, 6, 2, 1, -1, 1), (640, 6, 2, 1, 0, 1), (640, 6, 2, 1, 5, 0), (512, 6, 2, 1, -1, 1),
+                (512, 6, 2, 1, 0, 0),
+                # depth 7: phase-split passes around a per-CTA hit list: all of it in shared memory, a list
+                # of 64 / 1 batch(es) in shared memory and the rest in the HBM spill region, both CTA shapes
+                (640, 7, 2, 1, -1, 1), (640, 7, 2, 1, 64, 1), (640, 7, 2, 1, 1, 0), (512, 7, 2, 1, -1, 1),
+                (512, 7, 2, 1, 2, 0)]:
             c2.set_option("align_block", block)
             c2.set_option("align_depth", depth)
             c2.set_option("align_ticket_chunk", chunk)
@@ -544,7 +552,7 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
             dt, dr = pose_err(ro["T"], rq["T"])
             assert dt < POSE_T_TOL and dr < POSE_R_TOL, (tag, dt, dr)
         # the per-point correspondence flags of a cloud this size (depth 5, the 4-deep loop, 256-thread CTAs)
-        for block, depth, res in ((0, 0, -1), (640, 5, 0), (640, 4, -1), (256, 3, -1)):
+        for block, depth, res in ((0, 0, -1), (640, 7, 3), (640, 6, 0), (640, 5, 0), (640, 5, -1), (640, 4, -1), (256, 3, -1)):
             c2.set_option("align_block", block)
             c2.set_option("align_depth", depth)
             c2.set_option("align_resident", res)
@@ -574,7 +582,7 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
         with pytest.raises(capi.EskfError):
             c2.set_option("align_block", 500)
         with pytest.raises(capi.EskfError):
-            c2.set_option("align_depth", 6)
+            c2.set_option("align_depth", 8)
         with pytest.raises(capi.EskfError):
             c2.set_option("align_ticket_chunk", 3)
     finally:
