@@ -271,6 +271,9 @@ def impl_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+SAME_DEVICE = os.environ.get("ESKF_BENCH_SAME_DEVICE", "") not in ("", "0")  # tests: every rank on cuda:0, gloo
+
+
 class Dist:
     """torch.distributed plumbing (barrier, max / min over ranks); a no-op at world 1."""
 
@@ -278,13 +281,19 @@ class Dist:
         import torch
         self.torch = torch
         self.world = world
-        self.local = local_rank
+        self.local = 0 if SAME_DEVICE else local_rank
         self.dist = None
+        self.nccl = False
+        torch.cuda.set_device(self.local)
         if world > 1:
             import torch.distributed as dist
-            torch.cuda.set_device(local_rank)
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            if SAME_DEVICE:
+                dist.init_process_group("gloo")
+            else:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+                self.nccl = True
             self.dist = dist
+        self.dev = f"cuda:{self.local}" if (self.nccl or world == 1) else "cpu"
 
     def barrier(self):
         if self.dist is not None:
@@ -294,7 +303,7 @@ class Dist:
     def _reduce(self, vals, op):
         if self.dist is None:
             return list(vals)
-        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=f"cuda:{self.local}")
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
         self.dist.all_reduce(t, op=op)
         return [float(x) for x in t]
 
@@ -307,7 +316,7 @@ class Dist:
     def gather(self, val):
         if self.dist is None:
             return [float(val)]
-        t = self.torch.tensor([float(val)], dtype=self.torch.float64, device=f"cuda:{self.local}")
+        t = self.torch.tensor([float(val)], dtype=self.torch.float64, device=self.dev)
         out = [self.torch.empty_like(t) for _ in range(self.world)]
         self.dist.all_gather(out, t)
         return [float(o[0]) for o in out]
@@ -403,7 +412,7 @@ def dense_leg(args, capi, sharded, D, rank, world, local_rank):
     hi = D.max(*r_conv["T"].ravel())
     parity = {"identical_pose_on_all_ranks": bool(lo == hi), "converged_iterations": r_conv["iterations"],
               "converged": bool(r_conv["converged"])}
-    if world > 1:
+    if world > 1 and D.nccl:
         # the same registration with an NCCL all-reduce between two launches per iteration (baseline)
         cb = sharded.TorchAllReduce()
         ts = []
@@ -790,6 +799,7 @@ def main():
 
     from eskf_lio_b200 import capi, odometry, sharded
     D = Dist(world, local_rank)
+    local_rank = D.local
     D.barrier()
     d = dense_leg(args, capi, sharded, D, rank, world, local_rank)
     D.barrier()
@@ -844,9 +854,10 @@ def main():
                 "unsharded_ms_per_gn_iteration_rank0": d["unsharded_ms_launch_rank0"] / DENSE_ITERS,
                 "sharded_ms_per_gn_iteration": ms_it,
                 "note": "both measured as single launches in this process group"}
-            line["nccl_baseline"] = {"ms_per_gn_iteration": d["nccl_ms_launch"] / DENSE_ITERS,
-                                     "note": "eskf_align_cloud_sharded: two launches + an NCCL all-reduce of the "
-                                             "28 sums per iteration"}
+            if "nccl_ms_launch" in d:
+                line["nccl_baseline"] = {"ms_per_gn_iteration": d["nccl_ms_launch"] / DENSE_ITERS,
+                                         "note": "eskf_align_cloud_sharded: two launches + an NCCL all-reduce of "
+                                                 "the 28 sums per iteration"}
             if "weak_ms_launch" in d:
                 wit = d["weak_ms_launch"] / DENSE_ITERS
                 line["weak"] = {"points_per_gpu": DENSE_SRC, "ms_per_gn_iteration": wit,

@@ -170,7 +170,7 @@ struct eskf_ctx {
   int opt_align_stamps = 0;     // ESKF_ALIGN_STAMPS=1: globaltimer stamps of the iteration hand-off on stderr (traced calls)
   int opt_align_filter = 1;     // depth 4 (fat CTAs): probe the 8-bit L2-resident filter instead of the 16-bit tags
   int opt_align_cons = 0;       // depth 6: consumer warps per CTA (0 = follow the hit rate)
-  int opt_align_flags = 0;      // depth 5: L2 policy experiments (registration.cu, kFlag*)
+  int opt_align_flags = 16;     // L2 policy of the large-cloud kernels (registration.cu, kFlag*): 16 = filter windows evict_last
   int opt_l2_carveout = 1;      // 0: no persisting-L2 set-aside (ESKF_L2_CARVEOUT=0; decided at context creation)
   int opt_align_ll = 1;         // depth 5: flagged-word (LL) pose broadcast instead of epoch word + second round trip
   size_t l2_persist_bytes = 0;  // persisting-L2 carve-out (0 = unavailable)

@@ -2833,10 +2833,12 @@ int read_back(eskf_ctx* ctx, const AlignArgs& a, const TraceLayout& L, int max_i
     const unsigned long long* s8 = reinterpret_cast<const unsigned long long*>(h + L.o_stamps);
     const int nit = st->iter < max_it ? st->iter : max_it;
     for (int k = 0; k < nit; ++k) {
-      std::fprintf(stderr, "[eskf stamps] it %d:", k);
+      char line[256];
+      int o = std::snprintf(line, sizeof line, "[eskf stamps] dev %d it %d:", ctx->device, k);
       for (int j = 1; j < 8; ++j)
-        std::fprintf(stderr, " %.1f", (static_cast<double>(s8[8 * k + j]) - static_cast<double>(s8[8 * k])) * 1e-3);
-      std::fprintf(stderr, "\n");
+        o += std::snprintf(line + o, sizeof line - static_cast<size_t>(o), " %.1f",
+                           (static_cast<double>(s8[8 * k + j]) - static_cast<double>(s8[8 * k])) * 1e-3);
+      std::fprintf(stderr, "%s\n", line);
     }
   }
   if (st->error) {

@@ -9,7 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_the_contract_line(tmp_path):
-    env = dict(os.environ, ESKF_BENCH_LEAD_IN="2", ESKF_BENCH_CACHE=str(tmp_path))
+    env = dict(os.environ, ESKF_BENCH_LEAD_IN="2", ESKF_BENCH_CACHE=str(tmp_path), ESKF_BENCH_DENSE_SRC="60000",
+               ESKF_BENCH_DENSE_MAP="200000", ESKF_BENCH_CPU_SAMPLE="20000")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
                           "--steps", "2", "--warmup", "3"], capture_output=True, text=True, timeout=600,
                          env=env, cwd=ROOT)
@@ -20,8 +21,9 @@ def test_reference_arm_prints_the_contract_line(tmp_path):
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
               "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
-    assert d["impl"] == "reference" and d["metric"] == "ms_per_frame" and d["unit"] == "ms"
-    assert d["higher_is_better"] is False and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["impl"] == "reference" and d["metric"] == "mpts_per_s_per_gn_iteration" and d["unit"] == "Mpts/s"
+    assert d["higher_is_better"] is True and d["scaling"] == "strong"
+    assert d["vs_baseline"] is None and d["data"] == "synthetic"
     assert "workload" in d["config"] and "model" not in d["config"]
     assert d["steps"] == 2 and d["value"] > 0 and d["value"] == d["cpu_baseline"]["value"] == d["e2e"]["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1

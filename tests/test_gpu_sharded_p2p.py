@@ -54,3 +54,29 @@ def test_single_rank_comm_is_plain_align():
     assert r1["iterations"] == r2["iterations"]
     np.testing.assert_array_equal(r1["T"], r2["T"])
     comm.close()
+
+
+def test_bench_sharded_arm_on_two_ranks(tmp_path):
+    """bench.py's N > 1 arm (the line the driver's scaling run reads): configs[2] sharded over two
+    ranks — here both on cuda:0 over gloo, shrunk sizes — with its in-run parity block."""
+    port = 29300 + os.getpid() % 300
+    env = dict(os.environ, ESKF_BENCH_SAME_DEVICE="1", ESKF_BENCH_DENSE_SRC="150001",
+               ESKF_BENCH_DENSE_MAP="600000", ESKF_BENCH_CACHE=str(tmp_path))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+           "--gpus", "2", "--steps", "3", "--warmup", "3", "--no-frame", "--no-batch"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    if out.returncode != 0 and any(k in out.stderr for k in ("busy or unavailable", "exclusive", "EXCLUSIVE")):
+        pytest.skip("the GPU is in exclusive-process mode: two ranks cannot share it")
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["metric"] == "mpts_per_s_per_gn_iteration" and d["scaling"] == "strong" and d["n_gpus"] == 2
+    assert d["higher_is_better"] is True and d["steps"] == 3 and d["value"] > 0 and d["e2e"]["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 75001 * 96 and d["gpu_launches"] >= 3
+    par = d["parity"]
+    assert par["identical_pose_on_all_ranks"] and par["ncorr_equal_to_unsharded"]
+    assert par["converged_iterations"] == par["unsharded_iterations"]
+    assert par["pose_vs_unsharded"]["m"] < 1e-8 and par["pose_vs_unsharded"]["rad"] < 1e-8
+    assert d["roofline"]["frac"] > 0 and "weak" in d
