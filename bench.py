@@ -359,8 +359,7 @@ def dense_leg(args, capi, sharded, D, rank, world, local_rank):
     e2e_cloud = capi.Cloud(ctx, max(e - b, 64))
     ctx.sync()
 
-    def step(k):
-        return gmap.align_cloud_p2p(clouds[k % DENSE_SOURCES], guess, comm, fixed_iterations=DENSE_ITERS)
+    step, _ = gmap.p2p_stepper(clouds, guess, comm, DENSE_ITERS)  # (arguments marshalled once)
 
     def step_e2e(k):
         px, pc = pinned[k % DENSE_SOURCES]

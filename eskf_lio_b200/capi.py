@@ -465,6 +465,27 @@ class Map:
                                          comm._h, C.c_int(fixed_iterations), _d(T), C.byref(info)))
         return _info_dict(T, info, bufs)
 
+    def p2p_stepper(self, clouds, guess, comm: "Comm", fixed_iterations):
+        """step(k): eskf_align_cloud_p2p on clouds[k % len(clouds)] with every argument marshalled once
+        (a timed loop then measures the library call, not Python's argument handling).  Returns
+        (step, T) where T receives the last pose."""
+        prm = IcpParams(100, 1, 1e-6, 0.9999)
+        info = AlignInfo()
+        T = np.zeros(16)
+        g = _f64(guess).copy()
+        fn = lib().eskf_align_cloud_p2p
+        args = [(self.ctx._h, self._h, c._h, _d(g), C.byref(prm), comm._h, C.c_int(fixed_iterations), _d(T),
+                 C.byref(info)) for c in clouds]
+        n = len(args)
+
+        def step(k):
+            st = fn(*args[k % n])
+            if st != OK:
+                check(st)
+
+        step._keep = (prm, info, g, clouds)
+        return step, T
+
     def align_cloud_sharded(self, cloud: Cloud, guess, allreduce, max_iteration=100,
                             translation_sq_threshold=1e-6, cosine_threshold=0.9999,
                             neighbor_mode=1, fixed_iterations=0, trace=False):

@@ -249,6 +249,7 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
   if (const char* e = getenv("ESKF_ALIGN_RESIDENT")) ctx->opt_align_resident = atoi(e);
   if (const char* e = getenv("ESKF_ALIGN_FAT_POINTS")) ctx->opt_align_fat_points = atoll(e);
   if (const char* e = getenv("ESKF_ALIGN_LL")) ctx->opt_align_ll = atoi(e) != 0;
+  if (const char* e = getenv("ESKF_ALIGN_XCHG_LL")) ctx->opt_align_xchg_ll = atoi(e) != 0;
   if (const char* e = getenv("ESKF_ALIGN_FLAGS")) ctx->opt_align_flags = atoi(e);
   if (const char* e = getenv("ESKF_ALIGN_FILTER")) ctx->opt_align_filter = atoi(e) != 0;
   if (const char* e = getenv("ESKF_ALIGN_STAMPS")) ctx->opt_align_stamps = atoi(e) != 0;
@@ -375,6 +376,8 @@ int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
   } else if (n == "align_flags") {
     ESKF_REQUIRE(value >= 0 && value < 256, "align_flags is a bit mask below 256");
     ctx->opt_align_flags = static_cast<int>(value);
+  } else if (n == "align_xchg_ll") {
+    ctx->opt_align_xchg_ll = value != 0;
   } else if (n == "align_ll") {
     ctx->opt_align_ll = value != 0;
   } else if (n == "align_ticket_chunk") {
@@ -738,7 +741,7 @@ int eskf_comm_create(eskf_ctx* ctx, int rank, int world, eskf_comm** out) {
   c->ctx = ctx;
   c->rank = rank;
   c->world = world;
-  const size_t bytes = static_cast<size_t>(4) * world * 32 * sizeof(double);  // [call parity][iteration parity][rank][32]
+  const size_t bytes = static_cast<size_t>(4) * world * 64 * sizeof(double);  // [call parity][iteration parity][rank][64]
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->local), bytes);
   if (e == cudaSuccess) e = cudaMemset(c->local, 0, bytes);
   if (e != cudaSuccess) {

@@ -172,6 +172,7 @@ struct eskf_ctx {
   int opt_align_cons = 0;       // depth 6: consumer warps per CTA (0 = follow the hit rate)
   int opt_align_flags = 16;     // L2 policy of the large-cloud kernels (registration.cu, kFlag*): 16 = filter windows evict_last
   int opt_l2_carveout = 1;      // 0: no persisting-L2 set-aside (ESKF_L2_CARVEOUT=0; decided at context creation)
+  int opt_align_xchg_ll = 1;    // multi-GPU H/b exchange: flagged words (1) or data words + a release flag (0)
   int opt_align_ll = 1;         // depth 5: flagged-word (LL) pose broadcast instead of epoch word + second round trip
   size_t l2_persist_bytes = 0;  // persisting-L2 carve-out (0 = unavailable)
   size_t l2_window_max = 0;     // max access-policy window
@@ -226,7 +227,7 @@ struct eskf_map {
 struct eskf_comm {
   eskf_ctx* ctx = nullptr;
   int rank = 0, world = 1;
-  double* local = nullptr;                  // [2 call parities][2 iteration parities][world][32] doubles, cudaMalloc'ed
+  double* local = nullptr;                  // [2 call parities][2 iteration parities][world][64] 8-byte words, cudaMalloc'ed
   double* peers[ESKF_MAX_WORLD] = {};       // peers[rank] == local
   bool opened[ESKF_MAX_WORLD] = {};         // mapped with cudaIpcOpenMemHandle
   bool connected = false;

@@ -29,7 +29,7 @@ constexpr int kT = 256;   // default CTA size (small clouds; the 7-neighbour / f
 constexpr int kMaxT = 768;  // largest CTA size a variant may use (one CTA of 24 warps per SM)
 constexpr int kAcc = 28;  // A(6) B(9) D(6) b(6) + correspondence count
 constexpr int kMaxWorld = ESKF_MAX_WORLD;
-constexpr int kMailStride = 32;  // doubles per (parity, source rank): 28 sums, [28] = flag
+constexpr int kMailStride = 64;  // 8-byte words per (ring slot, source rank): 28 sums + flag, or 56 flagged words
 // measured on B200 (dense config, us per GN iteration at 0.1 m / 0.5 m voxels): FOLD 1 with
 // 3 CTAs/SM 86.7 / 160.2; FOLD 4 or 8 need 2 CTAs/SM (the partial sums stay live across the
 // load phase) 96 / 155; FOLD > 1 at 3 CTAs/SM spills: 192 / 255.
@@ -119,6 +119,7 @@ struct AlignParams {
   int ll;                   // 1: the next pose reaches the CTAs as flagged words (LL), no epoch round trip
   unsigned flags;           // depth 5 cache-policy experiments (eskf_ctx option "align_flags", see kFlag*)
   int n_cons;               // depth 6: consumer warps per CTA (0 = follow the hit rate)
+  int xchg_ll;              // multi-GPU: 1 = flagged-word exchange of the sums, 0 = data + release flag
   unsigned long long* stamps;  // nullable: [max_it][8] globaltimer stamps of the iteration hand-off (ESKF_ALIGN_STAMPS=1)
   uint32_t* spill;          // depth 7: [G][10][spill_cap] words, hit-list entries beyond shared memory
   unsigned spill_cap;
@@ -2356,6 +2357,58 @@ __device__ __forceinline__ bool exchange_sums(const AlignParams& P, int it, doub
   return *s_flag != 0;
 }
 
+// The same exchange with flagged words (the default, eskf_ctx option align_xchg_ll): every sum travels
+// as two 8-byte words {half of the fp64, tag of this call and iteration}; an 8-byte store is single-copy
+// atomic, so a word whose tag matches carries its payload and nothing needs a release fence (a
+// st.release.sys waits for the acknowledgement of every earlier peer write: a full NVLink round trip per
+// iteration) nor a second, dependent read of the data after the flag.  Thread k of the last CTA sends
+// word k % 56 to peer k / 56, then polls word k % 56 of source rank k / 56 in its own mailbox.
+constexpr int kXWords = 2 * kAcc;  // 56
+static_assert(kXWords <= kMailStride, "flagged words of one contribution fit its mailbox slot");
+__device__ __forceinline__ bool exchange_sums_ll(const AlignParams& P, int it, double* s_sum, int* s_flag,
+                                                 unsigned* s_words /* [kMaxWorld][kXWords] */) {
+  const unsigned t = threadIdx.x;
+  const int W = P.world;
+  const size_t ring = ((static_cast<size_t>(P.seq) & 1u) << 1) | static_cast<size_t>(it & 1);
+  const unsigned tag = ((P.seq & 0xffffu) << 16) | (static_cast<unsigned>(it + 1) & 0xffffu);
+  if (t == 0) *s_flag = 1;
+  for (unsigned k = t; k < static_cast<unsigned>(kXWords * W); k += blockDim.x) {
+    const unsigned w = k % kXWords, peer = k / kXWords;
+    const double d = s_sum[w >> 1];
+    const unsigned payload = (w & 1u) ? static_cast<unsigned>(__double2hiint(d)) : static_cast<unsigned>(__double2loint(d));
+    volatile unsigned long long* dst = reinterpret_cast<volatile unsigned long long*>(
+        P.peers[peer] + (ring * W + P.rank) * kMailStride + w);
+    *dst = (static_cast<unsigned long long>(tag) << 32) | payload;
+  }
+  __syncthreads();  // (s_flag; every thread's sends are issued)
+  for (unsigned k = t; k < static_cast<unsigned>(kXWords * W); k += blockDim.x) {
+    const unsigned w = k % kXWords, src = k / kXWords;
+    const volatile unsigned long long* box = reinterpret_cast<const volatile unsigned long long*>(
+        P.peers[P.rank] + (ring * W + src) * kMailStride + w);
+    unsigned long long v = *box;
+    unsigned spins = 0;
+    while (static_cast<unsigned>(v >> 32) != tag) {
+      __nanosleep(20);
+      v = *box;
+      if (++spins > 32u * kSpinLimit || ((spins & 255u) == 0u && ld_acquire_u32(&P.st->error) != 0)) {  // several seconds
+        atomicExch(&P.st->error, 2u);
+        *s_flag = 0;
+        break;
+      }
+    }
+    s_words[src * kXWords + w] = static_cast<unsigned>(v);
+  }
+  __syncthreads();
+  if (t < kAcc) {
+    double s = 0.0;
+    for (int r = 0; r < W; ++r)  // rank order: every rank forms the bit-identical total
+      s += __hiloint2double(static_cast<int>(s_words[r * kXWords + 2 * t + 1]), static_cast<int>(s_words[r * kXWords + 2 * t]));
+    s_sum[t] = s;
+  }
+  __syncthreads();
+  return *s_flag != 0;
+}
+
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -2374,6 +2427,7 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
   __shared__ double s_sum[kAcc];
   __shared__ double s_solve[96];
   __shared__ int s_last, s_done, s_xchg;
+  __shared__ unsigned s_xw[kMaxWorld * 2 * kAcc];  // flagged words received from every rank
   extern __shared__ __align__(128) unsigned char s_dyn[];  // depth 5: [NW][k_res + kRing] tiles, then the ring's mbarriers
   const unsigned G = gridDim.x, t = threadIdx.x;
   AlignState* st = P.st;
@@ -2468,7 +2522,7 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
       final_reduce<NW>(P.partials, G, s_part, s_sum);
       ESKF_STAMP(t == 0, 3);
       bool ok = true;
-      if (P.world > 1) ok = exchange_sums(P, it, s_sum, &s_xchg);
+      if (P.world > 1) ok = P.xchg_ll ? exchange_sums_ll(P, it, s_sum, &s_xchg, s_xw) : exchange_sums(P, it, s_sum, &s_xchg);
       ESKF_STAMP(t == 0, 4);
       if (t < 32) {
         if (ok) solve_and_update_fast(P, s_sum, s_Ttot, it, s_solve);
@@ -2742,6 +2796,7 @@ int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, T
   P->flags = static_cast<unsigned>(ctx->opt_align_flags);
   if (dyn_smem) *dyn_smem = 0;
   P->n_cons = ctx->opt_align_cons;
+  P->xchg_ll = ctx->opt_align_xchg_ll;
   {
     const int vi = variant_index(ctx, a);
     if ((vi == V_F32_N1_T768D4 || vi == V_F32_N1_T640D4 || vi == V_F32_N1_T512D4) && ctx->opt_align_filter && dyn_smem)

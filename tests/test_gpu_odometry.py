@@ -48,8 +48,9 @@ def test_sequence_matches_oracle(log, oracle_run, device_resident):
     assert [r[0] for r in rec] == [r[0] for r in o_rec]          # Gauss-Newton iteration counts
     assert [r[1] for r in rec] == [r[1] for r in o_rec]          # keyframe gate decisions
     assert [r[3] for r in rec] == [r[3] for r in o_rec]          # filter state history length
-    # occupancy: identical while the poses agree to ~1e-9 m, bar a voxel-face flip
-    assert all(abs(int(a[2]) - int(b[2])) <= 3 for a, b in zip(rec, o_rec))
+    # occupancy after every frame: identical (north_star; the poses agree to ~1e-9 m, so a point would
+    # have to sit within that of a voxel face to flip)
+    assert [int(r[2]) for r in rec] == [int(r[2]) for r in o_rec]
     st = od.last_state(with_P=True)
     assert np.linalg.norm(st["p"] - o_state["p"]) < 1e-5 and np.linalg.norm(st["v"] - o_state["v"]) < 1e-3
     assert np.linalg.norm(st["P"] - o_state["P"]) / np.linalg.norm(o_state["P"]) < 1e-6

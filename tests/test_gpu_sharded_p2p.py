@@ -14,13 +14,16 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_ranks_fused_exchange_matches_unsharded():
-    port = 29600 + os.getpid() % 300
+@pytest.mark.parametrize("xchg_ll", [1, 0])
+def test_two_ranks_fused_exchange_matches_unsharded(xchg_ll):
+    """xchg_ll 1: the sums travel as flagged 8-byte words (default); 0: data words + a release flag."""
+    port = 29600 + os.getpid() % 300 + xchg_ll
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "scripts", "dense_sharded.py"), "--same-device", "--backend", "gloo",
            "--src", "150001", "--map", "600000", "--voxel", "0.25", "--iters", "4", "--reps", "1"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT,
+                         env=dict(os.environ, ESKF_ALIGN_XCHG_LL=str(xchg_ll)))
     if out.returncode != 0 and any(k in out.stderr for k in ("busy or unavailable", "exclusive", "EXCLUSIVE")):
         pytest.skip("the GPU is in exclusive-process mode: two ranks cannot share it")
     assert out.returncode == 0, out.stderr[-2000:]
