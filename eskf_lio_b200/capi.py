@@ -50,7 +50,7 @@ SYMBOLS = [
     "eskf_cloud_download", "eskf_cloud_size", "eskf_cloud_transform", "eskf_cloud_copy",
     "eskf_map_create", "eskf_map_destroy", "eskf_map_insert", "eskf_map_insert_cloud",
     "eskf_map_evict", "eskf_map_size", "eskf_map_capacity", "eskf_map_compact", "eskf_map_query", "eskf_map_export",
-    "eskf_preprocess", "eskf_preprocess_cloud", "eskf_downsample_cov",
+    "eskf_ctx_set_range_crop", "eskf_preprocess", "eskf_preprocess_cloud", "eskf_downsample_cov",
     "eskf_align", "eskf_align_cloud", "eskf_align_cloud_begin", "eskf_align_end", "eskf_align_batch",
     "eskf_linearize",
     "eskf_align_cloud_fixed",
@@ -161,6 +161,10 @@ class Context:
 
     def set_option(self, name: str, value: int):
         check(lib().eskf_ctx_set_option(self._h, name.encode(), C.c_int64(int(value))))
+
+    def set_range_crop(self, min_range: float = 0.0, max_range: float = 0.0):
+        """Range crop of the preprocessor (LiDAR frame; max_range 0 = unbounded; (0, 0) = off)."""
+        check(lib().eskf_ctx_set_range_crop(self._h, C.c_double(min_range), C.c_double(max_range)))
 
     def align_end(self):
         info, bufs = _make_info(1, False)

@@ -143,6 +143,12 @@ struct eskf_ctx {
   eskf::DevBuf segs;       // deskew segments
   eskf::DevBuf work;       // align working positions (SoA)
   eskf::DevBuf spill;      // align depth 7: hit-list entries beyond shared memory
+  // range crop of the preprocessor (eskf_ctx_set_range_crop; off by default: the reference has none)
+  bool crop = false;
+  double crop_min2 = 0.0, crop_max2 = 0.0;  // squared bounds, LiDAR frame
+  eskf::DevBuf crop_orig;   // [n'] index of every surviving point in the uncropped sweep
+  eskf::DevBuf crop_cnt;    // per-block survivor counts + the total
+  eskf_cloud* crop_cloud = nullptr;  // the surviving points (what the rest of the preprocessor runs on)
   eskf::DevBuf partials;   // align per-block partial sums
   eskf::DevBuf astate;     // align state + traces
   eskf::DevBuf misc;       // small outputs (query / export counters)
@@ -258,6 +264,7 @@ struct VoxelizeArgs {
   double T1[12];
   const DeskewSeg* segs;
   int n_segs;
+  const uint32_t* orig;  // nullable: point i is point orig[i] of the sweep the deskew segments index (range crop)
   int mode;  // 0: runs in sorted order (map insert), 1: kept points in source order (preprocess)
   HostMail* mail;     // mode 1, nullable: publish n_out / error words here when known
   unsigned mail_seq;

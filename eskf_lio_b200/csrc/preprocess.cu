@@ -60,6 +60,7 @@ struct KnnParams {
   double* ocov;
   size_t opitch;
   uint32_t* osrc;
+  const uint32_t* orig;   // nullable: source index -> index in the uncropped sweep (range crop)
   float4* oc4;
   float2* oc2;
   const uint4* levels;    // block-range tables (common.cuh)
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(128) knn_cov_kernel(KnnParams P) {
       P.oz[r] = qz;
 #pragma unroll
       for (int k = 0; k < 9; ++k) P.ocov[k * P.opitch + r] = R[k];
-      P.osrc[r] = P.kept_src[r];
+      P.osrc[r] = P.orig != nullptr ? P.orig[P.kept_src[r]] : P.kept_src[r];
       P.oc4[r] = make_float4(static_cast<float>(R[0]), static_cast<float>(R[1]),
                              static_cast<float>(R[2]), static_cast<float>(R[4]));
       P.oc2[r] = make_float2(static_cast<float>(R[5]), static_cast<float>(R[8]));
@@ -725,7 +726,7 @@ __global__ void __launch_bounds__(64) knn_finish_kernel(KnnParams P) {
   P.oz[r] = P.sz[j0];
 #pragma unroll
   for (int k = 0; k < 9; ++k) P.ocov[k * P.opitch + r] = R[k];
-  P.osrc[r] = P.kept_src[r];
+  P.osrc[r] = P.orig != nullptr ? P.orig[P.kept_src[r]] : P.kept_src[r];
   P.oc4[r] = make_float4(static_cast<float>(R[0]), static_cast<float>(R[1]), static_cast<float>(R[2]),
                          static_cast<float>(R[4]));
   P.oc2[r] = make_float2(static_cast<float>(R[5]), static_cast<float>(R[8]));
@@ -882,7 +883,8 @@ int check_header(eskf_ctx* ctx, unsigned* n_out) {
 
 // raw (device, xyz only) -> out (device, xyz + cov + src index)
 int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
-                      const std::vector<DeskewSeg>& segs, double voxel, eskf_cloud* out) {
+                      const std::vector<DeskewSeg>& segs, double voxel, eskf_cloud* out,
+                      const uint32_t* orig = nullptr) {
   const unsigned n = static_cast<unsigned>(raw->n);
   ESKF_TRY(cloud_reserve(out, raw->n, true));
   VoxelizeArgs a;
@@ -913,6 +915,7 @@ int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
     a.segs = ctx->segs.as<DeskewSeg>();
     a.n_segs = static_cast<int>(segs.size());
   }
+  a.orig = orig;
   a.mode = 1;
   const bool mapped = ctx->opt_mapped_results && ctx->mail_h != nullptr && !ctx->opt_trace;
   if (mapped) {
@@ -943,6 +946,7 @@ int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
   P.ocov = out->cov;
   P.opitch = out->cap;
   P.osrc = out->src;
+  P.orig = orig;
   P.oc4 = out->c4;
   P.oc2 = out->c2;
   P.levels = v.levels;
@@ -1024,6 +1028,104 @@ int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
   return ESKF_OK;
 }
 
+// ---- range crop ------------------------------------------------------------
+// north_star names a range crop in the preprocessor; the reference has none
+// (src/CloudPreprocessor.cpp:10-23), so the oracle defines it (oracle.preprocess):
+// a point of the incoming sweep survives iff min^2 <= x^2 + y^2 + z^2 <= max^2 in
+// the LiDAR frame (fp64, ((x*x + y*y) + z*z), no FMA); T_il and the deskew act on
+// every point exactly as before (segments and the sweep's end time come from the
+// full stamp array), and the cropped points are erased ahead of
+// voxelDownsampleAndEstimateCovariances: they neither claim a voxel nor count as
+// neighbours.  Here: a stable compaction of the raw sweep (two small kernels)
+// into a scratch cloud + the surviving points' original indices, which the
+// voxelize kernel uses to find a point's deskew segment and the k-NN kernels to
+// report source indices.
+constexpr int kCropT = 256;
+
+__device__ __forceinline__ bool crop_keeps(double x, double y, double z, double min2, double max2) {
+  const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+  return r2 >= min2 && r2 <= max2;
+}
+
+__global__ void __launch_bounds__(kCropT) crop_count_kernel(const double* x, const double* y, const double* z,
+                                                           unsigned n, double min2, double max2, unsigned* counts) {
+  const unsigned i = blockIdx.x * kCropT + threadIdx.x;
+  const bool keep = i < n && crop_keeps(x[i], y[i], z[i], min2, max2);
+  const unsigned c = __syncthreads_count(keep);
+  if (threadIdx.x == 0) counts[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(kCropT) crop_scatter_kernel(const double* x, const double* y, const double* z,
+                                                             unsigned n, double min2, double max2,
+                                                             const unsigned* counts, unsigned n_blocks, double* ox,
+                                                             double* oy, double* oz, uint32_t* orig, unsigned* total) {
+  __shared__ unsigned s_warp[kCropT / 32];
+  __shared__ unsigned s_base;
+  const unsigned t = threadIdx.x, lane = t & 31, w = t >> 5;
+  // survivors in the blocks before this one
+  unsigned part = 0;
+  for (unsigned b = t; b < blockIdx.x; b += kCropT) part += counts[b];
+  part = warp_reduce_add(part);
+  if (lane == 0) s_warp[w] = part;
+  __syncthreads();
+  if (t == 0) {
+    unsigned base = 0;
+    for (int k = 0; k < kCropT / 32; ++k) base += s_warp[k];
+    s_base = base;
+  }
+  __syncthreads();
+  const unsigned i = blockIdx.x * kCropT + t;
+  double px = 0.0, py = 0.0, pz = 0.0;
+  bool keep = false;
+  if (i < n) {
+    px = x[i]; py = y[i]; pz = z[i];
+    keep = crop_keeps(px, py, pz, min2, max2);
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  __syncthreads();
+  if (lane == 0) s_warp[w] = __popc(m);
+  __syncthreads();
+  unsigned off = s_base;
+  for (unsigned k = 0; k < w; ++k) off += s_warp[k];
+  if (keep) {
+    const unsigned o = off + __popc(m & ((1u << lane) - 1u));
+    ox[o] = px; oy[o] = py; oz[o] = pz;
+    orig[o] = i;
+  }
+  if (blockIdx.x == n_blocks - 1 && t == 0) {
+    unsigned tot = s_base;
+    for (int k = 0; k < kCropT / 32; ++k) tot += s_warp[k];
+    *total = tot;
+  }
+}
+
+// raw -> ctx->crop_cloud (+ ctx->crop_orig); the survivor count comes back with one small copy
+int crop_device(eskf_ctx* ctx, const eskf_cloud* raw) {
+  const unsigned n = static_cast<unsigned>(raw->n);
+  const unsigned blocks = (n + kCropT - 1) / kCropT;
+  if (!ctx->crop_cloud) ESKF_TRY(eskf_cloud_create(ctx, raw->n, &ctx->crop_cloud));
+  ESKF_TRY(cloud_reserve(ctx->crop_cloud, raw->n, false));
+  ESKF_TRY(ctx->crop_orig.ensure(static_cast<size_t>(n) * sizeof(uint32_t)));
+  ESKF_TRY(ctx->crop_cnt.ensure((static_cast<size_t>(blocks) + 1) * sizeof(unsigned)));
+  unsigned* counts = ctx->crop_cnt.as<unsigned>();
+  crop_count_kernel<<<blocks, kCropT, 0, ctx->stream>>>(raw->x(), raw->y(), raw->z(), n, ctx->crop_min2,
+                                                        ctx->crop_max2, counts);
+  ESKF_CUDA(cudaGetLastError());
+  eskf_cloud* c = ctx->crop_cloud;
+  crop_scatter_kernel<<<blocks, kCropT, 0, ctx->stream>>>(raw->x(), raw->y(), raw->z(), n, ctx->crop_min2,
+                                                          ctx->crop_max2, counts, blocks, c->x(), c->y(), c->z(),
+                                                          ctx->crop_orig.as<uint32_t>(), counts + blocks);
+  ESKF_CUDA(cudaGetLastError());
+  count_launch(ctx, 2);
+  unsigned* h = nullptr;
+  ESKF_TRY(ctx_pinned(ctx, sizeof(unsigned), reinterpret_cast<void**>(&h)));
+  ESKF_CUDA(cudaMemcpyAsync(h, counts + blocks, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  ESKF_CUDA(cudaStreamSynchronize(ctx->stream));
+  c->n = *h;
+  c->has_cov = c->has_c32 = c->has_src = false;
+  return ESKF_OK;
+}
+
 }  // namespace
 }  // namespace eskf
 
@@ -1051,7 +1153,24 @@ int eskf_preprocess_cloud(eskf_ctx* ctx, eskf_cloud* raw, const double* point_ti
   }
   raw->has_cov = false;
   raw->has_c32 = false;
+  if (ctx->crop) {
+    ESKF_TRY(crop_device(ctx, raw));
+    if (ctx->crop_cloud->n == 0) {
+      out->n = 0;
+      return ESKF_OK;
+    }
+    return preprocess_device(ctx, ctx->crop_cloud, T_il, segs, voxel_size, out, ctx->crop_orig.as<uint32_t>());
+  }
   return preprocess_device(ctx, raw, T_il, segs, voxel_size, out);
+}
+
+int eskf_ctx_set_range_crop(eskf_ctx* ctx, double min_range, double max_range) {
+  ESKF_REQUIRE(ctx, "null ctx");
+  ESKF_REQUIRE(min_range >= 0.0 && (max_range == 0.0 || max_range >= min_range), "range crop needs 0 <= min <= max (max 0: unbounded)");
+  ctx->crop = min_range > 0.0 || max_range > 0.0;
+  ctx->crop_min2 = min_range * min_range;
+  ctx->crop_max2 = max_range > 0.0 ? max_range * max_range : 1.7976931348623157e308;
+  return ESKF_OK;
 }
 
 int eskf_preprocess(eskf_ctx* ctx, const double* xyz, const double* point_time, size_t n,

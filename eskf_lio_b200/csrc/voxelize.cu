@@ -118,12 +118,13 @@ __global__ void __launch_bounds__(kT) voxelize_kernel(VoxParams P) {
       double z = P.a.in_z[static_cast<size_t>(i) * stride];
       if (P.a.has_T1) transform_point_rn(P.a.T1, x, y, z);
       if (P.a.n_segs > 0) {
-        int lo = 0, hi = P.a.n_segs;  // first segment with end > i
+        const unsigned oi = P.a.orig != nullptr ? P.a.orig[i] : i;  // (segments index the uncropped sweep)
+        int lo = 0, hi = P.a.n_segs;  // first segment with end > oi
         while (lo < hi) {
           int mid = (lo + hi) >> 1;
-          if (P.a.segs[mid].end > i) hi = mid; else lo = mid + 1;
+          if (P.a.segs[mid].end > oi) hi = mid; else lo = mid + 1;
         }
-        if (lo < P.a.n_segs && i >= P.a.segs[lo].begin) transform_point_rn(P.a.segs[lo].T, x, y, z);
+        if (lo < P.a.n_segs && oi >= P.a.segs[lo].begin) transform_point_rn(P.a.segs[lo].T, x, y, z);
       }
       P.a.out_x[i] = x;
       P.a.out_y[i] = y;

@@ -12,7 +12,8 @@ class CloudPreprocessor
 {
 public:
   explicit CloudPreprocessor(const Config & config)
-  : voxelSize_(config.cloud_preprocessor.voxel_size), deviceResident_(config.device_resident)
+  : voxelSize_(config.cloud_preprocessor.voxel_size), minRange_(config.cloud_preprocessor.min_range),
+    maxRange_(config.cloud_preprocessor.max_range), deviceResident_(config.device_resident)
   {
     Quaterniond q;
     q.x = config.lidar_extrinsics.quaternion[0];
@@ -78,6 +79,8 @@ private:
     PointCloud & cloud, const double * pointTime, const double * T_il, const eskf_state * states,
     std::size_t nStates) const
   {
+    // (the context is shared by the host classes: the crop is this preprocessor's setting, stated per call)
+    gpuCheck(eskf_ctx_set_range_crop(GpuContext::get(), minRange_, maxRange_), "eskf_ctx_set_range_crop");
     if (deviceResident_) {
       // raw scan: already in HBM (uploaded on arrival) or uploaded now
       std::shared_ptr<eskf_cloud> raw = cloud.device_;
@@ -114,6 +117,7 @@ private:
   }
 
   double voxelSize_;
+  double minRange_, maxRange_;
   bool deviceResident_;
   Isometry3d T_il_;
   mutable DeviceCloudPool rawPool_, outPool_;

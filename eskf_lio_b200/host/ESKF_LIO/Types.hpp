@@ -223,7 +223,13 @@ struct Config
     // allocates device memory and costs milliseconds, so the default covers a 100 m window.
     std::size_t capacity_hint = std::size_t(1) << 20;
   } local_map;
-  struct {double voxel_size = 0.3;} cloud_preprocessor;
+  struct {
+    double voxel_size = 0.3;
+    // range crop in the LiDAR frame (BASELINE.json north_star; not in the reference: off by default;
+    // max_range 0 = unbounded) -- eskf_ctx_set_range_crop
+    double min_range = 0.0;
+    double max_range = 0.0;
+  } cloud_preprocessor;
   struct {
     double quaternion[4] = {0.7071068, -0.7071068, 0.0, 0.0};  // x,y,z,w
     double translation[3] = {-0.001, -0.00855, 0.055};

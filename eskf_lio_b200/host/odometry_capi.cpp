@@ -6,6 +6,7 @@
 #include <string>
 
 #include "ESKF_LIO/Odometry.hpp"
+#include "ESKF_LIO/SensorLog.hpp"
 #include "eskf_host.h"
 
 using namespace ESKF_LIO;
@@ -239,6 +240,109 @@ int eskf_odom_launch_count(eskf_odom * o, uint64_t * n)
 {
   if (!o || !n) {return fail("null argument");}
   return guarded([&] {gpuCheck(eskf_ctx_launch_count(GpuContext::get(), n), "eskf_ctx_launch_count");});
+}
+
+// ---- flat binary sensor log (ESKF_LIO/SensorLog.hpp) -------------------------
+int eskf_odom_replay_log(eskf_odom * o, const char * path, double * poses, size_t capacity, size_t * n_frames)
+{
+  if (!o || !path || !n_frames) {return fail("null argument");}
+  *n_frames = 0;
+  return guarded(
+    [&] {
+      SensorLogReader rd(path);
+      // sweeps handed to the odometry but not consumed yet: in device-resident mode the per-point
+      // stamps are read in place when the frame is processed, so their buffers stay alive here
+      std::deque<std::pair<std::vector<float>, std::vector<double>>> pending;
+      for (;;) {
+        const SensorLogReader::Type t = rd.next();
+        if (t == SensorLogReader::kEnd) {break;}
+        if (t == SensorLogReader::kImu) {
+          auto m = std::make_shared<ImuMeasurement>();  // ImuSubscriber::imuCallback (Subscriber.hpp:38-52)
+          m->timestamp = rd.stamp;
+          m->angularVelocity = Vector3d(rd.gyro[0], rd.gyro[1], rd.gyro[2]);
+          m->acceleration = Vector3d(rd.acc[0], rd.acc[1], rd.acc[2]);
+          o->imu->push(std::move(m));
+        } else {
+          if (rd.pointTime.empty()) {continue;}
+          pending.emplace_back(std::move(rd.xyz), std::move(rd.pointTime));  // cloudCallback (:80-103)
+          o->odom->feedLidar(pending.back().first.data(), pending.back().second.data(), pending.back().second.size());
+        }
+        // one trip of Odometry::run's loop per delivery, more while frames keep going through
+        while (o->odom->spinOnce()) {
+          if (poses && *n_frames < capacity) {
+            const auto M = o->odom->lastTransform().matrix();
+            std::memcpy(poses + 16 * *n_frames, M.data(), sizeof(double) * 16);
+          }
+          ++*n_frames;
+          if (!pending.empty()) {pending.pop_front();}
+        }
+      }
+    });
+}
+
+int eskf_log_summary(const char * path, uint64_t counts[3], double stamps[2])
+{
+  if (!path || !counts || !stamps) {return fail("null argument");}
+  return guarded(
+    [&] {
+      SensorLogReader rd(path);
+      counts[0] = counts[1] = counts[2] = 0;
+      stamps[0] = stamps[1] = 0.0;
+      bool first = true;
+      for (;;) {
+        const SensorLogReader::Type t = rd.next();
+        if (t == SensorLogReader::kEnd) {break;}
+        double a, b;
+        if (t == SensorLogReader::kImu) {
+          ++counts[0];
+          a = b = rd.stamp;
+        } else {
+          ++counts[1];
+          counts[2] += rd.pointTime.size();
+          if (rd.pointTime.empty()) {continue;}
+          a = rd.pointTime.front();
+          b = rd.pointTime.back();
+        }
+        if (first || a < stamps[0]) {stamps[0] = a;}
+        if (first || b > stamps[1]) {stamps[1] = b;}
+        first = false;
+      }
+    });
+}
+
+struct eskf_log_writer
+{
+  std::unique_ptr<SensorLogWriter> w;
+};
+
+int eskf_log_writer_open(const char * path, eskf_log_writer ** out)
+{
+  if (!path || !out) {return fail("null argument");}
+  *out = nullptr;
+  return guarded(
+    [&] {
+      auto h = std::make_unique<eskf_log_writer>();
+      h->w = std::make_unique<SensorLogWriter>(path);
+      *out = h.release();
+    });
+}
+
+int eskf_log_writer_imu(eskf_log_writer * w, double stamp, const double gyro[3], const double acc[3])
+{
+  if (!w || !gyro || !acc) {return fail("null argument");}
+  return guarded([&] {w->w->writeImu(stamp, gyro, acc);});
+}
+
+int eskf_log_writer_lidar(eskf_log_writer * w, const float * xyz, const double * point_time, size_t n)
+{
+  if (!w || (n && (!xyz || !point_time))) {return fail("null argument");}
+  return guarded([&] {w->w->writeLidar(xyz, point_time, n);});
+}
+
+int eskf_log_writer_close(eskf_log_writer * w)
+{
+  delete w;
+  return 0;
 }
 
 }  // extern "C"

@@ -45,7 +45,9 @@ SYMBOLS = ["eskf_host_last_error", "eskf_odom_default_config", "eskf_odom_create
            "eskf_odom_destroy", "eskf_odom_feed_imu", "eskf_odom_feed_lidar",
            "eskf_odom_feed_lidar_cloud", "eskf_odom_context",
            "eskf_odom_spin_once", "eskf_odom_last_pose", "eskf_odom_last_state",
-           "eskf_odom_info_get", "eskf_odom_map", "eskf_odom_launch_count"]
+           "eskf_odom_info_get", "eskf_odom_map", "eskf_odom_launch_count",
+           "eskf_odom_replay_log", "eskf_log_summary", "eskf_log_writer_open", "eskf_log_writer_imu",
+           "eskf_log_writer_lidar", "eskf_log_writer_close"]
 
 _lib = None
 
@@ -176,6 +178,15 @@ class Odometry:
         n = C.c_uint64(0)
         _check(lib().eskf_odom_launch_count(self._h, C.byref(n)))
         return int(n.value)
+
+    def replay_log(self, path: str, max_frames: int = 1 << 16):
+        """Replay a flat binary sensor log (eskf_lio_b200.sensor_log / SensorLog.hpp) through the
+        odometry; returns the poses of the frames that went through."""
+        poses = np.zeros((max_frames, 16))
+        n = C.c_size_t(0)
+        _check(lib().eskf_odom_replay_log(self._h, path.encode(), poses.ctypes.data_as(_dp),
+                                          C.c_size_t(max_frames), C.byref(n)))
+        return [poses[i].reshape(4, 4).copy() for i in range(min(n.value, max_frames))]
 
 
 def run_sequence(odom, scans, imu, on_frame=None):

@@ -190,6 +190,14 @@ int eskf_map_export(eskf_map* m, size_t capacity, size_t* n, int32_t* key_xyz, u
  * first-point-per-voxel downsample, 30-NN covariance + regularisation.
  * Outputs (capacity n points each, any may be NULL) are in ascending source
  * index order; *n_out = kept points.  The input buffer is NOT modified. */
+/* Range crop ahead of the downsample (BASELINE.json north_star "voxel-grid downsample and range crop";
+ * the reference's preprocessor has none, seam: src/CloudPreprocessor.cpp:16-20): a point of the sweep
+ * survives iff min_range^2 <= x^2 + y^2 + z^2 <= max_range^2 in the LiDAR frame (as delivered, before
+ * T_il); max_range 0 = unbounded; (0, 0) = off, the default.  T_il and the deskew act on every point
+ * as before (segments and the sweep's end time come from the full stamp array); cropped points are
+ * erased ahead of voxelDownsampleAndEstimateCovariances.  Source indices reported by the preprocessor
+ * stay indices into the uncropped sweep.  Applies to every later eskf_preprocess* call on ctx. */
+int eskf_ctx_set_range_crop(eskf_ctx* ctx, double min_range, double max_range);
 int eskf_preprocess(eskf_ctx* ctx, const double* xyz, const double* point_time, size_t n,
                     const double T_il[16], const eskf_state* states, size_t n_states,
                     double voxel_size, size_t* n_out, double* xyz_out, double* cov_out,

@@ -92,6 +92,23 @@ int eskf_odom_map(eskf_odom* o, void** map_handle);
 /* kernels launched so far by the host classes' context (bench "gpu_launches") */
 int eskf_odom_launch_count(eskf_odom* o, uint64_t* n);
 
+/* ---- flat binary sensor log (eskf_lio_b200/host/ESKF_LIO/SensorLog.hpp): the wire format of
+ * the reference's two subscribers without ROS (include/ESKF_LIO/Subscriber.hpp:38-52 sensor_msgs/Imu,
+ * :80-103 sensor_msgs/PointCloud2 with float32 x, y, z + float64 "timestamp" per point), records in
+ * callback order.  "ESKFLOG1", u32 version 1, u32 0; then {u32 type, u32 count, payload}:
+ * type 1 = IMU {f64 stamp, f64 gyro[3], f64 acc[3]}, type 2 = sweep of count x {f32 x, y, z, f64 stamp}. */
+/* Replays a log through the odometry: every record is delivered the way its callback would
+ * (feed_imu / feed_lidar) followed by trips of Odometry::run's loop.  poses (nullable): row-major
+ * 4x4 of every frame that went through, at most `capacity` of them; *n_frames = all of them. */
+int eskf_odom_replay_log(eskf_odom* o, const char* path, double* poses, size_t capacity, size_t* n_frames);
+/* counts = {IMU records, sweeps, points}, stamps = {earliest, latest}; needs no GPU */
+int eskf_log_summary(const char* path, uint64_t counts[3], double stamps[2]);
+typedef struct eskf_log_writer eskf_log_writer;
+int eskf_log_writer_open(const char* path, eskf_log_writer** out);
+int eskf_log_writer_imu(eskf_log_writer* w, double stamp, const double gyro[3], const double acc[3]);
+int eskf_log_writer_lidar(eskf_log_writer* w, const float* xyz, const double* point_time, size_t n);
+int eskf_log_writer_close(eskf_log_writer* w);
+
 #ifdef __cplusplus
 }
 #endif

@@ -323,7 +323,26 @@ def deskew(xyz, point_time, states):
     return xyz
 
 
-def preprocess(xyz, point_time, T_il, states, voxel_size):
+def preprocess(xyz, point_time, T_il, states, voxel_size, min_range=0.0, max_range=0.0):
+    """CloudPreprocessor::process (src/CloudPreprocessor.cpp:10-23).  min_range / max_range: the range
+    crop BASELINE.json's north_star names and the reference lacks, DEFINED here: a point survives iff
+    min^2 <= ((x*x + y*y) + z*z) <= max^2 in the LiDAR frame (max 0 = unbounded); T_il (:16) and the
+    deskew (:17-19) act on every point of the sweep, the cropped ones are erased ahead of
+    voxelDownsampleAndEstimateCovariances (:22); returned source indices index the uncropped sweep."""
+    if min_range > 0.0 or max_range > 0.0:
+        raw = _f64(xyz, (-1, 3))
+        r2 = (raw[:, 0] * raw[:, 0] + raw[:, 1] * raw[:, 1]) + raw[:, 2] * raw[:, 2]
+        keep = r2 >= min_range * min_range
+        if max_range > 0.0:
+            keep &= r2 <= max_range * max_range
+        p, _ = transform_cloud(raw, None, T_il)
+        if states is not None and len(states[0]) > 0:
+            p = deskew(p, point_time, states)
+        idx = np.nonzero(keep)[0]
+        if len(idx) == 0:
+            return np.zeros((0, 3)), np.zeros((0, 3, 3)), np.zeros(0, dtype=np.uint32)
+        op, oc, osrc = downsample_cov(p[idx], voxel_size)
+        return op, oc, idx[osrc].astype(np.uint32)
     xyz = _f64(xyz, (-1, 3)).copy()
     n = xyz.shape[0]
     t = _f64(point_time if point_time is not None else np.zeros(n))

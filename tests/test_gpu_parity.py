@@ -289,6 +289,68 @@ def test_preprocess_with_deskew(ctx, oracle, frames):
     assert np.abs(gc - oc).max() < 1e-7
 
 
+def _deskew_states(t):
+    t0, t1 = t[0], max(t[-1], t.max())
+    ts = t0 - 0.006 + 0.0025 * np.arange(int((t1 - t0 + 0.02) / 0.0025) + 4)
+    s = ts - t0
+    pos = np.stack([1.2 * s, 0.3 * s * s, 0.05 * np.sin(8 * s)], axis=1)
+    ang = 0.4 * s
+    quat = np.stack([0.02 * np.sin(ang), 0.01 * np.sin(ang), np.sin(ang / 2), np.cos(ang / 2)], axis=1)
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    return ts, pos, quat
+
+
+def test_preprocess_with_unsorted_stamps(ctx, oracle, frames):
+    """stamps that are not non-decreasing (ring-major / merged sweeps): the segments must be
+    the reference's forward linear scan (src/CloudPreprocessor.cpp:54-61), which the oracle restates and
+    tests/test_reference_shim.py holds to the reference's own sources."""
+    xyz, t = frames.raw[1]
+    rng = np.random.default_rng(3)
+    blocks = np.array_split(np.arange(len(t)), 37)
+    tu = t[np.concatenate([blocks[k] for k in rng.permutation(len(blocks))])].copy()
+    assert np.any(np.diff(tu) < 0)
+    states = _deskew_states(t)
+    op, oc, osrc = oracle.preprocess(xyz, tu, frames.T_il, states, 0.5)
+    gp, gc, gsrc = ctx.preprocess(xyz, tu, frames.T_il, states, 0.5)
+    np.testing.assert_array_equal(gsrc, osrc)
+    np.testing.assert_array_equal(gp, op)
+    assert np.abs(gc - oc).max() < 1e-7
+    sp, _, ssrc = oracle.preprocess(xyz, t, frames.T_il, states, 0.5)
+    assert len(ssrc) != len(osrc) or not np.array_equal(sp, op)   # (a different segmentation than the sorted one)
+
+
+@pytest.mark.parametrize("with_states", [False, True])
+def test_range_crop_matches_oracle(ctx, oracle, frames, with_states):
+    """north_star's range crop (defined by the oracle, off by default): kept set, source indices and
+    positions bit-exact, covariances within 1e-7; edge cases: everything cropped, one-sided bounds."""
+    xyz, t = frames.raw[2]
+    states = _deskew_states(t) if with_states else None
+    r = np.linalg.norm(xyz, axis=1)
+    lo, hi = float(np.quantile(r, 0.15)), float(np.quantile(r, 0.85))
+    try:
+        for mn, mx in ((lo, hi), (lo, 0.0), (0.0, hi), (float(r[17]), float(r[17]) * (1 + 1e-15) + 20.0)):
+            ctx.set_range_crop(mn, mx)
+            op, oc, osrc = oracle.preprocess(xyz, t, frames.T_il, states, 0.5, min_range=mn, max_range=mx)
+            gp, gc, gsrc = ctx.preprocess(xyz, t, frames.T_il, states, 0.5)
+            assert 0 < len(osrc) < len(oracle.preprocess(xyz, t, frames.T_il, states, 0.5)[2])
+            np.testing.assert_array_equal(gsrc, osrc)          # indices into the uncropped sweep
+            np.testing.assert_array_equal(gp, op)
+            assert np.abs(gc - oc).max() < 1e-7
+            assert np.all(r[gsrc] >= mn * (1 - 1e-12)) and (mx == 0.0 or np.all(r[gsrc] <= mx * (1 + 1e-12)))
+        ctx.set_range_crop(1e6, 0.0)                             # nothing survives
+        gp, gc, gsrc = ctx.preprocess(xyz, t, frames.T_il, states, 0.5)
+        assert len(gp) == 0 and len(gsrc) == 0
+        with pytest.raises(capi.EskfError):
+            ctx.set_range_crop(5.0, 1.0)
+        ctx.set_range_crop(0.0, 0.0)                             # off again: the plain result
+        op, oc, osrc = oracle.preprocess(xyz, t, frames.T_il, states, 0.5)
+        gp, gc, gsrc = ctx.preprocess(xyz, t, frames.T_il, states, 0.5)
+        np.testing.assert_array_equal(gsrc, osrc)
+        np.testing.assert_array_equal(gp, op)
+    finally:
+        ctx.set_range_crop(0.0, 0.0)
+
+
 # ------------------------------------------------------------ registration
 def test_linearize_correspondences_and_Hb(ctx, oracle, frames):
     om, gm = frames.build_maps(oracle, capi, ctx, 4)

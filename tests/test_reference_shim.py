@@ -268,6 +268,64 @@ def test_preprocess_matches(ref, case, voxel):
     assert np.median(np.abs(rc - oc).reshape(len(rc), -1).max(axis=1)) < med
 
 
+def unsorted_stamps(t, seed=3):
+    """Ring-major style stamps: the sweep's stamps permuted in blocks, so they are not monotonic
+    (the reference's deskew, src/CloudPreprocessor.cpp:54-61, scans them linearly whatever their order)."""
+    rng = np.random.default_rng(seed)
+    blocks = np.array_split(np.arange(len(t)), 37)
+    order = np.concatenate([blocks[k] for k in rng.permutation(len(blocks))])
+    return t[order].copy()
+
+
+def test_preprocess_with_unsorted_stamps_matches(ref):
+    """per-point stamps that are not non-decreasing.  The oracle (and the CUDA path, see
+    tests/test_gpu_parity.py) must follow the reference's forward linear scan, not a binary search."""
+    xyz, t, states = sweep_and_states(7, late_states=3)
+    tu = unsorted_stamps(t)
+    assert np.any(np.diff(tu) < 0)
+    T_il = S.default_T_il()
+    op, oc, _ = O.preprocess(xyz, tu, T_il, states, 0.5)
+    rp, rc = ref.preprocess(xyz, tu, T_il, states, 0.5)
+    assert len(rp) == len(op) > 1000
+    (op, oc), (rp, rc) = rows_sorted(op, oc), rows_sorted(rp, rc)
+    if exact(ref):
+        np.testing.assert_array_equal(rp, op)
+    else:
+        assert np.abs(rp - op).max() < 1e-12
+    # and the result differs from the sorted-stamp one: the test exercises a different segmentation
+    sp, _, _ = O.preprocess(xyz, t, T_il, states, 0.5)
+    assert len(sp) != len(op) or np.abs(rows_sorted(sp, np.zeros((len(sp), 3, 3)))[0] - op).max() > 1e-6
+
+
+def test_range_crop_definition(ref):
+    """The range crop the oracle defines (the reference has none): equal to running the reference's
+    transform + deskew on the whole sweep, erasing the out-of-range points, then the reference's own
+    downsample + covariance step on what is left; off by default."""
+    xyz, t, states = sweep_and_states(7, late_states=3)
+    T_il = S.default_T_il()
+    r = np.linalg.norm(xyz, axis=1)
+    lo, hi = float(np.quantile(r, 0.2)), float(np.quantile(r, 0.8))
+    op, oc, osrc = O.preprocess(xyz, t, T_il, states, 0.5, min_range=lo, max_range=hi)
+    assert len(op) > 500 and np.all(r[osrc] >= lo) and np.all(r[osrc] <= hi)
+    p0, _, s0 = O.preprocess(xyz, t, T_il, states, 0.5)
+    assert not np.all((r[s0] >= lo) & (r[s0] <= hi))            # the uncropped run keeps out-of-range points
+    # composition on the reference side: its own deskew of the full sweep (voxel size tiny: every point
+    # survives the reference's downsample step, giving the deskewed positions), then its downsample on the rest
+    keep = ((xyz[:, 0] * xyz[:, 0] + xyz[:, 1] * xyz[:, 1]) + xyz[:, 2] * xyz[:, 2] >= lo * lo) & \
+           ((xyz[:, 0] * xyz[:, 0] + xyz[:, 1] * xyz[:, 1]) + xyz[:, 2] * xyz[:, 2] <= hi * hi)
+    pd = O.deskew(O.transform_cloud(xyz, None, T_il)[0], t, states)
+    rp, rc = ref.preprocess(pd[keep], t[keep], np.eye(4), None, 0.5)
+    assert len(rp) == len(op)
+    (a, ac), (b, bc) = rows_sorted(op, oc), rows_sorted(rp, rc)
+    np.testing.assert_array_equal(a, b)
+    assert np.abs(ac - bc).max() < 5e-8
+    # max_range 0 = unbounded; (0, 0) = off
+    q, _, qs = O.preprocess(xyz, t, T_il, states, 0.5, min_range=lo)
+    assert np.all(r[qs] >= lo) and np.any(r[qs] > hi)
+    z, _, zs = O.preprocess(xyz, t, T_il, states, 0.5, min_range=0.0, max_range=0.0)
+    np.testing.assert_array_equal(zs, s0)
+
+
 # ----------------------------------------------------------- ErrorStateKF.cpp
 def test_filter_predict_update_match(ref, frames):
     om, rm = build_maps(ref, frames, 4)
