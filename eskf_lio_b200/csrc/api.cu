@@ -42,11 +42,13 @@ int ctx_pinned(eskf_ctx* ctx, size_t bytes, void** out) {
 }
 
 int wait_mail(eskf_ctx* ctx, const volatile unsigned* word, unsigned seq) {
+  // (acquire loads: the payload words the device wrote before the sequence word must not be read ahead
+  // of it on weakly ordered hosts -- Grace / aarch64; a plain load on x86)
   for (unsigned spins = 1;; ++spins) {
-    if (*word == seq) return ESKF_OK;
+    if (__atomic_load_n(const_cast<const unsigned*>(word), __ATOMIC_ACQUIRE) == seq) return ESKF_OK;
     if ((spins & 2047u) == 0u) {  // every few microseconds: is the stream still busy?
       const cudaError_t q = cudaStreamQuery(ctx->stream);
-      if (q == cudaSuccess) return *word == seq ? ESKF_OK : 1;
+      if (q == cudaSuccess) return __atomic_load_n(const_cast<const unsigned*>(word), __ATOMIC_ACQUIRE) == seq ? ESKF_OK : 1;
       if (q != cudaErrorNotReady) {
         set_error("stream error while waiting for a kernel result: %s", cudaGetErrorString(q));
         return ESKF_ERR_CUDA;

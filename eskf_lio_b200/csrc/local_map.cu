@@ -154,6 +154,12 @@ __global__ void __launch_bounds__(128) insert_runs_kernel(InsertParams P) {
     const int kx = static_cast<int>(compact3(mk >> 2)) + m0;
     const int ky = static_cast<int>(compact3(mk >> 1)) + m1;
     const int kz = static_cast<int>(compact3(mk)) + m2;
+    if (!(coord_in_range(kx) && coord_in_range(ky) && coord_in_range(kz))) {
+      // outside the 21-bit key range: pack_key would alias a real voxel.  Dropped and counted, like
+      // the sort-free path does (eskf_map_size reports ESKF_ERR_RANGE)
+      atomicAdd(P.d_count + 3, static_cast<unsigned long long>(j1 - j0));
+      continue;
+    }
     bool is_new;
     const uint32_t s = find_or_claim(P.tags, P.slots, P.n_slots, pack_key(kx, ky, kz), &is_new);
     if (s == kNoSlot) {
@@ -531,7 +537,10 @@ int rebuild(eskf_map* m, uint64_t new_slots, int evict, const double* pos, doubl
   } else {
     ESKF_TRY(alloc_table(ctx, new_slots, &nt, &ns, &nm));
   }
-  ESKF_CUDA(cudaMemsetAsync(m->d_count, 0, 3 * sizeof(unsigned long long), ctx->stream));  // [3] is sticky
+  // [0] survivors and [2] removed are recounted; [1] table-full and [3] key-range errors are sticky
+  // until a caller has seen them (eskf_map_size): a rebuild must not swallow a pending overflow
+  ESKF_CUDA(cudaMemsetAsync(m->d_count, 0, sizeof(unsigned long long), ctx->stream));
+  ESKF_CUDA(cudaMemsetAsync(m->d_count + 2, 0, sizeof(unsigned long long), ctx->stream));
   RehashParams P;
   P.old_tags = m->tags;
   P.old_slots = m->slots;
@@ -583,8 +592,9 @@ int rebuild(eskf_map* m, uint64_t new_slots, int evict, const double* pos, doubl
   ++m->version;
   m->count_upper = h[0];
   if (removed) *removed = h[2];
-  if (h[1] != 0) {
-    set_error("voxel table overflow during rebuild");
+  if (h[1] != 0) {  // (also an overflow of an earlier insert nobody has asked about: reported once)
+    cudaMemsetAsync(m->d_count + 1, 0, sizeof(unsigned long long), ctx->stream);
+    set_error("voxel table overflow (%llu runs dropped by an insert or by this rebuild)", h[1]);
     return ESKF_ERR_CAPACITY;
   }
   return ESKF_OK;
@@ -822,6 +832,7 @@ int eskf_map_size(eskf_map* m, uint64_t* n_voxels) {
   *n_voxels = h[0];
   m->count_upper = h[0];
   if (h[1] != 0) {
+    cudaMemsetAsync(m->d_count + 1, 0, sizeof(unsigned long long), ctx->stream);  // reported once
     set_error("voxel table overflowed (%llu runs dropped)", h[1]);
     return ESKF_ERR_CAPACITY;
   }

@@ -53,7 +53,11 @@ public:
     create();
   }
 
-  ~LocalMap() {eskf_map_destroy(map_);}
+  ~LocalMap()
+  {
+    const auto guard = GpuContext::lock();
+    eskf_map_destroy(map_);
+  }
   LocalMap(const LocalMap &) = delete;
   LocalMap & operator=(const LocalMap &) = delete;
 
@@ -181,6 +185,7 @@ public:
 private:
   void create()
   {
+    context_ = GpuContext::share();  // the map's context must outlive the map (static / global odometries)
     gpuCheck(
       eskf_map_create(
         GpuContext::get(), voxelSize_, static_cast<uint32_t>(maxNumPointsPerVoxel_), capacityHint_,
@@ -216,6 +221,7 @@ private:
   bool verbose_ = true;
   bool lastInserted_ = false;
   uint64_t lastRemoved_ = 0;
+  std::shared_ptr<GpuContext> context_;  // declared before map_: destroyed after it
   eskf_map * map_ = nullptr;
 };
 }  // namespace ESKF_LIO

@@ -20,6 +20,7 @@
 #define ESKF_LIO_B200_ODOMETRY_HPP_
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <memory>
 
@@ -87,6 +88,7 @@ public:
       if (lidarMeas.has_value()) {lidarMeas_ = lidarMeas.value();}
     }
     if (lidarMeas_ == nullptr) {return false;}
+    const auto guard = GpuContext::lock();  // (feedLidar may be uploading from the subscriber's thread)
 
     const double lidarEndTime = lidarMeas_->endTime;
     lidarClock_ = lidarEndTime;
@@ -137,6 +139,7 @@ public:
     auto measurement = std::make_shared<LidarMeasurement>();
     auto cloud = std::make_shared<PointCloud>();
     if (deviceResident_) {
+      const auto guard = GpuContext::lock();  // (the subscriber thread's entry into the shared context)
       cloud->device_ = rawPool_.acquire(n);
       gpuCheck(eskf_cloud_upload_f32(cloud->device_.get(), xyz, n), "eskf_cloud_upload_f32");
       measurement->pointTimeView = pointTime;  // the caller keeps both buffers until the frame is consumed
@@ -183,7 +186,7 @@ private:
   }
 
   bool initialized_ = false;
-  bool exitFlag_ = false;
+  std::atomic<bool> exitFlag_{false};  // setExit() comes from another thread (src/main.cpp:63-68)
   ImuBuffer imuBuffer_;
   CloudBuffer cloudBuffer_;
   std::shared_ptr<ErrorStateKF> kalmanFilter_;

@@ -179,13 +179,25 @@ def test_insert_list_path_equals_sorted_path(ctx, oracle, frames):
     assert oc.max() == 120
 
 
-def test_key_range_error(ctx):
-    gm = capi.Map(ctx, 0.01, 10, 64)
-    pts = np.array([[0.0, 0.0, 0.0], [2.0e4, 0.0, 0.0]])  # 2e6 voxels > 2^20
-    gm.insert(pts, np.repeat(np.eye(3)[None], 2, axis=0), np.eye(4))
-    with pytest.raises(capi.EskfError) as e:
-        gm.size()
-    assert e.value.status == 5
+@pytest.mark.parametrize("sorted_path", [0, 1])
+def test_key_range_error(ctx, sorted_path):
+    """A point whose voxel coordinate leaves the 21-bit key range is dropped and reported on BOTH insert
+    paths (the sorted path used to fold it into an aliased voxel), the in-range points of the
+    batch land where they belong."""
+    ctx.set_option("map_insert_sorted", sorted_path)
+    try:
+        gm = capi.Map(ctx, 0.01, 10, 64)
+        pts = np.array([[0.0, 0.0, 0.0], [2.0e4, 0.0, 0.0], [0.015, 0.0, 0.0]])  # 2e6 voxels > 2^20
+        gm.insert(pts, np.repeat(np.eye(3)[None], 3, axis=0), np.eye(4))
+        with pytest.raises(capi.EskfError) as e:
+            gm.size()
+        assert e.value.status == 5
+        keys, hit, count, mean, _ = gm.query(pts[[0, 2]])
+        assert hit.all() and count.tolist() == [1, 1]
+        np.testing.assert_array_equal(mean, pts[[0, 2]])
+        assert keys.tolist() == [[0, 0, 0], [1, 0, 0]]
+    finally:
+        ctx.set_option("map_insert_sorted", 0)
 
 
 # -------------------------------------------------------------- preprocess
