@@ -519,6 +519,13 @@ __device__ __forceinline__ uint2 ldg_u2_hint(const void* p, uint64_t pol) {
   asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
   return v;
 }
+__device__ __forceinline__ uint4 ldg_u4_hint(const void* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ float2 ldg_f2_hint(const void* p, uint64_t pol) {
   float2 v;
   asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
@@ -540,6 +547,11 @@ constexpr unsigned kFlagNoRecPrefetch = 4u;    // no prefetch.global.L2::evict_l
 constexpr unsigned kFlagFiltPolicyShift = 3u;  // bits 3-4: filter windows: 0 evict_normal, 1 evict_first, 2 evict_last
 constexpr unsigned kFlagStoreFirst = 32u;      // position write-back marked evict_first
 constexpr unsigned kFlagCovAllLanes = 64u;     // every lane loads its source covariance (a coalesced stream)
+// depth 8 ablations (timing experiments only: results are wrong with any of them set)
+constexpr unsigned kFlagNoProbe = 256u;        // no filter probes: every point misses
+constexpr unsigned kFlagNoGather = 512u;       // probes, but candidates are dropped: no record / covariance gathers, no algebra
+constexpr unsigned kFlagNoStore = 1024u;       // transformed positions are not written back
+constexpr unsigned kFlagNoPrefetch = 2048u;    // no L2 prefetch of the positions
 
 // generic-proxy writes (other SMs' position stores of the previous iteration, acquired through the
 // iteration hand-off) -> this thread's async-proxy reads
@@ -768,10 +780,7 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
   auto window4 = [&](const Slim& q) -> uint4 {
     if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
     if (use_filter) {
-      const uint8_t* w = P.filt + (q.home & ~7u);
-      const uint2 lo = ldg_u2_hint(w, pol_filt);
-      const uint2 hi = ldg_u2_hint(w + 8, pol_filt);  // (the filter is padded: no wrap)
-      return make_uint4(lo.x, lo.y, hi.x, hi.y);
+      return ldg_u4_hint(P.filt + q.home, pol_filt);  // the home is bucket-aligned: the 16 filter bytes of its bucket
     }
     const uint32_t b0 = q.home & ~(kTagAlign - 1u);
     return load_tag_window(P.tags, b0, wrap4(b0));
@@ -1044,6 +1053,7 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
 struct RingState {   // per warp, lives across the passes of one launch
   unsigned issued;   // bulk loads issued so far   (slot = n % kRing, parity = (n / kRing) & 1)
   unsigned consumed;
+  unsigned phase;    // depth 9: bit s = the parity slot s's mbarrier completes next (flips per LOADED tile)
 };
 
 template <typename F, int NW>
@@ -1187,10 +1197,7 @@ __device__ __forceinline__ double accumulate_points_resident(const AlignParams& 
   };
   auto window = [&](const Slim& q) -> uint4 {
     if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
-    const uint8_t* b = P.filt + (q.home & ~7u);
-    const uint2 lo = ldg_u2_hint(b, pol_filt);
-    const uint2 hi = ldg_u2_hint(b + 8, pol_filt);  // (the filter is padded: no wrap)
-    return make_uint4(lo.x, lo.y, hi.x, hi.y);
+    return ldg_u4_hint(P.filt + q.home, pol_filt);  // the home is bucket-aligned: the 16 filter bytes of its bucket
   };
   auto scan = [&](Slim& q, uint4 w) {
     if (q.tag == 0u) return;
@@ -1451,10 +1458,7 @@ __device__ __forceinline__ double accumulate_points_roles(const AlignParams& P, 
     };
     auto window = [&](const Slim& q) -> uint4 {
       if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
-      const uint8_t* w = P.filt + (q.home & ~7u);
-      const uint2 lo = ldg_u2_hint(w, pol_filt);
-      const uint2 hi = ldg_u2_hint(w + 8, pol_filt);  // (the filter is padded: no wrap)
-      return make_uint4(lo.x, lo.y, hi.x, hi.y);
+      return ldg_u4_hint(P.filt + q.home, pol_filt);  // the home is bucket-aligned: the 16 filter bytes of its bucket
     };
     // candidate slot of q given its first window (kNoCand: the voxel is not in the map)
     auto scan = [&](const Slim& q, uint4 w) -> uint32_t {
@@ -1792,10 +1796,7 @@ __device__ __forceinline__ double accumulate_points_split(const AlignParams& P, 
     };
     auto window = [&](const Slim& q) -> uint4 {
       if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
-      const uint8_t* w = P.filt + (q.home & ~7u);
-      const uint2 lo = ldg_u2_hint(w, pol_filt);
-      const uint2 hi = ldg_u2_hint(w + 8, pol_filt);  // (the filter is padded: no wrap)
-      return make_uint4(lo.x, lo.y, hi.x, hi.y);
+      return ldg_u4_hint(P.filt + q.home, pol_filt);  // the home is bucket-aligned: the 16 filter bytes of its bucket
     };
     auto scan = [&](const Slim& q, uint4 w) -> uint32_t {
       if (q.tag == 0u) return kNoCand;
@@ -1971,6 +1972,384 @@ __device__ __forceinline__ double accumulate_points_split(const AlignParams& P, 
       rec = nrec;
       j += NW;
     }
+  }
+  return acc;
+}
+
+
+// ------------------------------------------------------------------------
+// Large clouds (depth 8): the depth-4 register pipeline with the candidate
+// correspondences PARKED per warp until there are 32 of them.
+//
+// What depths 5-7 taught (profiles/r2_align_experiments.md): the kernel is bound
+// by instruction issue and latency, not by HBM; the per-point algebra + the
+// reduce-scatter (~430 of the ~700 warp instructions of a depth-4 trip) run for
+// 32 lanes of which 27 % have a correspondence on the dense config; and every
+// form of cross-warp hand-over (queues, fences, barriers) costs more than the
+// dense algebra saves.  So every warp stays on its own, as in depth 4, but a
+// trip only LOOKS UP its tile: transform, key, 8-bit filter window (requested a
+// trip ahead), scan.  Lanes with a candidate park 10 words (position, offset
+// from the voxel centre, key, slot, point index) in the warp's own ring in
+// shared memory — no atomics, no fences: only this warp touches it — and once 32
+// are parked the warp pops them as ONE dense batch: record + source covariance
+// loads go out, and the batch is linearised when the next one is ready to go (or
+// at the end of the pass), i.e. ~4 trips later on the dense config.  The landing
+// registers of the gathers are therefore always full, the algebra and the
+// 31-shuffle reduce-scatter run once per 32 correspondences instead of once per
+// 32 points.
+constexpr unsigned kPark = 128;  // entries of a warp's ring (a trip parks at most 32, a pop takes 32)
+constexpr int kRing9 = 6;        // depth 9: tiles of positions in flight per warp
+constexpr unsigned kWarpBytes9 = 10u * kPark * 4u + kRing9 * kTileBytes + 32u;  // parked words | ring | tile ids
+
+// RING > 0: the raw positions arrive through a per-warp ring of RING tiles filled by cp.async.bulk
+// (3 x 256 B per tile, completion on an mbarrier, L2 evict-first) and requested RING trips before they
+// are used: with lookup-only trips (~0.5 us) one tile per warp in flight (12 KB per SM) held the
+// position stream to ~1.2 TB/s (ablation, profiles/r2_align_experiments.md).  RING == 0: register loads
+// one trip ahead + an L2 prefetch.
+template <typename F, int NW, int RING>
+__device__ __forceinline__ double accumulate_points_parked(const AlignParams& P, const double* sT, const F* sR,
+                                                           bool first, bool write_hit, uint32_t* park /* [10][kPark] */,
+                                                           double* ring_sm /* [RING][96] */, unsigned* tq /* [RING] */,
+                                                           uint64_t* wbar /* [RING] */, RingState& ring) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned wglobal = blockIdx.x * NW + (threadIdx.x >> 5);
+  const unsigned wstride = gridDim.x * NW;
+  const double* sx = first ? P.x0 : P.wx;
+  const double* sy = first ? P.y0 : P.wy;
+  const double* sz = first ? P.z0 : P.wz;
+  const unsigned n_tiles = (P.n + 31u) / 32u;
+  const double inv_voxel = 1.0 / P.voxel;
+  const uint64_t pol_rec = l2_policy(P.flags & kFlagRecPolicyMask);
+  const uint64_t pol_filt = l2_policy((P.flags >> kFlagFiltPolicyShift) & 3u);
+  const bool rec_prefetch = (P.flags & kFlagNoRecPrefetch) == 0u;
+
+  // tiles: fixed stride for the first 13/16 of a pass, then tickets (see accumulate_points_pipelined)
+  const bool dynamic = P.dynamic_tiles != 0 && n_tiles >= 8u * wstride;
+  const unsigned k_static = dynamic ? (n_tiles - n_tiles * 3u / 16u) / wstride : 0xffffffffu;
+  const unsigned dyn_base = dynamic ? k_static * wstride : 0u;
+  const unsigned chunk = static_cast<unsigned>(P.ticket_chunk);
+  unsigned k_next = 0;
+  unsigned tk_cur = 0, tk_next = 0;
+  auto next_tile = [&]() -> unsigned {
+    unsigned t;
+    if (k_next < k_static) {
+      t = wglobal + k_next * wstride;
+    } else {
+      const unsigned sub = (k_next - k_static) & (chunk - 1u);
+      if (sub == 0u) {
+        tk_cur = tk_next;  // (waits for the atomic issued >= one call ago)
+        if (lane == 0) tk_next = atomicAdd(&P.st->tile_counter, chunk);
+      }
+      t = dyn_base + __shfl_sync(0xffffffffu, tk_cur, 0) + sub;
+    }
+    if (t > n_tiles) t = n_tiles;
+    ++k_next;
+    if (k_next == k_static && lane == 0) tk_next = atomicAdd(&P.st->tile_counter, chunk);  // first chunk
+    return t;
+  };
+  // the positions of a statically dealt tile are pulled into L2 a few trips ahead (3 x 256 B, 64 B per
+  // lane of lanes 0..11): a lookup trip is shorter than an HBM round trip
+  const bool abl_noprobe = (P.flags & kFlagNoProbe) != 0u, abl_nogather = (P.flags & kFlagNoGather) != 0u;
+  const bool abl_nostore = (P.flags & kFlagNoStore) != 0u, abl_noprefetch = (P.flags & kFlagNoPrefetch) != 0u;
+  auto prefetch_pos = [&](unsigned k) {
+    const unsigned tp = wglobal + k * wstride;
+    if (!abl_noprefetch && k < k_static && tp < n_tiles && lane < 24u) {  // one 32 B sector per lane: 3 x 256 B
+      const double* base = lane < 8u ? sx : lane < 16u ? sy : sz;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + static_cast<size_t>(tp) * 32u + 4u * (lane & 7u)));
+    }
+  };
+
+  struct Slim {
+    F px, py, pz, dx, dy, dz;
+    uint32_t klo, khi, home, tag;  // tag: 8-bit filter tag, 0 = no lookup
+    unsigned i;                    // point index (>= P.n: none)
+  };
+  struct Entry {
+    F px, py, pz, dx, dy, dz;
+    uint32_t klo, khi, cand, idx;
+  };
+  struct RecRegs {
+    uint2 key;
+    float4 pa, pc;
+    float2 pd;
+    float4 s4;
+    float2 s2;
+  };
+  auto load_pos = [&](unsigned tile, double& x, double& y, double& z) {
+    const unsigned i = tile * 32u + lane;
+    x = y = z = 0.0;
+    if (tile < n_tiles && i < P.n) {
+      x = first ? __ldcs(sx + i) : __ldcg(sx + i);
+      y = first ? __ldcs(sy + i) : __ldcg(sy + i);
+      z = first ? __ldcs(sz + i) : __ldcg(sz + i);
+    }
+  };
+  auto xform = [&](unsigned tile, double x, double y, double z, Slim& q) {
+    const unsigned i = tile * 32u + lane;
+    q.tag = 0u;
+    q.home = 0u;
+    q.i = 0xffffffffu;
+    if (tile >= n_tiles || i >= P.n) return;
+    q.i = i;
+    transform_point_rn(sT, x, y, z);
+    if (!abl_nostore) {
+      P.wx[i] = x;
+      P.wy[i] = y;
+      P.wz[i] = z;
+    }
+    const int kx = voxel_coord(x, P.voxel, inv_voxel);
+    const int ky = voxel_coord(y, P.voxel, inv_voxel);
+    const int kz = voxel_coord(z, P.voxel, inv_voxel);
+    if (coord_in_range(kx) && coord_in_range(ky) && coord_in_range(kz)) {
+      const uint64_t key = pack_key(kx, ky, kz);
+      const SlotAddr ad = slot_addr(key, P.n_slots);
+      q.klo = static_cast<uint32_t>(key);
+      q.khi = static_cast<uint32_t>(key >> 32);
+      q.home = ad.home;
+      q.tag = filter_tag(ad.tag);
+      q.px = F(x); q.py = F(y); q.pz = F(z);
+      // the residual against the voxel mean is formed relative to the voxel centre
+      q.dx = F(x - __dmul_rn(static_cast<double>(kx) + 0.5, P.voxel));
+      q.dy = F(y - __dmul_rn(static_cast<double>(ky) + 0.5, P.voxel));
+      q.dz = F(z - __dmul_rn(static_cast<double>(kz) + 0.5, P.voxel));
+    }
+  };
+  auto window = [&](const Slim& q) -> uint4 {
+    if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
+    if (abl_noprobe) return make_uint4(q.klo & 0u, 0u, 0u, 0u);
+    return ldg_u4_hint(P.filt + q.home, pol_filt);  // the home is bucket-aligned: the 16 filter bytes of its bucket
+  };
+  auto scan = [&](const Slim& q, uint4 w) -> uint32_t {
+    if (q.tag == 0u) return kNoCand;
+    uint32_t b0 = q.home & ~7u;
+    uint32_t r = scan_filter_window(w, q.home & 7u, q.tag);
+    uint32_t scanned = 16u - (q.home & 7u);
+    while (r == kMore && scanned < P.n_slots) {
+      b0 += 16u;
+      if (b0 >= P.n_slots) b0 -= P.n_slots;
+      const uint2 lo = __ldg(reinterpret_cast<const uint2*>(P.filt + b0));
+      const uint2 hi = __ldg(reinterpret_cast<const uint2*>(P.filt + b0 + 8));
+      r = scan_filter_window(make_uint4(lo.x, lo.y, hi.x, hi.y), 0u, q.tag);
+      scanned += 16u;
+    }
+    if (r >= 16u) return kNoCand;
+    uint32_t c = b0 + r;
+    if (c >= P.n_slots) c -= P.n_slots;
+    return c;
+  };
+
+  // ---- the warp's ring of parked candidates (SoA: field f of entry e at park[f * kPark + e % kPark])
+  unsigned head = 0, tail = 0;  // entries [head, tail) are parked (warp-uniform)
+  auto park_hits = [&](const Slim& q, uint32_t cand) {
+    const bool has = cand != kNoCand;
+    const unsigned mask = __ballot_sync(0xffffffffu, has);
+    if (write_hit && !has && q.i < P.n) P.hit[q.i] = 0;
+    if (has) {
+      uint32_t* w = park + ((tail + __popc(mask & ((1u << lane) - 1u))) & (kPark - 1u));
+      w[0] = __float_as_uint(static_cast<float>(q.px));
+      w[kPark] = __float_as_uint(static_cast<float>(q.py));
+      w[2 * kPark] = __float_as_uint(static_cast<float>(q.pz));
+      w[3 * kPark] = __float_as_uint(static_cast<float>(q.dx));
+      w[4 * kPark] = __float_as_uint(static_cast<float>(q.dy));
+      w[5 * kPark] = __float_as_uint(static_cast<float>(q.dz));
+      w[6 * kPark] = q.klo;
+      w[7 * kPark] = q.khi;
+      w[8 * kPark] = cand;
+      w[9 * kPark] = q.i;
+    }
+    tail += __popc(mask);
+    __syncwarp();  // parked entries are read by other lanes of this warp
+  };
+  // pop up to 32 parked entries as a dense batch and send its gathers off
+  auto pop_batch = [&](Entry& e, RecRegs& r) {
+    const unsigned avail = tail - head;
+    const unsigned take = avail < 32u ? avail : 32u;
+    e.cand = kNoCand;
+    r.key = make_uint2(0u, 0u);
+    if (lane < take) {
+      const uint32_t* w = park + ((head + lane) & (kPark - 1u));
+      e.px = F(__uint_as_float(w[0])); e.py = F(__uint_as_float(w[kPark])); e.pz = F(__uint_as_float(w[2 * kPark]));
+      e.dx = F(__uint_as_float(w[3 * kPark])); e.dy = F(__uint_as_float(w[4 * kPark]));
+      e.dz = F(__uint_as_float(w[5 * kPark]));
+      e.klo = w[6 * kPark]; e.khi = w[7 * kPark]; e.cand = w[8 * kPark]; e.idx = w[9 * kPark];
+      const float4* rec = reinterpret_cast<const float4*>(P.slots + e.cand);
+      if (rec_prefetch) prefetch_record(rec);  // (evict_last: the voxels a registration keeps touching stay in L2)
+      r.key = ldg_u2_hint(rec, pol_rec);
+      r.pa = ldg_f4_hint(rec + 1, pol_rec);
+      r.pc = ldg_f4_hint(rec + 2, pol_rec);
+      r.pd = ldg_f2_hint(rec + 3, pol_rec);
+      r.s4 = __ldcs(P.c4 + e.idx);
+      r.s2 = __ldcs(P.c2 + e.idx);
+    }
+    head += take;
+    __syncwarp();  // the slots may be parked over from here on
+  };
+  double acc = 0.0;
+  F v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = F(0);
+  auto compute = [&](const Entry& e, const RecRegs& r) {
+    float4 pa = r.pa, pc = r.pc;
+    float2 pd = r.pd;
+    bool hit = false;
+    if (e.cand != kNoCand) {
+      hit = r.key.x == e.klo && r.key.y == e.khi;
+      if (!hit) {  // 8-bit filter collision (1/255 per occupied probe): walk on, slowly
+        const uint64_t key = (static_cast<uint64_t>(e.khi) << 32) | e.klo;
+        const SlotAddr ad = slot_addr(key, P.n_slots);
+        const VoxelSlot* far = resolve_probe_filter(P.filt, P.slots, P.n_slots, key,
+                                                    next_slot(e.cand, P.n_slots), filter_tag(ad.tag));
+        if (far != nullptr) {
+          hit = true;
+          pa = __ldg(reinterpret_cast<const float4*>(far) + 1);
+          pc = __ldg(reinterpret_cast<const float4*>(far) + 2);
+          pd = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float4*>(far) + 3));
+        }
+      }
+      if (write_hit) P.hit[e.idx] = hit ? 1 : 0;
+    }
+    if (hit) {
+      F cr[6];
+      rotate_sym<F>(sR, F(r.s4.x), F(r.s4.y), F(r.s4.z), F(r.s4.w), F(r.s2.x), F(r.s2.y), cr);
+      point_terms<F, true>(e.px, e.py, e.pz, e.dx - F(pa.x), e.dy - F(pa.y), e.dz - F(pa.z),
+                           cr[0] + F(pc.x), cr[1] + F(pc.y), cr[2] + F(pc.z), cr[3] + F(pc.w),
+                           cr[4] + F(pd.x), cr[5] + F(pd.y), v);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 28; ++k) v[k] = F(0);
+    }
+    acc += static_cast<double>(warp_reduce_scatter32<F>(v, lane));
+  };
+
+  // ---- the lookup pipeline.  Across the loop's back edge a warp has in flight: the filter window of
+  // tile A (requested a full trip ago, scanned this trip), the raw positions of tile B (register loads
+  // issued a trip ago, or the head of the bulk-copy ring) and possibly a batch of gathers.
+  const uint64_t pol_stream = l2_policy_evict_first();
+  auto ring_issue = [&](unsigned t) {  // request the positions of tile t into the ring's next slot
+    const unsigned slot = ring.issued % (RING > 0 ? RING : 1);
+    if (lane == 0) tq[slot] = t;
+    if (t < n_tiles) {
+      if (lane == 0) {
+        double* dst = ring_sm + slot * 96u;
+        uint64_t* bar = wbar + slot;
+        mbar_arrive_expect_tx(bar, kTileBytes);
+        bulk_load(dst, sx + static_cast<size_t>(t) * 32u, 256u, bar, pol_stream);
+        bulk_load(dst + 32, sy + static_cast<size_t>(t) * 32u, 256u, bar, pol_stream);
+        bulk_load(dst + 64, sz + static_cast<size_t>(t) * 32u, 256u, bar, pol_stream);
+      }
+    }
+    ++ring.issued;
+  };
+  auto ring_consume = [&](unsigned& t, double& x, double& y, double& z) {  // oldest outstanding tile
+    const unsigned slot = ring.consumed % (RING > 0 ? RING : 1);
+    const unsigned parity = (ring.phase >> slot) & 1u;
+    __syncwarp();
+    t = tq[slot];
+    x = y = z = 0.0;
+    if (t < n_tiles) {
+      ring.phase ^= 1u << slot;
+      uint64_t* bar = wbar + slot;
+      if (!mbar_try_wait(bar, parity)) {
+        unsigned spins = 0;
+        while (!mbar_try_wait(bar, parity)) {
+          __nanosleep(20);
+          if (++spins > kSpinLimit) {
+            atomicExch(&P.st->error, 3u);
+            break;
+          }
+        }
+      }
+      const double* src = ring_sm + slot * 96u;
+      x = src[lane];
+      y = src[32 + lane];
+      z = src[64 + lane];
+    }
+    ++ring.consumed;
+  };
+  constexpr unsigned kAhead = 4;  // RING == 0: trips the L2 prefetch of the positions runs ahead
+  unsigned tile_a, tile_b = 0;
+  Slim qa, qb;
+  uint4 ta, tb;
+  double rx = 0.0, ry = 0.0, rz = 0.0;
+  unsigned trips = 2;
+  if constexpr (RING > 0) {
+    // (a slot's mbarrier completes a phase only when a load was issued for it: ring.phase tracks the
+    // parity per slot; slots that carried a tile id past the end change nothing)
+    if (!first && lane == 0) fence_proxy_async();  // other SMs' generic-proxy position stores -> these bulk reads
+    for (int d = 0; d < RING; ++d) ring_issue(next_tile());
+    double ax, ay, az;
+    ring_consume(tile_a, ax, ay, az);
+    xform(tile_a, ax, ay, az, qa);
+    ta = window(qa);
+    __syncwarp();
+    ring_issue(next_tile());
+  } else {
+#pragma unroll
+    for (unsigned k = 0; k < kAhead; ++k) prefetch_pos(k);
+    tile_a = next_tile();
+    tile_b = next_tile();
+    double ax, ay, az;
+    load_pos(tile_a, ax, ay, az);
+    load_pos(tile_b, rx, ry, rz);
+    xform(tile_a, ax, ay, az, qa);
+    ta = window(qa);
+  }
+  Entry be;
+  RecRegs br;
+  bool in_flight = false;
+  while (tile_a < n_tiles) {
+    // ---- 1. tile B: positions have arrived; transform, key, request its window; then the positions of
+    // a tile further on
+    if constexpr (RING > 0) {
+      ring_consume(tile_b, rx, ry, rz);
+      xform(tile_b, rx, ry, rz, qb);
+      tb = window(qb);
+      __syncwarp();  // every lane has read (and used) its entry of the slot that is refilled now
+      ring_issue(next_tile());
+    } else {
+      xform(tile_b, rx, ry, rz, qb);
+      tb = window(qb);
+    }
+    unsigned tile_c = 0;
+    if constexpr (RING == 0) {
+      tile_c = next_tile();
+      load_pos(tile_c, rx, ry, rz);
+      prefetch_pos(trips + kAhead - 1u);
+      ++trips;
+    }
+    // ---- 3. tile A: its window was requested a trip ago; scan, park the candidates
+    {
+      uint32_t cand = scan(qa, ta);
+      if (abl_nogather) {  // (ablation: the probe's result must stay live)
+        if (cand != kNoCand) acc += 1.0;
+        cand = kNoCand;
+      }
+      park_hits(qa, cand);
+    }
+    // ---- 4. 32 candidates parked: linearise the batch in flight, send the next one off
+    if (tail - head >= 32u) {
+      if (in_flight) compute(be, br);
+      pop_batch(be, br);
+      in_flight = true;
+    }
+    qa = qb;
+    ta = tb;
+    tile_a = tile_b;
+    if constexpr (RING == 0) tile_b = tile_c;
+  }
+  if constexpr (RING > 0) {
+    // drain: the ring still holds RING slots whose tile ids are past the end (nothing was loaded)
+    for (int d = 0; d < RING; ++d) {
+      unsigned t_;
+      double x_, y_, z_;
+      ring_consume(t_, x_, y_, z_);
+    }
+  }
+  // ---- end of the pass: what is in flight, then what is still parked
+  if (in_flight) compute(be, br);
+  while (tail != head) {
+    pop_batch(be, br);
+    compute(be, br);
   }
   return acc;
 }
@@ -2433,7 +2812,7 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
   AlignState* st = P.st;
   const int max_it = P.fixed_iterations > 0 ? P.fixed_iterations : P.max_iteration;
 
-  RingState ring = {0u, 0u};
+  RingState ring = {0u, 0u, 0u};
   double* wsm = nullptr;
   uint64_t* wbar = nullptr;
   HitQueue* hq = nullptr;
@@ -2451,6 +2830,12 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
     wsm = reinterpret_cast<double*>(s_dyn);  // the CTA's resident tiles
     hq = reinterpret_cast<HitQueue*>(s_dyn + static_cast<size_t>(P.k_res) * kTileBytes);
     if (t == 0) hq->tail = 0u;
+  }
+  if constexpr (DEPTH == 9) {
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + static_cast<size_t>(NW) * kWarpBytes9);
+    if (t < NW * kRing9) mbar_init(bars + t, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
   }
   if constexpr (DEPTH == 5) {
     const unsigned per_warp = static_cast<unsigned>(P.k_res + kRing) * 96u;  // doubles
@@ -2472,7 +2857,20 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
   for (int it = 0; it < max_it; ++it) {
     ESKF_STAMP(blockIdx.x == 0 && t == 0, 0);
     double acc;
-    if constexpr (DEPTH == 7) {
+    if constexpr (DEPTH == 9) {
+      // per warp: [10][kPark] parked words | [kRing9][96] doubles | [kRing9] tile ids (padded to 16 B); the
+      // rings' mbarriers after the last warp's area
+      unsigned char* wbase = s_dyn + static_cast<size_t>(t >> 5) * kWarpBytes9;
+      acc = accumulate_points_parked<F, NW, kRing9>(
+          P, s_T, s_R, it == 0, P.hit != nullptr && it == 0, reinterpret_cast<uint32_t*>(wbase),
+          reinterpret_cast<double*>(wbase + 10u * kPark * 4u),
+          reinterpret_cast<unsigned*>(wbase + 10u * kPark * 4u + kRing9 * kTileBytes),
+          reinterpret_cast<uint64_t*>(s_dyn + static_cast<size_t>(NW) * kWarpBytes9) + (t >> 5) * kRing9, ring);
+    } else if constexpr (DEPTH == 8) {
+      acc = accumulate_points_parked<F, NW, 0>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0,
+                                               reinterpret_cast<uint32_t*>(s_dyn) + static_cast<size_t>(t >> 5) * 10u * kPark,
+                                               nullptr, nullptr, nullptr, ring);
+    } else if constexpr (DEPTH == 7) {
       acc = accumulate_points_split<F, NW, 2>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0, hl, &s_tail);
     } else if constexpr (DEPTH == 6) {
       // pass set-up: empty queue; the share of consumer warps follows the hit rate of the last pass
@@ -2635,7 +3033,7 @@ struct Variant {
 // (ptxas budgets registers for the CTA size rounded up to a multiple of 128 threads).
 enum { V_F32_N1 = 0, V_F32_N7, V_F64_N1, V_F64_N7, V_F32_N1_T384, V_F32_N1_T768, V_F32_N1_T768D4,
        V_F32_N1_T640D4, V_F32_N1_T512D4, V_F32_N1_T640R, V_F32_N1_T512R, V_F32_N1_T640Q, V_F32_N1_T512Q,
-       V_F32_N1_T640S, V_F32_N1_T512S, V_COUNT };
+       V_F32_N1_T640S, V_F32_N1_T512S, V_F32_N1_T640P, V_F32_N1_T512P, V_F32_N1_T768P, V_F32_N1_T640B, V_F32_N1_T512B, V_COUNT };
 
 // measured on B200, dense config (2M pts, 10 iterations per launch):
 //   U=1/3 CTAs 1.267 ms, U=1/4 CTAs 1.246 ms, U=2/3 CTAs 1.303 ms,
@@ -2691,6 +3089,18 @@ Variant g_variants[V_COUNT] = {
      reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 640, 4>), 640, 640, 1, 3},
     {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 512, 7>),
      reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 512, 4>), 512, 512, 1, 3},
+    // depth 8 (depth 4's register pipeline, candidates parked per warp until 32 are there)
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 640, 8>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 640, 4>), 640, 640, 1, 4},
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 512, 8>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 512, 4>), 512, 512, 1, 4},
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 768, 8>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 768, 4>), 768, 768, 1, 4},
+    // depth 9 (depth 8 with the positions streamed through a cp.async.bulk ring)
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 640, 9>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 640, 4>), 640, 640, 1, 5},
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 512, 9>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 512, 4>), 512, 512, 1, 5},
 };
 
 // Large clouds (>= ctx->opt_align_fat_points, default 2^17) take one fat CTA per SM: fewer partial
@@ -2704,9 +3114,9 @@ int variant_index(const eskf_ctx* ctx, const AlignArgs& a) {
   if (threads == 0) threads = fat ? ESKF_ALIGN_FAT_T : kT;
   const int depth = ctx->opt_align_depth != 0 ? ctx->opt_align_depth : 4;
   switch (threads) {
-    case 768: return depth == 4 ? V_F32_N1_T768D4 : V_F32_N1_T768;
-    case 640: return depth == 7 ? V_F32_N1_T640S : depth == 6 ? V_F32_N1_T640Q : depth == 5 ? V_F32_N1_T640R : V_F32_N1_T640D4;
-    case 512: return depth == 7 ? V_F32_N1_T512S : depth == 6 ? V_F32_N1_T512Q : depth == 5 ? V_F32_N1_T512R : V_F32_N1_T512D4;
+    case 768: return depth == 8 ? V_F32_N1_T768P : depth == 4 ? V_F32_N1_T768D4 : V_F32_N1_T768;
+    case 640: return depth == 9 ? V_F32_N1_T640B : depth == 8 ? V_F32_N1_T640P : depth == 7 ? V_F32_N1_T640S : depth == 6 ? V_F32_N1_T640Q : depth == 5 ? V_F32_N1_T640R : V_F32_N1_T640D4;
+    case 512: return depth == 9 ? V_F32_N1_T512B : depth == 8 ? V_F32_N1_T512P : depth == 7 ? V_F32_N1_T512S : depth == 6 ? V_F32_N1_T512Q : depth == 5 ? V_F32_N1_T512R : V_F32_N1_T512D4;
     case 384: return V_F32_N1_T384;
     default: return V_F32_N1;
   }
@@ -2801,6 +3211,15 @@ int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, T
     const int vi = variant_index(ctx, a);
     if ((vi == V_F32_N1_T768D4 || vi == V_F32_N1_T640D4 || vi == V_F32_N1_T512D4) && ctx->opt_align_filter && dyn_smem)
       ESKF_TRY(map_probe_filter(m, &P->filt));  // depth 4 on the 8-bit filter
+  }
+  if (var.depth5 == 5 && dyn_smem) {
+    const size_t nw = static_cast<size_t>(var.threads / 32);
+    *dyn_smem = nw * kWarpBytes9 + nw * kRing9 * sizeof(uint64_t);
+    ESKF_TRY(map_probe_filter(m, &P->filt));
+  }
+  if (var.depth5 == 4 && dyn_smem) {
+    *dyn_smem = static_cast<size_t>(var.threads / 32) * 10u * kPark * sizeof(uint32_t);
+    ESKF_TRY(map_probe_filter(m, &P->filt));
   }
   if (var.depth5 == 3 && dyn_smem) {
     // hit list: as many 40 B entries as shared memory holds (a multiple of 32), the rest of a CTA's
