@@ -242,11 +242,11 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
   if (const char* e = getenv("ESKF_MAPPED_RESULTS")) ctx->opt_mapped_results = atoi(e) != 0;
   if (const char* e = getenv("ESKF_ALIGN_BLOCK")) {
     const int v = atoi(e);
-    if (v == 0 || v == 256 || v == 384 || v == 512 || v == 640 || v == 768) ctx->opt_align_block = v;
+    if (v == 0 || v == 256 || v == 384 || v == 448 || v == 512 || v == 640 || v == 768) ctx->opt_align_block = v;
   }
   if (const char* e = getenv("ESKF_ALIGN_DEPTH")) {
     const int v = atoi(e);
-    if (v == 0 || (v >= 3 && v <= 9)) ctx->opt_align_depth = v;
+    if (v == 0 || (v >= 3 && v <= 10)) ctx->opt_align_depth = v;
   }
   if (const char* e = getenv("ESKF_ALIGN_RESIDENT")) ctx->opt_align_resident = atoi(e);
   if (const char* e = getenv("ESKF_ALIGN_FAT_POINTS")) ctx->opt_align_fat_points = atoll(e);
@@ -360,11 +360,12 @@ int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
   } else if (n == "map_insert_sorted") {
     ctx->opt_insert_sorted = value != 0;
   } else if (n == "align_block") {
-    ESKF_REQUIRE(value == 0 || value == 256 || value == 384 || value == 512 || value == 640 || value == 768,
-                 "align_block must be 0 (by cloud size), 256, 384, 512, 640 or 768");
+    ESKF_REQUIRE(value == 0 || value == 256 || value == 384 || value == 448 || value == 512 || value == 640 ||
+                     value == 768,
+                 "align_block must be 0 (by cloud size), 256, 384, 448, 512, 640 or 768");
     ctx->opt_align_block = static_cast<int>(value);
   } else if (n == "align_depth") {
-    ESKF_REQUIRE(value == 0 || (value >= 3 && value <= 9), "align_depth must be 0 (default) or 3 .. 9");
+    ESKF_REQUIRE(value == 0 || (value >= 3 && value <= 10), "align_depth must be 0 (default) or 3 .. 10");
     ctx->opt_align_depth = static_cast<int>(value);
   } else if (n == "align_resident") {
     ESKF_REQUIRE(value >= -1 && value <= 1024, "align_resident must be -1 (auto) or a tile count");
@@ -384,6 +385,9 @@ int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
     ctx->opt_align_xchg_ll = value != 0;
   } else if (n == "align_ll") {
     ctx->opt_align_ll = value != 0;
+  } else if (n == "align_dyn16") {
+    ESKF_REQUIRE(value >= 1 && value <= 12, "align_dyn16 must be in [1, 12]");
+    ctx->opt_align_dyn16 = static_cast<int>(value);
   } else if (n == "align_ticket_chunk") {
     ESKF_REQUIRE(value == 1 || value == 2 || value == 4, "align_ticket_chunk must be 1, 2 or 4");
     ctx->opt_align_chunk = static_cast<int>(value);

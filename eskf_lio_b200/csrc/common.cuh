@@ -101,7 +101,14 @@ __host__ __device__ __forceinline__ uint64_t hash_key(uint64_t k) {
 // tried and measured SLOWER on B200 — 1.69 vs 1.20 ms per 10-iteration dense
 // launch — linear probing through interleaved bricks lengthens miss chains.)
 using tag_t = uint16_t;  // 2 B/slot: the tag array of 16M slots is 32 MB
-constexpr uint32_t kBucket = 16;
+// homes aligned to buckets of kBucket slots (a power of two <= 64; 1 = plain linear probing).  16 makes a
+// probe window one aligned 16 B load, but measured a net loss on B200: the register-pipelined kernel got 5 %
+// slower on the grown 0.1 m table and 9 % on the compact one (longer runs inside a bucket), the
+// parked-candidate kernel was unchanged (profiles/r2_align_experiments.md)
+#ifndef ESKF_BUCKET
+#define ESKF_BUCKET 1
+#endif
+constexpr uint32_t kBucket = ESKF_BUCKET;
 struct SlotAddr {
   uint32_t home;
   tag_t tag;

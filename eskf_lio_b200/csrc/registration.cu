@@ -49,7 +49,9 @@ constexpr bool kAssign = kFold == 1 && ESKF_TERMS_ASSIGN != 0;
 #define ESKF_COV_PREFETCH 0
 #endif
 #ifndef ESKF_POS_PREFETCH
-#define ESKF_POS_PREFETCH 0  // 4-deep rotation: L2-prefetch the positions of the tile this many trips ahead (0 = off)
+// 4-deep rotation: L2-prefetch the positions of the (statically dealt) tile this many trips ahead (0 = off).
+// Round 2, 512-thread CTAs on the 8-bit filter: 0 -> 86.5, 4 -> 85.4 us per dense iteration.
+#define ESKF_POS_PREFETCH 4
 #endif
 #ifndef ESKF_POS_AHEAD
 #define ESKF_POS_AHEAD 0  // 4-deep rotation: 1 = keep two tiles of raw positions in flight instead of one
@@ -96,6 +98,7 @@ struct AlignParams {
   int fixed_iterations;
   int dynamic_tiles;  // 1: warps pull tiles from a counter (load-balanced, summation order varies)
   int ticket_chunk;   // tiles per ticket in that dynamic tail (1, 2 or 4)
+  int dyn16;          // sixteenths of a pass dealt by tickets (eskf_ctx option align_dyn16, default 3)
   AlignState* st;
   double* partials;  // [G][kAcc]
   double* sums;      // [kAcc] (single_pass output / solve input)
@@ -526,6 +529,19 @@ __device__ __forceinline__ uint4 ldg_u4_hint(const void* p, uint64_t pol) {
                : "l"(p), "l"(pol));
   return v;
 }
+// the 16 filter bytes from slot (home & ~7) on (the filter is padded by 16 entries: no wrap): one aligned
+// 16 B load when homes are bucket-aligned (common.cuh kBucket), else two 8 B loads
+__device__ __forceinline__ uint4 ldg_u4_hint(const void* p, uint64_t pol);
+__device__ __forceinline__ uint4 filter_window(const uint8_t* filt, uint32_t home, uint64_t pol) {
+  if constexpr (kBucket >= 16u) {
+    return ldg_u4_hint(filt + home, pol);
+  } else {
+    const uint8_t* w = filt + (home & ~7u);
+    const uint2 lo = ldg_u2_hint(w, pol);
+    const uint2 hi = ldg_u2_hint(w + 8, pol);
+    return make_uint4(lo.x, lo.y, hi.x, hi.y);
+  }
+}
 __device__ __forceinline__ float2 ldg_f2_hint(const void* p, uint64_t pol) {
   float2 v;
   asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
@@ -680,7 +696,7 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
   // Clouds with fewer than 8 tiles per warp, or dynamic_tiles == 0
   // (ESKF_ALIGN_DYNAMIC=0), run fully static: bit-reproducible summation order.
   const bool dynamic = P.dynamic_tiles != 0 && n_tiles >= 8u * wstride;  // small clouds: nothing to balance
-  const unsigned k_static = dynamic ? (n_tiles - n_tiles * 3u / 16u) / wstride : 0xffffffffu;
+  const unsigned k_static = dynamic ? (n_tiles - n_tiles * static_cast<unsigned>(P.dyn16) / 16u) / wstride : 0xffffffffu;
   const unsigned dyn_base = dynamic ? k_static * wstride : 0u;
   // A ticket is worth `chunk` consecutive tiles (fewer same-address atomics, and chunk trips of
   // lead time): lane 0 keeps the chunk in use and the one requested ahead.
@@ -780,7 +796,7 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
   auto window4 = [&](const Slim& q) -> uint4 {
     if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
     if (use_filter) {
-      return ldg_u4_hint(P.filt + q.home, pol_filt);  // the home is bucket-aligned: the 16 filter bytes of its bucket
+      return filter_window(P.filt, q.home, pol_filt);
     }
     const uint32_t b0 = q.home & ~(kTagAlign - 1u);
     return load_tag_window(P.tags, b0, wrap4(b0));
@@ -1082,7 +1098,7 @@ __device__ __forceinline__ double accumulate_points_resident(const AlignParams& 
   const bool dynamic = P.dynamic_tiles != 0 && n_tiles >= 8u * wstride;
   unsigned k_static = 0xffffffffu;
   if (dynamic) {
-    k_static = (n_tiles - n_tiles * 3u / 16u) / wstride;
+    k_static = (n_tiles - n_tiles * static_cast<unsigned>(P.dyn16) / 16u) / wstride;
     if (k_static < K) k_static = K;
   }
   const unsigned dyn_base = dynamic ? k_static * wstride : 0u;
@@ -1197,7 +1213,7 @@ __device__ __forceinline__ double accumulate_points_resident(const AlignParams& 
   };
   auto window = [&](const Slim& q) -> uint4 {
     if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
-    return ldg_u4_hint(P.filt + q.home, pol_filt);  // the home is bucket-aligned: the 16 filter bytes of its bucket
+    return filter_window(P.filt, q.home, pol_filt);
   };
   auto scan = [&](Slim& q, uint4 w) {
     if (q.tag == 0u) return;
@@ -1458,7 +1474,7 @@ __device__ __forceinline__ double accumulate_points_roles(const AlignParams& P, 
     };
     auto window = [&](const Slim& q) -> uint4 {
       if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
-      return ldg_u4_hint(P.filt + q.home, pol_filt);  // the home is bucket-aligned: the 16 filter bytes of its bucket
+      return filter_window(P.filt, q.home, pol_filt);
     };
     // candidate slot of q given its first window (kNoCand: the voxel is not in the map)
     auto scan = [&](const Slim& q, uint4 w) -> uint32_t {
@@ -1796,7 +1812,7 @@ __device__ __forceinline__ double accumulate_points_split(const AlignParams& P, 
     };
     auto window = [&](const Slim& q) -> uint4 {
       if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
-      return ldg_u4_hint(P.filt + q.home, pol_filt);  // the home is bucket-aligned: the 16 filter bytes of its bucket
+      return filter_window(P.filt, q.home, pol_filt);
     };
     auto scan = [&](const Slim& q, uint4 w) -> uint32_t {
       if (q.tag == 0u) return kNoCand;
@@ -2025,7 +2041,7 @@ __device__ __forceinline__ double accumulate_points_parked(const AlignParams& P,
 
   // tiles: fixed stride for the first 13/16 of a pass, then tickets (see accumulate_points_pipelined)
   const bool dynamic = P.dynamic_tiles != 0 && n_tiles >= 8u * wstride;
-  const unsigned k_static = dynamic ? (n_tiles - n_tiles * 3u / 16u) / wstride : 0xffffffffu;
+  const unsigned k_static = dynamic ? (n_tiles - n_tiles * static_cast<unsigned>(P.dyn16) / 16u) / wstride : 0xffffffffu;
   const unsigned dyn_base = dynamic ? k_static * wstride : 0u;
   const unsigned chunk = static_cast<unsigned>(P.ticket_chunk);
   unsigned k_next = 0;
@@ -2117,7 +2133,7 @@ __device__ __forceinline__ double accumulate_points_parked(const AlignParams& P,
   auto window = [&](const Slim& q) -> uint4 {
     if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
     if (abl_noprobe) return make_uint4(q.klo & 0u, 0u, 0u, 0u);
-    return ldg_u4_hint(P.filt + q.home, pol_filt);  // the home is bucket-aligned: the 16 filter bytes of its bucket
+    return filter_window(P.filt, q.home, pol_filt);
   };
   auto scan = [&](const Slim& q, uint4 w) -> uint32_t {
     if (q.tag == 0u) return kNoCand;
@@ -2561,21 +2577,81 @@ __device__ __forceinline__ double compose_elem(const double* step, const double*
 // (every CTA tracks it in shared memory, see align_kernel: no global load).
 // Falls back to the pivoted restatement of Eigen's LDLT when a pivot is not
 // safely positive.
-__device__ __noinline__ void solve_and_update_fast(const AlignParams& P, const double* S, const double* Told,
-                                                   int it, double* sm) {
-  const unsigned lane = threadIdx.x & 31;
-  double* stp = sm + 36;  // 12: step
-  double* tot = sm + 60;  // 12: new total
-  AlignState* st = P.st;
-  if (lane == 0) {
+// Utils::se3ToSE3 (src/Utils.cpp:56-63) for a Gauss-Newton step: |phi| < 0.5 rad takes sin / cos from their
+// series (|error| < 1e-22, no library call on the solver's critical path), larger angles the library path
+__device__ __forceinline__ void se3_to_SE3_small(const double* se3, double* T) {
+  const double rx = se3[3], ry = se3[4], rz = se3[5];
+  const double n2 = rx * rx + ry * ry + rz * rz;
+  if (n2 >= 0.25) {
+    se3_to_SE3(se3, T);
+    return;
+  }
+  const double angle = sqrt(n2);
+  double ax = rx, ay = ry, az = rz;
+  if (n2 > 0.0) {
+    const double ia = 1.0 / angle;
+    ax *= ia; ay *= ia; az *= ia;
+  }
+  // s = x (1 - n2/6 (1 - n2/20 (1 - ...))),  c = 1 - n2/2 (1 - n2/12 (1 - ...))
+  double ps = 1.0, pc = 1.0;
+#pragma unroll
+  for (int k = 9; k >= 1; --k) {
+    ps = 1.0 - n2 * (1.0 / static_cast<double>((2 * k) * (2 * k + 1))) * ps;
+    pc = 1.0 - n2 * (1.0 / static_cast<double>((2 * k - 1) * (2 * k))) * pc;
+  }
+  const double s = angle * ps, c = pc;
+  double J[9];
+  if (angle < 1e-6) {
+    J[0] = 1; J[1] = 0; J[2] = 0; J[3] = 0; J[4] = 1; J[5] = 0; J[6] = 0; J[7] = 0; J[8] = 1;
+  } else {
+    const double f1 = ps, f2 = (1.0 - c) / angle, g = 1.0 - f1;
+    J[0] = f1 + g * ax * ax;      J[1] = g * ax * ay - f2 * az; J[2] = g * ax * az + f2 * ay;
+    J[3] = g * ay * ax + f2 * az; J[4] = f1 + g * ay * ay;      J[5] = g * ay * az - f2 * ax;
+    J[6] = g * az * ax - f2 * ay; J[7] = g * az * ay + f2 * ax; J[8] = f1 + g * az * az;
+  }
+  T[9] = J[0] * se3[0] + J[1] * se3[1] + J[2] * se3[2];
+  T[10] = J[3] * se3[0] + J[4] * se3[1] + J[5] * se3[2];
+  T[11] = J[6] * se3[0] + J[7] * se3[1] + J[8] * se3[2];
+  const double cx = (1.0 - c) * ax, cy = (1.0 - c) * ay, cz = (1.0 - c) * az;
+  const double sxv = s * ax, syv = s * ay, szv = s * az;
+  double tmp = cx * ay;
+  T[1] = tmp - szv; T[3] = tmp + szv;
+  tmp = cx * az;
+  T[2] = tmp + syv; T[6] = tmp - syv;
+  tmp = cy * az;
+  T[5] = tmp - sxv; T[7] = tmp + sxv;
+  T[0] = cx * ax + c; T[4] = cy * ay + c; T[8] = cz * az + c;
+}
+
+constexpr int kStampSlots = 12;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define ESKF_SUBSTAMP(slot) \
+  do { if (P.stamps != nullptr) P.stamps[kStampSlots * it + (slot)] = globaltimer_ns(); } while (0)
+
+// the math: lane 0 of the calling warp; results in sm: [36..47] step, [60..71] new total, [84] done, [85] converged
+__device__ __noinline__ void solve_compute(const AlignParams& P, const double* S, const double* Told, int it,
+                                           double* sm) {
+  double* stp = sm + 36;
+  double* tot = sm + 60;
+  if ((threadIdx.x & 31) == 0) {
+    // (index map known at compile time: shared-memory loads with immediate offsets)
+    constexpr unsigned char kHmap[36] = {0, 1, 2,  6,  7,  8,  1, 3,  4,  9,  10, 11, 2, 4, 5,  12, 13, 14,
+                                         6, 9, 12, 15, 16, 17, 7, 10, 13, 16, 18, 19, 8, 11, 14, 17, 19, 20};
     double H[36], nb[6], se3[6], step[12];
 #pragma unroll
-    for (int e = 0; e < 36; ++e) H[e] = S[c_hmap[e]];
+    for (int e = 0; e < 36; ++e) H[e] = S[kHmap[e]];
 #pragma unroll
     for (int i = 0; i < 6; ++i) nb[i] = -S[21 + i];
+    ESKF_SUBSTAMP(8);
     // JTJ.ldlt().solve(-JTr), Registration.cpp:78
     if (!ldlt_solve6_nopivot(H, nb, se3)) ldlt_solve6(H, nb, se3);
-    se3_to_SE3(se3, step);
+    ESKF_SUBSTAMP(9);
+    se3_to_SE3_small(se3, step);
+    ESKF_SUBSTAMP(10);
     // totalTransform = transformIter * totalTransform (Registration.cpp:20)
 #pragma unroll
     for (int e = 0; e < 12; ++e) tot[e] = compose_elem(step, Told, e);
@@ -2588,9 +2664,19 @@ __device__ __noinline__ void solve_and_update_fast(const AlignParams& P, const d
     const int done = P.fixed_iterations > 0 ? (it + 1 >= P.fixed_iterations) : (conv || it + 1 >= P.max_iteration);
     sm[84] = static_cast<double>(done);
     sm[85] = static_cast<double>(conv);
+    ESKF_SUBSTAMP(11);
   }
   __syncwarp();
-  // state + traces, one word per lane
+}
+
+// the bookkeeping: state + trace words, one per lane.  Nothing here is needed by the other CTAs to start
+// their next pass (the dynamic-tile counter is reset ahead of the pose broadcast), so in the persistent
+// kernels it runs AFTER the broadcast.
+__device__ __forceinline__ void solve_store(const AlignParams& P, const double* S, int it, const double* sm) {
+  const unsigned lane = threadIdx.x & 31;
+  const double* stp = sm + 36;
+  const double* tot = sm + 60;
+  AlignState* st = P.st;
   for (int e = lane; e < 36; e += 32)
     if (P.trace_H) P.trace_H[36 * it + e] = S[c_hmap[e]];
   if (lane < 6 && P.trace_b) P.trace_b[6 * it + lane] = S[21 + lane];
@@ -2606,12 +2692,18 @@ __device__ __noinline__ void solve_and_update_fast(const AlignParams& P, const d
     st->n_corr = nc;
     st->iter = it + 1;
     st->converged = static_cast<int>(sm[85]);
-    st->tile_counter = 0u;
     st->done = static_cast<int>(sm[84]);
   }
   if (lane == 0 && sm[84] != 0.0 && P.mail != nullptr)
     publish_result(P, tot, it + 1, static_cast<int>(sm[85]), static_cast<unsigned long long>(S[27]));
   __syncwarp();
+}
+
+__device__ __forceinline__ void solve_and_update_fast(const AlignParams& P, const double* S, const double* Told,
+                                                      int it, double* sm) {
+  solve_compute(P, S, Told, it, sm);
+  if ((threadIdx.x & 31) == 12) P.st->tile_counter = 0u;
+  solve_store(P, S, it, sm);
 }
 
 // ---- flagged-word ("LL") broadcast of the next pose ------------------------
@@ -2626,8 +2718,9 @@ constexpr int kLLWords = 25;
 __device__ __forceinline__ void ll_publish(const AlignParams& P, const double* sm, int it) {
   const unsigned lane = threadIdx.x & 31;
   const double* stp = sm + 36;
-  __threadfence();  // this warp's state stores (tile counter reset ...) and, cumulatively, every
-                    // CTA's position stores acquired with the tickets, before the words below
+  // release: the tile-counter reset and, cumulatively, every CTA's position stores acquired with the
+  // tickets, before the words below (fence.acq_rel: __threadfence() is the costlier fence.sc)
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
   volatile unsigned long long* box = P.llbox;
   const unsigned long long flag = static_cast<unsigned long long>(it + 1) << 32;
   if (lane < kLLWords) {
@@ -2661,7 +2754,7 @@ __device__ __forceinline__ int ll_receive(const AlignParams& P, int it, double* 
     }
   }
   ok = __all_sync(0xffffffffu, ok);
-  __threadfence();  // acquire side: the other CTAs' position stores before this CTA's next pass
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");  // acquire side: the other CTAs' position stores before this CTA's next pass
   const unsigned pa = static_cast<unsigned>(a);
   const unsigned src = (2u * lane) & 31u;
   const unsigned lo = __shfl_sync(0xffffffffu, pa, src), hi = __shfl_sync(0xffffffffu, pa, src + 1u);
@@ -2788,13 +2881,8 @@ __device__ __forceinline__ bool exchange_sums_ll(const AlignParams& P, int it, d
   return *s_flag != 0;
 }
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 #define ESKF_STAMP(cond, slot) \
-  do { if (P.stamps != nullptr && (cond)) P.stamps[8 * it + (slot)] = globaltimer_ns(); } while (0)
+  do { if (P.stamps != nullptr && (cond)) P.stamps[kStampSlots * it + (slot)] = globaltimer_ns(); } while (0)
 
 template <typename F, int U, int NN, int MINB, int T = kT, int DEPTH = 3>
 __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
@@ -2923,16 +3011,23 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
       if (P.world > 1) ok = P.xchg_ll ? exchange_sums_ll(P, it, s_sum, &s_xchg, s_xw) : exchange_sums(P, it, s_sum, &s_xchg);
       ESKF_STAMP(t == 0, 4);
       if (t < 32) {
-        if (ok) solve_and_update_fast(P, s_sum, s_Ttot, it, s_solve);
-        __syncwarp();
-        ESKF_STAMP(t == 0, 5);
         // (on an exchange timeout st->error is set: the waiters below bail out)
-        if (ll) {
-          if (ok) ll_publish(P, s_solve, it);
-        } else if (t == 0) {
-          st_release_u32(&st->epoch, static_cast<unsigned>(it + 1));
+        if (ok) {
+          solve_compute(P, s_sum, s_Ttot, it, s_solve);
+          if (t == 12) st->tile_counter = 0u;  // (the one store the next pass needs, ahead of the broadcast)
         }
-        ESKF_STAMP(t == 0, 6);
+        ESKF_STAMP(t == 0, 5);
+        if (ll) {
+          if (ok) {
+            ll_publish(P, s_solve, it);       // the other CTAs go on from here ...
+            ESKF_STAMP(t == 0, 6);
+            solve_store(P, s_sum, it, s_solve);  // ... while the state and trace words are written
+          }
+        } else {
+          if (ok) solve_store(P, s_sum, it, s_solve);
+          if (t == 0) st_release_u32(&st->epoch, static_cast<unsigned>(it + 1));
+          ESKF_STAMP(t == 0, 6);
+        }
       }
     }
     // everyone waits for the solver (bounded spin).  LL: the lanes of warp 0 poll the flagged words
@@ -3013,6 +3108,250 @@ __global__ void __launch_bounds__(T, MINB) linearize_pass_kernel(AlignParams P, 
   }
 }
 
+
+// ------------------------------------------------------------------------
+// Large clouds (depth 10): one Gauss-Newton iteration = three launches.
+//
+// Every persistent variant above ends up with 16-20 warps per SM (96-128
+// registers for the gathers' landing zone and the algebra) and ~13 stall cycles
+// per issued instruction per warp: 26-41 % of the issue slots
+// (profiles/r2_align_experiments.md).  The lookup half of the work — transform,
+// key, hash, one 16 B filter probe — needs ~40 registers.  So the iteration is cut
+// where the register needs differ:
+//   mk_lookup_kernel   1536 threads per SM.  A CTA round = 16 tiles (one per warp);
+//                      candidates are staged in shared memory, then appended to a
+//                      hit list in HBM with ONE global atomic per round and
+//                      coalesced 4-byte-per-lane stores (SoA, 40 B per candidate);
+//   mk_gather_kernel   dense batches of 32 candidates from the list: records +
+//                      source covariances (next batch in flight while the current
+//                      one is linearised), block reduce, last CTA sums the partials;
+//   solve_kernel       [NVLink exchange of the sums] 6x6 solve, pose, convergence.
+// No cooperative launch, no in-kernel hand-off; the launches of an iteration are
+// queued back to back (the host looks at the convergence word every few iterations
+// only: kernels of iterations past convergence return at once).
+constexpr int kMkLookupT = 512;
+constexpr int kMkGatherT = 640;
+constexpr unsigned kMkStage = kMkLookupT;  // candidates a CTA round can produce
+
+struct MkList {  // the hit list: field f of entry e at words[f * cap + e]
+  uint32_t* words;
+  unsigned* count;  // entries appended in this iteration (reset by the solve kernel)
+  unsigned cap;
+};
+
+__global__ void __launch_bounds__(kMkLookupT, 3) mk_lookup_kernel(AlignParams P, MkList L, int it) {
+  __shared__ double s_T[12];
+  __shared__ uint32_t s_stage[10][kMkStage];
+  __shared__ unsigned s_n, s_base;
+  const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  constexpr unsigned NW = kMkLookupT / 32;
+  const AlignState* st = P.st;
+  if (it > 0 && ld_cg(&st->done) != 0) return;
+  const bool first = it == 0;
+  if (t < 12) s_T[t] = first ? P.guess[t] : ld_cg(&st->T_step[t]);
+  if (t == 0) s_n = 0u;
+  __syncthreads();
+  const double* sx = first ? P.x0 : P.wx;
+  const double* sy = first ? P.y0 : P.wy;
+  const double* sz = first ? P.z0 : P.wz;
+  const unsigned n_tiles = (P.n + 31u) / 32u;
+  const double inv_voxel = 1.0 / P.voxel;
+  const uint64_t pol_filt = l2_policy((P.flags >> kFlagFiltPolicyShift) & 3u);
+  const bool write_hit = P.hit != nullptr && first;
+  for (unsigned base_tile = blockIdx.x * NW; base_tile < n_tiles; base_tile += gridDim.x * NW) {
+    const unsigned tile = base_tile + warp;
+    const unsigned i = tile * 32u + lane;
+    uint32_t cand = kNoCand, klo = 0u, khi = 0u;
+    float px = 0.f, py = 0.f, pz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+    if (tile < n_tiles && i < P.n) {
+      double x = first ? __ldcs(sx + i) : __ldcg(sx + i);
+      double y = first ? __ldcs(sy + i) : __ldcg(sy + i);
+      double z = first ? __ldcs(sz + i) : __ldcg(sz + i);
+      transform_point_rn(s_T, x, y, z);
+      P.wx[i] = x;
+      P.wy[i] = y;
+      P.wz[i] = z;
+      const int kx = voxel_coord(x, P.voxel, inv_voxel);
+      const int ky = voxel_coord(y, P.voxel, inv_voxel);
+      const int kz = voxel_coord(z, P.voxel, inv_voxel);
+      if (coord_in_range(kx) && coord_in_range(ky) && coord_in_range(kz)) {
+        const uint64_t key = pack_key(kx, ky, kz);
+        const SlotAddr ad = slot_addr(key, P.n_slots);
+        const uint32_t t8 = filter_tag(ad.tag);
+        uint32_t b0 = ad.home & ~7u;
+        uint32_t r = scan_filter_window(filter_window(P.filt, ad.home, pol_filt), ad.home & 7u, t8);
+        uint32_t scanned = 16u - (ad.home & 7u);
+        while (r == kMore && scanned < P.n_slots) {
+          b0 += 16u;
+          if (b0 >= P.n_slots) b0 -= P.n_slots;
+          r = scan_filter_window(filter_window(P.filt, b0, pol_filt), 0u, t8);
+          scanned += 16u;
+        }
+        if (r < 16u) {
+          cand = b0 + r;
+          if (cand >= P.n_slots) cand -= P.n_slots;
+          klo = static_cast<uint32_t>(key);
+          khi = static_cast<uint32_t>(key >> 32);
+          px = static_cast<float>(x); py = static_cast<float>(y); pz = static_cast<float>(z);
+          // the residual against the voxel mean is formed relative to the voxel centre
+          dx = static_cast<float>(x - __dmul_rn(static_cast<double>(kx) + 0.5, P.voxel));
+          dy = static_cast<float>(y - __dmul_rn(static_cast<double>(ky) + 0.5, P.voxel));
+          dz = static_cast<float>(z - __dmul_rn(static_cast<double>(kz) + 0.5, P.voxel));
+        }
+      }
+      if (write_hit && cand == kNoCand) P.hit[i] = 0;
+    }
+    // stage the round's candidates in shared memory (one shared-memory atomic per warp)
+    const unsigned mask = __ballot_sync(0xffffffffu, cand != kNoCand);
+    unsigned wbase = 0;
+    if (lane == 0 && mask != 0u) wbase = atomicAdd(&s_n, static_cast<unsigned>(__popc(mask)));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (cand != kNoCand) {
+      const unsigned e = wbase + __popc(mask & ((1u << lane) - 1u));
+      s_stage[0][e] = __float_as_uint(px); s_stage[1][e] = __float_as_uint(py); s_stage[2][e] = __float_as_uint(pz);
+      s_stage[3][e] = __float_as_uint(dx); s_stage[4][e] = __float_as_uint(dy); s_stage[5][e] = __float_as_uint(dz);
+      s_stage[6][e] = klo; s_stage[7][e] = khi; s_stage[8][e] = cand; s_stage[9][e] = i;
+    }
+    __syncthreads();
+    // ... and append them to the list: one global atomic per round, coalesced stores
+    const unsigned cnt = s_n;
+    if (t == 0) s_base = cnt != 0u ? atomicAdd(L.count, cnt) : 0u;
+    __syncthreads();
+    const unsigned gbase = s_base;
+    if (t < cnt && gbase + t < L.cap) {
+#pragma unroll
+      for (int f = 0; f < 10; ++f) L.words[static_cast<size_t>(f) * L.cap + gbase + t] = s_stage[f][t];
+    }
+    if (t == 0) s_n = 0u;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kMkGatherT, 1) mk_gather_kernel(AlignParams P, MkList L, int it) {
+  constexpr int NW = kMkGatherT / 32;
+  __shared__ float s_R[9];
+  __shared__ double s_part[NW][32];
+  __shared__ double s_sum[kAcc];
+  __shared__ int s_flag;
+  const unsigned t = threadIdx.x, lane = t & 31, G = gridDim.x;
+  AlignState* st = P.st;
+  if (it > 0 && ld_cg(&st->done) != 0) return;
+  if (t < 9) s_R[t] = it == 0 ? static_cast<float>(P.guess[t]) : ld_cg(&st->Rf[t]);
+  __syncthreads();
+  unsigned total = ld_cg(L.count);
+  if (total > L.cap) total = L.cap;
+  const unsigned n_batches = (total + 31u) / 32u;
+  const uint64_t pol_rec = l2_policy(P.flags & kFlagRecPolicyMask);
+  const bool rec_prefetch = (P.flags & kFlagNoRecPrefetch) == 0u;
+  const bool write_hit = P.hit != nullptr && it == 0;
+  struct Entry {
+    float px, py, pz, dx, dy, dz;
+    uint32_t klo, khi, cand, idx;
+  };
+  struct RecRegs {
+    uint2 key;
+    float4 pa, pc;
+    float2 pd;
+    float4 s4;
+    float2 s2;
+  };
+  auto fetch = [&](unsigned j, Entry& e, RecRegs& r) {
+    const unsigned idx = j * 32u + lane;
+    e.cand = kNoCand;
+    r.key = make_uint2(0u, 0u);
+    if (j >= n_batches || idx >= total) return;
+    const uint32_t* w = L.words + idx;
+    const size_t pitch = L.cap;
+    e.px = __uint_as_float(ld_cg(w)); e.py = __uint_as_float(ld_cg(w + pitch)); e.pz = __uint_as_float(ld_cg(w + 2 * pitch));
+    e.dx = __uint_as_float(ld_cg(w + 3 * pitch)); e.dy = __uint_as_float(ld_cg(w + 4 * pitch));
+    e.dz = __uint_as_float(ld_cg(w + 5 * pitch));
+    e.klo = ld_cg(w + 6 * pitch); e.khi = ld_cg(w + 7 * pitch); e.cand = ld_cg(w + 8 * pitch); e.idx = ld_cg(w + 9 * pitch);
+    const float4* rec = reinterpret_cast<const float4*>(P.slots + e.cand);
+    if (rec_prefetch) prefetch_record(rec);
+    r.key = ldg_u2_hint(rec, pol_rec);
+    r.pa = ldg_f4_hint(rec + 1, pol_rec);
+    r.pc = ldg_f4_hint(rec + 2, pol_rec);
+    r.pd = ldg_f2_hint(rec + 3, pol_rec);
+    r.s4 = __ldcs(P.c4 + e.idx);
+    r.s2 = __ldcs(P.c2 + e.idx);
+  };
+  double acc = 0.0;
+  float v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = 0.f;
+  auto compute = [&](const Entry& e, const RecRegs& r) {
+    float4 pa = r.pa, pc = r.pc;
+    float2 pd = r.pd;
+    bool hit = false;
+    if (e.cand != kNoCand) {
+      hit = r.key.x == e.klo && r.key.y == e.khi;
+      if (!hit) {  // 8-bit filter collision: walk on, slowly
+        const uint64_t key = (static_cast<uint64_t>(e.khi) << 32) | e.klo;
+        const SlotAddr ad = slot_addr(key, P.n_slots);
+        const VoxelSlot* far = resolve_probe_filter(P.filt, P.slots, P.n_slots, key, next_slot(e.cand, P.n_slots),
+                                                    filter_tag(ad.tag));
+        if (far != nullptr) {
+          hit = true;
+          pa = __ldg(reinterpret_cast<const float4*>(far) + 1);
+          pc = __ldg(reinterpret_cast<const float4*>(far) + 2);
+          pd = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float4*>(far) + 3));
+        }
+      }
+      if (write_hit) P.hit[e.idx] = hit ? 1 : 0;
+    }
+    if (hit) {
+      float cr[6];
+      rotate_sym<float>(s_R, r.s4.x, r.s4.y, r.s4.z, r.s4.w, r.s2.x, r.s2.y, cr);
+      point_terms<float, true>(e.px, e.py, e.pz, e.dx - pa.x, e.dy - pa.y, e.dz - pa.z, cr[0] + pc.x, cr[1] + pc.y,
+                               cr[2] + pc.z, cr[3] + pc.w, cr[4] + pd.x, cr[5] + pd.y, v);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 28; ++k) v[k] = 0.f;
+    }
+    acc += static_cast<double>(warp_reduce_scatter32<float>(v, lane));
+  };
+  const unsigned wglobal = blockIdx.x * NW + (t >> 5), wstride = G * NW;
+  Entry cur, nxt;
+  RecRegs rec, nrec;
+  unsigned j = wglobal;
+  fetch(j, cur, rec);
+  while (j < n_batches) {
+    fetch(j + wstride, nxt, nrec);
+    compute(cur, rec);
+    cur = nxt;
+    rec = nrec;
+    j += wstride;
+  }
+  block_reduce_store<NW>(acc, s_part, P.partials + static_cast<size_t>(blockIdx.x) * kAcc);
+  if (t == 0) {
+    const unsigned ticket = atom_add_acq_rel(&st->block_counter, 1u);
+    s_flag = (ticket == G * static_cast<unsigned>(it + 1) - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_flag) {
+    final_reduce<NW>(P.partials, G, s_part, s_sum);
+    if (t < kAcc) P.sums[t] = s_sum[t];
+  }
+}
+
+// [NVLink exchange of the sums,] solve, pose, convergence; resets the hit list for the next iteration
+__global__ void __launch_bounds__(kMkGatherT) mk_solve_kernel(AlignParams P, MkList L, int it) {
+  __shared__ double s_solve[96];
+  __shared__ double s_in[kAcc];
+  __shared__ double s_old[12];
+  __shared__ unsigned s_xw[kMaxWorld * 2 * kAcc];
+  __shared__ int s_xchg;
+  const unsigned t = threadIdx.x;
+  if (it > 0 && ld_cg(&P.st->done) != 0) return;
+  if (t < kAcc) s_in[t] = ld_cg(P.sums + t);
+  if (t < 12) s_old[t] = (it == 0) ? P.guess[t] : ld_cg(&P.st->T_total[t]);
+  if (t == 0) *L.count = 0u;
+  __syncthreads();
+  bool ok = true;
+  if (P.world > 1) ok = P.xchg_ll ? exchange_sums_ll(P, it, s_in, &s_xchg, s_xw) : exchange_sums(P, it, s_in, &s_xchg);
+  if (t < 32 && ok) solve_and_update_fast(P, s_in, s_old, it, s_solve);
+}
+
 // kernel variants: (math type, points per lane U, neighbourhood, min CTAs/SM)
 struct Variant {
   void* align;
@@ -3033,7 +3372,7 @@ struct Variant {
 // (ptxas budgets registers for the CTA size rounded up to a multiple of 128 threads).
 enum { V_F32_N1 = 0, V_F32_N7, V_F64_N1, V_F64_N7, V_F32_N1_T384, V_F32_N1_T768, V_F32_N1_T768D4,
        V_F32_N1_T640D4, V_F32_N1_T512D4, V_F32_N1_T640R, V_F32_N1_T512R, V_F32_N1_T640Q, V_F32_N1_T512Q,
-       V_F32_N1_T640S, V_F32_N1_T512S, V_F32_N1_T640P, V_F32_N1_T512P, V_F32_N1_T768P, V_F32_N1_T640B, V_F32_N1_T512B, V_COUNT };
+       V_F32_N1_T640S, V_F32_N1_T512S, V_F32_N1_T640P, V_F32_N1_T512P, V_F32_N1_T768P, V_F32_N1_T640B, V_F32_N1_T512B, V_F32_N1_T448D4, V_F32_N1_T384D4, V_COUNT };
 
 // measured on B200, dense config (2M pts, 10 iterations per launch):
 //   U=1/3 CTAs 1.267 ms, U=1/4 CTAs 1.246 ms, U=2/3 CTAs 1.303 ms,
@@ -3050,7 +3389,7 @@ enum { V_F32_N1 = 0, V_F32_N7, V_F64_N1, V_F64_N7, V_F32_N1_T384, V_F32_N1_T768,
 // 1 x 768 85.1 / 158.2; a slower box: 3 x 256 105.5 / 162.8, 1 x 768 101.3 / 158.8, 1 x 640 with the
 // 4-deep rotation 93.6 / 148.7, 1 x 512 4-deep 102.3 / 147.8, 1 x 768 4-deep (spills at 80 registers)
 // 177.7 / 241.1  (profiles/r1_align_ab.md)
-#define ESKF_ALIGN_FAT_T 640  // CTA size for clouds >= kFatCtaPoints (256 | 384 | 512 | 640 | 768)
+#define ESKF_ALIGN_FAT_T 512  // CTA size of the large-cloud kernel (256 | 384 | 448 | 512 | 640 | 768); round 2, on the 8-bit filter: 512 threads (128 registers) 86.6 us per dense iteration, 640 (96 registers) 95.2
 #endif
 
 Variant g_variants[V_COUNT] = {
@@ -3101,6 +3440,11 @@ Variant g_variants[V_COUNT] = {
      reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 640, 4>), 640, 640, 1, 5},
     {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 512, 9>),
      reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 512, 4>), 512, 512, 1, 5},
+    // depth 4 with fewer, fatter threads (144 / 168 registers)
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 448, 4>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 448, 4>), 448, 448, 1},
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 384, 4>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 384, 4>), 384, 384, 1},
 };
 
 // Large clouds (>= ctx->opt_align_fat_points, default 2^17) take one fat CTA per SM: fewer partial
@@ -3117,7 +3461,8 @@ int variant_index(const eskf_ctx* ctx, const AlignArgs& a) {
     case 768: return depth == 8 ? V_F32_N1_T768P : depth == 4 ? V_F32_N1_T768D4 : V_F32_N1_T768;
     case 640: return depth == 9 ? V_F32_N1_T640B : depth == 8 ? V_F32_N1_T640P : depth == 7 ? V_F32_N1_T640S : depth == 6 ? V_F32_N1_T640Q : depth == 5 ? V_F32_N1_T640R : V_F32_N1_T640D4;
     case 512: return depth == 9 ? V_F32_N1_T512B : depth == 8 ? V_F32_N1_T512P : depth == 7 ? V_F32_N1_T512S : depth == 6 ? V_F32_N1_T512Q : depth == 5 ? V_F32_N1_T512R : V_F32_N1_T512D4;
-    case 384: return V_F32_N1_T384;
+    case 448: return V_F32_N1_T448D4;
+    case 384: return depth == 4 && ctx->opt_align_depth == 4 ? V_F32_N1_T384D4 : V_F32_N1_T384;
     default: return V_F32_N1;
   }
 }
@@ -3136,7 +3481,7 @@ TraceLayout trace_layout(int max_it) {
   L.o_nc = L.o_b + static_cast<size_t>(max_it) * 6 * 8;
   L.o_step = L.o_nc + static_cast<size_t>(max_it) * 8;
   L.o_stamps = L.o_step + static_cast<size_t>(max_it) * 12 * 8;
-  L.total = L.o_stamps + static_cast<size_t>(max_it) * 8 * 8;
+  L.total = L.o_stamps + static_cast<size_t>(max_it) * kStampSlots * 8;
   return L;
 }
 static_assert(sizeof(AlignState) <= 512, "AlignState grew past its slot");
@@ -3189,6 +3534,7 @@ int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, T
   P->fixed_iterations = a.fixed_iterations;
   P->dynamic_tiles = ctx->opt_align_dynamic;
   P->ticket_chunk = ctx->opt_align_chunk;
+  P->dyn16 = ctx->opt_align_dyn16;
   P->st = reinterpret_cast<AlignState*>(base + L->o_state);
   P->partials = ctx->partials.as<double>();
   P->sums = reinterpret_cast<double*>(base + L->o_sums);
@@ -3209,7 +3555,8 @@ int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, T
   P->xchg_ll = ctx->opt_align_xchg_ll;
   {
     const int vi = variant_index(ctx, a);
-    if ((vi == V_F32_N1_T768D4 || vi == V_F32_N1_T640D4 || vi == V_F32_N1_T512D4) && ctx->opt_align_filter && dyn_smem)
+    if ((vi == V_F32_N1_T768D4 || vi == V_F32_N1_T640D4 || vi == V_F32_N1_T512D4 || vi == V_F32_N1_T448D4 ||
+         vi == V_F32_N1_T384D4) && ctx->opt_align_filter && dyn_smem)
       ESKF_TRY(map_probe_filter(m, &P->filt));  // depth 4 on the 8-bit filter
   }
   if (var.depth5 == 5 && dyn_smem) {
@@ -3309,9 +3656,9 @@ int read_back(eskf_ctx* ctx, const AlignArgs& a, const TraceLayout& L, int max_i
     for (int k = 0; k < nit; ++k) {
       char line[256];
       int o = std::snprintf(line, sizeof line, "[eskf stamps] dev %d it %d:", ctx->device, k);
-      for (int j = 1; j < 8; ++j)
-        o += std::snprintf(line + o, sizeof line - static_cast<size_t>(o), " %.1f",
-                           (static_cast<double>(s8[8 * k + j]) - static_cast<double>(s8[8 * k])) * 1e-3);
+      for (int j = 1; j < kStampSlots; ++j)
+        o += std::snprintf(line + o, sizeof line - static_cast<size_t>(o), "%s%.1f", j == 8 ? " | solve: " : " ",
+                           (static_cast<double>(s8[kStampSlots * k + j]) - static_cast<double>(s8[kStampSlots * k])) * 1e-3);
       std::fprintf(stderr, "%s\n", line);
     }
   }
@@ -3357,7 +3704,32 @@ struct PendingAlign {
   TraceLayout L;
   int max_it = 0;
   unsigned mail_seq = 0;
+  // depth 10: the iterations are separate launches, queued a group at a time
+  bool mk = false;
+  AlignParams P;
+  MkList list;
+  int mk_next = 0;      // first iteration not queued yet
+  int mk_lookup_grid = 0, mk_gather_grid = 0;
 };
+
+constexpr int kMkGroup = 8;  // iterations queued between two looks at the convergence word
+
+// queue iterations [pd->mk_next, upto) of a depth-10 registration
+int mk_enqueue(eskf_ctx* ctx, PendingAlign* pd, int upto) {
+  for (int it = pd->mk_next; it < upto; ++it) {
+    if (pd->mk_lookup_grid > 0) {
+      mk_lookup_kernel<<<pd->mk_lookup_grid, kMkLookupT, 0, ctx->stream>>>(pd->P, pd->list, it);
+      ESKF_CUDA(cudaGetLastError());
+    }
+    mk_gather_kernel<<<pd->mk_gather_grid, kMkGatherT, 0, ctx->stream>>>(pd->P, pd->list, it);
+    ESKF_CUDA(cudaGetLastError());
+    mk_solve_kernel<<<1, kMkGatherT, 0, ctx->stream>>>(pd->P, pd->list, it);
+    ESKF_CUDA(cudaGetLastError());
+    count_launch(ctx, pd->mk_lookup_grid > 0 ? 3 : 2);
+  }
+  pd->mk_next = upto;
+  return ESKF_OK;
+}
 PendingAlign* pending(eskf_ctx* ctx) {
   if (!ctx->pending_align) ctx->pending_align = std::shared_ptr<void>(new PendingAlign(), [](void* p) {
     delete static_cast<PendingAlign*>(p);
@@ -3435,6 +3807,32 @@ int align_begin(eskf_ctx* ctx, const AlignArgs& a, const eskf_align_info* info) 
     ctx->l2_win_ptr = nullptr;
     ctx->l2_win_bytes = 0;
   }
+  pd->mk = false;
+  if (ctx->opt_align_depth == 10 && !a.fp64_math && a.neighbor_mode != 7 && a.cloud &&
+      static_cast<int64_t>(a.cloud->n) >= ctx->opt_align_fat_points) {
+    // depth 10: three launches per Gauss-Newton iteration (see mk_lookup_kernel)
+    const unsigned n = static_cast<unsigned>(a.cloud->n);
+    const unsigned n_tiles = (n + 31u) / 32u;
+    const unsigned cap = (n + 63u) / 64u * 64u + 64u;
+    ESKF_TRY(ctx->spill.ensure(static_cast<size_t>(10) * cap * sizeof(uint32_t)));
+    ESKF_TRY(ctx->partials.ensure(static_cast<size_t>(ctx->sm_count) * kAcc * sizeof(double)));
+    P.partials = ctx->partials.as<double>();
+    ESKF_TRY(map_probe_filter(a.map, &P.filt));
+    pd->mk = true;
+    pd->P = P;
+    pd->list.words = ctx->spill.as<uint32_t>();
+    pd->list.count = &P.st->tile_counter;  // (zeroed with the state; reset by every solve)
+    pd->list.cap = cap;
+    const unsigned rounds = (n_tiles + kMkLookupT / 32 - 1u) / (kMkLookupT / 32);
+    pd->mk_lookup_grid = static_cast<int>(rounds < static_cast<unsigned>(3 * ctx->sm_count) ? rounds : 3u * ctx->sm_count);
+    pd->mk_gather_grid = ctx->sm_count;
+    pd->mk_next = 0;
+    trace_mark(ctx, "start");
+    ESKF_TRY(mk_enqueue(ctx, pd, a.fixed_iterations > 0 ? max_it : (max_it < kMkGroup ? max_it : kMkGroup)));
+    trace_mark(ctx, "align");
+    pd->active = true;
+    return ESKF_OK;
+  }
   void* args[] = {&P};
   const Variant& var = g_variants[variant_index(ctx, a)];
   trace_mark(ctx, "start");
@@ -3459,6 +3857,20 @@ int align_end(eskf_ctx* ctx, double T_out[16], eskf_align_info* info) {
       info->n_corr_last = 0;
     }
     return ESKF_OK;
+  }
+  if (pd->mk) {
+    // more iterations to queue?  (the kernels of iterations past convergence return at once)
+    while (pd->mk_next < pd->max_it) {
+      ESKF_CUDA(cudaStreamSynchronize(ctx->stream));
+      int* h = nullptr;
+      ESKF_TRY(ctx_pinned(ctx, sizeof(AlignState), reinterpret_cast<void**>(&h)));
+      ESKF_CUDA(cudaMemcpyAsync(h, ctx->astate.p, sizeof(AlignState), cudaMemcpyDeviceToHost, ctx->stream));
+      ESKF_CUDA(cudaStreamSynchronize(ctx->stream));
+      const AlignState* hs = reinterpret_cast<const AlignState*>(h);
+      if (hs->done || hs->error) break;
+      const int upto = pd->mk_next + kMkGroup < pd->max_it ? pd->mk_next + kMkGroup : pd->max_it;
+      ESKF_TRY(mk_enqueue(ctx, pd, upto));
+    }
   }
   const int rc = read_back(ctx, pd->a, pd->L, pd->max_it, T_out, info, pd->mail_seq);
   trace_flush(ctx, "align");

@@ -608,7 +608,9 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
                 # depth 8: depth 4's register pipeline with the candidates parked per warp until 32 are there
                 (640, 8, 2, 1, -1, 1), (640, 8, 1, 0, -1, 0), (512, 8, 4, 1, -1, 1), (768, 8, 2, 1, -1, 1),
                 # depth 9: depth 8 with the positions streamed through a cp.async.bulk ring
-                (512, 9, 2, 1, -1, 1), (512, 9, 1, 0, -1, 0), (640, 9, 4, 1, -1, 1)]:
+                (512, 9, 2, 1, -1, 1), (512, 9, 1, 0, -1, 0), (640, 9, 4, 1, -1, 1),
+                # depth 10: three launches per iteration (high-occupancy lookup -> hit list in HBM -> dense gather -> solve)
+                (0, 10, 2, 1, -1, 1)]:
             c2.set_option("align_block", block)
             c2.set_option("align_depth", depth)
             c2.set_option("align_ticket_chunk", chunk)
@@ -630,7 +632,7 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
             dt, dr = pose_err(ro["T"], rq["T"])
             assert dt < POSE_T_TOL and dr < POSE_R_TOL, (tag, dt, dr)
         # the per-point correspondence flags of a cloud this size (depth 5, the 4-deep loop, 256-thread CTAs)
-        for block, depth, res in ((0, 0, -1), (512, 9, -1), (640, 8, -1), (768, 8, -1), (640, 7, 3), (640, 6, 0), (640, 5, 0), (640, 5, -1), (640, 4, -1), (256, 3, -1)):
+        for block, depth, res in ((0, 0, -1), (0, 10, -1), (512, 9, -1), (640, 8, -1), (768, 8, -1), (640, 7, 3), (640, 6, 0), (640, 5, 0), (640, 5, -1), (640, 4, -1), (256, 3, -1)):
             c2.set_option("align_block", block)
             c2.set_option("align_depth", depth)
             c2.set_option("align_resident", res)
@@ -660,7 +662,7 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
         with pytest.raises(capi.EskfError):
             c2.set_option("align_block", 500)
         with pytest.raises(capi.EskfError):
-            c2.set_option("align_depth", 10)
+            c2.set_option("align_depth", 11)
         with pytest.raises(capi.EskfError):
             c2.set_option("align_ticket_chunk", 3)
     finally:
