@@ -22,7 +22,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstdint>
 #include <memory>
+#include <vector>
 
 #include "ESKF_LIO/CloudPreprocessor.hpp"
 #include "ESKF_LIO/ErrorStateKF.hpp"
@@ -57,6 +59,58 @@ public:
   {
     localMap_->setClock([this] {return lidarClock_;});
     localMap_->setVerbose(false);
+    warmUp(config);
+  }
+
+  // Not in the reference: one synthetic 64k-point frame through the three device calls on a scratch
+  // map, so that scratch-buffer allocations, lazily loaded kernels and the first cooperative launch
+  // are paid at construction instead of by the first real frames (the 1000-frame run of round 1 had one
+  // frame at 3.9 ms; round 2 measured 2.8 ms on the first registration and <= 0.58 ms on every other frame).
+  static void warmUp(const Config & config)
+  {
+    const auto guard = GpuContext::lock();
+    eskf_ctx * ctx = GpuContext::get();
+    constexpr std::size_t kSide = 256, kN = kSide * kSide;  // one sweep's worth of points
+    std::vector<float> xyz(3 * kN);
+    std::uint32_t lcg = 12345u;
+    auto jitter = [&lcg] {
+        lcg = lcg * 1664525u + 1013904223u;
+        return (static_cast<float>(lcg >> 8) / 16777216.0f - 0.5f) * 0.04f;
+      };
+    for (std::size_t i = 0; i < kSide; ++i) {
+      for (std::size_t j = 0; j < kSide; ++j) {  // a floor and, folded up at one edge, a wall
+        float * p = &xyz[3 * (i * kSide + j)];
+        const float u = 0.2f * static_cast<float>(i) - 25.0f, v = 0.2f * static_cast<float>(j) - 25.0f;
+        p[0] = u + jitter();
+        p[1] = (j < 200 ? v : 15.0f) + jitter();
+        p[2] = (j < 200 ? -1.5f : -1.5f + 0.2f * static_cast<float>(j - 200)) + jitter();
+      }
+    }
+    eskf_cloud * raw = nullptr, * ds = nullptr;
+    eskf_map * map = nullptr;
+    const double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    gpuCheck(eskf_cloud_create(ctx, kN, &raw), "eskf_cloud_create");
+    gpuCheck(eskf_cloud_create(ctx, kN, &ds), "eskf_cloud_create");
+    gpuCheck(
+      eskf_map_create(
+        ctx, config.local_map.voxel_size, static_cast<uint32_t>(config.local_map.max_num_points_per_voxel),
+        1u << 16, &map), "eskf_map_create");
+    const eskf_icp_params prm = {config.registration.max_iteration, config.registration.neighbor_mode,
+      config.registration.translation_sq_threshold, config.registration.cosine_threshold};
+    double T[16];
+    for (int pass = 0; pass < 2; ++pass) {  // (the second insert takes the "voxel exists" paths)
+      gpuCheck(eskf_cloud_upload_f32(raw, xyz.data(), kN), "eskf_cloud_upload_f32");
+      gpuCheck(eskf_ctx_set_range_crop(ctx, 0.0, 0.0), "eskf_ctx_set_range_crop");
+      gpuCheck(
+        eskf_preprocess_cloud(ctx, raw, nullptr, I, nullptr, 0, config.cloud_preprocessor.voxel_size, ds),
+        "eskf_preprocess_cloud");
+      if (pass == 1) {gpuCheck(eskf_align_cloud(ctx, map, ds, I, &prm, T, nullptr), "eskf_align_cloud");}
+      gpuCheck(eskf_map_insert_cloud(map, ds, I), "eskf_map_insert_cloud");
+    }
+    gpuCheck(eskf_ctx_sync(ctx), "eskf_ctx_sync");
+    eskf_map_destroy(map);
+    eskf_cloud_destroy(ds);
+    eskf_cloud_destroy(raw);
   }
 
   // src/Odometry.cpp:9-110

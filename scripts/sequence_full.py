@@ -32,7 +32,7 @@ def main():
     scans, imu = bench.make_log(a.frames, seed=43)
     t_gen = time.time() - t0
     od = odometry.Odometry(odometry.default_config(device_resident=1, **bench.odom_overrides()), 0)
-    dev_ms, removed, voxels, inserted = [], [], [], []
+    dev_ms, removed, voxels, inserted, iters = [], [], [], [], []
     prev = [0.0]
 
     def feed(i):
@@ -61,6 +61,7 @@ def main():
         removed.append(int(inf.last_removed))
         voxels.append(int(inf.map_voxels))
         inserted.append(int(inf.last_inserted))
+        iters.append(int(inf.last_iterations))
     info = od.info()
     dev = np.array(dev_ms)
     tr = S.corridor_trajectory()
@@ -79,7 +80,14 @@ def main():
            "filter_states": int(info.n_states),
            "vs_ground_truth": {"max_m": max(e[0] for e in gt_err), "max_rad": max(e[1] for e in gt_err),
                                "final_m": gt_err[-1][0]},
-           "distance_travelled_m": float(np.linalg.norm(poses[-1][:3, 3]))}
+           "distance_travelled_m": float(np.linalg.norm(poses[-1][:3, 3])),
+           "frames_over_1ms_device": int((dev > 1.0).sum()),
+           # the slowest frames: (frame, device ms, e2e wall ms, GN iterations, eviction sweep in this frame?)
+           "slowest_frames": [{"frame": int(i + 1), "device_ms": float(dev[i]), "wall_ms": float(wall[i + 1]),
+                               "gn_iterations": iters[i + 1],
+                               "eviction_sweep": bool(removed[i + 1] != removed[i])}
+                              for i in np.argsort(-dev)[:6]],
+           "gn_iterations": {"mean": float(np.mean(iters[1:])), "max": int(np.max(iters[1:]))}}
     od.close()
     if not a.no_oracle:
         import oracle as O
