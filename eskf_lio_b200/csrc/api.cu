@@ -246,7 +246,7 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
   }
   if (const char* e = getenv("ESKF_ALIGN_DEPTH")) {
     const int v = atoi(e);
-    if (v == 0 || (v >= 3 && v <= 10)) ctx->opt_align_depth = v;
+    if (v == 0 || (v >= 3 && v <= 11)) ctx->opt_align_depth = v;
   }
   if (const char* e = getenv("ESKF_ALIGN_RESIDENT")) ctx->opt_align_resident = atoi(e);
   if (const char* e = getenv("ESKF_ALIGN_FAT_POINTS")) ctx->opt_align_fat_points = atoll(e);
@@ -365,7 +365,7 @@ int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
                  "align_block must be 0 (by cloud size), 256, 384, 448, 512, 640 or 768");
     ctx->opt_align_block = static_cast<int>(value);
   } else if (n == "align_depth") {
-    ESKF_REQUIRE(value == 0 || (value >= 3 && value <= 10), "align_depth must be 0 (default) or 3 .. 10");
+    ESKF_REQUIRE(value == 0 || (value >= 3 && value <= 11), "align_depth must be 0 (default) or 3 .. 11");
     ctx->opt_align_depth = static_cast<int>(value);
   } else if (n == "align_resident") {
     ESKF_REQUIRE(value >= -1 && value <= 1024, "align_resident must be -1 (auto) or a tile count");

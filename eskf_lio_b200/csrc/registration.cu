@@ -2022,7 +2022,7 @@ constexpr unsigned kWarpBytes9 = 10u * kPark * 4u + kRing9 * kTileBytes + 32u;  
 // are used: with lookup-only trips (~0.5 us) one tile per warp in flight (12 KB per SM) held the
 // position stream to ~1.2 TB/s (ablation, profiles/r2_align_experiments.md).  RING == 0: register loads
 // one trip ahead + an L2 prefetch.
-template <typename F, int NW, int RING>
+template <typename F, int NW, int RING, int U = 1>
 __device__ __forceinline__ double accumulate_points_parked(const AlignParams& P, const double* sT, const F* sR,
                                                            bool first, bool write_hit, uint32_t* park /* [10][kPark] */,
                                                            double* ring_sm /* [RING][96] */, unsigned* tq /* [RING] */,
@@ -2237,6 +2237,79 @@ __device__ __forceinline__ double accumulate_points_parked(const AlignParams& P,
     acc += static_cast<double>(warp_reduce_scatter32<F>(v, lane));
   };
 
+  if constexpr (U > 1) {
+    // ---- U tiles per trip (depth 11): the U filter windows and the U position sets a trip requests are
+    // mutually independent, so a trip — now U x as long — covers a loaded memory round trip with
+    // instruction-level parallelism inside the warp instead of with more warps (of which the register
+    // file allows 16)
+    static_assert(RING == 0, "U > 1 uses register loads");
+    unsigned tile_a[U], tile_b[U];
+    Slim qa[U], qb[U];
+    uint4 ta[U], tb[U];
+    double rx[U], ry[U], rz[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) tile_a[u] = next_tile();
+#pragma unroll
+    for (int u = 0; u < U; ++u) tile_b[u] = next_tile();
+    {
+      double ax[U], ay[U], az[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) load_pos(tile_a[u], ax[u], ay[u], az[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) load_pos(tile_b[u], rx[u], ry[u], rz[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        xform(tile_a[u], ax[u], ay[u], az[u], qa[u]);
+        ta[u] = window(qa[u]);
+      }
+    }
+    Entry be;
+    RecRegs br;
+    bool in_flight = false;
+    while (tile_a[0] < n_tiles) {
+      // 1. tiles B: positions have arrived; transform, key, request their windows
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        xform(tile_b[u], rx[u], ry[u], rz[u], qb[u]);
+        tb[u] = window(qb[u]);
+      }
+      // 2. positions of the tiles after those
+      unsigned tile_c[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        tile_c[u] = next_tile();
+        load_pos(tile_c[u], rx[u], ry[u], rz[u]);
+      }
+      // 3. tiles A: windows requested a trip ago; scan, park; a dense batch whenever 32 are parked
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        uint32_t cand = scan(qa[u], ta[u]);
+        if (abl_nogather) {
+          if (cand != kNoCand) acc += 1.0;
+          cand = kNoCand;
+        }
+        park_hits(qa[u], cand);
+        if (tail - head >= 32u) {
+          if (in_flight) compute(be, br);
+          pop_batch(be, br);
+          in_flight = true;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        qa[u] = qb[u];
+        ta[u] = tb[u];
+        tile_a[u] = tile_b[u];
+        tile_b[u] = tile_c[u];
+      }
+    }
+    if (in_flight) compute(be, br);
+    while (tail != head) {
+      pop_batch(be, br);
+      compute(be, br);
+    }
+    return acc;
+  }
   // ---- the lookup pipeline.  Across the loop's back edge a warp has in flight: the filter window of
   // tile A (requested a full trip ago, scanned this trip), the raw positions of tile B (register loads
   // issued a trip ago, or the head of the bulk-copy ring) and possibly a batch of gathers.
@@ -2954,6 +3027,10 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
           reinterpret_cast<double*>(wbase + 10u * kPark * 4u),
           reinterpret_cast<unsigned*>(wbase + 10u * kPark * 4u + kRing9 * kTileBytes),
           reinterpret_cast<uint64_t*>(s_dyn + static_cast<size_t>(NW) * kWarpBytes9) + (t >> 5) * kRing9, ring);
+    } else if constexpr (DEPTH == 11) {
+      acc = accumulate_points_parked<F, NW, 0, 2>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0,
+                                                          reinterpret_cast<uint32_t*>(s_dyn) + static_cast<size_t>(t >> 5) * 10u * kPark,
+                                                          nullptr, nullptr, nullptr, ring);
     } else if constexpr (DEPTH == 8) {
       acc = accumulate_points_parked<F, NW, 0>(P, s_T, s_R, it == 0, P.hit != nullptr && it == 0,
                                                reinterpret_cast<uint32_t*>(s_dyn) + static_cast<size_t>(t >> 5) * 10u * kPark,
@@ -3372,7 +3449,7 @@ struct Variant {
 // (ptxas budgets registers for the CTA size rounded up to a multiple of 128 threads).
 enum { V_F32_N1 = 0, V_F32_N7, V_F64_N1, V_F64_N7, V_F32_N1_T384, V_F32_N1_T768, V_F32_N1_T768D4,
        V_F32_N1_T640D4, V_F32_N1_T512D4, V_F32_N1_T640R, V_F32_N1_T512R, V_F32_N1_T640Q, V_F32_N1_T512Q,
-       V_F32_N1_T640S, V_F32_N1_T512S, V_F32_N1_T640P, V_F32_N1_T512P, V_F32_N1_T768P, V_F32_N1_T640B, V_F32_N1_T512B, V_F32_N1_T448D4, V_F32_N1_T384D4, V_COUNT };
+       V_F32_N1_T640S, V_F32_N1_T512S, V_F32_N1_T640P, V_F32_N1_T512P, V_F32_N1_T768P, V_F32_N1_T640B, V_F32_N1_T512B, V_F32_N1_T448D4, V_F32_N1_T384D4, V_F32_N1_T512U2, V_F32_N1_T384U2, V_COUNT };
 
 // measured on B200, dense config (2M pts, 10 iterations per launch):
 //   U=1/3 CTAs 1.267 ms, U=1/4 CTAs 1.246 ms, U=2/3 CTAs 1.303 ms,
@@ -3445,6 +3522,11 @@ Variant g_variants[V_COUNT] = {
      reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 448, 4>), 448, 448, 1},
     {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 384, 4>),
      reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 384, 4>), 384, 384, 1},
+    // depth 11 (parked candidates, 2 tiles of lookups per trip; 3 per trip measured 157 us at 384 threads)
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 512, 11>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 512, 4>), 512, 512, 1, 4},
+    {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 384, 11>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 384, 4>), 384, 384, 1, 4},
 };
 
 // Large clouds (>= ctx->opt_align_fat_points, default 2^17) take one fat CTA per SM: fewer partial
@@ -3460,9 +3542,10 @@ int variant_index(const eskf_ctx* ctx, const AlignArgs& a) {
   switch (threads) {
     case 768: return depth == 8 ? V_F32_N1_T768P : depth == 4 ? V_F32_N1_T768D4 : V_F32_N1_T768;
     case 640: return depth == 9 ? V_F32_N1_T640B : depth == 8 ? V_F32_N1_T640P : depth == 7 ? V_F32_N1_T640S : depth == 6 ? V_F32_N1_T640Q : depth == 5 ? V_F32_N1_T640R : V_F32_N1_T640D4;
-    case 512: return depth == 9 ? V_F32_N1_T512B : depth == 8 ? V_F32_N1_T512P : depth == 7 ? V_F32_N1_T512S : depth == 6 ? V_F32_N1_T512Q : depth == 5 ? V_F32_N1_T512R : V_F32_N1_T512D4;
+    case 512: return depth == 11 ? V_F32_N1_T512U2 : depth == 9 ? V_F32_N1_T512B : depth == 8 ? V_F32_N1_T512P : depth == 7 ? V_F32_N1_T512S : depth == 6 ? V_F32_N1_T512Q : depth == 5 ? V_F32_N1_T512R : V_F32_N1_T512D4;
     case 448: return V_F32_N1_T448D4;
-    case 384: return depth == 4 && ctx->opt_align_depth == 4 ? V_F32_N1_T384D4 : V_F32_N1_T384;
+    case 384: return depth == 11 ? V_F32_N1_T384U2 :
+                     depth == 4 && ctx->opt_align_depth == 4 ? V_F32_N1_T384D4 : V_F32_N1_T384;
     default: return V_F32_N1;
   }
 }

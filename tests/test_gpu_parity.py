@@ -610,7 +610,9 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
                 # depth 9: depth 8 with the positions streamed through a cp.async.bulk ring
                 (512, 9, 2, 1, -1, 1), (512, 9, 1, 0, -1, 0), (640, 9, 4, 1, -1, 1),
                 # depth 10: three launches per iteration (high-occupancy lookup -> hit list in HBM -> dense gather -> solve)
-                (0, 10, 2, 1, -1, 1)]:
+                (0, 10, 2, 1, -1, 1),
+                # depth 11: parked candidates with 2 tiles of lookups per trip
+                (512, 11, 2, 1, -1, 1), (384, 11, 1, 0, -1, 0)]:
             c2.set_option("align_block", block)
             c2.set_option("align_depth", depth)
             c2.set_option("align_ticket_chunk", chunk)
@@ -662,7 +664,7 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
         with pytest.raises(capi.EskfError):
             c2.set_option("align_block", 500)
         with pytest.raises(capi.EskfError):
-            c2.set_option("align_depth", 11)
+            c2.set_option("align_depth", 12)
         with pytest.raises(capi.EskfError):
             c2.set_option("align_ticket_chunk", 3)
     finally:
