@@ -50,7 +50,7 @@ SYMBOLS = [
     "eskf_cloud_download", "eskf_cloud_size", "eskf_cloud_transform", "eskf_cloud_copy",
     "eskf_map_create", "eskf_map_destroy", "eskf_map_insert", "eskf_map_insert_cloud",
     "eskf_map_evict", "eskf_map_size", "eskf_map_capacity", "eskf_map_compact", "eskf_map_query", "eskf_map_export",
-    "eskf_ctx_set_range_crop", "eskf_preprocess", "eskf_preprocess_cloud", "eskf_downsample_cov",
+    "eskf_ctx_set_range_crop", "eskf_stamps_sorted", "eskf_preprocess", "eskf_preprocess_cloud", "eskf_downsample_cov",
     "eskf_align", "eskf_align_cloud", "eskf_align_cloud_begin", "eskf_align_end", "eskf_align_batch",
     "eskf_linearize",
     "eskf_align_cloud_fixed",
@@ -81,6 +81,14 @@ def lib():
             getattr(L, name)  # AttributeError if the ABI is incomplete
         _lib = L
     return _lib
+
+
+def stamps_sorted(point_time) -> bool:
+    """eskf_stamps_sorted: are the per-point stamps non-decreasing (host-only, no GPU needed)."""
+    t = _f64(point_time)
+    f = lib().eskf_stamps_sorted
+    f.restype = C.c_int
+    return bool(f(_d(t), C.c_size_t(t.shape[0])))
 
 
 def check(status: int):

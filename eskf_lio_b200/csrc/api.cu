@@ -385,6 +385,9 @@ int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
     ctx->opt_align_xchg_ll = value != 0;
   } else if (n == "align_ll") {
     ctx->opt_align_ll = value != 0;
+  } else if (n == "stamps_sorted") {
+    ESKF_REQUIRE(value >= -1 && value <= 1, "stamps_sorted must be -1 (check), 0 or 1");
+    ctx->opt_stamps_sorted = static_cast<int>(value);
   } else if (n == "align_dyn16") {
     ESKF_REQUIRE(value >= 1 && value <= 12, "align_dyn16 must be in [1, 12]");
     ctx->opt_align_dyn16 = static_cast<int>(value);

@@ -169,6 +169,7 @@ struct eskf_ctx {
   int opt_knn_buffer = 128;
   int opt_insert_sorted = 0;    // 1: always take the radix-sort insert path
   int opt_align_block = 0;      // CTA size of the 1-neighbour fp32 align kernel: 0 = by cloud size, 256 | 384 | 512 | 640 | 768
+  int opt_stamps_sorted = -1;   // deskew: -1 = check the stamps (one pass over them), 1 = caller vouches they are non-decreasing, 0 = they are not
   int opt_align_dyn16 = 3;      // sixteenths of an align pass dealt by tickets (the rest is a fixed stride per warp)
   int opt_align_chunk = 2;      // tiles taken per ticket in the dynamic tail of an align pass (1 | 2 | 4)
   int opt_align_depth = 0;      // large-cloud align kernel: 0 = default (6), 3 | 4 = round-1 register pipelines, 5 = SM-resident positions + probe filter + bulk-copy ring, 6 = producer / consumer warps around a shared-memory hit queue
@@ -312,7 +313,7 @@ int map_probe_filter(const eskf_map* m, const uint8_t** filt);
 int wait_mail(eskf_ctx* ctx, const volatile unsigned* word, unsigned seq);
 
 int compute_deskew_segments(const double* point_time, size_t n, const eskf_state* states,
-                            size_t n_states, std::vector<DeskewSeg>* out);
+                            size_t n_states, std::vector<DeskewSeg>* out, int sorted_hint = -1);
 
 // registration.cu ---------------------------------------------------------
 struct AlignArgs {

@@ -59,7 +59,11 @@ public:
       o.attitude_xyzw[3] = states[i].attitude.w;
     }
     const auto T = T_il_.matrix();
+    gpuCheck(
+      eskf_ctx_set_option(GpuContext::get(), "stamps_sorted", lidarMeas->stampsSorted),
+      "eskf_ctx_set_option(stamps_sorted)");
     run(*lidarMeas->cloud, pointTime, T.data(), st.data(), st.size());
+    gpuCheck(eskf_ctx_set_option(GpuContext::get(), "stamps_sorted", -1), "eskf_ctx_set_option(stamps_sorted)");
     lidarMeas->pointTime.clear();
     lidarMeas->pointTime.shrink_to_fit();
     lidarMeas->pointTimeView = nullptr;

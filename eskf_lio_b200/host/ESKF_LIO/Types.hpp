@@ -177,6 +177,7 @@ struct LidarMeasurement
   // frame has been consumed.  Null => pointTime is used.
   const double * pointTimeView = nullptr;
   std::size_t pointTimeCount = 0;
+  int stampsSorted = -1;  // 1 / 0: stamps known (not) non-decreasing (checked on arrival), -1: unknown
 };
 using LidarMeasurementPtr = std::shared_ptr<LidarMeasurement>;
 

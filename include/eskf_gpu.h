@@ -120,12 +120,25 @@ int eskf_ctx_launch_count(eskf_ctx* ctx, uint64_t* n);
  *   "knn_buffer"           candidates the 30-NN selection keeps in shared memory before it falls
  *                          back to serial insertion (1..128, default 128; tests force the fallback)
  *   "align_block"          CTA size of the 1-neighbour fp32 registration kernel: 0 = chosen by cloud
- *                          size (default); 256, 384 or 768 threads (24 warps per SM), 640 or 512
- *                          (20 / 16 warps with 96 / 128 registers, 4-deep load rotation)
- *   "align_depth"          load rotation of the 768-thread kernel: 3 = loads issued and consumed in
- *                          the same trip, 4 = consumed one trip later; 0 = the build's default
+ *                          size (default: 256 threads x 3 CTAs per SM, or one 512-thread CTA per SM
+ *                          from "align_fat_points" points on); 256, 384, 448, 512, 640 or 768
+ *   "align_fat_points"     cloud size from which the one-CTA-per-SM shape is used (default 131072)
+ *   "align_depth"          arrangement of a pass over a large cloud: 0 = default (4), 3 = loads issued
+ *                          and consumed in the same trip, 4 = consumed one trip later (register
+ *                          rotation), 5..11 = the experimental arrangements of DESIGN.md section 8
+ *                          (shared-memory staging by cp.async.bulk, role-specialised warps, phase
+ *                          split, parked candidates, three launches per iteration): same results
+ *   "align_filter"         1 = large clouds probe the 8-bit filter derived from the tags (default), 0 =
+ *                          the 16-bit tags
+ *   "align_flags"          L2 eviction-policy bits of the pass (default 16 = filter windows evict_last)
+ *   "align_ll"             1 = the step of an iteration reaches the CTAs as flagged 8-byte words
+ *                          (default), 0 = data + release flag
+ *   "align_xchg_ll"        the same choice for the exchange of the sums between GPUs (default 1)
  *   "align_ticket_chunk"   warp tiles taken per ticket in the load-balanced tail of a pass over a
- *                          large cloud (1, 2 or 4; default 2) */
+ *                          large cloud (1, 2 or 4; default 2)
+ *   "align_dyn16"          sixteenths of a pass dealt by tickets (1..12, default 3)
+ *   "stamps_sorted"        deskew: -1 = check the per-point stamps on every call (default), 1 / 0 = the
+ *                          caller states they are / are not non-decreasing (see eskf_stamps_sorted) */
 int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value);
 /* CUDA-event timing on the context's own stream (bench.py's roofline leg) */
 int eskf_ctx_timer_start(eskf_ctx* ctx);
@@ -198,6 +211,15 @@ int eskf_map_export(eskf_map* m, size_t capacity, size_t* n, int32_t* key_xyz, u
  * erased ahead of voxelDownsampleAndEstimateCovariances.  Source indices reported by the preprocessor
  * stay indices into the uncropped sweep.  Applies to every later eskf_preprocess* call on ctx. */
 int eskf_ctx_set_range_crop(eskf_ctx* ctx, double min_range, double max_range);
+
+/* 1 when the per-point stamps are non-decreasing (the reference's own precondition for deskew,
+ * src/CloudPreprocessor.cpp:33), else 0.  The preprocessor needs to know: on sorted stamps the segment
+ * ends of the reference's forward scan (:54-61) are binary searches, otherwise the scan itself is taken.
+ * By default it checks on every call (one pass over the stamps on the host, on the frame's critical
+ * path); a caller that ran this when the sweep arrived passes the answer with
+ * eskf_ctx_set_option(ctx, "stamps_sorted", 0 | 1) before eskf_preprocess* (-1 = check, the default).
+ * A wrong 1 is not detected.  Host-only, needs no GPU. */
+int eskf_stamps_sorted(const double* point_time, size_t n);
 int eskf_preprocess(eskf_ctx* ctx, const double* xyz, const double* point_time, size_t n,
                     const double T_il[16], const eskf_state* states, size_t n_states,
                     double voxel_size, size_t* n_out, double* xyz_out, double* cov_out,

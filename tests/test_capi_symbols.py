@@ -105,3 +105,17 @@ def test_align_batch_argument_checks_without_gpu(built):
     assert "distinct" in str(e.value)
     with pytest.raises(ValueError):
         capi.align_batch([Fake(0x1000)], [Fake(1)], [], [])
+
+
+def test_stamps_sorted_host_helper(built):
+    """eskf_stamps_sorted (host-only): the precondition of the reference's deskew
+    (src/CloudPreprocessor.cpp:33) as a question; equal stamps count as sorted, block boundaries
+    of the vectorised loop (4096) and tiny inputs are covered."""
+    import numpy as np
+    t = np.arange(20000) * 1.5e-6
+    assert capi.stamps_sorted(t) and capi.stamps_sorted(t[:1]) and capi.stamps_sorted(t[:0])
+    assert capi.stamps_sorted(np.repeat(t[:100], 3))
+    for k in (1, 2, 4095, 4096, 4097, 8192, 19999):
+        u = t.copy()
+        u[k] = u[k - 1] - 1e-9
+        assert not capi.stamps_sorted(u), k

@@ -329,6 +329,21 @@ def test_preprocess_with_unsorted_stamps(ctx, oracle, frames):
     assert np.abs(gc - oc).max() < 1e-7
     sp, _, ssrc = oracle.preprocess(xyz, t, frames.T_il, states, 0.5)
     assert len(ssrc) != len(osrc) or not np.array_equal(sp, op)   # (a different segmentation than the sorted one)
+    # the caller's answer instead of the per-call check (option "stamps_sorted"): same results
+    assert not capi.stamps_sorted(tu) and capi.stamps_sorted(t)
+    try:
+        ctx.set_option("stamps_sorted", 0)
+        hp, _, hsrc = ctx.preprocess(xyz, tu, frames.T_il, states, 0.5)
+        np.testing.assert_array_equal(hsrc, osrc)
+        np.testing.assert_array_equal(hp, op)
+        ctx.set_option("stamps_sorted", 1)
+        hp, _, hsrc = ctx.preprocess(xyz, t, frames.T_il, states, 0.5)
+        np.testing.assert_array_equal(hsrc, ssrc)
+        np.testing.assert_array_equal(hp, sp)
+        with pytest.raises(capi.EskfError):
+            ctx.set_option("stamps_sorted", 2)
+    finally:
+        ctx.set_option("stamps_sorted", -1)
 
 
 @pytest.mark.parametrize("with_states", [False, True])
