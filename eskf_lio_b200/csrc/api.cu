@@ -21,6 +21,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int voxelize_max_blocks(int sm_count, int* out);
+int voxelize_cluster_max(int* out);
 int align_max_blocks(int sm_count, int* out);
 int align_sharded(eskf_ctx* ctx, const AlignArgs& a, eskf_allreduce_fn allreduce, void* user,
                   double T_out[16], eskf_align_info* info);
@@ -239,6 +240,10 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
   if (const char* e = getenv("ESKF_ALIGN_DYNAMIC")) ctx->opt_align_dynamic = atoi(e) != 0;
   if (const char* e = getenv("ESKF_L2_PERSIST")) ctx->opt_l2_persist = atoi(e) != 0;
   if (const char* e = getenv("ESKF_TRACE")) ctx->opt_trace = atoi(e) != 0;
+  if (const char* e = getenv("ESKF_VOX_CLUSTER")) {
+    const int v = atoi(e);
+    if (v == 0 || v == 1 || v == 8 || v == 16) ctx->opt_vox_cluster = v;
+  }
   if (const char* e = getenv("ESKF_MAPPED_RESULTS")) ctx->opt_mapped_results = atoi(e) != 0;
   if (const char* e = getenv("ESKF_ALIGN_BLOCK")) {
     const int v = atoi(e);
@@ -282,6 +287,7 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
   }
   cudaGetLastError();
   int st = voxelize_max_blocks(ctx->sm_count, &ctx->max_blocks_voxelize);
+  if (st == ESKF_OK) st = voxelize_cluster_max(&ctx->vox_cluster_max);
   if (st == ESKF_OK) st = align_max_blocks(ctx->sm_count, &ctx->max_blocks_align);
   if (st == ESKF_OK) {
     void* hp = nullptr;
@@ -319,7 +325,7 @@ int eskf_ctx_destroy(eskf_ctx* ctx) {
   ctx->crop_cloud = nullptr;
   eskf::DevBuf* bufs[] = {&ctx->stage, &ctx->sortbuf, &ctx->hist, &ctx->hdr, &ctx->runs,
                           &ctx->sorted_xyz, &ctx->segs, &ctx->work, &ctx->spill, &ctx->partials, &ctx->astate,
-                          &ctx->misc, &ctx->knn_levels, &ctx->knn_nbr, &ctx->link, &ctx->crop_orig, &ctx->crop_cnt};
+                          &ctx->misc, &ctx->knn_levels, &ctx->knn_nbr, &ctx->link, &ctx->crop_orig, &ctx->crop_cnt, &ctx->vox_stamps};
   for (auto* b : bufs) b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->mail_h) cudaFreeHost(ctx->mail_h);
@@ -385,6 +391,9 @@ int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
     ctx->opt_align_xchg_ll = value != 0;
   } else if (n == "align_ll") {
     ctx->opt_align_ll = value != 0;
+  } else if (n == "vox_cluster") {
+    ESKF_REQUIRE(value == 0 || value == 1 || value == 8 || value == 16, "vox_cluster must be 0, 1, 8 or 16");
+    ctx->opt_vox_cluster = static_cast<int>(value);
   } else if (n == "stamps_sorted") {
     ESKF_REQUIRE(value >= -1 && value <= 1, "stamps_sorted must be -1 (check), 0 or 1");
     ctx->opt_stamps_sorted = static_cast<int>(value);

@@ -63,7 +63,7 @@ struct KnnParams {
   const uint32_t* orig;   // nullable: source index -> index in the uncropped sweep (range crop)
   float4* oc4;
   float2* oc2;
-  const uint4* levels;    // block-range tables (common.cuh)
+  uint4* levels;          // block-range tables (common.cuh); read by the search, emptied again by the finish kernel
   unsigned level_stride;
   uint32_t* nbr;          // [kKnn][nbr_pitch] neighbour source indices, ascending distance
   uint32_t* nbr_cnt;      // [n_kept]
@@ -678,6 +678,18 @@ __global__ void __launch_bounds__(kSearchThreads) knn_search_kernel(KnnParams P)
 // ===================================================================== K4b
 __global__ void __launch_bounds__(64) knn_finish_kernel(KnnParams P) {
   const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+  {
+    // the search is done with the block-range tables: empty the entries this sweep could have used, so
+    // that the next sweep's voxelize kernel need not (11 MB of stores for a 64k-point sweep, spread
+    // here over n threads of which two thirds have nothing else to do)
+    const unsigned bits = P.hdr->bits, nthreads = gridDim.x * blockDim.x;
+    const uint4 empty = make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (int L = 0; L < kKnnHashLevels; ++L) {
+      const unsigned slots = knn_level_slots(P.n, bits, L);
+      uint4* tab = P.levels + static_cast<size_t>(L) * P.level_stride;
+      for (unsigned k = r; k < slots; k += nthreads) tab[k] = empty;
+    }
+  }
   if (r >= P.hdr->n_out) return;
   const unsigned j0 = P.kept_pos[r];
   const int cnt = static_cast<int>(P.nbr_cnt[r]);
@@ -985,6 +997,7 @@ int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
     trace_mark(ctx, "knn_search");
     knn_finish_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(P);
     ESKF_CUDA(cudaGetLastError());
+    ctx->knn_levels_clean = true;
     trace_mark(ctx, "knn_finish");
     count_launch(ctx, 2);
   }

@@ -137,6 +137,9 @@ int eskf_ctx_launch_count(eskf_ctx* ctx, uint64_t* n);
  *   "align_ticket_chunk"   warp tiles taken per ticket in the load-balanced tail of a pass over a
  *                          large cloud (1, 2 or 4; default 2)
  *   "align_dyn16"          sixteenths of a pass dealt by tickets (1..12, default 3)
+ *   "vox_cluster"          1 = a batch of up to 65536 points is voxelised and sorted by ONE thread-block
+ *                          cluster (hardware cluster barriers between the phases; default), 0 = always the
+ *                          grid-wide kernel with software barriers, 8 = clusters capped at 8 CTAs
  *   "stamps_sorted"        deskew: -1 = check the per-point stamps on every call (default), 1 / 0 = the
  *                          caller states they are / are not non-decreasing (see eskf_stamps_sorted) */
 int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value);

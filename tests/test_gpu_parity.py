@@ -201,6 +201,50 @@ def test_key_range_error(ctx, sorted_path):
 
 
 # -------------------------------------------------------------- preprocess
+@pytest.mark.parametrize("cap", [1, 8])
+def test_voxelize_one_cluster_equals_grid_wide_kernel(ctx, oracle, frames, cap):
+    """A sweep is voxelised + radix-sorted by ONE thread-block cluster (hardware barriers; option
+    "vox_cluster", 16 CTAs or capped at 8) — every output must be bit-identical with the grid-wide kernel's
+    (software barriers), for the preprocessor (full sweep, a 2.5k-point one, deskew + crop) and for the
+    sorted map-insert path, and equal to the oracle's."""
+    xyz, t = frames.raw[3]
+    states = _deskew_states(t)
+    r = np.linalg.norm(xyz, axis=1)
+    cases = [(xyz, t, states, 0.3, (0.0, 0.0)), (xyz[:2500], t[:2500], None, 0.5, (0.0, 0.0)),
+             (xyz, t, states, 0.5, (float(np.quantile(r, 0.1)), float(np.quantile(r, 0.9)))), (xyz[:1], t[:1], None, 0.5, (0.0, 0.0)),
+             (xyz[:6000], t[:6000], None, 0.0007, (0.0, 0.0)), (xyz[:30000], t[:30000], states, 0.3, (0.0, 0.0))]   # > 16 bits per axis: key and index in separate arrays
+    out = {}
+    try:
+        for mode in (0, cap):
+            ctx.set_option("vox_cluster", mode)
+            res = []
+            for x, tt, st, v, (mn, mx) in cases:
+                ctx.set_range_crop(mn, mx)
+                res.append(ctx.preprocess(x, tt if st is not None else None, frames.T_il, st, v))
+            ctx.set_range_crop(0.0, 0.0)
+            ctx.set_option("map_insert_sorted", 1)
+            gm = capi.Map(ctx, 0.5, 50, 1 << 10)
+            for (p, c), T in zip(frames.ds[:3], frames.poses[:3]):
+                gm.insert(p, c, T)
+            ctx.set_option("map_insert_sorted", 0)
+            out[mode] = (res, gm.export())
+    finally:
+        ctx.set_option("vox_cluster", 1)
+        ctx.set_option("map_insert_sorted", 0)
+        ctx.set_range_crop(0.0, 0.0)
+    for (p0, c0, s0), (p1, c1, s1) in zip(out[0][0], out[cap][0]):
+        np.testing.assert_array_equal(s0, s1)
+        np.testing.assert_array_equal(p0, p1)
+        np.testing.assert_array_equal(c0, c1)
+    for u, v in zip(out[0][1], out[cap][1]):
+        np.testing.assert_array_equal(u, v)
+    x, tt, st, v, _ = cases[0]
+    op, oc, osrc = oracle.preprocess(x, tt, frames.T_il, st, v)
+    np.testing.assert_array_equal(out[cap][0][0][2], osrc)
+    np.testing.assert_array_equal(out[cap][0][0][0], op)
+    assert np.abs(out[cap][0][0][1] - oc).max() < 1e-7
+
+
 @pytest.mark.parametrize("voxel", [0.5, 0.3])
 def test_downsample_and_covariances(ctx, oracle, frames, voxel):
     xyz, t = frames.raw[2]
