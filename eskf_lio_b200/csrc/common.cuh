@@ -163,7 +163,8 @@ __host__ __device__ __forceinline__ uint64_t morton3(uint32_t x, uint32_t y, uin
 // costs one or two 16 B loads instead of two 16-step binary searches.
 // Entry (uint4): x,y = block key (Morton >> 3L) lo/hi, z = start, w = end;
 // all-ones = empty.  Level L's table starts at L * level_stride entries and
-// uses knn_level_slots() of them (a power of two >= 2 x the blocks it can hold).
+// uses knn_level_slots() of them (a power of two >= 2 x the blocks it can hold; the kernels size it by
+// the number of occupied voxels, the host reserves for one block per point).
 constexpr int kKnnHashLevels = 6;
 
 __host__ __device__ __forceinline__ unsigned knn_level_slots(unsigned n, unsigned bits, int L) {

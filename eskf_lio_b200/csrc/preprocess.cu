@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(kSearchThreads) knn_search_kernel(KnnParams P)
   __shared__ unsigned s_mask[kKnnHashLevels];
   const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   if (threadIdx.x < kKnnHashLevels)
-    s_mask[threadIdx.x] = knn_level_slots(P.n, P.hdr->bits, static_cast<int>(threadIdx.x)) - 1u;
+    s_mask[threadIdx.x] = knn_level_slots(P.hdr->n_out, P.hdr->bits, static_cast<int>(threadIdx.x)) - 1u;
   __syncthreads();
   const unsigned n_kept = P.hdr->n_out;
   const unsigned sel = P.hdr->sel;
@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(64) knn_finish_kernel(KnnParams P) {
     const unsigned bits = P.hdr->bits, nthreads = gridDim.x * blockDim.x;
     const uint4 empty = make_uint4(~0u, ~0u, ~0u, ~0u);
     for (int L = 0; L < kKnnHashLevels; ++L) {
-      const unsigned slots = knn_level_slots(P.n, bits, L);
+      const unsigned slots = knn_level_slots(P.hdr->n_out, bits, L);
       uint4* tab = P.levels + static_cast<size_t>(L) * P.level_stride;
       for (unsigned k = r; k < slots; k += nthreads) tab[k] = empty;
     }

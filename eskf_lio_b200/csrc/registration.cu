@@ -3079,7 +3079,7 @@ __global__ void __launch_bounds__(T, MINB) align_kernel(AlignParams P) {
       s_last = (ticket == G * static_cast<unsigned>(it + 1) - 1u) ? 1 : 0;
     }
     __syncthreads();
-    const bool ll = DEPTH >= 5 && P.ll != 0;
+    const bool ll = P.ll != 0;
     if (s_last) {
       ESKF_STAMP(t == 0, 2);
       final_reduce<NW>(P.partials, G, s_part, s_sum);

@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(256) knn_levels_kernel(const uint64_t* key0, c
   for (int L = 0; L < kKnnHashLevels; ++L) {
     head[L] = (dprev >> (3 * L)) != 0;
     tail[L] = (dnext >> (3 * L)) != 0;
-    mask[L] = knn_level_slots(n, bits, L) - 1u;
+    mask[L] = knn_level_slots(hdr->n_out, bits, L) - 1u;  // (occupied blocks of any level <= occupied voxels = kept points)
     const uint64_t bk = cur >> (3 * L);
     slot[L] = static_cast<unsigned>(hash_key(bk)) & mask[L];
     old[L] = 0ull;
