@@ -385,7 +385,7 @@ int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
     ESKF_REQUIRE(value >= 0 && value <= 20, "align_cons must be 0 (adaptive) or a warp count");
     ctx->opt_align_cons = static_cast<int>(value);
   } else if (n == "align_flags") {
-    ESKF_REQUIRE(value >= 0 && value < 4096, "align_flags is a bit mask below 4096");
+    ESKF_REQUIRE(value >= 0 && value < 16384, "align_flags is a bit mask below 16384");
     ctx->opt_align_flags = static_cast<int>(value);
   } else if (n == "align_xchg_ll") {
     ctx->opt_align_xchg_ll = value != 0;

@@ -263,6 +263,7 @@ __device__ __forceinline__ double accumulate_points(const AlignParams& P, const 
   const double* sy = first ? P.y0 : P.wy;
   const double* sz = first ? P.z0 : P.wz;
   const unsigned n_tiles = (P.n + tile_pts - 1) / tile_pts;
+  const double inv_voxel = 1.0 / P.voxel;
   double acc = 0.0;
   for (unsigned tile = wglobal; tile < n_tiles; tile += wstride) {
     const unsigned start = tile * tile_pts + lane;
@@ -299,9 +300,9 @@ __device__ __forceinline__ double accumulate_points(const AlignParams& P, const 
         __stcs(P.wy + i, y[u]);
         __stcs(P.wz + i, z[u]);
       }
-      kx[u] = voxel_coord(x[u], P.voxel);
-      ky[u] = voxel_coord(y[u], P.voxel);
-      kz[u] = voxel_coord(z[u], P.voxel);
+      kx[u] = voxel_coord(x[u], P.voxel, inv_voxel);  // (== the division, common.cuh)
+      ky[u] = voxel_coord(y[u], P.voxel, inv_voxel);
+      kz[u] = voxel_coord(z[u], P.voxel, inv_voxel);
 #pragma unroll
       for (int o = 0; o < NN; ++o) {
         const int vx = kx[u] + c_off7[o][0], vy = ky[u] + c_off7[o][1], vz = kz[u] + c_off7[o][2];
@@ -317,6 +318,41 @@ __device__ __forceinline__ double accumulate_points(const AlignParams& P, const 
     }
     // stage 3: resolve the lookups
     const VoxelSlot* slot[U][NN];
+#if !defined(ESKF_ABLATE)
+    if (NN > 1 && (P.flags & 4096u) != 0u) {  // (align_flags bit 4096: the round-1 order, one lookup after the other: 5-10 % slower)
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int o = 0; o < NN; ++o)
+          slot[u][o] = resolve_probe(P.tags, P.slots, P.n_slots, key[u][o], addr[u][o], tag0[u][o]);
+    } else if (NN > 1) {
+      // the neighbourhood's lookups together: the key words of every home slot whose tag matches are
+      // requested back to back (one HBM round trip for up to NN records instead of NN dependent ones);
+      // a lookup that has to walk on (tag of another key at home, or a 2^-16 tag collision) takes the
+      // serial path from where it stands
+      uint64_t hk[U][NN];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int o = 0; o < NN; ++o) {
+          hk[u][o] = kEmptyKey;
+          if (tag0[u][o] != 0u && tag0[u][o] == addr[u][o].tag) {
+            hk[u][o] = load_key(P.slots + addr[u][o].home);
+            // (the record's second 32 B sector, read once the key is confirmed)
+            if (P.flags & 8192u)  // (bit 8192; measured: no gain, 30 % slower on a table spread over 640 MB)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(P.slots + addr[u][o].home) + 32));
+          }
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int o = 0; o < NN; ++o) {
+          if (tag0[u][o] == 0u) slot[u][o] = nullptr;
+          else if (tag0[u][o] == addr[u][o].tag && hk[u][o] == key[u][o]) slot[u][o] = P.slots + addr[u][o].home;
+          else slot[u][o] = resolve_probe(P.tags, P.slots, P.n_slots, key[u][o], addr[u][o], tag0[u][o]);
+        }
+    }
+#endif
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -339,7 +375,7 @@ __device__ __forceinline__ double accumulate_points(const AlignParams& P, const 
           slot[u][o] = nullptr;
         }
 #else
-        slot[u][o] = resolve_probe(P.tags, P.slots, P.n_slots, key[u][o], addr[u][o], tag0[u][o]);
+        if (NN == 1) slot[u][o] = resolve_probe(P.tags, P.slots, P.n_slots, key[u][o], addr[u][o], tag0[u][o]);
 #endif
         if (write_hit && valid[u])
           P.hit[static_cast<size_t>(NN) * (start + 32u * u) + o] = slot[u][o] != nullptr ? 1 : 0;
