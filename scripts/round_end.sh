@@ -11,6 +11,8 @@ if [ -z "$SKIP_TESTS" ]; then python -m pytest tests -m gpu -x -q > gpurun_out/p
 [ -z "$SKIP_TESTS" ] && tail -2 gpurun_out/pytest_gpu_$TAG.log
 ncu --set full --clock-control none --import-source on -k regex:align_kernel -s 2 -c 1 -f \
     -o gpurun_out/prof_align_$TAG python scripts/dense_align.py --reps 1 --warmup 2 > gpurun_out/prof_align_$TAG.log 2>&1
+[ -n "$SKIP_FRAME_NCU" ] || ncu --set full --clock-control none --import-source on -k regex:voxelize_cluster -s 40 -c 1 -f \
+    -o gpurun_out/prof_voxcl_$TAG python scripts/frame_probe.py 44 > gpurun_out/prof_voxcl_$TAG.log 2>&1
 python scripts/summarize_profiles.py $TAG > /dev/null 2>&1
 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 tail -c 1200 gpurun_out/bench_$TAG.json

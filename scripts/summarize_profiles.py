@@ -102,6 +102,7 @@ def main():
     ncu_rep(tag, "prof_knns", "knn_search_kernel on a 64k-point frame (0.3 m voxels, ~20k kept points)")
     ncu_rep(tag, "prof_knnf", "knn_finish_kernel on a 64k-point frame")
     ncu_rep(tag, "prof_vox", "voxelize_kernel on a 64k-point frame")
+    ncu_rep(tag, "prof_voxcl", "voxelize_cluster_kernel (one 16-CTA cluster, DSMEM sort) on a 64k-point frame")
     ncu_rep(tag, "prof_ins", "insert_runs_kernel on one frame")
     ncu_rep(tag, "prof_fold", "fold_lists_kernel on one frame (sort-free map insert)")
     for n in (f"bench_{tag}.json", f"bench_ref_{tag}.json"):
