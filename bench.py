@@ -403,6 +403,10 @@ def dense_leg(args, capi, sharded, D, rank, world, local_rank):
         ncorr = [int(v) for v in r["ncorr"]]
     out["ms_launch"] = D.max(float(np.median(times)))[0]
     out["ncorr_fixed"] = ncorr
+    # which of the two large-cloud loop shapes this context's one-off timing kept (eskf_gpu.h "align_autotune")
+    tb = ctx.get_option("align_tuned_block")
+    out["kernel_shape"] = {512: "4-deep load rotation, 512 threads x 1 CTA/SM, 8-bit probe filter",
+                           256: "3-stage pipeline, 256 threads x 3 CTAs/SM, 16-bit tags"}.get(tb, f"{tb} threads")
 
     # ---- parity, in the same run
     D.barrier()
@@ -832,6 +836,7 @@ def main():
             "roofline": {
                 "bound": "hbm", "kernel": "align_kernel<float> (fused transform + voxel lookup + "
                                           "J^T W J / J^T W r + reduction + on-device solve + NVLink exchange)",
+                "kernel_shape": d["kernel_shape"] + " (chosen by the context's one-off timing of both on this device)",
                 "workload": f"{d['shard_points']} source points per GPU vs the {d['n_vox']}-voxel map, "
                             f"{DENSE_ITERS} GN iterations per launch",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

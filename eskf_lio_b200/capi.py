@@ -45,7 +45,7 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void
 SYMBOLS = [
     "eskf_abi_version", "eskf_last_error", "eskf_device_count", "eskf_host_alloc", "eskf_host_free",
     "eskf_ctx_create", "eskf_ctx_destroy", "eskf_ctx_sync", "eskf_ctx_stream",
-    "eskf_ctx_launch_count", "eskf_ctx_set_option", "eskf_ctx_timer_start", "eskf_ctx_timer_stop",
+    "eskf_ctx_launch_count", "eskf_ctx_set_option", "eskf_ctx_get_option", "eskf_ctx_timer_start", "eskf_ctx_timer_stop",
     "eskf_cloud_create", "eskf_cloud_destroy", "eskf_cloud_upload", "eskf_cloud_upload_f32",
     "eskf_cloud_download", "eskf_cloud_size", "eskf_cloud_transform", "eskf_cloud_copy",
     "eskf_map_create", "eskf_map_destroy", "eskf_map_insert", "eskf_map_insert_cloud",
@@ -169,6 +169,11 @@ class Context:
 
     def set_option(self, name: str, value: int):
         check(lib().eskf_ctx_set_option(self._h, name.encode(), C.c_int64(int(value))))
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int64(0)
+        check(lib().eskf_ctx_get_option(self._h, name.encode(), C.byref(v)))
+        return int(v.value)
 
     def set_range_crop(self, min_range: float = 0.0, max_range: float = 0.0):
         """Range crop of the preprocessor (LiDAR frame; max_range 0 = unbounded; (0, 0) = off)."""

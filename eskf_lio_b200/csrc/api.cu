@@ -240,6 +240,7 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
   if (const char* e = getenv("ESKF_ALIGN_DYNAMIC")) ctx->opt_align_dynamic = atoi(e) != 0;
   if (const char* e = getenv("ESKF_L2_PERSIST")) ctx->opt_l2_persist = atoi(e) != 0;
   if (const char* e = getenv("ESKF_TRACE")) ctx->opt_trace = atoi(e) != 0;
+  if (const char* e = getenv("ESKF_ALIGN_AUTOTUNE")) ctx->opt_align_autotune = atoi(e) != 0;
   if (const char* e = getenv("ESKF_VOX_CLUSTER")) {
     const int v = atoi(e);
     if (v == 0 || v == 1 || v == 8 || v == 16) ctx->opt_vox_cluster = v;
@@ -354,6 +355,23 @@ int eskf_ctx_launch_count(eskf_ctx* ctx, uint64_t* n) {
   return ESKF_OK;
 }
 
+int eskf_ctx_get_option(eskf_ctx* ctx, const char* name, int64_t* value) {
+  ESKF_REQUIRE(ctx && name && value, "null argument");
+  const std::string n(name);
+  if (n == "align_tuned_block") *value = ctx->tuned_block;          // 0 until a large cloud was registered
+  else if (n == "align_autotune") *value = ctx->opt_align_autotune;
+  else if (n == "align_block") *value = ctx->opt_align_block;
+  else if (n == "align_depth") *value = ctx->opt_align_depth;
+  else if (n == "vox_cluster") *value = ctx->opt_vox_cluster;
+  else if (n == "vox_cluster_max") *value = ctx->vox_cluster_max;   // CTAs of the largest placeable cluster (0: none)
+  else if (n == "stamps_sorted") *value = ctx->opt_stamps_sorted;
+  else {
+    set_error("unknown option '%s'", name);
+    return ESKF_ERR_INVALID;
+  }
+  return ESKF_OK;
+}
+
 int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
   ESKF_REQUIRE(ctx && name, "null argument");
   const std::string n(name);
@@ -391,6 +409,9 @@ int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
     ctx->opt_align_xchg_ll = value != 0;
   } else if (n == "align_ll") {
     ctx->opt_align_ll = value != 0;
+  } else if (n == "align_autotune") {
+    ctx->opt_align_autotune = value != 0;
+    ctx->tuned_block = 0;
   } else if (n == "vox_cluster") {
     ESKF_REQUIRE(value == 0 || value == 1 || value == 8 || value == 16, "vox_cluster must be 0, 1, 8 or 16");
     ctx->opt_vox_cluster = static_cast<int>(value);

@@ -158,6 +158,8 @@ struct eskf_ctx {
   int max_blocks_voxelize = 0;
   eskf::DevBuf vox_stamps;            // ESKF_TRACE: phase stamps of the one-cluster voxelize kernel
   bool knn_levels_clean = false;  // every entry of knn_levels is empty (kept so by knn_finish_kernel; false after (re)allocation or a failed call)
+  int tuned_block = 0;          // large clouds: CTA size the autotune chose (0: not tuned)
+  size_t tuned_n = 0;           // ... on a cloud of this many points
   int vox_cluster_max = 0;      // CTAs of the largest cluster the one-cluster voxelize kernel can be placed in (0: off)
   int max_blocks_align = 0;
   int opt_align_dynamic = 1;    // eskf_ctx_set_option knobs (initialised from the environment)
@@ -172,6 +174,7 @@ struct eskf_ctx {
   int opt_knn_buffer = 128;
   int opt_insert_sorted = 0;    // 1: always take the radix-sort insert path
   int opt_align_block = 0;      // CTA size of the 1-neighbour fp32 align kernel: 0 = by cloud size, 256 | 384 | 512 | 640 | 768
+  int opt_align_autotune = 1;   // time the two large-cloud loop shapes once per context and keep the faster one
   int opt_vox_cluster = 1;      // 0 = sweeps go through the grid-wide voxelize kernel, 1 = through one cluster when they fit, 8 = cluster capped at 8 CTAs
   int opt_stamps_sorted = -1;   // deskew: -1 = check the stamps (one pass over them), 1 = caller vouches they are non-decreasing, 0 = they are not
   int opt_align_dyn16 = 3;      // sixteenths of an align pass dealt by tickets (the rest is a fixed stride per warp)

@@ -3573,7 +3573,9 @@ int variant_index(const eskf_ctx* ctx, const AlignArgs& a) {
   if (base != V_F32_N1) return base;
   int threads = ctx->opt_align_block;  // 0 = choose by cloud size
   const bool fat = a.cloud && static_cast<int64_t>(a.cloud->n) >= ctx->opt_align_fat_points;
-  if (threads == 0) threads = fat ? ESKF_ALIGN_FAT_T : kT;
+  // (a large cloud: the 4-deep 512-thread shape, unless this context's one-off timing of the two shapes
+  // on its own device and data said the 3-stage 256-thread one is faster there: autotune_fat below)
+  if (threads == 0) threads = fat ? (ctx->tuned_block != 0 && ctx->opt_align_depth == 0 ? ctx->tuned_block : ESKF_ALIGN_FAT_T) : kT;
   const int depth = ctx->opt_align_depth != 0 ? ctx->opt_align_depth : 4;
   switch (threads) {
     case 768: return depth == 8 ? V_F32_N1_T768P : depth == 4 ? V_F32_N1_T768D4 : V_F32_N1_T768;
@@ -3859,46 +3861,9 @@ PendingAlign* pending(eskf_ctx* ctx) {
 }  // namespace
 
 // launch the persistent Gauss-Newton kernel and return; align_end collects the result
-int align_begin(eskf_ctx* ctx, const AlignArgs& a, const eskf_align_info* info) {
-  ESKF_CUDA(cudaSetDevice(ctx->device));
-  PendingAlign* pd = pending(ctx);
-  ESKF_REQUIRE(!pd->active, "a registration is already in flight on this context (call eskf_align_end)");
-  const int max_it = a.fixed_iterations > 0 ? a.fixed_iterations : a.max_iteration;
-  const bool p2p = a.comm != nullptr && a.comm->world > 1;
-  pd->a = a;
-  pd->max_it = max_it;
-  pd->mail_seq = 0u;
-  pd->trivial = a.cloud && a.cloud->n == 0 && !p2p;
-  if (pd->trivial) {
-    pd->active = true;
-    return ESKF_OK;
-  }
-  AlignParams P;
-  TraceLayout L;
-  int G = 1;
-  size_t dyn_smem = 0;
-  ESKF_TRY(fill_params(ctx, a, max_it, &P, &L, &G, &dyn_smem));
-  pd->L = L;
-  if (p2p) {
-    eskf_comm* c = a.comm;
-    ESKF_REQUIRE(c->ctx == ctx, "communicator belongs to another context");
-    ESKF_REQUIRE(c->connected, "communicator is not connected (eskf_comm_connect)");
-    ESKF_REQUIRE(max_it < 65535, "too many iterations for the exchange flag encoding");
-    P.world = c->world;
-    P.rank = c->rank;
-    P.seq = ++c->seq;
-    for (int r = 0; r < c->world; ++r) P.peers[r] = c->peers[r];
-  }
-  const bool want_trace = info && (info->trace_H || info->trace_b || info->trace_ncorr || info->trace_step);
-  if (ctx->opt_mapped_results && ctx->mail_h != nullptr && !want_trace && !ctx->opt_trace) {
-    pd->mail_seq = ++ctx->align_seq;
-    if (pd->mail_seq == 0u) pd->mail_seq = ++ctx->align_seq;
-    P.mail = ctx->mail_d;
-    P.mail_seq = pd->mail_seq;
-  }
-  ESKF_CUDA(cudaMemsetAsync(ctx->astate.p, 0, L.o_H, ctx->stream));
-  // keep the probed tag array resident in L2 across iterations (the position /
-  // covariance streams would otherwise evict it every pass)
+// keep the probed tag array (or filter) resident in L2 across iterations (the position /
+// covariance streams would otherwise evict it every pass): a persisting access-policy window on the stream
+int apply_l2_window(eskf_ctx* ctx, const AlignParams& P, const AlignArgs& a) {
   if (ctx->opt_l2_persist && ctx->l2_persist_bytes > 0) {
     cudaStreamAttrValue attr;
     std::memset(&attr, 0, sizeof attr);
@@ -3926,6 +3891,115 @@ int align_begin(eskf_ctx* ctx, const AlignArgs& a, const eskf_align_info* info) 
     ctx->l2_win_ptr = nullptr;
     ctx->l2_win_bytes = 0;
   }
+  return ESKF_OK;
+}
+
+// The pool's B200s fall into two kinds on the dense pass (same clocks, same binary): on one the 4-deep
+// 512-thread shape runs a 2 M-point iteration in ~86 us and the 3-stage 256-thread shape in ~88-98, on the
+// other 103 and 90 (profiles/r2_align_experiments.md section 8).  Nothing the API reports tells them apart, so
+// the first large-cloud registration of a context times both shapes on its own device, map and cloud (6
+// iterations each, results discarded, no exchange) and the context keeps the faster one; again when the
+// cloud size changes by more than 2x.  Both shapes give the same correspondence sets and poses equal to
+// rounding (tests).  Off: option "align_autotune" 0, or any explicit "align_block" / "align_depth".
+int autotune_fat(eskf_ctx* ctx, const AlignArgs& a) {
+  const int cand[2] = {ESKF_ALIGN_FAT_T, kT};
+  AlignArgs ta = a;
+  constexpr int kTuneIters = 6, kTuneReps = 4;  // (the first launch of a shape warms up; the fastest of the rest counts)
+  ta.fixed_iterations = kTuneIters;
+  ta.max_iteration = kTuneIters;
+  ta.comm = nullptr;
+  ta.d_hit = nullptr;
+  cudaEvent_t e0, e1;
+  ESKF_CUDA(cudaEventCreate(&e0));
+  ESKF_CUDA(cudaEventCreate(&e1));
+  float best = 0.f;
+  int best_block = 0, rc = ESKF_OK;
+  for (int c = 0; c < 2 && rc == ESKF_OK; ++c) {
+    ctx->tuned_block = cand[c];
+    float t_min = 0.f;
+    for (int rep = 0; rep < kTuneReps && rc == ESKF_OK; ++rep) {
+      AlignParams P;
+      TraceLayout L;
+      int G = 1;
+      size_t dyn_smem = 0;
+      rc = fill_params(ctx, ta, kTuneIters, &P, &L, &G, &dyn_smem);
+      if (rc != ESKF_OK) break;
+      rc = apply_l2_window(ctx, P, ta);
+      if (rc != ESKF_OK) break;
+      void* args[] = {&P};
+      const Variant& var = g_variants[variant_index(ctx, ta)];
+      cudaError_t e = cudaMemsetAsync(ctx->astate.p, 0, L.o_H, ctx->stream);
+      if (e == cudaSuccess) e = cudaEventRecord(e0, ctx->stream);
+      if (e == cudaSuccess) e = cudaLaunchCooperativeKernel(var.align, dim3(G), dim3(var.threads), args, dyn_smem, ctx->stream);
+      if (e == cudaSuccess) e = cudaEventRecord(e1, ctx->stream);
+      if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+      float ms = 0.f;
+      if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+      if (e != cudaSuccess) {
+        set_error("autotune: %s", cudaGetErrorString(e));
+        rc = ESKF_ERR_CUDA;
+        break;
+      }
+      count_launch(ctx);
+      if (rep > 0 && (t_min == 0.f || ms < t_min)) t_min = ms;
+    }
+    if (rc == ESKF_OK && (best_block == 0 || t_min < best)) {
+      best = t_min;
+      best_block = cand[c];
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  ctx->tuned_block = rc == ESKF_OK ? best_block : 0;
+  ctx->tuned_n = rc == ESKF_OK ? a.cloud->n : 0;
+  if (ctx->opt_trace && rc == ESKF_OK)
+    std::fprintf(stderr, "[eskf trace] align autotune: %d threads for %zu points\n", best_block, static_cast<size_t>(a.cloud->n));
+  return rc;
+}
+
+int align_begin(eskf_ctx* ctx, const AlignArgs& a, const eskf_align_info* info) {
+  ESKF_CUDA(cudaSetDevice(ctx->device));
+  PendingAlign* pd = pending(ctx);
+  ESKF_REQUIRE(!pd->active, "a registration is already in flight on this context (call eskf_align_end)");
+  const int max_it = a.fixed_iterations > 0 ? a.fixed_iterations : a.max_iteration;
+  const bool p2p = a.comm != nullptr && a.comm->world > 1;
+  pd->a = a;
+  pd->max_it = max_it;
+  pd->mail_seq = 0u;
+  pd->trivial = a.cloud && a.cloud->n == 0 && !p2p;
+  if (pd->trivial) {
+    pd->active = true;
+    return ESKF_OK;
+  }
+  if (ctx->opt_align_autotune && ctx->opt_align_block == 0 && ctx->opt_align_depth == 0 && !a.fp64_math &&
+      a.neighbor_mode == 1 && a.cloud && static_cast<int64_t>(a.cloud->n) >= ctx->opt_align_fat_points &&
+      (ctx->tuned_block == 0 || a.cloud->n > 2 * ctx->tuned_n || 2 * a.cloud->n < ctx->tuned_n))
+    ESKF_TRY(autotune_fat(ctx, a));
+  AlignParams P;
+  TraceLayout L;
+  int G = 1;
+  size_t dyn_smem = 0;
+  ESKF_TRY(fill_params(ctx, a, max_it, &P, &L, &G, &dyn_smem));
+  pd->L = L;
+  if (p2p) {
+    eskf_comm* c = a.comm;
+    ESKF_REQUIRE(c->ctx == ctx, "communicator belongs to another context");
+    ESKF_REQUIRE(c->connected, "communicator is not connected (eskf_comm_connect)");
+    ESKF_REQUIRE(max_it < 65535, "too many iterations for the exchange flag encoding");
+    P.world = c->world;
+    P.rank = c->rank;
+    P.seq = ++c->seq;
+    for (int r = 0; r < c->world; ++r) P.peers[r] = c->peers[r];
+  }
+  const bool want_trace = info && (info->trace_H || info->trace_b || info->trace_ncorr || info->trace_step);
+  if (ctx->opt_mapped_results && ctx->mail_h != nullptr && !want_trace && !ctx->opt_trace) {
+    pd->mail_seq = ++ctx->align_seq;
+    if (pd->mail_seq == 0u) pd->mail_seq = ++ctx->align_seq;
+    P.mail = ctx->mail_d;
+    P.mail_seq = pd->mail_seq;
+  }
+  ESKF_CUDA(cudaMemsetAsync(ctx->astate.p, 0, L.o_H, ctx->stream));
+  ESKF_TRY(apply_l2_window(ctx, P, a));
   pd->mk = false;
   if (ctx->opt_align_depth == 10 && !a.fp64_math && a.neighbor_mode != 7 && a.cloud &&
       static_cast<int64_t>(a.cloud->n) >= ctx->opt_align_fat_points) {

@@ -137,12 +137,21 @@ int eskf_ctx_launch_count(eskf_ctx* ctx, uint64_t* n);
  *   "align_ticket_chunk"   warp tiles taken per ticket in the load-balanced tail of a pass over a
  *                          large cloud (1, 2 or 4; default 2)
  *   "align_dyn16"          sixteenths of a pass dealt by tickets (1..12, default 3)
+ *   "align_autotune"       1 = the first registration of a large cloud on a context times the two loop
+ *                          shapes (4-deep 512 threads, 3-stage 256 threads) on its own device and data and
+ *                          keeps the faster one (default; the pool's GPUs differ); 0 = always the 4-deep one.
+ *                          Ignored while "align_block" or "align_depth" is set explicitly
  *   "vox_cluster"          1 = a batch of up to 65536 points is voxelised and sorted by ONE thread-block
  *                          cluster (hardware cluster barriers between the phases; default), 0 = always the
  *                          grid-wide kernel with software barriers, 8 = clusters capped at 8 CTAs
  *   "stamps_sorted"        deskew: -1 = check the per-point stamps on every call (default), 1 / 0 = the
  *                          caller states they are / are not non-decreasing (see eskf_stamps_sorted) */
 int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value);
+/* Read-back of a few of them and of what the context found out about its device: "align_tuned_block"
+ * (CTA size the large-cloud autotune settled on, 0 = not run yet), "align_autotune", "align_block",
+ * "align_depth", "vox_cluster", "vox_cluster_max" (CTAs of the largest cluster the device places for the
+ * one-cluster voxelize kernel, 0 = none), "stamps_sorted". */
+int eskf_ctx_get_option(eskf_ctx* ctx, const char* name, int64_t* value);
 /* CUDA-event timing on the context's own stream (bench.py's roofline leg) */
 int eskf_ctx_timer_start(eskf_ctx* ctx);
 int eskf_ctx_timer_stop(eskf_ctx* ctx, float* elapsed_ms);

@@ -20,7 +20,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from eskf_lio_b200 import capi, synth as S  # noqa: E402
 
 DEFAULTS = {"align_block": 0, "align_depth": 0, "align_ticket_chunk": 2, "align_dyn16": 3, "align_dynamic_tiles": 1,
-            "align_resident": -1, "align_ll": 1, "align_flags": 16, "align_cons": 0, "align_filter": 1, "l2_persist": 1, "align_fat_points": 1 << 17}
+            "align_resident": -1, "align_ll": 1, "align_flags": 16, "align_cons": 0, "align_filter": 1, "l2_persist": 1, "align_fat_points": 1 << 17,
+            "align_autotune": 0}
 
 
 def apply(ctx, cell):

@@ -692,6 +692,21 @@ def test_align_large_cloud_cta_shapes_and_ticket_chunks(oracle):
             assert rq["iterations"] == ro["iterations"], tag
             dt, dr = pose_err(ro["T"], rq["T"])
             assert dt < POSE_T_TOL and dr < POSE_R_TOL, (tag, dt, dr)
+        # the (0, 0) cell went through the context's one-off timing of the two large-cloud loop shapes
+        assert c2.get_option("align_tuned_block") in (256, 512)
+        for block, depth in ((0, 0),):
+            c2.set_option("align_block", block)
+            c2.set_option("align_depth", depth)
+            c2.set_option("align_resident", -1)
+            for tune in (0, 1, 1):
+                c2.set_option("align_autotune", tune)   # (setting it forgets the earlier choice)
+                assert c2.get_option("align_tuned_block") == 0
+                rq = gm.align_cloud(cl, guess, trace=True)
+                assert c2.get_option("align_tuned_block") == (0 if tune == 0 else c2.get_option("align_tuned_block"))
+                assert (c2.get_option("align_tuned_block") in (256, 512)) == bool(tune)
+                np.testing.assert_array_equal(rq["ncorr"], ro["ncorr"])
+                dt, dr = pose_err(ro["T"], rq["T"])
+                assert dt < POSE_T_TOL and dr < POSE_R_TOL, (tune, dt, dr)
         # the per-point correspondence flags of a cloud this size (depth 5, the 4-deep loop, 256-thread CTAs)
         for block, depth, res in ((0, 0, -1), (0, 10, -1), (512, 9, -1), (640, 8, -1), (768, 8, -1), (640, 7, 3), (640, 6, 0), (640, 5, 0), (640, 5, -1), (640, 4, -1), (256, 3, -1)):
             c2.set_option("align_block", block)
