@@ -326,7 +326,7 @@ int eskf_ctx_destroy(eskf_ctx* ctx) {
   ctx->crop_cloud = nullptr;
   eskf::DevBuf* bufs[] = {&ctx->stage, &ctx->sortbuf, &ctx->hist, &ctx->hdr, &ctx->runs,
                           &ctx->sorted_xyz, &ctx->segs, &ctx->work, &ctx->spill, &ctx->partials, &ctx->astate,
-                          &ctx->misc, &ctx->knn_levels, &ctx->knn_nbr, &ctx->link, &ctx->crop_orig, &ctx->crop_cnt, &ctx->vox_stamps};
+                          &ctx->misc, &ctx->knn_levels, &ctx->knn_nbr, &ctx->link, &ctx->crop_orig, &ctx->crop_cnt, &ctx->vox_stamps, &ctx->xform};
   for (auto* b : bufs) b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->mail_h) cudaFreeHost(ctx->mail_h);

@@ -156,6 +156,7 @@ struct eskf_ctx {
   size_t pinned_bytes = 0;
   eskf_cloud* tmp_cloud[3] = {nullptr, nullptr, nullptr};  // host-buffer entry points
   int max_blocks_voxelize = 0;
+  eskf::DevBuf xform;                 // transformed sweep when the preprocessor must leave its input as delivered
   eskf::DevBuf vox_stamps;            // ESKF_TRACE: phase stamps of the one-cluster voxelize kernel
   bool knn_levels_clean = false;  // every entry of knn_levels is empty (kept so by knn_finish_kernel; false after (re)allocation or a failed call)
   int tuned_block = 0;          // large clouds: CTA size the autotune chose (0: not tuned)

@@ -890,21 +890,33 @@ int check_header(eskf_ctx* ctx, unsigned* n_out) {
   return ESKF_OK;
 }
 
-// raw (device, xyz only) -> out (device, xyz + cov + src index)
-int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
+// raw (device, xyz only) -> out (device, xyz + cov + src index).  Launch only; preprocess_finish waits
+// for the kept-point count.  keep_input: the transformed positions go to a scratch buffer and raw stays
+// as delivered (so that the call can be repeated with other deskew segments).
+int preprocess_launch(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
                       const std::vector<DeskewSeg>& segs, double voxel, eskf_cloud* out,
-                      const uint32_t* orig = nullptr) {
+                      const uint32_t* orig, bool keep_input, bool* mapped_out) {
   const unsigned n = static_cast<unsigned>(raw->n);
   ESKF_TRY(cloud_reserve(out, raw->n, true));
+  double* tx = raw->x();
+  double* ty = raw->y();
+  double* tz = raw->z();
+  if (keep_input) {
+    const size_t pitch = (static_cast<size_t>(n) + 63) / 64 * 64;
+    ESKF_TRY(ctx->xform.ensure(3 * pitch * sizeof(double)));
+    tx = ctx->xform.as<double>();
+    ty = tx + pitch;
+    tz = ty + pitch;
+  }
   VoxelizeArgs a;
   std::memset(&a, 0, sizeof a);
   a.in_x = raw->x();
   a.in_y = raw->y();
   a.in_z = raw->z();
   a.in_stride = 1;
-  a.out_x = raw->x();
-  a.out_y = raw->y();
-  a.out_z = raw->z();
+  a.out_x = tx;
+  a.out_y = ty;
+  a.out_z = tz;
   a.cov = nullptr;
   a.n = n;
   a.voxel = voxel;
@@ -944,9 +956,9 @@ int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
   P.sidx[1] = v.idx[1];
   P.kept_src = v.kept_src;
   P.kept_pos = v.kept_pos;
-  P.px = raw->x();
-  P.py = raw->y();
-  P.pz = raw->z();
+  P.px = tx;
+  P.py = ty;
+  P.pz = tz;
   P.n = n;
   P.voxel = voxel;
   P.ox = out->x();
@@ -1001,6 +1013,11 @@ int preprocess_device(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il,
     trace_mark(ctx, "knn_finish");
     count_launch(ctx, 2);
   }
+  *mapped_out = mapped;
+  return ESKF_OK;
+}
+
+int preprocess_finish(eskf_ctx* ctx, eskf_cloud* out, bool mapped) {
   unsigned n_out = 0;
   int waited = 1;
   if (mapped) {
@@ -1143,6 +1160,23 @@ using namespace eskf;
 
 extern "C" {
 
+namespace {
+int preprocess_launch_any(eskf_ctx* ctx, eskf_cloud* raw, const double* T_il, const std::vector<DeskewSeg>& segs,
+                          double voxel_size, eskf_cloud* out, bool keep_input, bool* mapped, bool* empty) {
+  *empty = false;
+  if (ctx->crop) {
+    ESKF_TRY(crop_device(ctx, raw));  // (reads raw, writes the scratch cloud: raw stays as delivered)
+    if (ctx->crop_cloud->n == 0) {
+      *empty = true;
+      return ESKF_OK;
+    }
+    return eskf::preprocess_launch(ctx, ctx->crop_cloud, T_il, segs, voxel_size, out, ctx->crop_orig.as<uint32_t>(),
+                                   false, mapped);
+  }
+  return eskf::preprocess_launch(ctx, raw, T_il, segs, voxel_size, out, nullptr, keep_input, mapped);
+}
+}  // namespace
+
 int eskf_preprocess_cloud(eskf_ctx* ctx, eskf_cloud* raw, const double* point_time,
                           const double T_il[16], const eskf_state* states, size_t n_states,
                           double voxel_size, eskf_cloud* out) {
@@ -1156,22 +1190,30 @@ int eskf_preprocess_cloud(eskf_ctx* ctx, eskf_cloud* raw, const double* point_ti
     out->n = 0;
     return ESKF_OK;
   }
+  // Deskew segments need to know whether the stamps are non-decreasing (compute_deskew_segments).
+  // Unless the caller says (option "stamps_sorted"), the answer is taken for granted, the kernels are
+  // launched, and the one pass over the stamps that settles it runs on the host WHILE the GPU works
+  // (the host would only be waiting for the kept-point count); if the stamps turn out unsorted the call is
+  // repeated with the segments of the reference's forward scan -- the first attempt left raw untouched.
   std::vector<DeskewSeg> segs;
+  const bool optimistic = n_states > 0 && ctx->opt_stamps_sorted < 0;
   if (n_states > 0) {
     ESKF_REQUIRE(states && point_time, "deskew needs states and point_time");
-    ESKF_TRY(compute_deskew_segments(point_time, raw->n, states, n_states, &segs, ctx->opt_stamps_sorted));
+    ESKF_TRY(compute_deskew_segments(point_time, raw->n, states, n_states, &segs, optimistic ? 1 : ctx->opt_stamps_sorted));
   }
   raw->has_cov = false;
   raw->has_c32 = false;
-  if (ctx->crop) {
-    ESKF_TRY(crop_device(ctx, raw));
-    if (ctx->crop_cloud->n == 0) {
-      out->n = 0;
-      return ESKF_OK;
-    }
-    return preprocess_device(ctx, ctx->crop_cloud, T_il, segs, voxel_size, out, ctx->crop_orig.as<uint32_t>());
+  bool mapped = false, empty = false;
+  ESKF_TRY(preprocess_launch_any(ctx, raw, T_il, segs, voxel_size, out, optimistic, &mapped, &empty));
+  if (optimistic && !eskf_stamps_sorted(point_time, raw->n)) {
+    ESKF_TRY(compute_deskew_segments(point_time, raw->n, states, n_states, &segs, 0));
+    ESKF_TRY(preprocess_launch_any(ctx, raw, T_il, segs, voxel_size, out, false, &mapped, &empty));
   }
-  return preprocess_device(ctx, raw, T_il, segs, voxel_size, out);
+  if (empty) {
+    out->n = 0;
+    return ESKF_OK;
+  }
+  return eskf::preprocess_finish(ctx, out, mapped);
 }
 
 int eskf_stamps_sorted(const double* point_time, size_t n) {

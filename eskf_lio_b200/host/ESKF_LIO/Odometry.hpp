@@ -205,8 +205,6 @@ public:
       }
       measurement->pointTime.assign(pointTime, pointTime + n);
     }
-    // (while the upload runs: the deskew wants to know, and here it is off the frame's critical path)
-    measurement->stampsSorted = eskf_stamps_sorted(pointTime, n);
     measurement->startTime = pointTime[0];
     measurement->endTime = pointTime[n - 1];
     measurement->cloud = std::move(cloud);
@@ -223,7 +221,6 @@ public:
     cloud->device_ = std::shared_ptr<eskf_cloud>(raw, [](eskf_cloud *) {});  // borrowed
     measurement->pointTimeView = pointTime;
     measurement->pointTimeCount = n;
-    measurement->stampsSorted = eskf_stamps_sorted(pointTime, n);
     measurement->startTime = pointTime[0];
     measurement->endTime = pointTime[n - 1];
     measurement->cloud = std::move(cloud);

@@ -177,7 +177,7 @@ struct LidarMeasurement
   // frame has been consumed.  Null => pointTime is used.
   const double * pointTimeView = nullptr;
   std::size_t pointTimeCount = 0;
-  int stampsSorted = -1;  // 1 / 0: stamps known (not) non-decreasing (checked on arrival), -1: unknown
+  int stampsSorted = -1;  // 1 / 0: the driver knows the stamps are (not) non-decreasing, -1: unknown (the preprocessor finds out while the GPU works)
 };
 using LidarMeasurementPtr = std::shared_ptr<LidarMeasurement>;
 

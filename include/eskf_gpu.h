@@ -144,8 +144,8 @@ int eskf_ctx_launch_count(eskf_ctx* ctx, uint64_t* n);
  *   "vox_cluster"          1 = a batch of up to 65536 points is voxelised and sorted by ONE thread-block
  *                          cluster (hardware cluster barriers between the phases; default), 0 = always the
  *                          grid-wide kernel with software barriers, 8 = clusters capped at 8 CTAs
- *   "stamps_sorted"        deskew: -1 = check the per-point stamps on every call (default), 1 / 0 = the
- *                          caller states they are / are not non-decreasing (see eskf_stamps_sorted) */
+ *   "stamps_sorted"        deskew: -1 = find out on every call, overlapped with the kernels (default), 1 / 0 =
+ *                          the caller states they are / are not non-decreasing (see eskf_stamps_sorted) */
 int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value);
 /* Read-back of a few of them and of what the context found out about its device: "align_tuned_block"
  * (CTA size the large-cloud autotune settled on, 0 = not run yet), "align_autotune", "align_block",
@@ -227,16 +227,17 @@ int eskf_ctx_set_range_crop(eskf_ctx* ctx, double min_range, double max_range);
 /* 1 when the per-point stamps are non-decreasing (the reference's own precondition for deskew,
  * src/CloudPreprocessor.cpp:33), else 0.  The preprocessor needs to know: on sorted stamps the segment
  * ends of the reference's forward scan (:54-61) are binary searches, otherwise the scan itself is taken.
- * By default it checks on every call (one pass over the stamps on the host, on the frame's critical
- * path); a caller that ran this when the sweep arrived passes the answer with
- * eskf_ctx_set_option(ctx, "stamps_sorted", 0 | 1) before eskf_preprocess* (-1 = check, the default).
- * A wrong 1 is not detected.  Host-only, needs no GPU. */
+ * By default eskf_preprocess* assumes sorted stamps, launches its kernels and runs this check on the host
+ * while the GPU works; if the stamps are not sorted it repeats the call with the scan's segments (the
+ * first attempt leaves the raw cloud untouched).  A caller that knows states it with
+ * eskf_ctx_set_option(ctx, "stamps_sorted", 0 | 1) and saves the pass (-1 = find out, the default); a
+ * wrong 1 is not detected.  Host-only, needs no GPU. */
 int eskf_stamps_sorted(const double* point_time, size_t n);
 int eskf_preprocess(eskf_ctx* ctx, const double* xyz, const double* point_time, size_t n,
                     const double T_il[16], const eskf_state* states, size_t n_states,
                     double voxel_size, size_t* n_out, double* xyz_out, double* cov_out,
                     uint32_t* src_index_out);
-/* device form: raw (device, clobbered like the reference mutates
+/* device form: raw (device; may be clobbered, like the reference mutates
  * lidarMeas->cloud) -> out (device, with covariances). point_time is a host
  * array of raw->size doubles or NULL when n_states == 0. */
 int eskf_preprocess_cloud(eskf_ctx* ctx, eskf_cloud* raw, const double* point_time,
