@@ -697,15 +697,42 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
     }
   };
   auto wrap4 = [&](uint32_t b) -> uint32_t { return b + 4u == P.n_slots ? 0u : b + 4u; };
+  // large clouds probe the map's 8-bit filter (16 slots per 16 B window, held in L2 by an eviction
+  // hint) instead of the 16-bit tags: eskf_ctx option align_filter, fill_params
+  // (DEPTH 4 decides at run time; the 3-stage loop exists with the filter compiled in, DEPTH 2, for
+  // large clouds, and without it, DEPTH 3, which is what every frame runs: no extra registers there)
+  const bool use_filter = DEPTH == 4 ? P.filt != nullptr : DEPTH == 2;
+  const uint64_t pol_filt = l2_policy((P.flags >> kFlagFiltPolicyShift) & 3u);
   // first tag window of a transformed point (zeros = "empty" when it has no lookup)
   auto first_window = [&](const PtState& s) -> uint4 {
     if (s.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
+    if (use_filter) return filter_window(P.filt, s.home, pol_filt);
     const uint32_t b = s.home & ~(kTagAlign - 1u);
     return load_tag_window(P.tags, b, wrap4(b));
   };
   // finish the tag scan of s given its first window w (rarely needs more windows)
   auto finish_scan = [&](PtState& s, uint4 w) {
     if (s.tag == 0u) return;
+    if (use_filter) {
+      uint32_t b0 = s.home & ~7u;
+      uint32_t r = scan_filter_window(w, s.home & 7u, filter_tag(s.tag));
+      uint32_t scanned = 16u - (s.home & 7u);
+      while (r == kMore && scanned < P.n_slots) {
+        b0 += 16u;
+        if (b0 >= P.n_slots) b0 -= P.n_slots;
+        const uint2 lo = __ldg(reinterpret_cast<const uint2*>(P.filt + b0));
+        const uint2 hi = __ldg(reinterpret_cast<const uint2*>(P.filt + b0 + 8));
+        r = scan_filter_window(make_uint4(lo.x, lo.y, hi.x, hi.y), 0u, filter_tag(s.tag));
+        scanned += 16u;
+      }
+      if (r < 16u) {
+        uint32_t c = b0 + r;
+        if (c >= P.n_slots) c -= P.n_slots;
+        s.cand = c;
+        prefetch_record(P.slots + s.cand);
+      }
+      return;
+    }
     uint32_t b = s.home & ~(kTagAlign - 1u), b2 = wrap4(b);
     uint32_t r = scan_tag_window(w, s.home & (kTagAlign - 1u), s.tag);
     uint32_t scanned = 8u - (s.home & (kTagAlign - 1u));
@@ -827,8 +854,6 @@ __device__ __forceinline__ double accumulate_points_pipelined(const AlignParams&
       q.dz = F(z - __dmul_rn(static_cast<double>(kz) + 0.5, P.voxel));
     }
   };
-  const bool use_filter = P.filt != nullptr;  // (eskf_ctx option align_filter: the 8-bit L2-resident probe filter)
-  const uint64_t pol_filt = l2_policy((P.flags >> kFlagFiltPolicyShift) & 3u);
   auto window4 = [&](const Slim& q) -> uint4 {
     if (q.tag == 0u) return make_uint4(0u, 0u, 0u, 0u);
     if (use_filter) {
@@ -3485,7 +3510,7 @@ struct Variant {
 // (ptxas budgets registers for the CTA size rounded up to a multiple of 128 threads).
 enum { V_F32_N1 = 0, V_F32_N7, V_F64_N1, V_F64_N7, V_F32_N1_T384, V_F32_N1_T768, V_F32_N1_T768D4,
        V_F32_N1_T640D4, V_F32_N1_T512D4, V_F32_N1_T640R, V_F32_N1_T512R, V_F32_N1_T640Q, V_F32_N1_T512Q,
-       V_F32_N1_T640S, V_F32_N1_T512S, V_F32_N1_T640P, V_F32_N1_T512P, V_F32_N1_T768P, V_F32_N1_T640B, V_F32_N1_T512B, V_F32_N1_T448D4, V_F32_N1_T384D4, V_F32_N1_T512U2, V_F32_N1_T384U2, V_COUNT };
+       V_F32_N1_T640S, V_F32_N1_T512S, V_F32_N1_T640P, V_F32_N1_T512P, V_F32_N1_T768P, V_F32_N1_T640B, V_F32_N1_T512B, V_F32_N1_T448D4, V_F32_N1_T384D4, V_F32_N1_T512U2, V_F32_N1_T384U2, V_F32_N1_F, V_COUNT };
 
 // measured on B200, dense config (2M pts, 10 iterations per launch):
 //   U=1/3 CTAs 1.267 ms, U=1/4 CTAs 1.246 ms, U=2/3 CTAs 1.303 ms,
@@ -3563,6 +3588,9 @@ Variant g_variants[V_COUNT] = {
      reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 512, 4>), 512, 512, 1, 4},
     {reinterpret_cast<void*>(align_kernel<float, 1, 1, 1, 384, 11>),
      reinterpret_cast<void*>(linearize_pass_kernel<float, 1, 1, 1, 384, 4>), 384, 384, 1, 4},
+    // the 3-stage loop on the 8-bit probe filter (large clouds; "align_block" 257)
+    {reinterpret_cast<void*>(align_kernel<float, ESKF_ALIGN_U, 1, ESKF_ALIGN_MINB, kT, 2>),
+     reinterpret_cast<void*>(linearize_pass_kernel<float, ESKF_ALIGN_U, 1, ESKF_ALIGN_MINB>), kT, kT * ESKF_ALIGN_U, 1},
 };
 
 // Large clouds (>= ctx->opt_align_fat_points, default 2^17) take one fat CTA per SM: fewer partial
@@ -3584,6 +3612,7 @@ int variant_index(const eskf_ctx* ctx, const AlignArgs& a) {
     case 448: return V_F32_N1_T448D4;
     case 384: return depth == 11 ? V_F32_N1_T384U2 :
                      depth == 4 && ctx->opt_align_depth == 4 ? V_F32_N1_T384D4 : V_F32_N1_T384;
+    case 257: return V_F32_N1_F;
     default: return V_F32_N1;
   }
 }
@@ -3676,9 +3705,14 @@ int fill_params(eskf_ctx* ctx, const AlignArgs& a, int max_it, AlignParams* P, T
   P->xchg_ll = ctx->opt_align_xchg_ll;
   {
     const int vi = variant_index(ctx, a);
-    if ((vi == V_F32_N1_T768D4 || vi == V_F32_N1_T640D4 || vi == V_F32_N1_T512D4 || vi == V_F32_N1_T448D4 ||
-         vi == V_F32_N1_T384D4) && ctx->opt_align_filter && dyn_smem)
-      ESKF_TRY(map_probe_filter(m, &P->filt));  // depth 4 on the 8-bit filter
+    // large clouds probe the 8-bit filter (frames keep the 16-bit tags: their map changes every frame and
+    // the filter would have to follow it)
+    const bool fat = static_cast<int64_t>(n) >= ctx->opt_align_fat_points;
+    const bool d4 = vi == V_F32_N1_T768D4 || vi == V_F32_N1_T640D4 || vi == V_F32_N1_T512D4 || vi == V_F32_N1_T448D4 ||
+                    vi == V_F32_N1_T384D4;
+    (void)fat;
+    if ((d4 || vi == V_F32_N1_F) && ctx->opt_align_filter && dyn_smem) ESKF_TRY(map_probe_filter(m, &P->filt));
+    ESKF_REQUIRE(vi != V_F32_N1_F || P->filt != nullptr, "align_block 257 (3-stage loop on the probe filter) needs align_filter on");
   }
   if (var.depth5 == 5 && dyn_smem) {
     const size_t nw = static_cast<size_t>(var.threads / 32);
@@ -3902,7 +3936,7 @@ int apply_l2_window(eskf_ctx* ctx, const AlignParams& P, const AlignArgs& a) {
 // cloud size changes by more than 2x.  Both shapes give the same correspondence sets and poses equal to
 // rounding (tests).  Off: option "align_autotune" 0, or any explicit "align_block" / "align_depth".
 int autotune_fat(eskf_ctx* ctx, const AlignArgs& a) {
-  const int cand[2] = {ESKF_ALIGN_FAT_T, kT};
+  const int cand[3] = {ESKF_ALIGN_FAT_T, kT, 257};  // 4-deep 512 on the filter; 3-stage 256 on the tags; 3-stage 256 on the filter
   AlignArgs ta = a;
   constexpr int kTuneIters = 6, kTuneReps = 4;  // (the first launch of a shape warms up; the fastest of the rest counts)
   ta.fixed_iterations = kTuneIters;
@@ -3914,7 +3948,7 @@ int autotune_fat(eskf_ctx* ctx, const AlignArgs& a) {
   ESKF_CUDA(cudaEventCreate(&e1));
   float best = 0.f;
   int best_block = 0, rc = ESKF_OK;
-  for (int c = 0; c < 2 && rc == ESKF_OK; ++c) {
+  for (int c = 0; c < (ctx->opt_align_filter ? 3 : 2) && rc == ESKF_OK; ++c) {
     ctx->tuned_block = cand[c];
     float t_min = 0.f;
     for (int rep = 0; rep < kTuneReps && rc == ESKF_OK; ++rep) {
