@@ -3931,14 +3931,18 @@ int apply_l2_window(eskf_ctx* ctx, const AlignParams& P, const AlignArgs& a) {
 // The pool's B200s fall into two kinds on the dense pass (same clocks, same binary): on one the 4-deep
 // 512-thread shape runs a 2 M-point iteration in ~86 us and the 3-stage 256-thread shape in ~88-98, on the
 // other 103 and 90 (profiles/r2_align_experiments.md section 8).  Nothing the API reports tells them apart, so
-// the first large-cloud registration of a context times both shapes on its own device, map and cloud (6
-// iterations each, results discarded, no exchange) and the context keeps the faster one; again when the
+// the first large-cloud registration of a context times both shapes on its own device, map and cloud (6 to
+// 48 iterations per launch, results discarded, no exchange) and the context keeps the faster one; again when the
 // cloud size changes by more than 2x.  Both shapes give the same correspondence sets and poses equal to
 // rounding (tests).  Off: option "align_autotune" 0, or any explicit "align_block" / "align_depth".
 int autotune_fat(eskf_ctx* ctx, const AlignArgs& a) {
   const int cand[3] = {ESKF_ALIGN_FAT_T, kT, 257};  // 4-deep 512 on the filter; 3-stage 256 on the tags; 3-stage 256 on the filter
   AlignArgs ta = a;
-  constexpr int kTuneIters = 6, kTuneReps = 4;  // (the first launch of a shape warms up; the fastest of the rest counts)
+  // (the first launch of a shape warms up; the fastest of the rest counts.  Enough iterations per launch
+  // that the shapes' difference, a few per cent, stands clear of the launch overhead: ~1 ms of kernel)
+  constexpr int kTuneReps = 4;
+  const size_t per_it = a.cloud->n > 0 ? a.cloud->n : 1;
+  const int kTuneIters = static_cast<int>(std::min<size_t>(48, std::max<size_t>(6, 12000000 / per_it)));
   ta.fixed_iterations = kTuneIters;
   ta.max_iteration = kTuneIters;
   ta.comm = nullptr;
