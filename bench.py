@@ -407,7 +407,8 @@ def dense_leg(args, capi, sharded, D, rank, world, local_rank):
     tb = ctx.get_option("align_tuned_block")
     out["kernel_shape"] = {512: "4-deep load rotation, 512 threads x 1 CTA/SM, 8-bit probe filter",
                            256: "3-stage pipeline, 256 threads x 3 CTAs/SM, 16-bit tags",
-                           257: "3-stage pipeline, 256 threads x 3 CTAs/SM, 8-bit probe filter"}.get(tb, f"{tb} threads")
+                           257: "3-stage pipeline, 256 threads x 3 CTAs/SM, 8-bit probe filter",
+                           769: "3-stage pipeline, 768 threads x 1 CTA/SM, 16-bit tags"}.get(tb, f"{tb} threads")
 
     # ---- parity, in the same run
     D.barrier()

@@ -248,7 +248,7 @@ int eskf_ctx_create(int device, void* cuda_stream, eskf_ctx** out) {
   if (const char* e = getenv("ESKF_MAPPED_RESULTS")) ctx->opt_mapped_results = atoi(e) != 0;
   if (const char* e = getenv("ESKF_ALIGN_BLOCK")) {
     const int v = atoi(e);
-    if (v == 0 || v == 256 || v == 257 || v == 384 || v == 448 || v == 512 || v == 640 || v == 768) ctx->opt_align_block = v;
+    if (v == 0 || v == 256 || v == 257 || v == 384 || v == 448 || v == 512 || v == 640 || v == 768 || v == 769) ctx->opt_align_block = v;
   }
   if (const char* e = getenv("ESKF_ALIGN_DEPTH")) {
     const int v = atoi(e);
@@ -385,8 +385,8 @@ int eskf_ctx_set_option(eskf_ctx* ctx, const char* name, int64_t value) {
     ctx->opt_insert_sorted = value != 0;
   } else if (n == "align_block") {
     ESKF_REQUIRE(value == 0 || value == 256 || value == 257 || value == 384 || value == 448 || value == 512 ||
-                     value == 640 || value == 768,
-                 "align_block must be 0 (by cloud size), 256, 257 (256 threads, 3-stage loop on the probe filter), 384, 448, 512, 640 or 768");
+                     value == 640 || value == 768 || value == 769,
+                 "align_block must be 0 (by cloud size), 256, 257 (256 threads, 3-stage loop on the probe filter), 384, 448, 512, 640, 768 or 769 (768 threads, 3-stage loop)");
     ctx->opt_align_block = static_cast<int>(value);
   } else if (n == "align_depth") {
     ESKF_REQUIRE(value == 0 || (value >= 3 && value <= 11), "align_depth must be 0 (default) or 3 .. 11");

@@ -3613,6 +3613,7 @@ int variant_index(const eskf_ctx* ctx, const AlignArgs& a) {
     case 384: return depth == 11 ? V_F32_N1_T384U2 :
                      depth == 4 && ctx->opt_align_depth == 4 ? V_F32_N1_T384D4 : V_F32_N1_T384;
     case 257: return V_F32_N1_F;
+    case 769: return V_F32_N1_T768;  // (the 3-stage loop at 768 threads whatever "align_depth" says)
     default: return V_F32_N1;
   }
 }
@@ -3936,7 +3937,8 @@ int apply_l2_window(eskf_ctx* ctx, const AlignParams& P, const AlignArgs& a) {
 // cloud size changes by more than 2x.  Both shapes give the same correspondence sets and poses equal to
 // rounding (tests).  Off: option "align_autotune" 0, or any explicit "align_block" / "align_depth".
 int autotune_fat(eskf_ctx* ctx, const AlignArgs& a) {
-  const int cand[3] = {ESKF_ALIGN_FAT_T, kT, 257};  // 4-deep 512 on the filter; 3-stage 256 on the tags; 3-stage 256 on the filter
+  // 4-deep 512 on the filter; 3-stage 3 x 256 on the tags; 3-stage 1 x 768 on the tags; 3-stage 3 x 256 on the filter
+  const int cand[4] = {ESKF_ALIGN_FAT_T, kT, 769, 257};
   AlignArgs ta = a;
   // (the first launch of a shape warms up; the fastest of the rest counts.  Enough iterations per launch
   // that the shapes' difference, a few per cent, stands clear of the launch overhead: ~1 ms of kernel)
@@ -3952,7 +3954,7 @@ int autotune_fat(eskf_ctx* ctx, const AlignArgs& a) {
   ESKF_CUDA(cudaEventCreate(&e1));
   float best = 0.f;
   int best_block = 0, rc = ESKF_OK;
-  for (int c = 0; c < (ctx->opt_align_filter ? 3 : 2) && rc == ESKF_OK; ++c) {
+  for (int c = 0; c < (ctx->opt_align_filter ? 4 : 3) && rc == ESKF_OK; ++c) {
     ctx->tuned_block = cand[c];
     float t_min = 0.f;
     for (int rep = 0; rep < kTuneReps && rc == ESKF_OK; ++rep) {

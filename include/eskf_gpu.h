@@ -121,7 +121,9 @@ int eskf_ctx_launch_count(eskf_ctx* ctx, uint64_t* n);
  *                          back to serial insertion (1..128, default 128; tests force the fallback)
  *   "align_block"          CTA size of the 1-neighbour fp32 registration kernel: 0 = chosen by cloud
  *                          size (default: 256 threads x 3 CTAs per SM, or one 512-thread CTA per SM
- *                          from "align_fat_points" points on); 256, 384, 448, 512, 640 or 768
+ *                          from "align_fat_points" points on); 256, 384, 448, 512, 640 or 768; 257 = 256
+ *                          threads with the 3-stage loop on the probe filter, 769 = 768 threads with the
+ *                          3-stage loop (what the autotune calls its candidates)
  *   "align_fat_points"     cloud size from which the one-CTA-per-SM shape is used (default 131072)
  *   "align_depth"          arrangement of a pass over a large cloud: 0 = default (4), 3 = loads issued
  *                          and consumed in the same trip, 4 = consumed one trip later (register
@@ -138,8 +140,8 @@ int eskf_ctx_launch_count(eskf_ctx* ctx, uint64_t* n);
  *                          large cloud (1, 2 or 4; default 2)
  *   "align_dyn16"          sixteenths of a pass dealt by tickets (1..12, default 3)
  *   "align_autotune"       1 = the first registration of a large cloud on a context times the two loop
- *                          shapes (4-deep 512 threads, 3-stage 256 threads) on its own device and data and
- *                          keeps the faster one (default; the pool's GPUs differ); 0 = always the 4-deep one.
+ *                          shapes (4-deep 512 threads; 3-stage 3 x 256 or 1 x 768 threads, on the tags or the
+ *                          filter) on its own device and data and keeps the fastest (default; the pool's GPUs differ); 0 = always the 4-deep one.
  *                          Ignored while "align_block" or "align_depth" is set explicitly
  *   "vox_cluster"          1 = a batch of up to 65536 points is voxelised and sorted by ONE thread-block
  *                          cluster (hardware cluster barriers between the phases; default), 0 = always the
