@@ -9,7 +9,8 @@ TAG=${1:-r2}
 mkdir -p gpurun_out
 if [ -z "$SKIP_TESTS" ]; then python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_$TAG.log; fi
 [ -z "$SKIP_TESTS" ] && tail -2 gpurun_out/pytest_gpu_$TAG.log
-ncu --set full --clock-control none --import-source on -k regex:align_kernel -s 10 -c 1 -f \
+# (the first registration of the process autotunes: 4 shapes x 4 launches, then 2 warm-ups, then the launch captured)
+ncu --set full --clock-control none --import-source on -k regex:align_kernel -s 18 -c 1 -f \
     -o gpurun_out/prof_align_$TAG python scripts/dense_align.py --reps 1 --warmup 2 > gpurun_out/prof_align_$TAG.log 2>&1
 [ -n "$SKIP_FRAME_NCU" ] || ncu --set full --clock-control none --import-source on -k regex:voxelize_cluster -s 40 -c 1 -f \
     -o gpurun_out/prof_voxcl_$TAG python scripts/frame_probe.py 44 > gpurun_out/prof_voxcl_$TAG.log 2>&1
