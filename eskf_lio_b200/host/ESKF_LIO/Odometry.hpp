@@ -98,11 +98,21 @@ public:
     const eskf_icp_params prm = {config.registration.max_iteration, config.registration.neighbor_mode,
       config.registration.translation_sq_threshold, config.registration.cosine_threshold};
     double T[16];
+    // (the second pass deskews against two identity states, so that the segment table and the scratch
+    // buffer of the deskewing call exist before the first real sweep needs them)
+    std::vector<double> stamps(kN);
+    for (std::size_t i = 0; i < kN; ++i) {stamps[i] = 1e-6 * static_cast<double>(i);}
+    eskf_state st[2] = {};
+    st[0].timestamp = -1.0;
+    st[1].timestamp = 1.0;
+    st[0].attitude_xyzw[3] = st[1].attitude_xyzw[3] = 1.0;
     for (int pass = 0; pass < 2; ++pass) {  // (the second insert takes the "voxel exists" paths)
       gpuCheck(eskf_cloud_upload_f32(raw, xyz.data(), kN), "eskf_cloud_upload_f32");
       gpuCheck(eskf_ctx_set_range_crop(ctx, 0.0, 0.0), "eskf_ctx_set_range_crop");
       gpuCheck(
-        eskf_preprocess_cloud(ctx, raw, nullptr, I, nullptr, 0, config.cloud_preprocessor.voxel_size, ds),
+        eskf_preprocess_cloud(
+          ctx, raw, pass == 1 ? stamps.data() : nullptr, I, pass == 1 ? st : nullptr, pass == 1 ? 2 : 0,
+          config.cloud_preprocessor.voxel_size, ds),
         "eskf_preprocess_cloud");
       if (pass == 1) {gpuCheck(eskf_align_cloud(ctx, map, ds, I, &prm, T, nullptr), "eskf_align_cloud");}
       gpuCheck(eskf_map_insert_cloud(map, ds, I), "eskf_map_insert_cloud");
