@@ -300,7 +300,9 @@ public:
     for (int i = 0; i < 3; ++i) {
       for (int j = 0; j < 3; ++j) {G(6 + i, 6 + j) = (i == j ? 1.0 : 0.0) - 0.5 * skew(i, j);}
     }
-    Pn = G * Pn * G.transpose();
+    // G P G^T as (G (G P)^T)^T: both products have the sparse G on the left (24 non-zeros; the matrix
+    // product skips zero left entries), same terms in the same order as the dense form
+    Pn = (G * (G * Pn).transpose()).transpose();
     fromMat18(Pn, newState.P);
 
     states_.push_back(newState);
