@@ -101,3 +101,66 @@ def test_direct7_superset_of_direct1(oracle, small_scene):
     H7, b7, hit7, n7 = m.linearize(qw, qcw, 7)
     np.testing.assert_array_equal(hit7[:, 0], hit1[:, 0])
     assert n7 > n1 and n7 == hit7.sum()
+
+
+def _states_for(t):
+    t0, t1 = float(t.min()), float(t.max())
+    ts = t0 - 0.006 + 0.0025 * np.arange(int((t1 - t0 + 0.02) / 0.0025) + 4)
+    s = ts - t0
+    pos = np.stack([1.2 * s, 0.3 * s * s, 0.05 * np.sin(8 * s)], axis=1)
+    ang = 0.4 * s
+    quat = np.stack([0.02 * np.sin(ang), 0.01 * np.sin(ang), np.sin(ang / 2), np.cos(ang / 2)], axis=1)
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    return ts, pos, quat
+
+
+def test_deskew_unsorted_stamps_matches_numpy(oracle, small_scene):
+    """Stamps that are not non-decreasing (ring-major / merged sweeps): the C++ oracle and the NumPy
+    one both restate the reference's forward scan (src/CloudPreprocessor.cpp:54-61) — independently —
+    and must pick the same segments; the result differs from the sorted-stamp one."""
+    _, _, scans = small_scene
+    xyz, t = scans[2][0][::8], scans[2][1][::8]
+    rng = np.random.default_rng(11)
+    blocks = np.array_split(np.arange(len(t)), 23)
+    tu = t[np.concatenate([blocks[k] for k in rng.permutation(len(blocks))])].copy()
+    assert np.any(np.diff(tu) < 0)
+    # (the sweep's end time is its LAST stamp, :29 — keep it the largest, as the sorted sweep has it)
+    tu[-1] = t.max()
+    ts, pos, quat = _states_for(t)
+    out = oracle.deskew(xyz, tu, (ts, pos, quat))
+    ref = NP.deskew(xyz, tu, ts, pos, quat)
+    np.testing.assert_allclose(out, ref, atol=1e-11)
+    srt = oracle.deskew(xyz, t, (ts, pos, quat))
+    assert np.abs(out - srt).max() > 1e-3
+
+
+@pytest.mark.parametrize("bounds", [(3.0, 40.0), (5.0, 0.0), (0.0, 25.0)])
+def test_range_crop_definition_matches_numpy(oracle, small_scene, bounds):
+    """The range crop the oracle DEFINES (BASELINE north_star; the reference has none): restated in
+    NumPy from the sentence in oracle.preprocess's docstring — raw LiDAR-frame range, every point
+    transformed and deskewed as before, cropped points erased ahead of the downsample, source indices
+    into the uncropped sweep."""
+    _, _, scans = small_scene
+    xyz, t = scans[1][0][::4], scans[1][1][::4]
+    T_il = S.default_T_il()
+    states = _states_for(t)
+    mn, mx = bounds
+    op, oc, osrc = oracle.preprocess(xyz, t, T_il, states, 0.5, min_range=mn, max_range=mx)
+    r2 = (xyz[:, 0] * xyz[:, 0] + xyz[:, 1] * xyz[:, 1]) + xyz[:, 2] * xyz[:, 2]
+    keep = r2 >= mn * mn
+    if mx > 0.0:
+        keep &= r2 <= mx * mx
+    idx = np.nonzero(keep)[0]
+    assert 0 < len(idx) < len(xyz)
+    p = NP.transform_cloud(xyz, None, T_il)[0]
+    p = NP.deskew(p, t, *states)
+    rp, rc, rsrc = NP.downsample_cov(p[idx], 0.5)
+    np.testing.assert_array_equal(osrc.astype(np.int64), idx[rsrc])
+    np.testing.assert_allclose(op, rp, atol=1e-11)
+    # (the deskewed positions of the two oracles differ by ~1e-11: the covariances follow, amplified by the eigen-gap)
+    assert np.abs(oc - rc).max() < 1e-6 and np.median(np.abs(oc - rc)) < 1e-9
+    # and with the crop off the two agree as well (same helper path)
+    op0, _, osrc0 = oracle.preprocess(xyz, t, T_il, states, 0.5)
+    rp0, _, rsrc0 = NP.downsample_cov(p, 0.5)
+    np.testing.assert_array_equal(osrc0.astype(np.int64), rsrc0)
+    np.testing.assert_allclose(op0, rp0, atol=1e-11)
