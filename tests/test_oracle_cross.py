@@ -134,7 +134,7 @@ def test_deskew_unsorted_stamps_matches_numpy(oracle, small_scene):
     assert np.abs(out - srt).max() > 1e-3
 
 
-@pytest.mark.parametrize("bounds", [(3.0, 40.0), (5.0, 0.0), (0.0, 25.0)])
+@pytest.mark.parametrize("bounds", [(0.15, 0.85), (0.15, None), (None, 0.85)])  # quantiles of the raw range
 def test_range_crop_definition_matches_numpy(oracle, small_scene, bounds):
     """The range crop the oracle DEFINES (BASELINE north_star; the reference has none): restated in
     NumPy from the sentence in oracle.preprocess's docstring — raw LiDAR-frame range, every point
@@ -144,9 +144,10 @@ def test_range_crop_definition_matches_numpy(oracle, small_scene, bounds):
     xyz, t = scans[1][0][::4], scans[1][1][::4]
     T_il = S.default_T_il()
     states = _states_for(t)
-    mn, mx = bounds
-    op, oc, osrc = oracle.preprocess(xyz, t, T_il, states, 0.5, min_range=mn, max_range=mx)
     r2 = (xyz[:, 0] * xyz[:, 0] + xyz[:, 1] * xyz[:, 1]) + xyz[:, 2] * xyz[:, 2]
+    mn = float(np.sqrt(np.quantile(r2, bounds[0]))) if bounds[0] is not None else 0.0
+    mx = float(np.sqrt(np.quantile(r2, bounds[1]))) if bounds[1] is not None else 0.0
+    op, oc, osrc = oracle.preprocess(xyz, t, T_il, states, 0.5, min_range=mn, max_range=mx)
     keep = r2 >= mn * mn
     if mx > 0.0:
         keep &= r2 <= mx * mx
@@ -157,8 +158,21 @@ def test_range_crop_definition_matches_numpy(oracle, small_scene, bounds):
     rp, rc, rsrc = NP.downsample_cov(p[idx], 0.5)
     np.testing.assert_array_equal(osrc.astype(np.int64), idx[rsrc])
     np.testing.assert_allclose(op, rp, atol=1e-11)
-    # (the deskewed positions of the two oracles differ by ~1e-11: the covariances follow, amplified by the eigen-gap)
-    assert np.abs(oc - rc).max() < 1e-6 and np.median(np.abs(oc - rc)) < 1e-9
+    # (the deskewed positions of the two oracles differ by ~1e-11; the covariances follow, amplified by 1 / the
+    # gap between the two smallest eigenvalues -- line-like neighbourhoods leave the flattened axis undetermined)
+    worst = np.abs(oc - rc).reshape(len(oc), -1).max(axis=1)
+    # Neighbourhoods that are coplanar to rounding (the horizontal beam's returns): the raw covariance's
+    # smallest eigenvalue is +-1e-18, and a true SVD (NumPy here, Eigen's JacobiSVD in the reference,
+    # src/CloudPreprocessor.cpp:120-123) returns u3 = -v3 when rounding made it negative, so U F V^T carries
+    # -0.01 along the normal; the C++ oracle and the CUDA path form U F U^T (+0.01, what the
+    # regularisation means).  Those points are compared up to that sign.
+    flipped = np.linalg.eigvalsh(rc)[:, 0] < 0.0
+    assert np.mean(flipped) < 0.05
+    assert np.median(worst) < 1e-9 and worst[~flipped].max() < 1e-6
+    if flipped.any():
+        assert np.abs(worst[flipped] - 0.02).max() < 1e-6
+        ev = np.linalg.eigvalsh(oc[flipped])
+        np.testing.assert_allclose(ev, np.tile([1e-2, 1.0, 1.0], (len(ev), 1)), atol=1e-9)
     # and with the crop off the two agree as well (same helper path)
     op0, _, osrc0 = oracle.preprocess(xyz, t, T_il, states, 0.5)
     rp0, _, rsrc0 = NP.downsample_cov(p, 0.5)
